@@ -1,0 +1,243 @@
+"""Synthetic problem instances and the plain-numpy problem
+description (`ProblemSpec`) that the C-ABI binding and the oracle binding both consume.
+
+The reference ships no data (examples/data is git-ignored), so every instance here is
+generated: coordinates U[0,1000)^2 from SplitMix64(seed), distance matrix = the examples'
+`round(sqrt(dx^2+dy^2), 3)` truncation (examples/tsp/src/domain/location.rs:38-50),
+variable bounds / semantic groups exactly as the examples' cotwin builders declare them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+
+NQUEENS, TSP, VRP, VRP_SERVICE = 0, 1, 2, 3
+KIND_NAMES = {NQUEENS: "nqueens", TSP: "tsp", VRP: "vrp", VRP_SERVICE: "vrp_service"}
+LEVELS = {NQUEENS: 1, TSP: 2, VRP: 3, VRP_SERVICE: 3}
+
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+
+
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    """n outputs of SplitMix64 started at `seed` (vectorised, wraps mod 2^64)."""
+    with np.errstate(over="ignore"):
+        idx = np.arange(1, n + 1, dtype=np.uint64)
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + idx * _GOLDEN
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def uniform01(seed: int, n: int) -> np.ndarray:
+    return (splitmix64(seed, n) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def randint(seed: int, n: int, lo: int, hi_inclusive: int) -> np.ndarray:
+    span = np.uint64(hi_inclusive - lo + 1)
+    return (splitmix64(seed, n) % span).astype(np.int64) + lo
+
+
+def round3(d: np.ndarray) -> np.ndarray:
+    """greyjack/src/utils/math_utils.rs:10-13 with precision 3 (truncation toward -inf)."""
+    fl = np.floor(d)
+    return fl + np.floor((d - fl) * 1000.0) / 1000.0
+
+
+def distance_matrix(xy: np.ndarray) -> np.ndarray:
+    """examples/tsp/src/domain/location.rs:38-50; xy is [n,2] (latitude, longitude)."""
+    dlat = xy[None, :, 0] - xy[:, None, 0]
+    dlon = xy[None, :, 1] - xy[:, None, 1]
+    a = dlat * dlat
+    b = dlon * dlon
+    return round3(round3(np.sqrt(a + b)))
+
+
+@dataclass
+class ProblemSpec:
+    kind: int
+    n_vars: int
+    lower_bounds: np.ndarray
+    upper_bounds: np.ndarray
+    frozen: Optional[np.ndarray] = None          # uint8 [n_vars]
+    initial: Optional[np.ndarray] = None         # f64 [n_vars]; NaN = None
+    groups: Dict[str, np.ndarray] = field(default_factory=dict)  # semantic group -> var ids
+    column_id: Optional[np.ndarray] = None       # int64 [n_vars] (nqueens)
+    n_locations: int = 0
+    distance_matrix: Optional[np.ndarray] = None  # f64 [L,L]
+    coords: Optional[np.ndarray] = None          # f64 [L,2]
+    n_depots: int = 0
+    n_vehicles: int = 0
+    vehicle_depot: Optional[np.ndarray] = None   # int64 [K]
+    vehicle_capacity: Optional[np.ndarray] = None  # uint64 [K]
+    work_day_start: Optional[np.ndarray] = None
+    work_day_end: Optional[np.ndarray] = None
+    demand: Optional[np.ndarray] = None          # uint64 [L]
+    tw_start: Optional[np.ndarray] = None
+    tw_end: Optional[np.ndarray] = None
+    service_time: Optional[np.ndarray] = None
+    time_windowed: bool = False
+    weights: np.ndarray = field(default_factory=lambda: np.ones(4, dtype=np.float64))
+    score_precision: Optional[list] = None       # Solver::solve arg 5
+    name: str = ""
+
+    @property
+    def levels(self) -> int:
+        return LEVELS[self.kind]
+
+
+def nqueens(n: int, seed: int = 45) -> ProblemSpec:
+    """examples/nqueens: row_id[i] in [0, n-1], column_id[i] = i, base = seeded permutation
+    (domain_builder.rs: DomainBuilder::new(n, seed)); one semantic group "common"."""
+    perm = np.arange(n, dtype=np.int64)
+    r = splitmix64(seed, n)
+    for i in range(n - 1, 0, -1):  # Fisher-Yates
+        j = int(r[i] % np.uint64(i + 1))
+        perm[i], perm[j] = perm[j], perm[i]
+    return ProblemSpec(
+        kind=NQUEENS, n_vars=n,
+        lower_bounds=np.zeros(n), upper_bounds=np.full(n, float(n - 1)),
+        initial=perm.astype(np.float64),
+        groups={"common": np.arange(n, dtype=np.int32)},
+        column_id=np.arange(n, dtype=np.int64),
+        score_precision=None, name=f"nqueens-{n}")
+
+
+def tsp(n_cities: int, seed: int = 1, greedy: bool = True) -> ProblemSpec:
+    """examples/tsp: n_stops = n_cities-1 variables in [1, n_cities-1], depot = location 0
+    (persistence/cotwin_builder.rs:49-77)."""
+    xy = uniform01(seed, 2 * n_cities).reshape(n_cities, 2) * 1000.0
+    D = distance_matrix(xy)
+    n = n_cities - 1
+    init = np.arange(1, n_cities, dtype=np.float64)
+    spec = ProblemSpec(
+        kind=TSP, n_vars=n,
+        lower_bounds=np.ones(n), upper_bounds=np.full(n, float(n_cities - 1)),
+        initial=init, groups={"common": np.arange(n, dtype=np.int32)},
+        n_locations=n_cities, distance_matrix=D, coords=xy, n_depots=1,
+        score_precision=[3, 3], name=f"tsp-{n_cities}")
+    if greedy:
+        spec.initial = tsp_greedy(D)
+    return spec
+
+
+def tsp_greedy(D: np.ndarray) -> np.ndarray:
+    """Nearest-neighbour init, examples/tsp/src/persistence/cotwin_builder.rs:87-117
+    (ties -> lowest id)."""
+    L = D.shape[0]
+    used = np.zeros(L, dtype=bool)
+    used[0] = True
+    out = np.empty(L - 1, dtype=np.float64)
+    prev = 0
+    for i in range(L - 1):
+        row = np.where(used, np.inf, D[prev])
+        best = int(np.argmin(row))
+        used[best] = True
+        out[i] = best
+        prev = best
+    return out
+
+
+def _vrp_common(kind, n_customers, n_vehicles, n_depots, seed, time_windowed, greedy):
+    L = n_depots + n_customers
+    xy = uniform01(seed, 2 * L).reshape(L, 2) * 1000.0
+    D = distance_matrix(xy)
+    demand = np.zeros(L, dtype=np.uint64)
+    demand[n_depots:] = randint(seed + 101, n_customers, 1, 100).astype(np.uint64)
+    total = int(demand.sum())
+    cap = int(np.ceil(1.1 * total / n_vehicles))
+    tw_start = np.zeros(L, dtype=np.uint64)
+    tw_end = np.zeros(L, dtype=np.uint64)
+    service = np.zeros(L, dtype=np.uint64)
+    day_start = np.zeros(n_vehicles, dtype=np.uint64)
+    day_end = np.zeros(n_vehicles, dtype=np.uint64)
+    if time_windowed:
+        st = randint(seed + 202, n_customers, 0, 43200)
+        width = randint(seed + 303, n_customers, 3600, 14400)
+        tw_start[n_depots:] = st.astype(np.uint64)
+        tw_end[n_depots:] = (st + width).astype(np.uint64)
+        service[n_depots:] = randint(seed + 404, n_customers, 300, 900).astype(np.uint64)
+        day_end[:] = 86400
+    n = 2 * n_customers
+    lb = np.empty(n); ub = np.empty(n)
+    lb[0::2] = 0.0; ub[0::2] = float(n_vehicles - 1)        # vehicle_id
+    lb[1::2] = float(n_depots); ub[1::2] = float(L - 1)     # customer_id
+    veh_ids = np.arange(0, n, 2, dtype=np.int32)
+    cus_ids = np.arange(1, n, 2, dtype=np.int32)
+    groups = {"vehicle_assignment": veh_ids, "customer_assignment": cus_ids}
+    if kind == VRP:
+        # examples/vrp/src/persistence/cotwin_builder.rs:127-133: both variables also sit
+        # in "common"; vrp_service keeps the two groups disjoint (:128-132 there).
+        groups["common"] = np.arange(n, dtype=np.int32)
+    spec = ProblemSpec(
+        kind=kind, n_vars=n, lower_bounds=lb, upper_bounds=ub, groups=groups,
+        n_locations=L, distance_matrix=D, coords=xy, n_depots=n_depots,
+        n_vehicles=n_vehicles,
+        vehicle_depot=(np.arange(n_vehicles) % n_depots).astype(np.int64),
+        vehicle_capacity=np.full(n_vehicles, cap, dtype=np.uint64),
+        work_day_start=day_start, work_day_end=day_end,
+        demand=demand, tw_start=tw_start, tw_end=tw_end, service_time=service,
+        time_windowed=time_windowed, score_precision=[0, 0, 3],
+        name=f"{KIND_NAMES[kind]}-{n_customers}x{n_vehicles}" + ("-tw" if time_windowed else ""))
+    spec.initial = vrp_greedy(spec) if greedy else vrp_round_robin(spec)
+    return spec
+
+
+def cvrp(n_customers: int, n_vehicles: int, seed: int = 2, greedy: bool = True) -> ProblemSpec:
+    """Config C3: 1 depot, demand U{1..100}, capacity = ceil(1.1*sum/k); examples/vrp."""
+    return _vrp_common(VRP, n_customers, n_vehicles, 1, seed, False, greedy)
+
+
+def vrptw(n_stops: int, n_vehicles: int, n_depots: int = 5, seed: int = 3,
+          service_variant: bool = True, greedy: bool = True) -> ProblemSpec:
+    """Config C4: time-window VRP; service_variant picks the vrp_service lateness rule
+    (SURVEY.md Q3)."""
+    kind = VRP_SERVICE if service_variant else VRP
+    return _vrp_common(kind, n_stops, n_vehicles, n_depots, seed, True, greedy)
+
+
+def vrp_round_robin(spec: ProblemSpec) -> np.ndarray:
+    n_stops = spec.n_vars // 2
+    out = np.empty(spec.n_vars)
+    out[0::2] = np.arange(n_stops) % spec.n_vehicles
+    out[1::2] = np.arange(n_stops) + spec.n_depots
+    return out
+
+
+def vrp_greedy(spec: ProblemSpec) -> np.ndarray:
+    """examples/vrp/src/persistence/cotwin_builder.rs:153-255: fill vehicles one by one with
+    the nearest unassigned customer until the next one no longer fits.  Customers left over
+    (reference: None -> random sample) are appended round-robin here so that the start
+    vector is deterministic."""
+    L, nd, K = spec.n_locations, spec.n_depots, spec.n_vehicles
+    D = spec.distance_matrix
+    used = np.zeros(L, dtype=bool)
+    used[:nd] = True
+    veh, cus = [], []
+    remaining = L - nd
+    for k in range(K):
+        if remaining <= 0:
+            break
+        prev = int(spec.vehicle_depot[k])
+        cap = int(spec.vehicle_capacity[k])
+        collected = 0
+        while collected < cap and remaining > 0:
+            row = np.where(used, np.inf, D[prev])
+            best = int(np.argmin(row))
+            dem = int(spec.demand[best])
+            if collected + dem <= cap:
+                collected += dem
+                used[best] = True
+                remaining -= 1
+                veh.append(k); cus.append(best)
+                prev = best
+            else:
+                break
+    left = np.nonzero(~used)[0]
+    for j, c in enumerate(left):
+        veh.append(j % K); cus.append(int(c))
+    out = np.empty(spec.n_vars)
+    out[0::2] = veh
+    out[1::2] = cus
+    return out
