@@ -1,0 +1,341 @@
+// gj_eval.cuh -- full-evaluation device functions, one per constraint model of the
+// reference's examples.  Each is written against a `Src` functor that yields the decoded
+// value of planning variable i of ONE candidate, so the same arithmetic serves
+//   * request_score_plain  (f64 rows from the caller, int32 rows of a device population)
+//   * request_score_incremental (base + delta list materialised in shared memory)
+//   * the island kernels (base + move descriptor).
+//
+// N-Queens / TSP: one warp per candidate; distinct counts via a shared-memory bitmap,
+// distances gathered from the (L2-resident) matrix, warp-shuffle reductions.
+// VRP: one CTA per candidate; stable counting sort of the stops by vehicle in shared
+// memory, then one thread walks one route in the reference's own order.
+#pragma once
+
+#include "gj_device.cuh"
+
+// ---- candidate sources ----------------------------------------------------------------
+
+struct GjSrcF64 {           // a row of the caller's Vec<Vec<f64>>, decoded on the fly
+    const double* row;
+    const GjProblemDev* P;
+    __device__ __forceinline__ int operator()(int i) const { return gj_decode(*P, i, row[i]); }
+};
+
+struct GjSrcI32 {           // a row of an int32 device population, or a smem copy
+    const int32_t* row;
+    __device__ __forceinline__ int operator()(int i) const { return row[i]; }
+};
+
+// ---- N-Queens -----------------------------------------------------------------------
+// examples/nqueens/src/score/incremental_score_calculator.rs:44-56 (ISC) and
+// plain_score_calculator.rs:37-59 (PSC): (N - |rows|) + (N - |col+row|) + (N - |col-row|).
+// bm: rows | desc | asc bitmaps, P.bm_words + P.desc_words + P.asc_words words.
+template <class Src>
+__device__ __forceinline__ double gj_nqueens_eval_warp(const GjProblemDev& P, const Src& src,
+                                                       uint32_t* bm, int lane) {
+    const int n = P.n_vars;
+    const int total_words = P.bm_words + P.desc_words + P.asc_words;
+    for (int w = lane; w < total_words; w += 32) bm[w] = 0u;
+    __syncwarp();
+    uint32_t* bm_desc = bm + P.bm_words;
+    uint32_t* bm_asc = bm_desc + P.desc_words;
+    for (int i = lane; i < n; i += 32) {
+        int row = src(i);
+        int col = P.column_id[i];
+        unsigned r = (unsigned)(row - P.val_lo);
+        unsigned d = (unsigned)(col + row - P.desc_lo);
+        unsigned a = (unsigned)(col - row - P.asc_lo);
+        atomicOr(&bm[r >> 5], 1u << (r & 31));
+        atomicOr(&bm_desc[d >> 5], 1u << (d & 31));
+        atomicOr(&bm_asc[a >> 5], 1u << (a & 31));
+    }
+    __syncwarp();
+    int u_rows = 0, u_desc = 0, u_asc = 0;
+    for (int w = lane; w < P.bm_words; w += 32) u_rows += __popc(bm[w]);
+    for (int w = lane; w < P.desc_words; w += 32) u_desc += __popc(bm_desc[w]);
+    for (int w = lane; w < P.asc_words; w += 32) u_asc += __popc(bm_asc[w]);
+    u_rows = gj_warp_sum(u_rows);
+    u_desc = gj_warp_sum(u_desc);
+    u_asc = gj_warp_sum(u_asc);
+    __syncwarp();
+    double a = (double)(n - u_rows), b = (double)(n - u_desc), c = (double)(n - u_asc);
+    return a + b + c;
+}
+
+// ---- TSP -----------------------------------------------------------------------------
+// examples/tsp/src/score/incremental_score_calculator.rs:71-80 and
+// plain_score_calculator.rs:34-43, 70-84: hard = n_stops - |{location ids}|,
+// soft = D[0][s0] + D[s_last][0] + sum_i D[s_{i-1}][s_i].  The reference folds the sum
+// sequentially; here each lane accumulates a strided partial and the partials are
+// tree-reduced (documented float tolerance 1e-12 relative; the integer level is exact).
+template <class Src>
+__device__ __forceinline__ void gj_tsp_eval_warp(const GjProblemDev& P, const Src& src,
+                                                 uint32_t* bm, int lane, double& dup,
+                                                 double& dist) {
+    const int n = P.n_vars;
+    const size_t L = (size_t)P.n_locations;
+    const double* __restrict__ D = P.D;
+    for (int w = lane; w < P.bm_words; w += 32) bm[w] = 0u;
+    __syncwarp();
+    double acc0 = 0.0, acc1 = 0.0;
+    int carry = 0;      // the depot (location 0) precedes stop 0
+    int v1 = 0;
+    for (int base = 0; base < n; base += 64) {
+        const int i0 = base + lane, i1 = base + 32 + lane;
+        const int v0 = (i0 < n) ? src(i0) : 0;
+        v1 = (i1 < n) ? src(i1) : 0;
+        int p0 = __shfl_up_sync(GJ_FULL_MASK, v0, 1);
+        int p1 = __shfl_up_sync(GJ_FULL_MASK, v1, 1);
+        const int last0 = __shfl_sync(GJ_FULL_MASK, v0, 31);
+        if (lane == 0) { p0 = carry; p1 = last0; }
+        carry = __shfl_sync(GJ_FULL_MASK, v1, 31);
+        double d0 = 0.0, d1 = 0.0;
+        if (i0 < n) d0 = __ldg(&D[(size_t)p0 * L + (size_t)v0]);
+        if (i1 < n) d1 = __ldg(&D[(size_t)p1 * L + (size_t)v1]);
+        if (i0 < n) { unsigned b = (unsigned)(v0 - P.val_lo); atomicOr(&bm[b >> 5], 1u << (b & 31)); }
+        if (i1 < n) { unsigned b = (unsigned)(v1 - P.val_lo); atomicOr(&bm[b >> 5], 1u << (b & 31)); }
+        acc0 += d0;
+        acc1 += d1;
+    }
+    // closing edge D[s_last][0]
+    if (lane == 0) {
+        const int last = src(n - 1);
+        acc0 += __ldg(&D[(size_t)last * L]);
+    }
+    __syncwarp();
+    int uniq = 0;
+    for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(bm[w]);
+    uniq = gj_warp_sum(uniq);
+    dist = gj_warp_sum(acc0 + acc1);
+    dup = (double)(n - uniq);
+    __syncwarp();
+}
+
+// ---- VRP -----------------------------------------------------------------------------
+// examples/vrp/src/score/incremental_score_calculator.rs:58-137 (ISC, file variant)
+// examples/vrp_service/src/score/incremental_score_calculator.rs:58-138 (ISC, service)
+// examples/vrp/src/score/plain_score_calculator.rs:51-233 (PSC)
+enum { GJ_TW_ISC_FILE = 0, GJ_TW_ISC_SERVICE = 1, GJ_TW_PSC = 2 };
+
+// Shared-memory plan of one VRP candidate (one CTA).
+struct GjVrpSmem {
+    uint32_t* bm;            // customer-id bitmap, P.bm_words
+    int* cnt;                // [n_warps][K] per-warp-block vehicle counts -> offsets
+    int* start;              // [K + 1] route starts in `bucket`
+    double* vdist;           // [K] per-vehicle distance
+    unsigned long long* acc; // [0] capacity penalty, [1] lateness penalty
+    uint16_t* veh;           // [n_stops] decoded vehicle ids (relative to veh_lo)
+    int32_t* cust;           // [n_stops] decoded customer ids
+    int32_t* bucket;         // [n_stops] customers grouped by vehicle, stop order kept
+};
+
+__host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_words, int n_warps) {
+    size_t b = 0;
+    b += (size_t)bm_words * 4;
+    b += (size_t)n_warps * (size_t)K * 4;
+    b += (size_t)(K + 1) * 4;
+    b = (b + 7) & ~(size_t)7;
+    b += (size_t)K * 8;
+    b += 16;
+    b += (size_t)n_stops * 4 * 2;
+    b += ((size_t)n_stops * 2 + 7) & ~(size_t)7;
+    return b;
+}
+
+__device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_stops, int K,
+                                                  int bm_words, int n_warps) {
+    GjVrpSmem s;
+    size_t o = 0;
+    s.bm = (uint32_t*)(smem + o); o += (size_t)bm_words * 4;
+    s.cnt = (int*)(smem + o); o += (size_t)n_warps * (size_t)K * 4;
+    s.start = (int*)(smem + o); o += (size_t)(K + 1) * 4;
+    o = (o + 7) & ~(size_t)7;
+    s.vdist = (double*)(smem + o); o += (size_t)K * 8;
+    s.acc = (unsigned long long*)(smem + o); o += 16;
+    s.cust = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
+    s.bucket = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
+    s.veh = (uint16_t*)(smem + o);
+    return s;
+}
+
+// Evaluates the candidate whose decoded (vehicle, customer) columns already sit in
+// s.veh / s.cust.  All threads of the CTA must call it.  Results valid in thread 0.
+__device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjVrpSmem& s,
+                                                int tw_mode, double& dup1000, double& cap,
+                                                double& dist, double& late) {
+    const int n = P.n_entities;
+    const int K = P.n_vehicles;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
+    const size_t L = (size_t)P.n_locations;
+    const double* __restrict__ D = P.D;
+
+    for (int w = tid; w < P.bm_words; w += nthr) s.bm[w] = 0u;
+    for (int w = tid; w < n_warps * K; w += nthr) s.cnt[w] = 0;
+    if (tid < 2) s.acc[tid] = 0ull;
+    __syncthreads();
+
+    // pass 1: customer bitmap + per-warp-block vehicle histogram.  Warp w owns the
+    // contiguous block of stops [w*blk, (w+1)*blk) so that block order == stop order.
+    const int blk = (n + n_warps - 1) / n_warps;
+    const int lo = warp * blk;
+    const int hi = min(n, lo + blk);
+    int* mycnt = s.cnt + warp * K;
+    for (int i = lo + lane; i < hi; i += 32) {
+        unsigned b = (unsigned)(s.cust[i] - P.val_lo);
+        atomicOr(&s.bm[b >> 5], 1u << (b & 31));
+        atomicAdd(&mycnt[s.veh[i]], 1);
+    }
+    __syncthreads();
+
+    // exclusive scan over (vehicle major, warp minor): cnt[w][v] -> first slot of warp
+    // w's stops of vehicle v; start[v] = route start.  K is small: one thread per vehicle
+    // sums its column, then a single warp scans the K totals.
+    for (int v = tid; v < K; v += nthr) {
+        int tot = 0;
+        for (int w = 0; w < n_warps; ++w) tot += s.cnt[w * K + v];
+        s.start[v + 1] = tot;
+    }
+    if (tid == 0) s.start[0] = 0;
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < K; base += 32) {
+            int v = base + lane;
+            int x = (v < K) ? s.start[v + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(GJ_FULL_MASK, x, o);
+                if (lane >= o) x += y;
+            }
+            if (v < K) s.start[v + 1] = x + carry;
+            carry += __shfl_sync(GJ_FULL_MASK, x, 31);
+        }
+    }
+    __syncthreads();
+    for (int v = tid; v < K; v += nthr) {
+        int off = s.start[v];
+        for (int w = 0; w < n_warps; ++w) {
+            int c = s.cnt[w * K + v];
+            s.cnt[w * K + v] = off;
+            off += c;
+        }
+    }
+    __syncthreads();
+
+    // pass 2: stable scatter.  Each warp walks its block in order, 32 stops at a time;
+    // lanes with the same vehicle are ranked by lane id (= stop order).
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + lane;
+        const bool on = i < hi;
+        const int v = on ? (int)s.veh[i] : (0x10000 + lane);
+        const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
+        const int rank = __popc(grp & ((1u << lane) - 1u));
+        int slot = 0;
+        if (on) slot = mycnt[v];
+        __syncwarp();
+        if (on) {
+            s.bucket[slot + rank] = s.cust[i];
+            if (rank == 0) mycnt[v] = slot + __popc(grp);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // route walks: one thread per vehicle, in the reference's own order.
+    unsigned long long my_cap = 0ull, my_late = 0ull;
+    for (int v = tid; v < K; v += nthr) {
+        const int b = s.start[v], e = s.start[v + 1];
+        const int len = e - b;
+        double current_distance = 0.0;
+        if (len != 0) {
+            const int32_t* st = s.bucket + b;
+            const size_t depot = (size_t)P.veh_depot[v];
+            current_distance += __ldg(&D[depot * L + (size_t)st[0]]);
+            current_distance += __ldg(&D[(size_t)st[len - 1] * L + depot]);
+            double fold = 0.0;
+            unsigned long long load = (unsigned long long)P.cust[st[0]].x;
+#pragma unroll 4
+            for (int i = 1; i < len; ++i) {
+                fold = fold + __ldg(&D[(size_t)st[i - 1] * L + (size_t)st[i]]);
+                load += (unsigned long long)P.cust[st[i]].x;
+            }
+            current_distance += fold;
+            const unsigned long long capv = P.veh_capacity[v];
+            if (load > capv) my_cap += load - capv;
+
+            if (P.time_windowed) {
+                unsigned long long arrival = P.day_start[v];
+                const unsigned long long day_end = P.day_end[v];
+                const int upto = (tw_mode == GJ_TW_PSC) ? len - 1 : len;
+                for (int i = 0; i < upto; ++i) {
+                    const uint4 c = P.cust[st[i]];
+                    const unsigned long long ws = c.y, we = c.z, sv = c.w;
+                    if (arrival < ws) arrival = ws;
+                    if (tw_mode == GJ_TW_ISC_FILE) {
+                        if (arrival + sv > we) my_late += (arrival + sv) - we;
+                    } else {
+                        if (arrival > we + sv) my_late += arrival - (we + sv);
+                    }
+                    arrival += sv;
+                }
+                if (arrival > day_end) my_late += arrival - day_end;
+            }
+        }
+        s.vdist[v] = current_distance;
+    }
+    if (my_cap) atomicAdd(&s.acc[0], my_cap);
+    if (my_late) atomicAdd(&s.acc[1], my_late);
+    __syncthreads();
+
+    if (warp == 0) {
+        int uniq = 0;
+        for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(s.bm[w]);
+        uniq = gj_warp_sum(uniq);
+        if (lane == 0) {
+            // vehicle_distances.iter().sum(): sequential, vehicle order (ISC :132)
+            double sum_distance = 0.0;
+            for (int v = 0; v < K; ++v) sum_distance += s.vdist[v];
+            dist = sum_distance;
+            dup1000 = 1000.0 * (double)(n - uniq);
+            cap = (double)s.acc[0];
+            late = (double)s.acc[1];
+        }
+    }
+}
+
+// ---- weighted combination -------------------------------------------------------------
+// score_calculators/plain_score_calculator.rs:79-90 / incremental_score_calculator.rs:84-95:
+// sum = null_score; for each constraint: sum += score_i.mul(weight_i).
+__device__ __forceinline__ void gj_combine_nqueens(const GjProblemDev& P, double v, double* out) {
+    double acc = 0.0;
+    acc += P.w[0] * v;
+    out[0] = acc;
+}
+
+__device__ __forceinline__ void gj_combine_tsp(const GjProblemDev& P, bool isc, double dup,
+                                               double dist, double* out) {
+    double h = 0.0, f = 0.0;
+    if (isc) {
+        h += P.w[0] * dup; f += P.w[0] * dist;
+    } else {
+        h += P.w[0] * dup; f += P.w[0] * 0.0;
+        h += P.w[1] * 0.0; f += P.w[1] * dist;
+    }
+    out[0] = h; out[1] = f;
+}
+
+__device__ __forceinline__ void gj_combine_vrp(const GjProblemDev& P, bool isc, double dup1000,
+                                               double cap, double dist, double late, double* out) {
+    double h = 0.0, m = 0.0, f = 0.0;
+    if (isc) {
+        const double hard = dup1000 + cap;
+        h += P.w[0] * hard; m += P.w[0] * late; f += P.w[0] * dist;
+    } else {
+        h += P.w[0] * dup1000; m += P.w[0] * 0.0; f += P.w[0] * 0.0;
+        h += P.w[1] * cap;     m += P.w[1] * 0.0; f += P.w[1] * 0.0;
+        h += P.w[2] * 0.0;     m += P.w[2] * 0.0; f += P.w[2] * dist;
+        if (P.time_windowed) { h += P.w[3] * 0.0; m += P.w[3] * late; f += P.w[3] * 0.0; }
+    }
+    out[0] = h; out[1] = m; out[2] = f;
+}

@@ -1,0 +1,7 @@
+"""greyjack_b200 -- Python harness over the C-ABI CUDA engine (libgreyjack_b200.so).
+
+The product is the shared library (greyjack-solver-rust_b200/csrc, include/greyjack_b200.h);
+this package only mirrors the reference's host-side names for tests, bench.py and demos."""
+from . import instances  # noqa: F401
+from ._lib import GjError, LIB_PATH, load  # noqa: F401
+from .problem import Problem, deltas_to_csr  # noqa: F401

@@ -1,0 +1,257 @@
+/*
+ * greyjack_b200.h -- C ABI of the B200-native candidate-scoring engine for GreyJack.
+ *
+ * This is the drop-in boundary for ONE hot path of CameleoGrey/greyjack-solver-rust:
+ * scoring populations and move neighbourhoods against the constraint model, plus the
+ * move generation / selection / migration that sit directly either side of it.  The
+ * reference has no FFI (it is all Rust trait objects); each entry point below names
+ * the reference interface it replaces (paths relative to the reference root).  A Rust
+ * maintainer binds these with an `extern "C"` block -- see INTEGRATION.md.
+ *
+ * Conventions: every call returns gj_status (0 = ok); on failure gj_last_error()
+ * (thread-local) describes it -- nothing panics or throws across the ABI (the
+ * reference itself panics: cotwin.rs:55, agent_base.rs:142).  All buffers are owned by
+ * the caller.  A handle is single-threaded like the reference's `&mut self` scorer
+ * (oop_score_requester.rs:336,443); distinct handles are independent and each is bound
+ * to one CUDA device.  There is NO CPU fallback: without a CUDA device every compute
+ * entry point fails with GJ_ERR_CUDA.
+ *
+ * Variable order: the reference's enumeration (oop_score_requester.rs:93-123): entity
+ * by entity, field by field.  N-Queens: row_id per queen.  TSP: location_vec_id per
+ * stop.  VRP: [vehicle_id_0, customer_id_0, vehicle_id_1, customer_id_1, ...].
+ * Candidates travel as f64 even for integer variables, exactly like the reference's
+ * Vec<f64>; decoding (frozen -> initial, clamp by total_cmp, rint ties-to-ceil) follows
+ * variables/gj_integer.rs:66-83 and utils/math_utils.rs:6-8 on the device.
+ */
+#ifndef GREYJACK_B200_H
+#define GREYJACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GJ_API
+#else
+#define GJ_API __attribute__((visibility("default")))
+#endif
+
+typedef int32_t gj_status;
+enum {
+    GJ_OK = 0,
+    GJ_ERR_INVALID = 1,   /* bad argument / malformed description           */
+    GJ_ERR_CUDA = 2,      /* CUDA runtime failure or no device              */
+    GJ_ERR_UNSUPPORTED = 3,
+    GJ_ERR_OOM = 4
+};
+
+/* Constraint models = the reference's example score calculators. */
+enum {
+    GJ_NQUEENS = 0,      /* examples/nqueens/src/score/{plain,incremental}_score_calculator.rs   */
+    GJ_TSP = 1,          /* examples/tsp/src/score/{plain,incremental}_score_calculator.rs       */
+    GJ_VRP = 2,          /* examples/vrp/src/score/* (CVRP, and VRPTW when time_windowed)        */
+    GJ_VRP_SERVICE = 3   /* examples/vrp_service/src/score/* (lateness rule of :121-122)         */
+};
+
+/* Move ids, in the order of Mover::do_move's thresholds (mover.rs:105-121). */
+enum {
+    GJ_MOVE_CHANGE = 0, GJ_MOVE_SWAP = 1, GJ_MOVE_SWAP_EDGES = 2,
+    GJ_MOVE_SCRAMBLE = 3, GJ_MOVE_INSERTION = 4, GJ_MOVE_INVERSE = 5
+};
+
+/* Agents = AgentBuildersVariants (agents/agent_builders_variants.rs:9-18). */
+enum { GJ_AGENT_TABU_SEARCH = 0, GJ_AGENT_LATE_ACCEPTANCE = 1, GJ_AGENT_GENETIC_ALGORITHM = 2 };
+
+typedef struct gj_problem gj_problem;   /* Cotwin + OOPScoreRequester + VariablesManager */
+typedef struct gj_islands gj_islands;   /* a group of Agents resident on one GPU          */
+
+/*
+ * Problem description == what CotwinBuilderTrait::build_cotwin hands to the score
+ * requester (cotwin/cotwin_builder_trait.rs:7-11): planning variables (GJInteger
+ * bounds / frozen / initial / semantic groups, variables/gj_integer.rs:21-64), problem
+ * facts and the scorer's utility objects.
+ */
+typedef struct gj_problem_desc {
+    int32_t kind;                  /* GJ_NQUEENS .. GJ_VRP_SERVICE                       */
+    int32_t n_vars;
+    const double*  lower_bounds;   /* [n_vars]                                           */
+    const double*  upper_bounds;   /* [n_vars]                                           */
+    const uint8_t* frozen;         /* [n_vars] or NULL                                   */
+    const double*  initial;        /* [n_vars] or NULL; NaN = None (sampled uniformly)   */
+
+    /* semantic groups (variables_manager.rs:76-106), CSR over variable ids; frozen
+       variables are dropped from the groups by the library like the reference does. */
+    int32_t n_groups;
+    const int64_t* group_offsets;  /* [n_groups + 1]                                     */
+    const int32_t* group_var_ids;
+
+    const int64_t* column_id;      /* N-Queens: [n_vars] or NULL (= i)                   */
+
+    /* utility objects (examples' UtilityObjectVariants) */
+    int32_t n_locations;
+    const double* distance_matrix; /* row-major [n_locations]^2, or NULL if coords given */
+    const double* coords;          /* [n_locations][2] (lat, lon) or NULL: the matrix is
+                                      then built on the device with the examples' formula
+                                      round(sqrt(dlat^2+dlon^2), 3) applied twice
+                                      (tsp/src/domain/location.rs:38-50,
+                                       tsp/src/persistence/domain_builder.rs:42-46)      */
+    int32_t n_vehicles;
+    const int64_t*  vehicle_depot;     /* [n_vehicles] Vehicle.depot_vec_id              */
+    const uint64_t* vehicle_capacity;
+    const uint64_t* work_day_start;
+    const uint64_t* work_day_end;
+    const uint64_t* demand;            /* [n_locations] Customer.demand                  */
+    const uint64_t* tw_start;
+    const uint64_t* tw_end;
+    const uint64_t* service_time;
+    int32_t time_windowed;             /* VehicleRoutingPlan.time_windowed               */
+
+    /* set_constraint_weights (plain_score_calculator.rs:40-42); PSC constraint order:
+       nqueens [all_different]; tsp [no_duplicating_stops, minimize_distance];
+       vrp [no_duplicating_stops, capacity, minimize_distance, late_arrival_penalty].
+       The ISC has a single all_in_one constraint and uses weights[0].                   */
+    double weights[4];
+
+    /* Solver::solve arg `score_precision: Option<Vec<u64>>` (solver.rs:29); -1 = None.  */
+    int64_t score_precision[3];
+} gj_problem_desc;
+
+GJ_API const char* gj_last_error(void);
+GJ_API int32_t     gj_abi_version(void);
+GJ_API int32_t     gj_device_count(void);
+
+/* OOPScoreRequester::new(cotwin) (oop_score_requester.rs:47-83): uploads everything. */
+GJ_API gj_status gj_problem_create(const gj_problem_desc* desc, int32_t device, gj_problem** out);
+GJ_API void      gj_problem_destroy(gj_problem* p);
+GJ_API int32_t   gj_problem_levels(const gj_problem* p);   /* ScoreTrait::precision_len  */
+GJ_API int32_t   gj_problem_n_vars(const gj_problem* p);
+/* {Plain,Incremental}ScoreCalculator::set_constraint_weights */
+GJ_API gj_status gj_problem_set_constraint_weights(gj_problem* p, const double* weights, int32_t n);
+/* Copies the device distance matrix back (checks / warm starts).  out: [L*L]. */
+GJ_API gj_status gj_problem_get_distance_matrix(gj_problem* p, double* out);
+
+/* Pinned host memory for candidate / delta / score buffers (optional; any host
+   pointer works, pinned ones make the copies asynchronous DMA).                        */
+GJ_API gj_status gj_host_alloc(size_t bytes, void** out);
+GJ_API void      gj_host_free(void* ptr);
+
+/*
+ * OOPScoreRequester::request_score_plain(&Vec<Vec<f64>>) -> Vec<Score>
+ * (oop_score_requester.rs:336-355 -> PlainScoreCalculator::get_score,
+ * plain_score_calculator.rs:60-94).  samples: host [S][n_vars] row-major;
+ * scores: host [S][levels], index = sample_id.  PSC semantics.
+ */
+GJ_API gj_status gj_score_plain(gj_problem* p, const double* samples, int64_t S, double* scores);
+
+/*
+ * OOPScoreRequester::request_score_incremental(&Vec<f64>, &Vec<Vec<(usize,f64)>>)
+ * (oop_score_requester.rs:443-463 -> IncrementalScoreCalculator::get_score,
+ * incremental_score_calculator.rs:60-99).  The delta lists arrive as CSR:
+ * sample j owns (var_ids[k], values[k]) for k in [offsets[j], offsets[j+1]).
+ * ISC (pseudo-incremental) semantics: every candidate = base with its deltas applied
+ * var-wise in emission order, then fully re-scored.
+ */
+GJ_API gj_status gj_score_incremental(gj_problem* p, const double* base,
+                                      const uint64_t* offsets, const uint64_t* var_ids,
+                                      const double* values, int64_t S, double* scores);
+
+/* Same two calls with every buffer already resident in device memory (HBM) and an
+   explicit cudaStream_t (NULL = default stream); asynchronous.                          */
+GJ_API gj_status gj_score_plain_device(gj_problem* p, const double* d_samples, int64_t S,
+                                       double* d_scores, void* stream);
+GJ_API gj_status gj_score_plain_i32_device(gj_problem* p, const int32_t* d_samples,
+                                           int64_t row_stride, int64_t S, double* d_scores,
+                                           void* stream);
+GJ_API gj_status gj_score_incremental_device(gj_problem* p, const double* d_base,
+                                             const uint64_t* d_offsets, const uint64_t* d_var_ids,
+                                             const double* d_values, int64_t S, double* d_scores,
+                                             void* stream);
+
+/*
+ * Agent builders.  Field names and meaning mirror the Rust `::new` argument lists:
+ *   TabuSearch::new(neighbours_count, tabu_entity_rate, compare_to_global,
+ *                   mutation_rate_multiplier, move_probas, migration_frequency, termination)
+ *                                                            (agents/tabu_search.rs:32-40)
+ *   LateAcceptance::new(late_acceptance_size, tabu_entity_rate, mutation_rate_multiplier,
+ *                   move_probas, migration_frequency, termination) (late_acceptance.rs:31-38)
+ *   GeneticAlgorithm::new(population_size, crossover_probability, p_best_rate,
+ *                   tabu_entity_rate, mutation_rate_multiplier, move_probas, migration_rate,
+ *                   migration_frequency, termination)          (genetic_algorithm.rs:34-44)
+ * Termination strategies stay on the host (they are trivial control logic).
+ */
+typedef struct gj_agent_params {
+    int32_t agent;                   /* GJ_AGENT_*                                       */
+    int32_t n_islands;               /* agents of this kind resident on this GPU
+                                        (Solver::solve n_jobs share, solver.rs:58-64)    */
+    uint64_t seed;                   /* Philox key; the reference is entropy-seeded      */
+    int64_t neighbours_count;        /* TS                                               */
+    int64_t late_acceptance_size;    /* LA                                               */
+    int64_t population_size;         /* GA                                               */
+    double  crossover_probability;   /* GA                                               */
+    double  p_best_rate;             /* GA                                               */
+    double  migration_rate;          /* GA                                               */
+    double  tabu_entity_rate;
+    int32_t compare_to_global;       /* TS                                               */
+    int32_t has_mutation_rate_multiplier;  /* Option<f64>: 0 = None (-> 0.0)             */
+    double  mutation_rate_multiplier;
+    int32_t has_move_probas;         /* Option<Vec<f64>>: 0 = None (uniform, mover.rs:38-48) */
+    double  move_probas[6];
+    int64_t migration_frequency;
+    int32_t reference_noop_moves;    /* 1 = reproduce the reference's incremental-form
+                                        no-op scramble / swap_edges(k=2);
+                                        0 = apply the plain-form permutation             */
+    int32_t reserved;
+} gj_agent_params;
+
+/* <Agent>::build_agent + Agent::init_population (agent_base.rs:190-218).  `initial`:
+   host [n_islands][n_vars] start vectors (InitialSolutionVariants) or NULL to use the
+   problem's initial values (None entries sampled uniformly in [lb, ub]).               */
+GJ_API gj_status gj_islands_create(gj_problem* p, const gj_agent_params* params,
+                                   const double* initial, gj_islands** out);
+GJ_API void      gj_islands_destroy(gj_islands* g);
+
+/* Agent::solve loop body x n_steps for every island, entirely on the device
+   (agent_base.rs:135-186: step_plain | step_incremental, sort, update_top_individual;
+   migration every migration_frequency steps inside the group, ring i -> i+1,
+   solver.rs:85-92; global best shared as in update_global_top :446-490).              */
+GJ_API gj_status gj_islands_step(gj_islands* g, int64_t n_steps, void* stream);
+
+/* Counters: candidates scored so far, steps done, accepted moves. */
+GJ_API gj_status gj_islands_stats(gj_islands* g, int64_t* candidates, int64_t* steps,
+                                  int64_t* accepted);
+
+/* agent_top_individual of one island, or (island < 0) the group's global_top_individual.
+   vars: host [n_vars] f64; score: host [levels] (rounded by score_precision).          */
+GJ_API gj_status gj_islands_best(gj_islands* g, int32_t island, double* vars, double* score);
+/* population[0] of one island (current, not best). */
+GJ_API gj_status gj_islands_current(gj_islands* g, int32_t island, double* vars, double* score);
+
+/* Cross-GPU migration plumbing (AgentToAgentUpdate, agent_to_agent_update.rs): packs
+   the migrants of the LAST island of this group into a device buffer / accepts migrants
+   into the FIRST island with the reference's acceptance rule (agent_base.rs:414-440).
+   The transport between ranks (NCCL send/recv over NVLink) is the caller's.
+   Layout: n_migrants x (n_vars int32 + levels f64), see gj_islands_migrant_bytes.      */
+GJ_API int64_t   gj_islands_migrant_bytes(const gj_islands* g);
+GJ_API gj_status gj_islands_export_migrants(gj_islands* g, void* d_buffer, void* stream);
+GJ_API gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buffer, void* stream);
+
+/*
+ * Test / inspection hook: runs ONE TabuSearch/LateAcceptance step of one island and
+ * returns what happened -- the generated moves as delta lists (CSR, capacities given
+ * by the caller), each candidate's rounded score, the selected index and whether it was
+ * accepted -- so the path can be checked move by move against the reference mover and
+ * scorer (mover.rs:145-421, tabu_search_base.rs:157-188).
+ */
+GJ_API gj_status gj_islands_trace_step(gj_islands* g, int32_t island,
+                                       uint64_t* offsets /*[K+1]*/, uint64_t* var_ids,
+                                       double* values, int64_t delta_capacity,
+                                       int32_t* move_kinds /*[K]*/, double* scores /*[K][levels]*/,
+                                       int64_t* selected, int32_t* accepted);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GREYJACK_B200_H */
