@@ -1,0 +1,909 @@
+// gj_islands.cu -- device-resident agents ("islands"): the reference's Agent::solve loop
+// (greyjack/src/agents/base/agent_base.rs:124-188) for TabuSearch and LateAcceptance,
+// with move generation, scoring, selection, ring migration and the shared global best all
+// on the GPU.  One launch handles every island of the group:
+//
+//   k_gen_moves      Mover::do_move x neighbours_count            (mover.rs:98-128)
+//   k_score_moves_*  request_score_incremental on base + move     (oop_score_requester.rs:443-463)
+//   k_select         build_updated_population_incremental + update_top_individual
+//                    (tabu_search_base.rs:157-188, late_acceptance_base.rs:188-241,
+//                     agent_base.rs:220-224)
+//   k_migrate_*      send_updates / receive_updates               (agent_base.rs:322-444)
+//   k_global_*       update_global_top                            (agent_base.rs:446-490)
+//
+// The GeneticAlgorithm agent lives in gj_islands_ga.cu.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "gj_eval.cuh"
+#include "gj_islands.hpp"
+
+static constexpr int kWarps = 4;
+
+// ---- generation -------------------------------------------------------------------------------
+__global__ void k_gen_moves(GjProblemDev P, GjGroups G, GjMoverParams M, uint64_t seed,
+                            uint64_t step, int I, int K, int island_base,
+                            const uint32_t* __restrict__ tabu_bits, int tabu_words_per_island,
+                            const int32_t* __restrict__ tabu_word_off, GjMove* __restrict__ moves) {
+    const int64_t total = (int64_t)I * K;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const int island = (int)(j / K), cand = (int)(j % K);
+        const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
+        moves[j] = gj_generate_move(P, G, M, seed, (uint32_t)(island_base + island), step,
+                                    (uint32_t)cand, bits, tabu_word_off);
+    }
+}
+
+// ---- scoring of base + move -----------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kWarps * 32)
+k_score_moves_warp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, int stride,
+                   const GjMove* __restrict__ moves, int K, int64_t total, int incremental,
+                   int noop, int isc, double* __restrict__ scores) {
+    extern __shared__ uint32_t smem_u32[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int words = P.bm_words + P.desc_words + P.asc_words;
+    const int per_warp = words + P.n_vars;
+    uint32_t* bm = smem_u32 + warp * per_warp;
+    int32_t* cand = (int32_t*)(bm + words);
+    const int64_t j = (int64_t)blockIdx.x * kWarps + warp;
+    if (j >= total) return;
+    const int32_t* base = cur + (size_t)(j / K) * stride;
+    for (int i = lane; i < P.n_vars; i += 32) cand[i] = base[i];
+    __syncwarp();
+    const GjMove m = moves[j];
+    gj_apply_move(P, m, G, incremental != 0, noop != 0, lane, 32,
+                  [&](int id) { return base[id]; }, [&](int id, int v) { cand[id] = v; });
+    __syncwarp();
+    GjSrcI32 src{cand};
+    GjScore s;
+    if constexpr (KIND == GJ_NQUEENS) {
+        gj_combine_nqueens(P, gj_nqueens_eval_warp(P, src, bm, lane), s.v);
+    } else {
+        double dup, dist;
+        gj_tsp_eval_warp(P, src, bm, lane, dup, dist);
+        gj_combine_tsp(P, isc != 0, dup, dist, s.v);
+    }
+    if (lane == 0) {
+        gj_score_round(s, P);           // agent_base.rs:311-314
+        for (int l = 0; l < P.levels; ++l) scores[j * P.levels + l] = s.v[l];
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_score_moves_vrp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, int stride,
+                  const GjMove* __restrict__ moves, int K, int64_t total, int incremental,
+                  int noop, int isc, double* __restrict__ scores) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = P.n_entities;
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kWarps);
+    const int64_t j = blockIdx.x;
+    const int32_t* base = cur + (size_t)(j / K) * stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 pr = *reinterpret_cast<const int2*>(base + 2 * i);
+        s.veh[i] = (uint16_t)pr.x;
+        s.cust[i] = pr.y;
+    }
+    __syncthreads();
+    const GjMove m = moves[j];
+    gj_apply_move(P, m, G, incremental != 0, noop != 0, threadIdx.x, blockDim.x,
+                  [&](int id) { return base[id]; },
+                  [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; });
+    __syncthreads();
+    const int tw_mode = isc ? (P.kind == GJ_VRP_SERVICE ? GJ_TW_ISC_SERVICE : GJ_TW_ISC_FILE) : GJ_TW_PSC;
+    double dup1000 = 0, cap = 0, dist = 0, late = 0;
+    gj_vrp_eval_cta(P, s, tw_mode, dup1000, cap, dist, late);
+    if (threadIdx.x == 0) {
+        GjScore sc;
+        gj_combine_vrp(P, isc != 0, dup1000, cap, dist, late, sc.v);
+        gj_score_round(sc, P);
+        for (int l = 0; l < 3; ++l) scores[j * 3 + l] = sc.v[l];
+    }
+}
+
+// ---- selection ----------------------------------------------------------------------------------
+struct GjSelectArgs {
+    int agent;                  // GJ_AGENT_TABU_SEARCH / GJ_AGENT_LATE_ACCEPTANCE
+    int K, stride, levels, n_vars;
+    int late_size;
+    int noop;
+    int n_groups;
+    const GjMove* moves;
+    const double* cand_scores;
+    int32_t* cur; double* cur_score;
+    int32_t* best; double* best_score;
+    int* dirty;
+    double* late; int* late_head; int* late_len;      // LA: circular deque per island
+    unsigned long long* counters;                     // [0] candidates [1] steps [2] accepted
+    // tabu state
+    uint32_t* tabu_bits; int tabu_words_per_island; const int32_t* tabu_word_off;
+    int32_t* tabu_ring; int tabu_ring_per_island; const int32_t* tabu_ring_off;
+    const int32_t* tabu_size; int* tabu_head; int* tabu_fill;
+    // trace
+    long long* selected_out; int* accepted_out;
+};
+
+__device__ __forceinline__ GjScore gj_load_score(const double* p, int levels) {
+    GjScore s;
+    for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.v[l] = (l < levels) ? p[l] : 0.0;
+    return s;
+}
+
+// positions a move selected (what select_non_tabu_ids pushed into the tabu deque)
+__device__ __forceinline__ int gj_move_selected(const GjMove& m, int* out) {
+    if (m.kind == GJ_MOVE_NULL) return 0;
+    if (m.kind == 3) { out[0] = m.a[0]; return 1; }
+    const int k = (m.kind >= 4) ? 2 : m.k;
+    for (int i = 0; i < k; ++i) out[i] = m.a[i];
+    return k;
+}
+
+__global__ void __launch_bounds__(256)
+k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
+    extern __shared__ int32_t smem_row[];          // [n_vars] copy of the base for in-place apply
+    __shared__ GjScore sh_score[8];
+    __shared__ int sh_idx[8];
+    __shared__ int sh_accept, sh_best;
+    __shared__ int sh_scan[256];
+    const int island = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int K = A.K, levels = A.levels;
+    const double* cs = A.cand_scores + (size_t)island * K * levels;
+
+    // first minimum by Ord::cmp (tabu_search_base.rs:166-171: min_by keeps the first)
+    GjScore mine; int mine_idx = -1;
+    for (int j = tid; j < K; j += blockDim.x) {
+        GjScore s = gj_load_score(cs + (size_t)j * levels, levels);
+        if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        GjScore other; int oidx = __shfl_xor_sync(GJ_FULL_MASK, mine_idx, o);
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) other.v[l] = __shfl_xor_sync(GJ_FULL_MASK, mine.v[l], o);
+        if (oidx >= 0) {
+            int c = (mine_idx < 0) ? 1 : gj_score_cmp(mine, other, levels);
+            if (c > 0 || (c == 0 && oidx < mine_idx)) { mine = other; mine_idx = oidx; }
+        }
+    }
+    if (lane == 0) { sh_score[warp] = mine; sh_idx[warp] = mine_idx; }
+    __syncthreads();
+    if (tid == 0) {
+        GjScore b = sh_score[0]; int bi = sh_idx[0];
+        for (int w = 1; w < nwarps; ++w) {
+            if (sh_idx[w] < 0) continue;
+            int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_score[w], levels);
+            if (c > 0 || (c == 0 && sh_idx[w] < bi)) { b = sh_score[w]; bi = sh_idx[w]; }
+        }
+        GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        bool accept;
+        if (A.agent == GJ_AGENT_TABU_SEARCH) {
+            accept = gj_score_le(b, cur, levels);                       // tabu_search_base.rs:174
+        } else {
+            // late_acceptance_base.rs:196-213
+            double* late = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
+            int head = A.late_head[island], len = A.late_len[island];
+            GjScore late_native = cur;
+            if (len > 0) {
+                int back = (head + len - 1) % A.late_size;
+                late_native = gj_load_score(late + (size_t)back * GJ_MAX_LEVELS, levels);
+            }
+            accept = gj_score_le(b, late_native, levels) || gj_score_le(b, cur, levels);
+            if (accept) {
+                // push_front; pop_back when longer than late_acceptance_size
+                head = (head + A.late_size - 1) % A.late_size;
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) late[(size_t)head * GJ_MAX_LEVELS + l] = b.v[l];
+                len = min(len + 1, A.late_size);
+                A.late_head[island] = head; A.late_len[island] = len;
+            }
+        }
+        if (accept)
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = b.v[l];
+        sh_accept = accept ? 1 : 0;
+        sh_best = bi;
+        if (A.selected_out) { A.selected_out[island] = bi; A.accepted_out[island] = accept ? 1 : 0; }
+        atomicAdd(&A.counters[0], (unsigned long long)K);
+        if (island == 0) atomicAdd(&A.counters[1], 1ull);
+        if (accept) atomicAdd(&A.counters[2], 1ull);
+    }
+    __syncthreads();
+    int32_t* cur_row = A.cur + (size_t)island * A.stride;
+    if (sh_accept) {
+        // apply the winning deltas to the stored individual (tabu_search_base.rs:175-178)
+        for (int i = tid; i < A.n_vars; i += blockDim.x) smem_row[i] = cur_row[i];
+        __syncthreads();
+        const GjMove m = A.moves[(size_t)island * K + sh_best];
+        gj_apply_move(P, m, G, true, A.noop != 0, tid, blockDim.x,
+                      [&](int id) { return smem_row[id]; }, [&](int id, int v) { cur_row[id] = v; });
+        if (tid == 0) A.dirty[island] = 1;
+        __syncthreads();
+    }
+    // update_top_individual (agent_base.rs:220-224): population[0] <= agent_top -> replace
+    if (A.dirty[island]) {
+        GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        if (gj_score_le(cur, top, levels)) {
+            int32_t* best_row = A.best + (size_t)island * A.stride;
+            for (int i = tid; i < A.n_vars; i += blockDim.x) best_row[i] = cur_row[i];
+            if (tid == 0)
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
+        }
+        __syncthreads();
+        if (tid == 0) A.dirty[island] = 0;
+    }
+
+    // tabu deque update (Mover::select_non_tabu_ids :75-96): every id selected this step is
+    // pushed in candidate order; the oldest ids fall out once the deque exceeds its size.
+    if (A.tabu_bits) {
+        uint32_t* bits_island = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
+        int32_t* ring_island = A.tabu_ring + (size_t)island * A.tabu_ring_per_island;
+        for (int g = 0; g < A.n_groups; ++g) {
+            const int T = A.tabu_size[g];
+            uint32_t* bits = bits_island + A.tabu_word_off[g];
+            int32_t* ring = ring_island + A.tabu_ring_off[g];
+            const int glen = G.offsets[g + 1] - G.offsets[g];
+            // count ids per candidate chunk (blockDim candidates at a time), in order
+            int head = A.tabu_head[island * A.n_groups + g];
+            int fill = A.tabu_fill[island * A.n_groups + g];
+            for (int base = 0; base < K; base += blockDim.x) {
+                const int j = base + tid;
+                int sel[GJ_MOVE_MAXK]; int cnt = 0;
+                if (j < K) {
+                    const GjMove m = A.moves[(size_t)island * K + j];
+                    if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
+                }
+                // exclusive scan of cnt over the block
+                sh_scan[tid] = cnt;
+                __syncthreads();
+                for (int o = 1; o < blockDim.x; o <<= 1) {
+                    int x = (tid >= o) ? sh_scan[tid - o] : 0;
+                    __syncthreads();
+                    sh_scan[tid] += x;
+                    __syncthreads();
+                }
+                const int total = sh_scan[blockDim.x - 1];
+                const int off = sh_scan[tid] - cnt;
+                // only the last T ids of the chunk can survive
+                const int skip = max(0, total - T);
+                for (int i = 0; i < cnt; ++i) {
+                    const int pos_in_chunk = off + i;
+                    if (pos_in_chunk < skip) continue;
+                    const int slot = (head + (pos_in_chunk - skip)) % T;
+                    ring[slot] = sel[i];
+                }
+                __syncthreads();
+                const int pushed = total - skip;
+                head = (head + pushed) % T;
+                fill = min(T, fill + pushed);
+            }
+            if (tid == 0) {
+                A.tabu_head[island * A.n_groups + g] = head;
+                A.tabu_fill[island * A.n_groups + g] = fill;
+            }
+            // rebuild the membership bitmap from the ring
+            const int words = (glen + 31) / 32;
+            for (int w = tid; w < words; w += blockDim.x) bits[w] = 0u;
+            __syncthreads();
+            for (int i = tid; i < fill; i += blockDim.x) {
+                const int pos = ring[i];
+                atomicOr(&bits[pos >> 5], 1u << (pos & 31));
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- migration (ring i -> i+1, solver.rs:85-92) ------------------------------------------------------
+// mailbox slot s: [stride int32][GJ_MAX_LEVELS f64]; slot[i+1] = island i's outgoing migrant,
+// slot[0] = what island 0 receives (the wrap-around or another GPU's last island).
+__device__ __forceinline__ size_t gj_slot_bytes(int stride) { return (size_t)stride * 4 + GJ_MAX_LEVELS * 8; }
+
+__global__ void k_migrate_pack(const int32_t* __restrict__ cur, const double* __restrict__ cur_score,
+                               int stride, int n_vars, unsigned char* mailbox) {
+    const int island = blockIdx.x;
+    unsigned char* slot = mailbox + (size_t)(island + 1) * gj_slot_bytes(stride);
+    int32_t* row = (int32_t*)slot;
+    double* sc = (double*)(slot + (size_t)stride * 4);
+    for (int i = threadIdx.x; i < n_vars; i += blockDim.x) row[i] = cur[(size_t)island * stride + i];
+    if (threadIdx.x < GJ_MAX_LEVELS) sc[threadIdx.x] = cur_score[(size_t)island * GJ_MAX_LEVELS + threadIdx.x];
+}
+
+__global__ void k_migrate_wrap(int I, int stride, unsigned char* mailbox) {
+    const size_t sb = gj_slot_bytes(stride);
+    const uint32_t* src = (const uint32_t*)(mailbox + (size_t)I * sb);
+    uint32_t* dst = (uint32_t*)mailbox;
+    for (size_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sb / 4; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+__global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, int late_size,
+                               const unsigned char* __restrict__ mailbox, int32_t* cur,
+                               double* cur_score, int* dirty, double* late, int* late_head,
+                               int* late_len) {
+    __shared__ int sh_take;
+    const int island = blockIdx.x;
+    const unsigned char* slot = mailbox + (size_t)island * gj_slot_bytes(stride);
+    const int32_t* row = (const int32_t*)slot;
+    const double* sc = (const double*)(slot + (size_t)stride * 4);
+    if (threadIdx.x == 0) {
+        GjScore mig = gj_load_score(sc, levels);
+        GjScore cs = gj_load_score(cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        bool take;
+        if (agent == GJ_AGENT_TABU_SEARCH) {
+            take = gj_score_le(mig, cs, levels);                    // agent_base.rs:429-434
+        } else {
+            // agent_base.rs:416-428 (late_scores.back() of an empty deque would panic in the
+            // reference; an empty deque falls back to the current score here)
+            double* lt = late + (size_t)island * late_size * GJ_MAX_LEVELS;
+            int head = late_head[island], len = late_len[island];
+            GjScore back = cs;
+            if (len > 0) back = gj_load_score(lt + (size_t)((head + len - 1) % late_size) * GJ_MAX_LEVELS, levels);
+            take = gj_score_le(mig, back, levels) || gj_score_le(mig, cs, levels);
+            if (take) {
+                head = (head + late_size - 1) % late_size;
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) lt[(size_t)head * GJ_MAX_LEVELS + l] = mig.v[l];
+                late_head[island] = head; late_len[island] = min(len + 1, late_size);
+            }
+        }
+        if (take) {
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = mig.v[l];
+            dirty[island] = 1;
+        }
+        sh_take = take ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_take)
+        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = row[i];
+}
+
+// ---- global best (update_global_top, agent_base.rs:446-490) ------------------------------------------
+__global__ void k_global_reduce(int I, int levels, int stride, int n_vars,
+                                const int32_t* __restrict__ best, const double* __restrict__ best_score,
+                                int32_t* gbest, double* gbest_score) {
+    __shared__ int sh_win;
+    if (threadIdx.x == 0) {
+        GjScore g = gj_load_score(gbest_score, levels);
+        int win = -1;
+        for (int i = 0; i < I; ++i) {
+            GjScore s = gj_load_score(best_score + (size_t)i * GJ_MAX_LEVELS, levels);
+            // `agent_top.score < global.score` (:451): strict
+            if (!gj_score_le(g, s, levels)) { g = s; win = i; }
+        }
+        if (win >= 0)
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = g.v[l];
+        sh_win = win;
+    }
+    __syncthreads();
+    if (sh_win >= 0)
+        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) gbest[i] = best[(size_t)sh_win * stride + i];
+}
+
+__global__ void k_global_adopt(int agent, int compare_to_global, int levels, int stride, int n_vars,
+                               int late_size, const int32_t* __restrict__ gbest,
+                               const double* __restrict__ gbest_score, const double* __restrict__ best_score,
+                               int32_t* cur, double* cur_score, int* dirty, double* late,
+                               int* late_head, int* late_len) {
+    __shared__ int sh_take;
+    const int island = blockIdx.x;
+    if (threadIdx.x == 0) {
+        GjScore g = gj_load_score(gbest_score, levels);
+        GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        // `global.score < agent_top.score` (:465-489)
+        bool take = !gj_score_le(top, g, levels);
+        if (agent == GJ_AGENT_TABU_SEARCH) take = take && compare_to_global;
+        if (take && agent == GJ_AGENT_LATE_ACCEPTANCE) {
+            double* lt = late + (size_t)island * late_size * GJ_MAX_LEVELS;
+            int head = (late_head[island] + late_size - 1) % late_size;
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+                lt[(size_t)head * GJ_MAX_LEVELS + l] = cur_score[(size_t)island * GJ_MAX_LEVELS + l];
+            late_head[island] = head; late_len[island] = min(late_len[island] + 1, late_size);
+        }
+        if (take) {
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = g.v[l];
+            dirty[island] = 1;
+        }
+        sh_take = take ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_take)
+        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = gbest[i];
+}
+
+// Expands move descriptors into the (column, value) lists of the reference's incremental form.
+__global__ void k_expand_moves(GjProblemDev P, GjGroups G, const int32_t* __restrict__ base,
+                               const GjMove* __restrict__ moves, int K, int noop,
+                               const uint64_t* __restrict__ offsets, uint64_t* ids, double* vals) {
+    const int j = blockIdx.x;
+    if (j >= K) return;
+    const GjMove m = moves[j];
+    const uint64_t o = offsets[j];
+    if (m.kind == GJ_MOVE_NULL) return;
+    const int32_t* g = G.ids + G.offsets[m.group];
+    if (m.kind <= 3) {
+        if (threadIdx.x == 0) {
+            int cols[GJ_MOVE_MAXPAIRS], v[GJ_MOVE_MAXPAIRS];
+            const int n = gj_small_move_pairs(m, g, true, noop != 0, [&](int id) { return base[id]; }, cols, v);
+            for (int i = 0; i < n; ++i) { ids[o + i] = (uint64_t)cols[i]; vals[o + i] = (double)gj_fix_column(P, cols[i], v[i]); }
+        }
+        return;
+    }
+    int lo, hi;
+    gj_segment_bounds(m, lo, hi);
+    const int len = hi - lo + 1;
+    for (int t = threadIdx.x; t < len; t += blockDim.x) {
+        const int s = gj_segment_src_slot(m, true, t, len);
+        ids[o + t] = (uint64_t)g[lo + t];
+        vals[o + t] = (double)gj_fix_column(P, g[lo + t], base[g[lo + s]]);
+    }
+}
+
+__global__ void k_i32_to_f64(const int32_t* __restrict__ in, double* __restrict__ out, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+// ===================================================================================================
+// host side
+// ===================================================================================================
+
+gj_islands::~gj_islands() {
+    cudaSetDevice(p->device);
+    for (void* a : allocs) cudaFree(a);
+}
+
+template <class T>
+static gj_status dev_alloc(gj_islands* g, size_t n, T** out, bool zero = true) {
+    void* d = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    GJ_CUDA_TRY(cudaMalloc(&d, bytes));
+    g->allocs.push_back(d);
+    if (zero) GJ_CUDA_TRY(cudaMemset(d, 0, bytes));
+    *out = (T*)d;
+    return GJ_OK;
+}
+
+template <class T>
+static gj_status dev_upload(gj_islands* g, const std::vector<T>& h, const T** out) {
+    T* d = nullptr;
+    gj_status rc = dev_alloc(g, h.size(), &d, false);
+    if (rc) return rc;
+    if (!h.empty()) GJ_CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = d;
+    return GJ_OK;
+}
+
+static uint64_t splitmix64(uint64_t& s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Mover::new thresholds (mover.rs:36-62)
+static gj_status build_thresholds(const gj_agent_params& prm, double* thr) {
+    double probas[6];
+    if (!prm.has_move_probas) {
+        // round(1/6, 3) each, remainder to move 0
+        const double inc = std::floor((1.0 / 6.0) * 1000.0) / 1000.0;
+        double sum = 0.0;
+        for (int i = 0; i < 6; ++i) { probas[i] = inc; sum += inc; }
+        probas[0] += 1.0 - sum;
+    } else {
+        double sum = 0.0;
+        for (int i = 0; i < 6; ++i) { probas[i] = prm.move_probas[i]; sum += probas[i]; }
+        const double r1 = std::floor(sum) + std::floor((sum - std::floor(sum)) * 10.0) / 10.0;
+        if (r1 != 1.0 && std::fabs(sum - 1.0) > 1e-9)
+            return gj_fail(GJ_ERR_INVALID, "Optional move probas sum must be equal to 1.0");
+    }
+    double acc = 0.0;
+    for (int i = 0; i < 6; ++i) { acc += probas[i]; thr[i] = acc; }
+    if (thr[5] < 1.0) thr[5] = 1.0;     // the reference panics when u exceeds the last threshold
+    return GJ_OK;
+}
+
+gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_params* prm) {
+    g->p = p;
+    g->prm = *prm;
+    g->I = prm->n_islands;
+    g->levels = p->dev.levels;
+    g->n_vars = p->dev.n_vars;
+    g->stride = (p->dev.n_vars + 3) & ~3;
+    g->noop = prm->reference_noop_moves ? 1 : 0;
+    gj_status rc;
+    if ((rc = build_thresholds(*prm, g->mover.thresholds))) return rc;
+    g->mover.tabu_entity_rate = prm->tabu_entity_rate;
+    g->mover.mutation_rate_multiplier = prm->has_mutation_rate_multiplier ? prm->mutation_rate_multiplier : 0.0;
+
+    // semantic groups
+    std::vector<int32_t> offs(1, 0), ids;
+    for (auto& grp : p->groups) {
+        ids.insert(ids.end(), grp.begin(), grp.end());
+        offs.push_back((int32_t)ids.size());
+    }
+    if (p->groups.empty() || p->groups.size() > 255) return gj_fail(GJ_ERR_INVALID, "1..255 semantic groups required");
+    g->groups.n_groups = (int)p->groups.size();
+    if ((rc = dev_upload(g, offs, &g->groups.offsets))) return rc;
+    if ((rc = dev_upload(g, ids, &g->groups.ids))) return rc;
+
+    // tabu deques: size = max(ceil(rate * group_len), 1) (tabu_search_base.rs:115-121)
+    if (prm->tabu_entity_rate != 0.0) {
+        std::vector<int32_t> word_off, ring_off, tsize;
+        int words = 0, ring = 0;
+        for (auto& grp : p->groups) {
+            word_off.push_back(words); ring_off.push_back(ring);
+            int T = std::max((int)std::ceil(prm->tabu_entity_rate * (double)grp.size()), 1);
+            T = std::min(T, std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK));   // keep free ids to draw from
+            T = std::max(T, 1);
+            tsize.push_back(T);
+            words += (int)((grp.size() + 31) / 32) + 1;
+            ring += T;
+        }
+        g->tabu_words = words; g->tabu_ring_len = ring;
+        if ((rc = dev_upload(g, word_off, &g->tabu_word_off))) return rc;
+        if ((rc = dev_upload(g, ring_off, &g->tabu_ring_off))) return rc;
+        if ((rc = dev_upload(g, tsize, &g->tabu_size))) return rc;
+        if ((rc = dev_alloc(g, (size_t)g->I * words, &g->tabu_bits))) return rc;
+        if ((rc = dev_alloc(g, (size_t)g->I * ring, &g->tabu_ring))) return rc;
+        if ((rc = dev_alloc(g, (size_t)g->I * g->groups.n_groups, &g->tabu_head))) return rc;
+        if ((rc = dev_alloc(g, (size_t)g->I * g->groups.n_groups, &g->tabu_fill))) return rc;
+    }
+    if ((rc = dev_alloc(g, 4, &g->counters))) return rc;
+    return GJ_OK;
+}
+
+// Start vectors: InitialSolutionVariants / GJInteger::get_initial_value (gj_integer.rs:98-112):
+// the given initial value, else a uniform sample in [lb, ub].
+void gj_islands_start_vector(const gj_problem* p, const double* given, uint64_t& rng, std::vector<int32_t>& row) {
+    const int n = p->dev.n_vars;
+    for (int i = 0; i < n; ++i) {
+        double x = given ? given[i] : p->initial[i];
+        if (p->frozen[i]) x = p->initial[i];
+        if (!(x == x) || x < p->lb[i] - 0.5 || (given == nullptr && !(p->initial[i] == p->initial[i]))) {
+            const int64_t lo = (int64_t)std::llround(p->lb[i]), hi = (int64_t)std::llround(p->ub[i]);
+            x = (double)(lo + (int64_t)(splitmix64(rng) % (uint64_t)(hi - lo + 1)));
+        }
+        // decode exactly like the device would (clamp + rint ties-to-ceil)
+        double lo = p->lb[i], hi = p->ub[i];
+        if (!p->frozen[i]) {
+            if (x < lo) x = lo;
+            if (x > hi) x = hi;
+            double f = std::floor(x), c = std::ceil(x);
+            x = (std::fabs(x - f) < std::fabs(c - x)) ? f : c;
+        }
+        row[i] = (int32_t)x;
+    }
+}
+
+static gj_status score_cur(gj_islands* g, cudaStream_t st) {
+    // Agent::init_population (agent_base.rs:206-213): the start vector scored through the ISC
+    // path as one delta list holding every variable; NOT rounded (rounding only happens in
+    // step_*).  Scored here by the int32 plain kernel with ISC semantics (same arithmetic).
+    return gj_launch_score_plain_i32(g->p, g->cur, g->stride, g->I, g->cand_scores, true, st);
+}
+
+__global__ void k_init_scores(int I, const double* __restrict__ scored, int levels, double* cur_score,
+                              double* best_score, double* gbest_score) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < I) {
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+            const double v = (l < levels) ? scored[(size_t)i * levels + l] : 0.0;
+            cur_score[(size_t)i * GJ_MAX_LEVELS + l] = v;
+            best_score[(size_t)i * GJ_MAX_LEVELS + l] = v;
+        }
+    }
+    if (i == 0)
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+            gbest_score[l] = (l < levels) ? 1.7976931348623157e308 : 0.0;   // get_stub_score()
+}
+
+static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const double* initial, gj_islands** out) {
+    std::unique_ptr<gj_islands> g(new gj_islands());
+    gj_status rc;
+    if ((rc = gj_islands_common_init(g.get(), p, prm))) return rc;
+    const bool ts = prm->agent == GJ_AGENT_TABU_SEARCH;
+    g->K = ts ? (int)prm->neighbours_count : 1;
+    if (g->K < 1) return gj_fail(GJ_ERR_INVALID, "neighbours_count must be >= 1");
+    if (!ts && prm->late_acceptance_size < 1) return gj_fail(GJ_ERR_INVALID, "late_acceptance_size must be >= 1");
+    const int I = g->I, stride = g->stride;
+    if ((rc = dev_alloc(g.get(), (size_t)I * stride, &g->cur))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)stride, &g->gbest))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->cur_score))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->best_score))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)GJ_MAX_LEVELS, &g->gbest_score))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I, &g->dirty))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I * g->K, &g->moves))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I * std::max(g->K, 1) * GJ_MAX_LEVELS, &g->cand_scores))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)(I + 1) * ((size_t)stride * 4 + GJ_MAX_LEVELS * 8), &g->mailbox))) return rc;
+    if (!ts) {
+        g->late_size = (int)prm->late_acceptance_size;
+        if ((rc = dev_alloc(g.get(), (size_t)I * g->late_size * GJ_MAX_LEVELS, &g->late))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I, &g->late_head))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I, &g->late_len))) return rc;
+    }
+    if ((rc = dev_alloc(g.get(), (size_t)I, &g->selected))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I, &g->accepted))) return rc;
+
+    std::vector<int32_t> host((size_t)I * stride, 0), row(p->dev.n_vars);
+    uint64_t rng = prm->seed ^ 0xA5A5A5A55A5A5A5Aull;
+    for (int i = 0; i < I; ++i) {
+        gj_islands_start_vector(p, initial ? initial + (size_t)i * p->dev.n_vars : nullptr, rng, row);
+        std::copy(row.begin(), row.end(), host.begin() + (size_t)i * stride);
+    }
+    GJ_CUDA_TRY(cudaMemcpy(g->cur, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+    GJ_CUDA_TRY(cudaMemcpy(g->best, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+    cudaStream_t st = p->stream;
+    if ((rc = score_cur(g.get(), st))) return rc;
+    k_init_scores<<<(I + 127) / 128, 128, 0, st>>>(I, g->cand_scores, g->levels, g->cur_score, g->best_score, g->gbest_score);
+    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    g->steps_to_send = (int64_t)std::max<int64_t>(1, prm->migration_frequency);
+    *out = g.release();
+    return GJ_OK;
+}
+
+static gj_status launch_score_moves(gj_islands* g, cudaStream_t st) {
+    const GjProblemDev& P = g->p->dev;
+    const int64_t total = (int64_t)g->I * g->K;
+    if (P.kind >= GJ_VRP) {
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kWarps);
+        if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_score_moves_vrp<<<(unsigned)total, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
+    } else {
+        size_t smem = (size_t)kWarps * (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
+        if (smem > 220 * 1024) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
+        unsigned grid = (unsigned)((total + kWarps - 1) / kWarps);
+        if (P.kind == GJ_NQUEENS) {
+            if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_warp<GJ_NQUEENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_score_moves_warp<GJ_NQUEENS><<<grid, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
+        } else {
+            if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_warp<GJ_TSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_score_moves_warp<GJ_TSP><<<grid, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
+        }
+    }
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+static GjSelectArgs make_select_args(gj_islands* g, bool trace) {
+    GjSelectArgs A{};
+    A.agent = g->prm.agent; A.K = g->K; A.stride = g->stride; A.levels = g->levels; A.n_vars = g->n_vars;
+    A.late_size = g->late_size; A.noop = g->noop; A.n_groups = g->groups.n_groups;
+    A.moves = g->moves; A.cand_scores = g->cand_scores;
+    A.cur = g->cur; A.cur_score = g->cur_score; A.best = g->best; A.best_score = g->best_score;
+    A.dirty = g->dirty; A.late = g->late; A.late_head = g->late_head; A.late_len = g->late_len;
+    A.counters = g->counters;
+    A.tabu_bits = g->tabu_bits; A.tabu_words_per_island = g->tabu_words; A.tabu_word_off = g->tabu_word_off;
+    A.tabu_ring = g->tabu_ring; A.tabu_ring_per_island = g->tabu_ring_len; A.tabu_ring_off = g->tabu_ring_off;
+    A.tabu_size = g->tabu_size; A.tabu_head = g->tabu_head; A.tabu_fill = g->tabu_fill;
+    A.selected_out = trace ? g->selected : nullptr; A.accepted_out = trace ? g->accepted : nullptr;
+    return A;
+}
+
+static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
+    const GjProblemDev& P = g->p->dev;
+    const int64_t total = (int64_t)g->I * g->K;
+    k_gen_moves<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+        P, g->groups, g->mover, g->prm.seed, g->step, g->I, g->K, g->island_base, g->tabu_bits,
+        g->tabu_words, g->tabu_word_off, g->moves);
+    GJ_CUDA_TRY(cudaGetLastError());
+    gj_status rc;
+    if ((rc = launch_score_moves(g, st))) return rc;
+    size_t smem = (size_t)g->n_vars * 4;
+    if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_select<<<g->I, 256, smem, st>>>(P, g->groups, make_select_args(g, trace));
+    GJ_CUDA_TRY(cudaGetLastError());
+    g->step += 1;
+    return GJ_OK;
+}
+
+gj_status gj_ls_migrate_pack(gj_islands* g, cudaStream_t st) {
+    k_migrate_pack<<<g->I, 128, 0, st>>>(g->cur, g->cur_score, g->stride, g->n_vars, g->mailbox);
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
+    k_migrate_recv<<<g->I, 128, 0, st>>>(g->prm.agent, g->levels, g->stride, g->n_vars, g->late_size,
+                                        g->mailbox, g->cur, g->cur_score, g->dirty, g->late,
+                                        g->late_head, g->late_len);
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
+    k_global_reduce<<<1, 256, 0, st>>>(g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score,
+                                      g->gbest, g->gbest_score);
+    GJ_CUDA_TRY(cudaGetLastError());
+    k_global_adopt<<<g->I, 128, 0, st>>>(g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
+                                        g->n_vars, g->late_size, g->gbest, g->gbest_score, g->best_score,
+                                        g->cur, g->cur_score, g->dirty, g->late, g->late_head, g->late_len);
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
+    gj_status rc;
+    for (int64_t s = 0; s < n_steps; ++s) {
+        if ((rc = ls_one_step(g, st, false))) return rc;
+        // agent_base.rs:161-183: every migration_frequency steps send + receive
+        g->steps_to_send -= 1;
+        if (g->steps_to_send <= 0) {
+            if (!g->external_ring) {
+                if ((rc = gj_ls_migrate_pack(g, st))) return rc;
+                k_migrate_wrap<<<8, 256, 0, st>>>(g->I, g->stride, g->mailbox);
+                GJ_CUDA_TRY(cudaGetLastError());
+                if ((rc = gj_ls_migrate_recv(g, st))) return rc;
+            }
+            g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
+        }
+        if ((rc = gj_ls_global_top(g, st))) return rc;      // agent_base.rs:185
+    }
+    return GJ_OK;
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------------------
+
+extern "C" gj_status gj_islands_create(gj_problem* p, const gj_agent_params* params,
+                                       const double* initial, gj_islands** out) {
+    if (!p || !params || !out) return gj_fail(GJ_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (params->n_islands < 1) return gj_fail(GJ_ERR_INVALID, "n_islands must be >= 1");
+    GJ_CUDA_TRY(cudaSetDevice(p->device));
+    switch (params->agent) {
+        case GJ_AGENT_TABU_SEARCH:
+        case GJ_AGENT_LATE_ACCEPTANCE: return ls_create(p, params, initial, out);
+        case GJ_AGENT_GENETIC_ALGORITHM: return gj_ga_create(p, params, initial, out);
+        default: return gj_fail(GJ_ERR_INVALID, "unknown agent kind");
+    }
+}
+
+extern "C" void gj_islands_destroy(gj_islands* g) { delete g; }
+
+extern "C" gj_status gj_islands_step(gj_islands* g, int64_t n_steps, void* stream) {
+    if (!g || n_steps < 0) return gj_fail(GJ_ERR_INVALID, "bad argument");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_step(g, n_steps, (cudaStream_t)stream);
+    return ls_step(g, n_steps, (cudaStream_t)stream);
+}
+
+extern "C" gj_status gj_islands_set_external_ring(gj_islands* g, int32_t on, int32_t island_base) {
+    if (!g) return gj_fail(GJ_ERR_INVALID, "null handle");
+    g->external_ring = on != 0;
+    g->island_base = island_base;
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_stats(gj_islands* g, int64_t* candidates, int64_t* steps, int64_t* accepted) {
+    if (!g) return gj_fail(GJ_ERR_INVALID, "null handle");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    unsigned long long h[4];
+    GJ_CUDA_TRY(cudaMemcpy(h, g->counters, sizeof(h), cudaMemcpyDeviceToHost));
+    if (candidates) *candidates = (int64_t)h[0];
+    if (steps) *steps = (int64_t)h[1];
+    if (accepted) *accepted = (int64_t)h[2];
+    return GJ_OK;
+}
+
+static gj_status fetch_individual(gj_islands* g, const int32_t* d_row, const double* d_score,
+                                  double* vars, double* score) {
+    std::vector<int32_t> row(g->n_vars);
+    double sc[GJ_MAX_LEVELS];
+    GJ_CUDA_TRY(cudaMemcpy(row.data(), d_row, (size_t)g->n_vars * 4, cudaMemcpyDeviceToHost));
+    GJ_CUDA_TRY(cudaMemcpy(sc, d_score, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (vars) for (int i = 0; i < g->n_vars; ++i) vars[i] = (double)row[i];
+    if (score) for (int l = 0; l < g->levels; ++l) score[l] = sc[l];
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_best(gj_islands* g, int32_t island, double* vars, double* score) {
+    if (!g || island >= g->I) return gj_fail(GJ_ERR_INVALID, "bad island");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    GJ_CUDA_TRY(cudaDeviceSynchronize());
+    if (island < 0) {
+        // the group's global_top_individual; before the first step it is still the stub
+        gj_status rc = (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) ? gj_ga_global_top(g, g->p->stream)
+                                                                   : gj_ls_global_top(g, g->p->stream);
+        if (rc) return rc;
+        GJ_CUDA_TRY(cudaStreamSynchronize(g->p->stream));
+        return fetch_individual(g, g->gbest, g->gbest_score, vars, score);
+    }
+    return fetch_individual(g, g->best + (size_t)island * g->stride,
+                            g->best_score + (size_t)island * GJ_MAX_LEVELS, vars, score);
+}
+
+extern "C" gj_status gj_islands_current(gj_islands* g, int32_t island, double* vars, double* score) {
+    if (!g || island < 0 || island >= g->I) return gj_fail(GJ_ERR_INVALID, "bad island");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    GJ_CUDA_TRY(cudaDeviceSynchronize());
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_current(g, island, vars, score);
+    return fetch_individual(g, g->cur + (size_t)island * g->stride,
+                            g->cur_score + (size_t)island * GJ_MAX_LEVELS, vars, score);
+}
+
+extern "C" int64_t gj_islands_migrant_bytes(const gj_islands* g) {
+    if (!g) return 0;
+    return (int64_t)g->migrants * (int64_t)((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
+}
+
+extern "C" gj_status gj_islands_export_migrants(gj_islands* g, void* d_buffer, void* stream) {
+    if (!g || !d_buffer) return gj_fail(GJ_ERR_INVALID, "bad argument");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gj_status rc;
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_export(g, d_buffer, st);
+    if ((rc = gj_ls_migrate_pack(g, st))) return rc;
+    const size_t sb = (size_t)g->stride * 4 + GJ_MAX_LEVELS * 8;
+    GJ_CUDA_TRY(cudaMemcpyAsync(d_buffer, g->mailbox + (size_t)g->I * sb, sb, cudaMemcpyDeviceToDevice, st));
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buffer, void* stream) {
+    if (!g || !d_buffer) return gj_fail(GJ_ERR_INVALID, "bad argument");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_import(g, d_buffer, st);
+    const size_t sb = (size_t)g->stride * 4 + GJ_MAX_LEVELS * 8;
+    GJ_CUDA_TRY(cudaMemcpyAsync(g->mailbox, d_buffer, sb, cudaMemcpyDeviceToDevice, st));
+    return gj_ls_migrate_recv(g, st);
+}
+
+extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64_t* offsets,
+                                           uint64_t* var_ids, double* values, int64_t delta_capacity,
+                                           int32_t* move_kinds, int32_t* move_desc, double* scores,
+                                           int64_t* selected, int32_t* accepted) {
+    if (!g || island < 0 || island >= g->I) return gj_fail(GJ_ERR_INVALID, "bad island");
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_fail(GJ_ERR_UNSUPPORTED, "trace_step is for TS / LA islands");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    cudaStream_t st = g->p->stream;
+    const GjProblemDev& P = g->p->dev;
+    const int K = g->K;
+    // base of the island BEFORE the step
+    std::vector<int32_t> base(g->n_vars);
+    GJ_CUDA_TRY(cudaMemcpy(base.data(), g->cur + (size_t)island * g->stride, (size_t)g->n_vars * 4, cudaMemcpyDeviceToHost));
+    int32_t* d_base = nullptr;
+    GJ_CUDA_TRY(cudaMalloc((void**)&d_base, (size_t)g->n_vars * 4));
+    GJ_CUDA_TRY(cudaMemcpy(d_base, base.data(), (size_t)g->n_vars * 4, cudaMemcpyHostToDevice));
+    gj_status rc = ls_one_step(g, st, true);
+    if (rc) { cudaFree(d_base); return rc; }
+    GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<GjMove> mv(K);
+    GJ_CUDA_TRY(cudaMemcpy(mv.data(), g->moves + (size_t)island * K, (size_t)K * sizeof(GjMove), cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> offs(K + 1, 0);
+    for (int j = 0; j < K; ++j) {
+        const GjMove& m = mv[j];
+        uint64_t n = 0;
+        if (m.kind == GJ_MOVE_NULL) n = 0;
+        else if (m.kind == 2) n = 2ull * m.k;
+        else if (m.kind <= 3) n = m.k;
+        else n = (uint64_t)(std::abs(m.a[0] - m.a[1]) + 1);
+        offs[j + 1] = offs[j] + n;
+        if (move_kinds) move_kinds[j] = m.kind;
+        if (move_desc) {
+            int32_t* d = move_desc + (size_t)j * 20;
+            d[0] = m.kind; d[1] = m.group; d[2] = m.k; d[3] = 0;
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) { d[4 + i] = m.a[i]; d[12 + i] = m.v[i]; }
+        }
+    }
+    if ((int64_t)offs[K] > delta_capacity) { cudaFree(d_base); return gj_fail(GJ_ERR_INVALID, "delta_capacity too small"); }
+    uint64_t *d_offs = nullptr, *d_ids = nullptr; double* d_vals = nullptr;
+    GJ_CUDA_TRY(cudaMalloc((void**)&d_offs, (size_t)(K + 1) * 8));
+    GJ_CUDA_TRY(cudaMalloc((void**)&d_ids, (size_t)(offs[K] + 1) * 8));
+    GJ_CUDA_TRY(cudaMalloc((void**)&d_vals, (size_t)(offs[K] + 1) * 8));
+    GJ_CUDA_TRY(cudaMemcpy(d_offs, offs.data(), (size_t)(K + 1) * 8, cudaMemcpyHostToDevice));
+    k_expand_moves<<<K, 128, 0, st>>>(P, g->groups, d_base, g->moves + (size_t)island * K, K, g->noop, d_offs, d_ids, d_vals);
+    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    if (offsets) std::copy(offs.begin(), offs.end(), offsets);
+    if (var_ids && offs[K]) GJ_CUDA_TRY(cudaMemcpy(var_ids, d_ids, (size_t)offs[K] * 8, cudaMemcpyDeviceToHost));
+    if (values && offs[K]) GJ_CUDA_TRY(cudaMemcpy(values, d_vals, (size_t)offs[K] * 8, cudaMemcpyDeviceToHost));
+    if (scores) GJ_CUDA_TRY(cudaMemcpy(scores, g->cand_scores + (size_t)island * K * g->levels, (size_t)K * g->levels * 8, cudaMemcpyDeviceToHost));
+    long long sel = 0; int acc = 0;
+    GJ_CUDA_TRY(cudaMemcpy(&sel, g->selected + island, 8, cudaMemcpyDeviceToHost));
+    GJ_CUDA_TRY(cudaMemcpy(&acc, g->accepted + island, 4, cudaMemcpyDeviceToHost));
+    if (selected) *selected = sel;
+    if (accepted) *accepted = acc;
+    cudaFree(d_base); cudaFree(d_offs); cudaFree(d_ids); cudaFree(d_vals);
+    // the trace bypasses migration / global-top bookkeeping of gj_islands_step on purpose
+    return GJ_OK;
+}

@@ -1,0 +1,67 @@
+// gj_islands.hpp -- state of a group of device-resident agents (opaque gj_islands handle).
+#pragma once
+
+#include <vector>
+
+#include "gj_internal.hpp"
+#include "gj_moves.cuh"
+
+struct gj_islands {
+    gj_problem* p = nullptr;
+    gj_agent_params prm{};
+    int I = 0;                   // islands in the group
+    int K = 1;                   // candidates per island per step (TS: neighbours; LA: 1)
+    int levels = 1, n_vars = 0, stride = 0;
+    int noop = 0;
+    int late_size = 0;
+    bool external_ring = false;  // migration transport handled by the caller (multi-GPU)
+    int island_base = 0;         // global id of island 0 (RNG key, ring position)
+    uint64_t step = 0;
+    int64_t steps_to_send = 1;
+    int64_t migrants = 1;        // individuals per exchange (GA: ceil(rate * pop))
+
+    GjGroups groups{};
+    GjMoverParams mover{};
+    std::vector<void*> allocs;
+
+    // local-search agents (TS / LA): population[0] per island
+    int32_t* cur = nullptr;  double* cur_score = nullptr;
+    int32_t* best = nullptr; double* best_score = nullptr;      // agent_top_individual
+    int32_t* gbest = nullptr; double* gbest_score = nullptr;    // global_top_individual
+    int* dirty = nullptr;
+    GjMove* moves = nullptr;
+    double* cand_scores = nullptr;
+    unsigned char* mailbox = nullptr;
+    double* late = nullptr; int* late_head = nullptr; int* late_len = nullptr;
+    long long* selected = nullptr; int* accepted = nullptr;
+
+    // tabu deques
+    uint32_t* tabu_bits = nullptr; int tabu_words = 0; const int32_t* tabu_word_off = nullptr;
+    int32_t* tabu_ring = nullptr; int tabu_ring_len = 0; const int32_t* tabu_ring_off = nullptr;
+    const int32_t* tabu_size = nullptr; int* tabu_head = nullptr; int* tabu_fill = nullptr;
+
+    unsigned long long* counters = nullptr;
+
+    // genetic algorithm (gj_islands_ga.cu)
+    int pop = 0, half = 0, n_cand = 0;
+    int32_t* pop_rows = nullptr;   // [I][pop][stride]
+    int32_t* pop_next = nullptr;
+    double* pop_scores = nullptr;  // [I][pop][3]
+    double* pop_scores_next = nullptr;
+    int32_t* cand_rows = nullptr;  // [I][n_cand][stride]
+    int* order = nullptr;          // [I][pop] rank -> row index after the sort
+    int* ga_src = nullptr;         // [I][pop] replacement source (trace)
+
+    ~gj_islands();
+};
+
+gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_params* prm);
+void gj_islands_start_vector(const gj_problem* p, const double* given, uint64_t& rng, std::vector<int32_t>& row);
+
+gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* initial, gj_islands** out);
+gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st);
+gj_status gj_ga_global_top(gj_islands* g, cudaStream_t st);
+gj_status gj_ga_current(gj_islands* g, int32_t island, double* vars, double* score);
+gj_status gj_ga_export(gj_islands* g, void* d_buffer, cudaStream_t st);
+gj_status gj_ga_import(gj_islands* g, const void* d_buffer, cudaStream_t st);
+gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st);

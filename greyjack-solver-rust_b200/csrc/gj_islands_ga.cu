@@ -1,0 +1,435 @@
+// gj_islands_ga.cu -- the GeneticAlgorithm agent on the device
+// (greyjack/src/agents/metaheuristic_bases/genetic_algorithm_base.rs, Agent::step_plain
+// agent_base.rs:273-298).  One generation of every island per launch sequence:
+//
+//   k_ga_offspring  select_p_best x2, cross, Mover::do_move(plain) x2, fix_variables (:141-187)
+//   plain scorer    request_score_plain on the offspring (PSC semantics) + round
+//   k_ga_replace    build_updated_population: candidate i vs random p-worst native (:198-213)
+//   k_ga_sort       population.sort() (agent_base.rs:149-151) -> rank table
+//   k_ga_top        update_top_individual (agent_base.rs:220-224)
+//   k_ga_migrate_*  send_updates / receive_updates for Population agents (:337-341, 405-412)
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "gj_eval.cuh"
+#include "gj_islands.hpp"
+
+struct GjGaArgs {
+    int I, pop, half, n_cand, stride, n_vars, levels, noop;
+    double crossover_probability, p_best_rate;
+    uint64_t seed, step;
+    int island_base;
+};
+
+__device__ __forceinline__ int gj_ga_p_rank(GjPhilox& rng, double p_best_rate, int pop, bool worst) {
+    // select_p_best / select_p_worst (genetic_algorithm_base.rs:83-103):
+    // p ~ U(1e-6, p_best_rate); last_top = ceil(p * pop); id ~ U[0, last_top) | U[pop-last_top, pop)
+    const double p = 0.000001 + gj_rng_f64(rng) * (p_best_rate - 0.000001);
+    int last_top = (int)ceil(p * (double)pop);
+    last_top = max(1, min(last_top, pop));
+    const int id = (int)gj_rng_below(rng, (uint32_t)last_top);
+    return worst ? (pop - last_top + id) : id;
+}
+
+// One CTA per offspring.
+__global__ void __launch_bounds__(128)
+k_ga_offspring(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A,
+               const int32_t* __restrict__ pop_rows, const int* __restrict__ order,
+               int32_t* __restrict__ cand_rows, GjMove* __restrict__ moves) {
+    __shared__ int sh_parent;
+    __shared__ GjMove sh_move;
+    const int island = blockIdx.x / A.n_cand;
+    const int c = blockIdx.x % A.n_cand;
+    const int q = c >> 1, child = c & 1;
+    if (threadIdx.x == 0) {
+        GjPhilox rng;
+        gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
+                    (uint32_t)(A.step >> 32), 0x40000000u + (uint32_t)q);
+        int r1 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false);
+        int r2 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false);
+        // cross (:105-134): ONE weight for every gene (vec![sample(); n] evaluates the RNG once);
+        // integer variables get rint(w) in {0, 1}, so the children are the parents, possibly
+        // swapped.  w ~ U[0,1]; rint ties (0.5) go to ceil.
+        if (gj_rng_f64(rng) <= A.crossover_probability) {
+            const double w = gj_rint(gj_rng_f64(rng));
+            if (w == 0.0) { int t = r1; r1 = r2; r2 = t; }
+        }
+        sh_parent = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
+        sh_move = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step,
+                                   (uint32_t)c, nullptr, nullptr);
+        moves[(size_t)island * A.n_cand + c] = sh_move;
+    }
+    __syncthreads();
+    const int32_t* parent = pop_rows + ((size_t)island * A.pop + sh_parent) * A.stride;
+    int32_t* out = cand_rows + ((size_t)island * A.n_cand + c) * A.stride;
+    for (int i = threadIdx.x; i < A.stride; i += blockDim.x) out[i] = (i < A.n_vars) ? parent[i] : 0;
+    __syncthreads();
+    // Mover::do_move(.., incremental = false) + fix_variables(changed columns)
+    const GjMove m = sh_move;
+    gj_apply_move(P, m, G, false, A.noop != 0, threadIdx.x, blockDim.x,
+                  [&](int id) { return parent[id]; }, [&](int id, int v) { out[id] = v; });
+}
+
+__global__ void k_round_scores(GjProblemDev P, double* scores, int64_t n) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        GjScore s;
+        for (int l = 0; l < P.levels; ++l) s.v[l] = scores[j * P.levels + l];
+        gj_score_round(s, P);
+        for (int l = 0; l < P.levels; ++l) scores[j * P.levels + l] = s.v[l];
+    }
+}
+
+// One CTA per (island, slot).
+__global__ void __launch_bounds__(128)
+k_ga_replace(GjGaArgs A, const int32_t* __restrict__ pop_rows, const double* __restrict__ pop_scores,
+             const int* __restrict__ order, const int32_t* __restrict__ cand_rows,
+             const double* __restrict__ cand_scores, int32_t* __restrict__ pop_next,
+             double* __restrict__ pop_scores_next, int* __restrict__ ga_src) {
+    __shared__ int sh_from_cand, sh_native;
+    const int island = blockIdx.x / A.pop, i = blockIdx.x % A.pop;
+    if (threadIdx.x == 0) {
+        GjPhilox rng;
+        gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
+                    (uint32_t)(A.step >> 32), 0x80000000u + (uint32_t)i);
+        const int rank = gj_ga_p_rank(rng, A.p_best_rate, A.pop, true);
+        const int native = order[(size_t)island * A.pop + rank];
+        GjScore c, w;
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+            c.v[l] = (l < A.levels) ? cand_scores[((size_t)island * A.n_cand + i) * A.levels + l] : 0.0;
+            w.v[l] = pop_scores[((size_t)island * A.pop + native) * GJ_MAX_LEVELS + l];
+        }
+        const bool take = gj_score_le(c, w, A.levels);      // :207
+        sh_from_cand = take ? 1 : 0;
+        sh_native = native;
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+            pop_scores_next[((size_t)island * A.pop + i) * GJ_MAX_LEVELS + l] = take ? c.v[l] : w.v[l];
+        if (ga_src) ga_src[(size_t)island * A.pop + i] = take ? i : -(rank + 1);
+    }
+    __syncthreads();
+    const int32_t* src = sh_from_cand ? cand_rows + ((size_t)island * A.n_cand + i) * A.stride
+                                      : pop_rows + ((size_t)island * A.pop + sh_native) * A.stride;
+    int32_t* dst = pop_next + ((size_t)island * A.pop + i) * A.stride;
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (int k = threadIdx.x; k < A.stride / 4; k += blockDim.x) d4[k] = s4[k];
+}
+
+// population.sort(): stable order by Ord::cmp == bitonic sort on (score, index).  One CTA per
+// island; the rank table lives in shared memory, scores are read through L1/L2.
+__global__ void __launch_bounds__(1024)
+k_ga_sort(int pop, int pop2, int levels, const double* __restrict__ pop_scores, int* __restrict__ order) {
+    extern __shared__ int sh_ord[];
+    const int island = blockIdx.x;
+    const double* sc = pop_scores + (size_t)island * pop * GJ_MAX_LEVELS;
+    for (int i = threadIdx.x; i < pop2; i += blockDim.x) sh_ord[i] = (i < pop) ? i : -1;
+    __syncthreads();
+    auto greater = [&](int a, int b) {      // a sorts after b ?  (-1 = padding, sorts last)
+        if (a < 0) return b >= 0;
+        if (b < 0) return false;
+        GjScore sa = {}, sb = {};
+        for (int l = 0; l < levels; ++l) { sa.v[l] = sc[(size_t)a * GJ_MAX_LEVELS + l]; sb.v[l] = sc[(size_t)b * GJ_MAX_LEVELS + l]; }
+        const int c = gj_score_cmp(sa, sb, levels);
+        return c > 0 || (c == 0 && a > b);
+    };
+    for (int k = 2; k <= pop2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < pop2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int a = sh_ord[i], b = sh_ord[ixj];
+                    const bool up = (i & k) == 0;
+                    if (greater(a, b) == up) { sh_ord[i] = b; sh_ord[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < pop; i += blockDim.x) order[(size_t)island * pop + i] = sh_ord[i];
+}
+
+// update_top_individual: population[0] <= agent_top -> replace (agent_base.rs:220-224)
+__global__ void k_ga_top(int pop, int stride, int n_vars, int levels, int n_cand,
+                         const int32_t* __restrict__ pop_rows, const double* __restrict__ pop_scores,
+                         const int* __restrict__ order, int32_t* best, double* best_score,
+                         unsigned long long* counters) {
+    __shared__ int sh_take;
+    const int island = blockIdx.x;
+    const int r0 = order[(size_t)island * pop];
+    if (threadIdx.x == 0) {
+        GjScore c = {}, t = {};
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+            c.v[l] = pop_scores[((size_t)island * pop + r0) * GJ_MAX_LEVELS + l];
+            t.v[l] = best_score[(size_t)island * GJ_MAX_LEVELS + l];
+        }
+        const bool take = gj_score_le(c, t, levels);
+        if (take) for (int l = 0; l < GJ_MAX_LEVELS; ++l) best_score[(size_t)island * GJ_MAX_LEVELS + l] = c.v[l];
+        sh_take = take ? 1 : 0;
+        if (counters) {
+            atomicAdd(&counters[0], (unsigned long long)n_cand);
+            if (island == 0) atomicAdd(&counters[1], 1ull);
+        }
+    }
+    __syncthreads();
+    if (sh_take) {
+        const int32_t* src = pop_rows + ((size_t)island * pop + r0) * stride;
+        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) best[(size_t)island * stride + i] = src[i];
+    }
+}
+
+// migrants = the island's first ceil(migration_rate * pop) individuals by rank
+// mailbox slot s (s = 0..I): [migrants][stride int32 + 3 f64]
+__global__ void k_ga_migrate_pack(int pop, int stride, int migrants, const int32_t* __restrict__ pop_rows,
+                                  const double* __restrict__ pop_scores, const int* __restrict__ order,
+                                  unsigned char* mailbox) {
+    const int island = blockIdx.x / migrants, mgr = blockIdx.x % migrants;
+    const size_t ind_bytes = (size_t)stride * 4 + GJ_MAX_LEVELS * 8;
+    unsigned char* slot = mailbox + ((size_t)(island + 1) * migrants + mgr) * ind_bytes;
+    const int r = order[(size_t)island * pop + mgr];
+    const int32_t* src = pop_rows + ((size_t)island * pop + r) * stride;
+    int32_t* row = (int32_t*)slot;
+    double* sc = (double*)(slot + (size_t)stride * 4);
+    for (int i = threadIdx.x; i < stride; i += blockDim.x) row[i] = src[i];
+    if (threadIdx.x < GJ_MAX_LEVELS) sc[threadIdx.x] = pop_scores[((size_t)island * pop + r) * GJ_MAX_LEVELS + threadIdx.x];
+}
+
+__global__ void k_copy_bytes(const unsigned char* src, unsigned char* dst, size_t bytes) {
+    const uint32_t* s = (const uint32_t*)src; uint32_t* d = (uint32_t*)dst;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes / 4; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+// receive_updates for Population agents: migrant i vs population[pop - count + i] (by rank);
+// replace when migrant <= native (agent_base.rs:405-412, 435-439)
+__global__ void k_ga_migrate_recv(int pop, int stride, int migrants, int levels,
+                                  const unsigned char* __restrict__ mailbox, int32_t* pop_rows,
+                                  double* pop_scores, const int* __restrict__ order) {
+    __shared__ int sh_take;
+    const int island = blockIdx.x / migrants, mgr = blockIdx.x % migrants;
+    const size_t ind_bytes = (size_t)stride * 4 + GJ_MAX_LEVELS * 8;
+    const unsigned char* slot = mailbox + ((size_t)island * migrants + mgr) * ind_bytes;
+    const int32_t* row = (const int32_t*)slot;
+    const double* sc = (const double*)(slot + (size_t)stride * 4);
+    const int r = order[(size_t)island * pop + (pop - migrants + mgr)];
+    if (threadIdx.x == 0) {
+        GjScore m = {}, n = {};
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) { m.v[l] = sc[l]; n.v[l] = pop_scores[((size_t)island * pop + r) * GJ_MAX_LEVELS + l]; }
+        const bool take = gj_score_le(m, n, levels);
+        if (take) for (int l = 0; l < GJ_MAX_LEVELS; ++l) pop_scores[((size_t)island * pop + r) * GJ_MAX_LEVELS + l] = m.v[l];
+        sh_take = take ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh_take) {
+        int32_t* dst = pop_rows + ((size_t)island * pop + r) * stride;
+        for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[i] = row[i];
+    }
+}
+
+__global__ void k_ga_init_scores(int I, int pop, int levels, const double* __restrict__ scored,
+                                 double* pop_scores, double* best_score, double* gbest_score) {
+    const int64_t n = (int64_t)I * pop;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+            pop_scores[j * GJ_MAX_LEVELS + l] = (l < levels) ? scored[j * levels + l] : 0.0;
+    if (blockIdx.x == 0 && threadIdx.x < GJ_MAX_LEVELS) {
+        gbest_score[threadIdx.x] = (threadIdx.x < levels) ? 1.7976931348623157e308 : 0.0;
+        for (int i = 0; i < I; ++i)
+            best_score[(size_t)i * GJ_MAX_LEVELS + threadIdx.x] = (threadIdx.x < levels) ? 1.7976931348623157e308 : 0.0;
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------
+
+template <class T>
+static gj_status ga_alloc(gj_islands* g, size_t n, T** out) {
+    void* d = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    GJ_CUDA_TRY(cudaMalloc(&d, bytes));
+    g->allocs.push_back(d);
+    GJ_CUDA_TRY(cudaMemset(d, 0, bytes));
+    *out = (T*)d;
+    return GJ_OK;
+}
+
+static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+static gj_status ga_sort_and_top(gj_islands* g, cudaStream_t st, bool count) {
+    const int pop2 = next_pow2(g->pop);
+    size_t smem = (size_t)pop2 * 4;
+    if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_ga_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ga_sort<<<g->I, 1024, smem, st>>>(g->pop, pop2, g->levels, g->pop_scores, g->order);
+    GJ_CUDA_TRY(cudaGetLastError());
+    k_ga_top<<<g->I, 128, 0, st>>>(g->pop, g->stride, g->n_vars, g->levels, g->n_cand, g->pop_rows,
+                                  g->pop_scores, g->order, g->best, g->best_score, count ? g->counters : nullptr);
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* initial, gj_islands** out) {
+    std::unique_ptr<gj_islands> g(new gj_islands());
+    gj_status rc;
+    if ((rc = gj_islands_common_init(g.get(), p, prm))) return rc;
+    if (prm->population_size < 2) return gj_fail(GJ_ERR_INVALID, "population_size must be >= 2");
+    if (prm->population_size > 65536) return gj_fail(GJ_ERR_UNSUPPORTED, "population_size > 65536");
+    if (!(prm->p_best_rate > 0.000001)) return gj_fail(GJ_ERR_INVALID, "p_best_rate must exceed 1e-6");
+    g->pop = (int)prm->population_size;
+    g->half = (int)std::ceil(0.5 * (double)g->pop);          // genetic_algorithm_base.rs:51
+    g->n_cand = 2 * g->half;
+    g->K = g->n_cand;
+    g->migrants = std::max<int64_t>(1, (int64_t)std::ceil(prm->migration_rate * (double)g->pop));   // agent_base.rs:339
+    g->migrants = std::min<int64_t>(g->migrants, g->pop);
+    const int I = g->I, stride = g->stride, pop = g->pop;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop * stride, &g->pop_rows))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop * stride, &g->pop_next))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop * GJ_MAX_LEVELS, &g->pop_scores))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop * GJ_MAX_LEVELS, &g->pop_scores_next))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand * stride, &g->cand_rows))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * std::max(g->n_cand, pop) * GJ_MAX_LEVELS, &g->cand_scores))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->moves))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->order))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_src))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->best_score))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)stride, &g->gbest))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)GJ_MAX_LEVELS, &g->gbest_score))) return rc;
+    const size_t ind_bytes = (size_t)stride * 4 + GJ_MAX_LEVELS * 8;
+    if ((rc = ga_alloc(g.get(), (size_t)(I + 1) * g->migrants * ind_bytes, &g->mailbox))) return rc;
+
+    // Agent::init_population (agent_base.rs:193-203): population_size samples scored in one
+    // plain batch.  `initial` (if given) seeds individual 0 of every island; the rest are
+    // sample_variables() draws (initial value where defined, else uniform).
+    {
+        std::vector<int32_t> host((size_t)I * pop * stride, 0), row(p->dev.n_vars);
+        uint64_t rng = prm->seed ^ 0x5DEECE66Dull;
+        for (int i = 0; i < I; ++i)
+            for (int k = 0; k < pop; ++k) {
+                const double* given = (initial && k == 0) ? initial + (size_t)i * p->dev.n_vars : nullptr;
+                gj_islands_start_vector(p, given, rng, row);
+                std::copy(row.begin(), row.end(), host.begin() + ((size_t)i * pop + k) * stride);
+            }
+        GJ_CUDA_TRY(cudaMemcpy(g->pop_rows, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+    }
+    cudaStream_t st = p->stream;
+    if ((rc = gj_launch_score_plain_i32(p, g->pop_rows, stride, (int64_t)I * pop, g->cand_scores, false, st))) return rc;
+    k_ga_init_scores<<<148, 256, 0, st>>>(I, pop, g->levels, g->cand_scores, g->pop_scores, g->best_score, g->gbest_score);
+    GJ_CUDA_TRY(cudaGetLastError());
+    if ((rc = ga_sort_and_top(g.get(), st, false))) return rc;
+    GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    g->steps_to_send = std::max<int64_t>(1, prm->migration_frequency);
+    *out = g.release();
+    return GJ_OK;
+}
+
+static GjGaArgs ga_args(gj_islands* g) {
+    GjGaArgs A{};
+    A.I = g->I; A.pop = g->pop; A.half = g->half; A.n_cand = g->n_cand; A.stride = g->stride;
+    A.n_vars = g->n_vars; A.levels = g->levels; A.noop = g->noop;
+    A.crossover_probability = g->prm.crossover_probability; A.p_best_rate = g->prm.p_best_rate;
+    A.seed = g->prm.seed; A.step = g->step; A.island_base = g->island_base;
+    return A;
+}
+
+static gj_status ga_migrate_pack(gj_islands* g, cudaStream_t st) {
+    k_ga_migrate_pack<<<g->I * (int)g->migrants, 128, 0, st>>>(g->pop, g->stride, (int)g->migrants, g->pop_rows,
+                                                             g->pop_scores, g->order, g->mailbox);
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+static gj_status ga_migrate_recv(gj_islands* g, cudaStream_t st) {
+    k_ga_migrate_recv<<<g->I * (int)g->migrants, 128, 0, st>>>(g->pop, g->stride, (int)g->migrants, g->levels,
+                                                             g->mailbox, g->pop_rows, g->pop_scores, g->order);
+    GJ_CUDA_TRY(cudaGetLastError());
+    // the next sample_candidates_plain starts with population.sort() (:157)
+    return ga_sort_and_top(g, st, false);
+}
+
+gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
+    const GjProblemDev& P = g->p->dev;
+    gj_status rc;
+    for (int64_t s = 0; s < n_steps; ++s) {
+        GjGaArgs A = ga_args(g);
+        k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves);
+        GJ_CUDA_TRY(cudaGetLastError());
+        const int64_t S = (int64_t)g->I * g->n_cand;
+        if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
+        k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
+        GJ_CUDA_TRY(cudaGetLastError());
+        k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,
+                                                   g->pop_next, g->pop_scores_next, g->ga_src);
+        GJ_CUDA_TRY(cudaGetLastError());
+        std::swap(g->pop_rows, g->pop_next);
+        std::swap(g->pop_scores, g->pop_scores_next);
+        if ((rc = ga_sort_and_top(g, st, true))) return rc;
+        g->step += 1;
+        g->steps_to_send -= 1;
+        if (g->steps_to_send <= 0) {
+            if (!g->external_ring) {
+                if ((rc = ga_migrate_pack(g, st))) return rc;
+                const size_t slot = (size_t)g->migrants * ((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
+                k_copy_bytes<<<64, 256, 0, st>>>(g->mailbox + (size_t)g->I * slot, g->mailbox, slot);
+                GJ_CUDA_TRY(cudaGetLastError());
+                if ((rc = ga_migrate_recv(g, st))) return rc;
+            }
+            g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
+        }
+        if ((rc = gj_ga_global_top(g, st))) return rc;
+    }
+    return GJ_OK;
+}
+
+// update_global_top for GA: only the "publish" half (agent_base.rs:451-461); Population agents
+// never adopt the global best (:487 `_ => ()`).
+__global__ void k_ga_global_reduce(int I, int levels, int stride, int n_vars, const int32_t* __restrict__ best,
+                                   const double* __restrict__ best_score, int32_t* gbest, double* gbest_score);
+
+gj_status gj_ga_global_top(gj_islands* g, cudaStream_t st) {
+    k_ga_global_reduce<<<1, 256, 0, st>>>(g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score);
+    GJ_CUDA_TRY(cudaGetLastError());
+    return GJ_OK;
+}
+
+__global__ void k_ga_global_reduce(int I, int levels, int stride, int n_vars, const int32_t* __restrict__ best,
+                                   const double* __restrict__ best_score, int32_t* gbest, double* gbest_score) {
+    __shared__ int sh_win;
+    if (threadIdx.x == 0) {
+        GjScore g = {};
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) g.v[l] = gbest_score[l];
+        int win = -1;
+        for (int i = 0; i < I; ++i) {
+            GjScore s = {};
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.v[l] = best_score[(size_t)i * GJ_MAX_LEVELS + l];
+            if (!gj_score_le(g, s, levels)) { g = s; win = i; }
+        }
+        if (win >= 0) for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = g.v[l];
+        sh_win = win;
+    }
+    __syncthreads();
+    if (sh_win >= 0)
+        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) gbest[i] = best[(size_t)sh_win * stride + i];
+}
+
+gj_status gj_ga_current(gj_islands* g, int32_t island, double* vars, double* score) {
+    int r0 = 0;
+    GJ_CUDA_TRY(cudaMemcpy(&r0, g->order + (size_t)island * g->pop, 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> row(g->n_vars);
+    double sc[GJ_MAX_LEVELS];
+    GJ_CUDA_TRY(cudaMemcpy(row.data(), g->pop_rows + ((size_t)island * g->pop + r0) * g->stride, (size_t)g->n_vars * 4, cudaMemcpyDeviceToHost));
+    GJ_CUDA_TRY(cudaMemcpy(sc, g->pop_scores + ((size_t)island * g->pop + r0) * GJ_MAX_LEVELS, sizeof(sc), cudaMemcpyDeviceToHost));
+    if (vars) for (int i = 0; i < g->n_vars; ++i) vars[i] = (double)row[i];
+    if (score) for (int l = 0; l < g->levels; ++l) score[l] = sc[l];
+    return GJ_OK;
+}
+
+gj_status gj_ga_export(gj_islands* g, void* d_buffer, cudaStream_t st) {
+    gj_status rc;
+    if ((rc = ga_migrate_pack(g, st))) return rc;
+    const size_t slot = (size_t)g->migrants * ((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
+    GJ_CUDA_TRY(cudaMemcpyAsync(d_buffer, g->mailbox + (size_t)g->I * slot, slot, cudaMemcpyDeviceToDevice, st));
+    return GJ_OK;
+}
+
+gj_status gj_ga_import(gj_islands* g, const void* d_buffer, cudaStream_t st) {
+    const size_t slot = (size_t)g->migrants * ((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
+    GJ_CUDA_TRY(cudaMemcpyAsync(g->mailbox, d_buffer, slot, cudaMemcpyDeviceToDevice, st));
+    return ga_migrate_recv(g, st);
+}

@@ -5,3 +5,5 @@ this package only mirrors the reference's host-side names for tests, bench.py an
 from . import instances  # noqa: F401
 from ._lib import GjError, LIB_PATH, load  # noqa: F401
 from .problem import Problem, deltas_to_csr  # noqa: F401
+from .agents import (GeneticAlgorithm, Islands, LateAcceptance, ScoreLimit, ScoreNoImprovement,  # noqa: F401
+                     StepsLimit, TabuSearch, TimeSpentLimit)

@@ -58,7 +58,7 @@ EXPORTED = [
     "gj_score_plain_device", "gj_score_plain_i32_device", "gj_score_incremental_device",
     "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_stats",
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",
-    "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step",
+    "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step",
 ]
 
 _lib = None

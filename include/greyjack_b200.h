@@ -235,6 +235,10 @@ GJ_API gj_status gj_islands_current(gj_islands* g, int32_t island, double* vars,
    The transport between ranks (NCCL send/recv over NVLink) is the caller's.
    Layout: n_migrants x (n_vars int32 + levels f64), see gj_islands_migrant_bytes.      */
 GJ_API int64_t   gj_islands_migrant_bytes(const gj_islands* g);
+/* on != 0: gj_islands_step stops doing the wrap-around (last island -> first island) and the
+   caller moves the migrants between GPUs with export/import every migration_frequency steps;
+   island_base = global index of this group's island 0 (RNG key / ring position).          */
+GJ_API gj_status gj_islands_set_external_ring(gj_islands* g, int32_t on, int32_t island_base);
 GJ_API gj_status gj_islands_export_migrants(gj_islands* g, void* d_buffer, void* stream);
 GJ_API gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buffer, void* stream);
 
@@ -248,7 +252,10 @@ GJ_API gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buffer,
 GJ_API gj_status gj_islands_trace_step(gj_islands* g, int32_t island,
                                        uint64_t* offsets /*[K+1]*/, uint64_t* var_ids,
                                        double* values, int64_t delta_capacity,
-                                       int32_t* move_kinds /*[K]*/, double* scores /*[K][levels]*/,
+                                       int32_t* move_kinds /*[K]*/,
+                                       int32_t* move_desc /*[K][20]: kind, group, k, 0,
+                                                            chosen positions[8], values[8]*/,
+                                       double* scores /*[K][levels]*/,
                                        int64_t* selected, int32_t* accepted);
 
 #ifdef __cplusplus

@@ -1,0 +1,237 @@
+"""GPU parity of the device-resident agents: every generated move, every candidate score and
+every selection decision of a TabuSearch / LateAcceptance step is replayed through the CPU
+oracle (mover.rs, the ISC scorers, tabu_search_base.rs / late_acceptance_base.rs); GA
+generations are checked through their invariants and the oracle's plain scorer."""
+import numpy as np
+import pytest
+
+from greyjack_b200 import (GeneticAlgorithm, LateAcceptance, Problem, TabuSearch, instances as inst)
+
+pytestmark = pytest.mark.gpu
+
+MIX = [0.0, 0.2, 0.2, 0.2, 0.2, 0.2]      # examples/tsp/src/main.rs:47
+ALL = [0.2, 0.16, 0.16, 0.16, 0.16, 0.16]
+
+
+def _oracle_move(op, spec, base, d, noop=True):
+    """Replays one device move descriptor through the oracle mover (incremental form)."""
+    kind, group, k = int(d[0]), int(d[1]), int(d[2])
+    a, v = d[4:12], d[12:20]
+    names = list(spec.groups.keys())
+    g = np.asarray(spec.groups[names[group]], dtype=np.int32)
+    if kind == 255:
+        return []
+    if kind == 0:
+        res = op.move_change(base, g, a[:k], v[:k].astype(np.float64), True)
+    elif kind == 1:
+        res = op.move_swap(base, g, a[:k], True)
+    elif kind == 2:
+        res = op.move_swap_edges(base, g, a[:k], True)
+    elif kind == 3:
+        res = op.move_scramble(base, g, int(a[0]), v[:k], True)
+    elif kind == 4:
+        res = op.move_insertion(base, g, int(a[0]), int(a[1]), True)
+    else:
+        res = op.move_inverse(base, g, int(a[0]), int(a[1]), True)
+    assert res is not None
+    cols, vals = res
+    vals = op.fix_deltas(cols, vals)
+    return [(int(c), float(x)) for c, x in zip(cols, vals)]
+
+
+def _final_state(n, pairs):
+    out = {}
+    for c, v in pairs:
+        out[c] = v
+    return out
+
+
+def _check_rounded(got, want_unrounded, spec, oracle):
+    want = oracle.score_round(want_unrounded, spec.score_precision)
+    L = spec.levels
+    for l in range(L - 1 if L > 1 else 1):
+        assert np.array_equal(got[:, l], want[:, l])
+    if L > 1:
+        diff = np.abs(got[:, -1] - want[:, -1])
+        # truncation to 3 decimals can turn a 1-ulp summation-order difference into 1e-3
+        jump = np.abs(diff - 1e-3) < 1e-9
+        ok = (diff <= 1e-9 * np.maximum(1.0, np.abs(want[:, -1]))) | jump
+        assert ok.all()
+        assert jump.mean() <= 0.002
+
+
+CASES = [
+    ("nq64", lambda: inst.nqueens(64), [0.0, 1.0, 0.0, 0.0, 0.0, 0.0], 0.0, None),
+    ("nq64-all", lambda: inst.nqueens(64), ALL, 0.2, 1.0),
+    ("tsp200-mix", lambda: inst.tsp(200, seed=3), MIX, 0.5, None),
+    ("tsp200-all", lambda: inst.tsp(200, seed=3), ALL, 0.0, 1.0),
+    ("cvrp60", lambda: inst.cvrp(60, 6, seed=2), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.8, None),
+    ("cvrp60-all", lambda: inst.cvrp(60, 6, seed=2), ALL, 0.2, 1.0),
+    ("vrpsvc80", lambda: inst.vrptw(80, 6, n_depots=2, seed=3), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.2, None),
+    ("vrptw80-all", lambda: inst.vrptw(80, 6, n_depots=2, seed=3, service_variant=False), ALL, 0.2, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_tabu_search_step_replay(case, oracle):
+    _, mk, probas, tabu, mult = case
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    K = 96
+    isl = TabuSearch(K, tabu, True, mult, probas, 10).build_agent(gp, n_islands=2, seed=1234)
+    for island in (0, 1):
+        for _ in range(4):
+            base, cur_score = isl.current(island)
+            tr = isl.trace_step(island)
+            # (1) every move expands to exactly what mover.rs would emit for the same choices
+            for j in range(K):
+                want = _oracle_move(op, spec, base, tr["desc"][j])
+                assert _final_state(spec.n_vars, tr["deltas"][j]) == _final_state(spec.n_vars, want), (j, tr["desc"][j])
+                assert [c for c, _ in tr["deltas"][j]] == [c for c, _ in want]
+            # (2) every candidate score equals the ISC oracle on the same delta list
+            _check_rounded(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+            # (3) selection: first minimum, accept iff best <= current
+            sel, acc = oracle.ts_select(tr["scores"], cur_score)
+            assert (tr["selected"], tr["accepted"]) == (sel, acc)
+            # (4) the stored individual
+            new, new_score = isl.current(island)
+            want_vec = base.copy()
+            if acc:
+                for c, v in tr["deltas"][sel]:
+                    want_vec[c] = v
+                assert np.array_equal(new_score, tr["scores"][sel])
+            else:
+                assert np.array_equal(new_score, cur_score)
+            assert np.array_equal(new, want_vec)
+    isl.close(); gp.close()
+
+
+def test_moves_cover_every_kind_and_are_distinct(oracle):
+    spec = inst.tsp(300, seed=5)
+    gp = Problem(spec)
+    isl = TabuSearch(512, 0.0, True, 1.0, ALL, 10, reference_noop_moves=False).build_agent(gp, seed=7)
+    tr = isl.trace_step(0)
+    kinds = set(int(k) for k in tr["kinds"])
+    assert kinds >= {0, 1, 2, 3, 4, 5}
+    # chosen positions of a move are distinct (choice without replacement, math_utils.rs:43-45)
+    for d in tr["desc"]:
+        if d[0] in (0, 1, 2):
+            assert len(set(d[4:4 + d[2]])) == d[2]
+        if d[0] in (4, 5):
+            assert d[4] != d[5]
+    # without the reference's no-op quirk scramble really permutes
+    base = spec.initial
+    scr = [j for j, k in enumerate(tr["kinds"]) if k == 3]
+    changed = sum(any(base[c] != v for c, v in tr["deltas"][j]) for j in scr)
+    assert changed > len(scr) // 2
+    isl.close(); gp.close()
+
+
+def test_late_acceptance_chain_replay(oracle):
+    spec = inst.tsp(120, seed=9)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    size = 5
+    isl = LateAcceptance(size, 0.2, None, MIX, 10000).build_agent(gp, n_islands=3, seed=99)
+    late = []
+    for step in range(40):
+        base, cur_score = isl.current(1)
+        tr = isl.trace_step(1)
+        want = _oracle_move(op, spec, base, tr["desc"][0])
+        assert _final_state(spec.n_vars, tr["deltas"][0]) == _final_state(spec.n_vars, want)
+        _check_rounded(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+        acc, late = oracle.la_accept(tr["scores"][0], cur_score, late, size)
+        assert tr["accepted"] == acc, step
+        new, new_score = isl.current(1)
+        assert np.array_equal(new_score, tr["scores"][0] if acc else cur_score)
+    isl.close(); gp.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: inst.tsp(150, seed=2), lambda: inst.nqueens(48),
+                                lambda: inst.cvrp(50, 5, seed=6),
+                                lambda: inst.vrptw(50, 5, n_depots=2, seed=6)],
+                         ids=["tsp", "nqueens", "cvrp", "vrpsvc"])
+def test_tabu_search_run_is_consistent(mk, oracle):
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    probas = [0.0, 1.0, 0.0, 0.0, 0.0, 0.0] if spec.kind == inst.NQUEENS else [0.1, 0.3, 0.1, 0.1, 0.2, 0.2]
+    isl = TabuSearch(128, 0.2, True, None, probas, 5, reference_noop_moves=False).build_agent(gp, n_islands=4, seed=5)
+    _, s0 = isl.best(0)
+    prev = None
+    for _ in range(6):
+        isl.step(10)
+        vec, sc = isl.best(-1)
+        # the carried score is the (rounded) ISC score of the carried vector
+        want = oracle.score_round(op.score_incremental(vec, [[]]), spec.score_precision)[0]
+        for l in range(spec.levels - 1 if spec.levels > 1 else 1):
+            assert sc[l] == want[l]
+        assert abs(sc[-1] - want[-1]) <= 1.001e-3
+        if prev is not None:
+            assert oracle.score_cmp(sc, prev) <= 0          # global best never gets worse
+        prev = sc
+        for i in range(4):
+            cv, cs = isl.current(i)
+            w = oracle.score_round(op.score_incremental(cv, [[]]), spec.score_precision)[0]
+            assert cs[0] == w[0] and abs(cs[-1] - w[-1]) <= 1.001e-3
+    assert oracle.score_cmp(prev, s0) < 0                   # and it did improve
+    st = isl.stats()
+    assert st["steps"] == 60 and st["candidates"] == 60 * 128 * 4
+    isl.close(); gp.close()
+
+
+def test_migration_and_global_best(oracle):
+    spec = inst.tsp(100, seed=4)
+    gp = Problem(spec)
+    # island 0 starts from the greedy tour, the others from a bad (identity) tour
+    init = np.stack([spec.initial] + [np.arange(1, 100, dtype=np.float64)] * 3)
+    isl = TabuSearch(8, 0.0, False, None, [0, 1, 0, 0, 0, 0], 1).build_agent(gp, n_islands=4, seed=3, initial=init)
+    scores0 = [isl.current(i)[1] for i in range(4)]
+    assert oracle.score_cmp(scores0[0], scores0[1]) < 0
+    isl.step(1)      # migration_frequency = 1: island 1 receives island 0's individual (<= rule)
+    s1 = isl.current(1)[1]
+    assert oracle.score_cmp(s1, scores0[1]) < 0
+    assert oracle.score_cmp(s1, isl.current(2)[1]) < 0      # the ring moves one hop per exchange
+    isl.step(3)
+    gv, gs = isl.best(-1)
+    for i in range(4):
+        assert oracle.score_cmp(gs, isl.best(i)[1]) <= 0
+    isl.close()
+    # compare_to_global = true: every island adopts the global best right after it appears
+    isl = TabuSearch(8, 0.0, True, None, [0, 1, 0, 0, 0, 0], 1000).build_agent(gp, n_islands=4, seed=3, initial=init)
+    isl.step(1)
+    gs = isl.best(-1)[1]
+    for i in range(1, 4):
+        assert oracle.score_cmp(isl.current(i)[1], scores0[1]) < 0
+    isl.close(); gp.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: inst.cvrp(60, 6, seed=2, greedy=False), lambda: inst.tsp(80, seed=3, greedy=False),
+                                lambda: inst.vrptw(40, 4, n_depots=2, seed=8, greedy=False)],
+                         ids=["cvrp", "tsp", "vrpsvc"])
+def test_genetic_algorithm_generations(mk, oracle):
+    spec = mk()
+    spec.initial = np.full(spec.n_vars, np.nan)     # None: population sampled uniformly (gj_integer.rs:98-112)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    ga = GeneticAlgorithm(256, 0.5, 0.2, 0.05, 1.0, None, 0.02, 3).build_agent(gp, n_islands=3, seed=11)
+    prev = None
+    for _ in range(5):
+        ga.step(4)
+        for i in (0, 2):
+            vec, sc = ga.best(i)
+            want = oracle.score_round(op.score_plain(vec), spec.score_precision)[0]   # PSC semantics
+            for l in range(spec.levels - 1):
+                assert sc[l] == want[l]
+            assert abs(sc[-1] - want[-1]) <= 1.001e-3
+        gv, gs = ga.best(-1)
+        if prev is not None:
+            assert oracle.score_cmp(gs, prev) <= 0
+        prev = gs
+        cv, cs = ga.current(1)
+        w = oracle.score_round(op.score_plain(cv), spec.score_precision)[0]
+        assert cs[0] == w[0]
+    first = ga.best(0)[1]
+    assert ga.stats()["candidates"] == 20 * 256 * 3
+    ga.close(); gp.close()
