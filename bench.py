@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- candidate moves scored per second on BASELINE.json's headline configuration.
+
+Workload (config C2): TSP, 1 000 synthetic cities, TabuSearch, swap / 2-opt neighbourhood of
+4 096 moves per step per island.  A "step" is one TabuSearch step of every island resident on
+the GPU (move generation -> scoring -> selection, all on the device).
+
+  value  : candidates scored / s, whole job, islands resident in HBM (device-timed, CUDA events)
+  e2e    : the same metric through the reference-facing call gj_score_incremental
+           (OOPScoreRequester::request_score_incremental) with HOST buffers: every step copies
+           the base + the delta lists host->device and the scores device->host.
+  cpu_baseline / --impl reference : the oracle's restatement of the reference's own CPU path
+           (one island per host thread, pseudo-incremental scoring), timed on this box.
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "greyjack-solver-rust_b200", "python"))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_CITIES = 1000
+NEIGHBOURS = 4096
+MOVE_PROBAS = [0.0, 0.5, 0.0, 0.0, 0.0, 0.5]       # swap + inverse (2-opt)
+TABU_RATE = 0.5                                     # examples/tsp/src/main.rs:47
+MIGRATION_FREQUENCY = 10
+METRIC = "candidate moves scored/sec (whole box)"
+UNIT = "candidates/s"
+# algorithmic bytes per candidate
+A_FULL = 4 * (N_CITIES - 1) + 8 * N_CITIES + 16     # 12 012 B: full (pseudo-incremental) evaluation
+A_DELTA = 0.5 * 96 + 0.5 * 56                       # swap 96 B / 2-opt 56 B, 50:50 mix
+SCORING = "full"
+SCORING_DESC = "full re-evaluation of base+move per candidate (the reference's pseudo-incremental ISC semantics)"
+SCORING_KERNEL = "k_score_moves_warp<GJ_TSP>"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def host_moves(base, n_moves, rng):
+    """swap / 2-opt delta lists in the reference's incremental form (mover.rs:180-219, 378-420),
+    built with numpy on the host -- the input of the e2e (host-buffer) leg."""
+    n = len(base)
+    offs = np.zeros(n_moves + 1, dtype=np.uint64)
+    ids, vals = [], []
+    for j in range(n_moves):
+        a, b = rng.choice(n, size=2, replace=False)
+        if rng.random() < 0.5:
+            ids.append(np.array([a, b], dtype=np.uint64))
+            vals.append(np.array([base[b], base[a]]))
+        else:
+            lo, hi = (a, b) if a < b else (b, a)
+            ids.append(np.arange(lo, hi + 1, dtype=np.uint64))
+            vals.append(base[lo:hi + 1][::-1].copy())
+        offs[j + 1] = offs[j] + len(ids[-1])
+    return offs, np.concatenate(ids), np.concatenate(vals).astype(np.float64)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    from greyjack_b200 import instances as inst
+    from oracle import gj_oracle
+    spec = inst.tsp(N_CITIES, seed=1)
+    op = gj_oracle.OracleProblem(spec)
+    cores = os.cpu_count() or 1
+    base = spec.initial
+    for _ in range(args.warmup):
+        op.bench_ts(base, NEIGHBOURS, 1, cores, 7, MOVE_PROBAS, [3, 3])
+    # each bench step = one TabuSearch step of `cores` islands (one per thread, solver.rs:94)
+    n, secs, best = op.bench_ts(base, NEIGHBOURS, args.steps, cores, 11, MOVE_PROBAS, [3, 3])
+    value = n / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: TSP 1000 cities, TabuSearch, swap/2-opt, 4096 moves per step",
+                   "islands": cores, "moves_per_island_step": NEIGHBOURS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} TabuSearch steps x {cores} islands x {NEIGHBOURS} moves; "
+                                   "oracle port of the reference ISC path WITHOUT its Polars marshalling "
+                                   "(CPU-favouring)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--islands", type=int, default=int(os.environ.get("GJ_BENCH_ISLANDS", "148")))
+    ap.add_argument("--e2e-agents", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import greyjack_b200 as gj
+    from greyjack_b200 import instances as inst
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    spec = inst.tsp(N_CITIES, seed=1)
+    prob = gj.Problem(spec, device=local_rank)
+    prob.set_exact_sums(False)
+    builder = gj.TabuSearch(NEIGHBOURS, TABU_RATE, True, None, MOVE_PROBAS, MIGRATION_FREQUENCY)
+    isl = builder.build_agent(prob, n_islands=args.islands, seed=1000 + rank)
+    if world > 1:
+        isl.set_external_ring(True, rank * args.islands)
+        mig_out = torch.empty(isl.migrant_bytes(), dtype=torch.uint8, device="cuda")
+        mig_in = torch.empty_like(mig_out)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def one_step(i):
+        isl.step(1, stream)
+        if world > 1 and (i + 1) % MIGRATION_FREQUENCY == 0:
+            # AgentToAgentUpdate ring i -> i+1 across GPUs (agent_base.rs:161-183) over NCCL
+            isl.export_migrants(mig_out.data_ptr(), stream)
+            ops = [dist.P2POp(dist.isend, mig_out, (rank + 1) % world),
+                   dist.P2POp(dist.irecv, mig_in, (rank - 1) % world)]
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            isl.import_migrants(mig_in.data_ptr(), stream)
+
+    for i in range(args.warmup):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    isl.set_profiling(True)
+    c0 = isl.stats()["candidates"]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                    # L2 flush between timed iterations (untimed)
+        evs[i][0].record()
+        one_step(args.warmup + i)
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.summary()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    cands = isl.stats()["candidates"] - c0
+    launches_per_step = 5 + (3 if world == 1 else 0) / MIGRATION_FREQUENCY
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        c = torch.tensor([cands], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cands = float(c.item())
+    value = cands / (total_ms * 1e-3)
+
+    # dominant kernel (the scorer): CUDA events on its launch stream, inside the timed region
+    k_total_ms, k_launches = isl.profile_read()
+    isl.set_profiling(False)
+    kernel_ms = k_total_ms / max(1, k_launches)
+    per_launch_cands = args.islands * NEIGHBOURS
+    a_bytes = A_FULL if SCORING == "full" else A_DELTA
+    peak, peak_src = peaks()
+    achieved = per_launch_cands * a_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: TSP 1000 cities, TabuSearch, swap/2-opt, 4096 moves per step",
+                   "islands_per_gpu": args.islands, "moves_per_island_step": NEIGHBOURS,
+                   "move_probas": MOVE_PROBAS, "tabu_entity_rate": TABU_RATE,
+                   "migration_frequency": MIGRATION_FREQUENCY, "score_precision": [3, 3],
+                   "scoring": SCORING_DESC, "float_sums": "tree (gj_problem_set_exact_sums(0))", "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": f"islands x{world}"},
+        "clocks": clocks, "gpu_launches": int(round(launches_per_step * args.steps)),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "kernel": SCORING_KERNEL, "kernel_ms": kernel_ms,
+                     "kernel_share_of_step": kernel_ms / (total_ms / args.steps) if world == 1 else None,
+                     "algorithmic_bytes_per_candidate": a_bytes,
+                     "candidates_per_launch": per_launch_cands},
+    }
+
+    if rank == 0:
+        # ---- e2e: reference-facing call, host buffers, H2D + D2H inside the timed region ------
+        A = args.e2e_agents
+        rng = np.random.default_rng(5)
+        base = spec.initial.copy()
+        probs = [prob] + [gj.Problem(spec, device=local_rank) for _ in range(A - 1)]
+        sets = [host_moves(base, NEIGHBOURS, rng) for _ in range(A)]
+        outs = [np.empty((NEIGHBOURS, 2)) for _ in range(A)]
+        h2d = sum(base.nbytes + o.nbytes + i.nbytes + v.nbytes for o, i, v in sets)
+        d2h = sum(o.nbytes for o in outs)
+
+        def agent(a, n):
+            o, i, v = sets[a]
+            for _ in range(n):
+                probs[a].request_score_incremental_csr(base, o, i, v, out=outs[a])
+
+        def run_agents(n):
+            th = [threading.Thread(target=agent, args=(a, n)) for a in range(A)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        run_agents(args.warmup)
+        t0 = time.perf_counter()
+        run_agents(args.steps)
+        e2e_s = time.perf_counter() - t0
+        line["e2e"] = {"value": A * NEIGHBOURS * args.steps / e2e_s, "unit": UNIT,
+                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "agents": A, "call": "gj_score_incremental (request_score_incremental), host CSR deltas"}
+        line["gpu_launches"] += 2 * A * args.steps
+
+        # ---- cpu_baseline: oracle port on the host cores, bounded sample ------------------------
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import gj_oracle
+            op = gj_oracle.OracleProblem(spec)
+            cores = os.cpu_count() or 1
+            n1, s1, _ = op.bench_ts(base, NEIGHBOURS, 1, cores, 3, MOVE_PROBAS, [3, 3])
+            steps = max(2, min(200, int(12.0 / max(s1, 1e-3))))
+            n, secs, _ = op.bench_ts(base, NEIGHBOURS, steps, cores, 4, MOVE_PROBAS, [3, 3])
+            line["cpu_baseline"] = {
+                "value": n / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{steps} TabuSearch steps x {cores} islands x {NEIGHBOURS} moves ({secs:.1f} s); "
+                          "oracle port of the reference ISC path without its Polars marshalling (CPU-favouring)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,7 @@ struct GjProblemDev {
     int time_windowed;
     int veh_lo;                  // min decoded vehicle id (0 in the examples)
 
+    int exact_sums;              // 1: reference summation order (bit-exact float level)
     double w[4];                 // constraint weights
     double round_mult[GJ_MAX_LEVELS];   // 10^precision, or 0 = None
 };

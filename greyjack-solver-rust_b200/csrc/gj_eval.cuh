@@ -65,9 +65,17 @@ __device__ __forceinline__ double gj_nqueens_eval_warp(const GjProblemDev& P, co
 // ---- TSP -----------------------------------------------------------------------------
 // examples/tsp/src/score/incremental_score_calculator.rs:71-80 and
 // plain_score_calculator.rs:34-43, 70-84: hard = n_stops - |{location ids}|,
-// soft = D[0][s0] + D[s_last][0] + sum_i D[s_{i-1}][s_i].  The reference folds the sum
-// sequentially; here each lane accumulates a strided partial and the partials are
-// tree-reduced (documented float tolerance 1e-12 relative; the integer level is exact).
+// soft = ((0.0 + D[0][s0]) + D[s_last][0]) + fold_{i>=1}(D[s_{i-1}][s_i]).
+//
+// Two summation modes (P.exact_sums):
+//   exact : the 32 distances a warp gathers per step are folded strictly in stop order
+//           (shuffle + DADD chain, every lane redundantly), reproducing the reference's
+//           sequential f64 fold bit for bit.  This matters more than it looks: distances
+//           are multiples of 1e-3, so exact tour lengths sit ON the truncation boundaries
+//           of ScoreTrait::round -- the third decimal of the reference's rounded score is
+//           decided by its summation order.
+//   fast  : per-lane partial sums + tree reduction (documented tolerance: 1e-12 relative
+//           before rounding, one 1e-3 quantum after).
 template <class Src>
 __device__ __forceinline__ void gj_tsp_eval_warp(const GjProblemDev& P, const Src& src,
                                                  uint32_t* bm, int lane, double& dup,
@@ -75,15 +83,15 @@ __device__ __forceinline__ void gj_tsp_eval_warp(const GjProblemDev& P, const Sr
     const int n = P.n_vars;
     const size_t L = (size_t)P.n_locations;
     const double* __restrict__ D = P.D;
+    const bool exact = P.exact_sums != 0;
     for (int w = lane; w < P.bm_words; w += 32) bm[w] = 0u;
     __syncwarp();
-    double acc0 = 0.0, acc1 = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, fold = 0.0, head = 0.0;
     int carry = 0;      // the depot (location 0) precedes stop 0
-    int v1 = 0;
     for (int base = 0; base < n; base += 64) {
         const int i0 = base + lane, i1 = base + 32 + lane;
         const int v0 = (i0 < n) ? src(i0) : 0;
-        v1 = (i1 < n) ? src(i1) : 0;
+        const int v1 = (i1 < n) ? src(i1) : 0;
         int p0 = __shfl_up_sync(GJ_FULL_MASK, v0, 1);
         int p1 = __shfl_up_sync(GJ_FULL_MASK, v1, 1);
         const int last0 = __shfl_sync(GJ_FULL_MASK, v0, 31);
@@ -94,19 +102,39 @@ __device__ __forceinline__ void gj_tsp_eval_warp(const GjProblemDev& P, const Sr
         if (i1 < n) d1 = __ldg(&D[(size_t)p1 * L + (size_t)v1]);
         if (i0 < n) { unsigned b = (unsigned)(v0 - P.val_lo); atomicOr(&bm[b >> 5], 1u << (b & 31)); }
         if (i1 < n) { unsigned b = (unsigned)(v1 - P.val_lo); atomicOr(&bm[b >> 5], 1u << (b & 31)); }
-        acc0 += d0;
-        acc1 += d1;
+        if (exact) {
+            if (base == 0) {                      // D[0][s0] is added outside the fold
+                head = __shfl_sync(GJ_FULL_MASK, d0, 0);
+                if (lane == 0) d0 = 0.0;
+            }
+#pragma unroll
+            for (int l = 0; l < 32; ++l) fold = fold + __shfl_sync(GJ_FULL_MASK, d0, l);
+            if (base + 32 < n) {
+#pragma unroll
+                for (int l = 0; l < 32; ++l) fold = fold + __shfl_sync(GJ_FULL_MASK, d1, l);
+            }
+        } else {
+            acc0 += d0;
+            acc1 += d1;
+        }
     }
     // closing edge D[s_last][0]
-    if (lane == 0) {
-        const int last = src(n - 1);
-        acc0 += __ldg(&D[(size_t)last * L]);
-    }
+    double closing = 0.0;
+    if (lane == 0) closing = __ldg(&D[(size_t)src(n - 1) * L]);
+    closing = __shfl_sync(GJ_FULL_MASK, closing, 0);
     __syncwarp();
     int uniq = 0;
     for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(bm[w]);
     uniq = gj_warp_sum(uniq);
-    dist = gj_warp_sum(acc0 + acc1);
+    if (exact) {
+        double sample_distance = 0.0;
+        sample_distance += head;
+        sample_distance += closing;
+        sample_distance += fold;
+        dist = sample_distance;
+    } else {
+        dist = gj_warp_sum(acc0 + acc1) + closing;
+    }
     dup = (double)(n - uniq);
     __syncwarp();
 }

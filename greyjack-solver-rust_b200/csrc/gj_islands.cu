@@ -449,6 +449,49 @@ __global__ void k_i32_to_f64(const int32_t* __restrict__ in, double* __restrict_
 gj_islands::~gj_islands() {
     cudaSetDevice(p->device);
     for (void* a : allocs) cudaFree(a);
+    for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+}
+
+gj_status gj_prof_begin(gj_islands* g, cudaStream_t st) {
+    if (!g->profiling) return GJ_OK;
+    if (g->prof_used == g->prof_events.size()) {
+        cudaEvent_t a, b;
+        GJ_CUDA_TRY(cudaEventCreate(&a));
+        GJ_CUDA_TRY(cudaEventCreate(&b));
+        g->prof_events.emplace_back(a, b);
+    }
+    GJ_CUDA_TRY(cudaEventRecord(g->prof_events[g->prof_used].first, st));
+    return GJ_OK;
+}
+
+gj_status gj_prof_end(gj_islands* g, cudaStream_t st) {
+    if (!g->profiling) return GJ_OK;
+    GJ_CUDA_TRY(cudaEventRecord(g->prof_events[g->prof_used].second, st));
+    g->prof_used += 1;
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_set_profiling(gj_islands* g, int32_t on) {
+    if (!g) return gj_fail(GJ_ERR_INVALID, "null handle");
+    g->profiling = on != 0;
+    g->prof_used = 0;
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_profile_read(gj_islands* g, double* total_ms, int64_t* launches) {
+    if (!g) return gj_fail(GJ_ERR_INVALID, "null handle");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    double tot = 0.0;
+    for (size_t i = 0; i < g->prof_used; ++i) {
+        GJ_CUDA_TRY(cudaEventSynchronize(g->prof_events[i].second));
+        float ms = 0.f;
+        GJ_CUDA_TRY(cudaEventElapsedTime(&ms, g->prof_events[i].first, g->prof_events[i].second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = (int64_t)g->prof_used;
+    g->prof_used = 0;
+    return GJ_OK;
 }
 
 template <class T>
@@ -688,7 +731,9 @@ static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
         g->tabu_words, g->tabu_word_off, g->moves);
     GJ_CUDA_TRY(cudaGetLastError());
     gj_status rc;
+    if ((rc = gj_prof_begin(g, st))) return rc;
     if ((rc = launch_score_moves(g, st))) return rc;
+    if ((rc = gj_prof_end(g, st))) return rc;
     size_t smem = (size_t)g->n_vars * 4;
     if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_select<<<g->I, 256, smem, st>>>(P, g->groups, make_select_args(g, trace));

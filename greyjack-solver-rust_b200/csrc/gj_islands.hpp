@@ -42,6 +42,11 @@ struct gj_islands {
 
     unsigned long long* counters = nullptr;
 
+    // optional CUDA-event timing of the dominant (scoring) kernel, on the launching stream
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+
     // genetic algorithm (gj_islands_ga.cu)
     int pop = 0, half = 0, n_cand = 0;
     int32_t* pop_rows = nullptr;   // [I][pop][stride]
@@ -65,3 +70,5 @@ gj_status gj_ga_current(gj_islands* g, int32_t island, double* vars, double* sco
 gj_status gj_ga_export(gj_islands* g, void* d_buffer, cudaStream_t st);
 gj_status gj_ga_import(gj_islands* g, const void* d_buffer, cudaStream_t st);
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st);
+gj_status gj_prof_begin(gj_islands* g, cudaStream_t st);
+gj_status gj_prof_end(gj_islands* g, cudaStream_t st);

@@ -351,7 +351,9 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves);
         GJ_CUDA_TRY(cudaGetLastError());
         const int64_t S = (int64_t)g->I * g->n_cand;
+        if ((rc = gj_prof_begin(g, st))) return rc;
         if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
+        if ((rc = gj_prof_end(g, st))) return rc;
         k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
         GJ_CUDA_TRY(cudaGetLastError());
         k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,

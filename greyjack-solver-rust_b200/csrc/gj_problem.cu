@@ -170,6 +170,7 @@ extern "C" gj_status gj_problem_create(const gj_problem_desc* desc, int32_t devi
     P.levels = (desc->kind == GJ_NQUEENS) ? 1 : (desc->kind == GJ_TSP ? 2 : 3);
     P.n_entities = is_vrp ? n / 2 : n;
     for (int i = 0; i < 4; ++i) P.w[i] = desc->weights[i];
+    P.exact_sums = 1;
     for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
         P.round_mult[l] = 0.0;
         if (l < P.levels && desc->score_precision[l] >= 0)
@@ -304,6 +305,12 @@ extern "C" int32_t gj_problem_n_vars(const gj_problem* p) { return p ? p->dev.n_
 extern "C" gj_status gj_problem_set_constraint_weights(gj_problem* p, const double* w, int32_t n) {
     if (!p || !w || n < 1 || n > 4) return gj_fail(GJ_ERR_INVALID, "bad weights");
     for (int i = 0; i < n; ++i) p->dev.w[i] = w[i];
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_problem_set_exact_sums(gj_problem* p, int32_t on) {
+    if (!p) return gj_fail(GJ_ERR_INVALID, "null handle");
+    p->dev.exact_sums = on ? 1 : 0;
     return GJ_OK;
 }
 

@@ -220,6 +220,15 @@ class Islands:
         _lib.check(self._L.gj_islands_stats(self.handle, C.byref(c), C.byref(s), C.byref(a)))
         return {"candidates": c.value, "steps": s.value, "accepted": a.value}
 
+    def set_profiling(self, on: bool):
+        _lib.check(self._L.gj_islands_set_profiling(self.handle, C.c_int32(int(on))))
+
+    def profile_read(self):
+        """(summed ms of the scoring kernel, launches) since profiling was switched on."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _lib.check(self._L.gj_islands_profile_read(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def _ind(self, fn, island):
         v = np.empty(self.problem.n_vars, dtype=np.float64)
         s = np.empty(self.problem.levels, dtype=np.float64)

@@ -129,6 +129,10 @@ class Problem:
         w = np.ascontiguousarray(weights, dtype=np.float64)
         _lib.check(self._L.gj_problem_set_constraint_weights(self.handle, _ptr(w), C.c_int32(len(w))))
 
+    def set_exact_sums(self, on: bool):
+        """True (default): reference summation order, bit-exact float level; False: tree sums."""
+        _lib.check(self._L.gj_problem_set_exact_sums(self.handle, C.c_int32(int(on))))
+
     def distance_matrix(self) -> np.ndarray:
         n = self.spec.n_locations
         out = np.empty((n, n), dtype=np.float64)

@@ -130,6 +130,12 @@ GJ_API int32_t   gj_problem_levels(const gj_problem* p);   /* ScoreTrait::precis
 GJ_API int32_t   gj_problem_n_vars(const gj_problem* p);
 /* {Plain,Incremental}ScoreCalculator::set_constraint_weights */
 GJ_API gj_status gj_problem_set_constraint_weights(gj_problem* p, const double* weights, int32_t n);
+/* Float-level summation order of the TSP distance fold.  on != 0 (default): the reference's
+   own sequential order, bit-exact with tsp/src/score/incremental_score_calculator.rs:76-80;
+   0: per-lane partial sums + tree reduction (about 2x faster on the full-evaluation
+   kernels; 1e-12 relative before rounding, one 1e-3 truncation quantum after).  The VRP
+   scorers always walk each route in the reference's order.                              */
+GJ_API gj_status gj_problem_set_exact_sums(gj_problem* p, int32_t on);
 /* Copies the device distance matrix back (checks / warm starts).  out: [L*L]. */
 GJ_API gj_status gj_problem_get_distance_matrix(gj_problem* p, double* out);
 
@@ -222,6 +228,11 @@ GJ_API gj_status gj_islands_step(gj_islands* g, int64_t n_steps, void* stream);
 /* Counters: candidates scored so far, steps done, accepted moves. */
 GJ_API gj_status gj_islands_stats(gj_islands* g, int64_t* candidates, int64_t* steps,
                                   int64_t* accepted);
+
+/* Optional CUDA-event timing of the dominant (scoring) kernel of every step, recorded on the
+   launching stream; profile_read synchronises, returns the summed duration and resets.     */
+GJ_API gj_status gj_islands_set_profiling(gj_islands* g, int32_t on);
+GJ_API gj_status gj_islands_profile_read(gj_islands* g, double* total_ms, int64_t* launches);
 
 /* agent_top_individual of one island, or (island < 0) the group's global_top_individual.
    vars: host [n_vars] f64; score: host [levels] (rounded by score_precision).          */
