@@ -20,6 +20,8 @@ gj_status gj_fail(gj_status code, const std::string& msg) {
 
 extern "C" const char* gj_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t gj_abi_version(void) { return 1; }
+extern "C" size_t gj_sizeof_problem_desc(void) { return sizeof(gj_problem_desc); }
+extern "C" size_t gj_sizeof_agent_params(void) { return sizeof(gj_agent_params); }
 extern "C" int32_t gj_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -44,13 +44,13 @@ class AgentParams(C.Structure):
         ("mutation_rate_multiplier", C.c_double),
         ("has_move_probas", C.c_int32), ("move_probas", C.c_double * 6),
         ("migration_frequency", C.c_int64),
-        ("reference_noop_moves", C.c_int32), ("reserved", C.c_int32),
+        ("reference_noop_moves", C.c_int32), ("scoring_mode", C.c_int32),
     ]
 
 
 # every symbol include/greyjack_b200.h declares
 EXPORTED = [
-    "gj_last_error", "gj_abi_version", "gj_device_count",
+    "gj_last_error", "gj_abi_version", "gj_device_count", "gj_sizeof_problem_desc", "gj_sizeof_agent_params",
     "gj_problem_create", "gj_problem_destroy", "gj_problem_levels", "gj_problem_n_vars",
     "gj_problem_set_constraint_weights", "gj_problem_set_exact_sums", "gj_problem_get_distance_matrix",
     "gj_host_alloc", "gj_host_free",

@@ -62,6 +62,18 @@ enum {
     GJ_MOVE_SCRAMBLE = 3, GJ_MOVE_INSERTION = 4, GJ_MOVE_INVERSE = 5
 };
 
+/* How TabuSearch / LateAcceptance islands score base + move.
+   FULL : every candidate is materialised and fully re-scored -- the reference's own
+          pseudo-incremental ISC semantics, bit-exact incl. the float level
+          when exact sums are on.
+   DELTA: the island keeps per-solution state on the device (value counts, exact base score)
+          and a candidate's score is base + the change over the O(k) constraint terms the move
+          touches.  Integer levels are bit-exact with FULL; the float level agrees to 1e-12
+          relative before ScoreTrait::round (one 10^-precision quantum after).  Moves the
+          delta evaluator does not cover (listed in DESIGN.md) are re-scored by the FULL
+          kernel inside the same step.                                                      */
+enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1 };
+
 /* Agents = AgentBuildersVariants (agents/agent_builders_variants.rs:9-18). */
 enum { GJ_AGENT_TABU_SEARCH = 0, GJ_AGENT_LATE_ACCEPTANCE = 1, GJ_AGENT_GENETIC_ALGORITHM = 2 };
 
@@ -122,6 +134,10 @@ typedef struct gj_problem_desc {
 GJ_API const char* gj_last_error(void);
 GJ_API int32_t     gj_abi_version(void);
 GJ_API int32_t     gj_device_count(void);
+/* sizeof(gj_problem_desc) / sizeof(gj_agent_params) as compiled: lets a foreign binding
+   (Rust #[repr(C)], ctypes) verify its struct layout at start-up.                       */
+GJ_API size_t      gj_sizeof_problem_desc(void);
+GJ_API size_t      gj_sizeof_agent_params(void);
 
 /* OOPScoreRequester::new(cotwin) (oop_score_requester.rs:47-83): uploads everything. */
 GJ_API gj_status gj_problem_create(const gj_problem_desc* desc, int32_t device, gj_problem** out);
@@ -209,7 +225,7 @@ typedef struct gj_agent_params {
     int32_t reference_noop_moves;    /* 1 = reproduce the reference's incremental-form
                                         no-op scramble / swap_edges(k=2);
                                         0 = apply the plain-form permutation             */
-    int32_t reserved;
+    int32_t scoring_mode;            /* GJ_SCORING_*: how TS / LA islands score a neighbour     */
 } gj_agent_params;
 
 /* <Agent>::build_agent + Agent::init_population (agent_base.rs:190-218).  `initial`:
