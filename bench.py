@@ -38,9 +38,12 @@ UNIT = "candidates/s"
 # algorithmic bytes per candidate
 A_FULL = 4 * (N_CITIES - 1) + 8 * N_CITIES + 16     # 12 012 B: full (pseudo-incremental) evaluation
 A_DELTA = 0.5 * 96 + 0.5 * 56                       # swap 96 B / 2-opt 56 B, 50:50 mix
-SCORING = "full"
-SCORING_DESC = "full re-evaluation of base+move per candidate (the reference's pseudo-incremental ISC semantics)"
-SCORING_KERNEL = "k_score_moves_warp<GJ_TSP>"
+SCORING_DESC = {
+    "full": "full re-evaluation of base+move per candidate (the reference's pseudo-incremental ISC semantics)",
+    "delta": "delta evaluation against the island's cached state (move generated in registers, O(k) edges "
+             "gathered from the L2-resident matrix); accepted neighbours re-scored by the full evaluator",
+}
+SCORING_KERNEL = {"full": "k_score_moves_warp<GJ_TSP>", "delta": "k_score_delta<GJ_TSP>"}
 
 
 def peaks():
@@ -147,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--islands", type=int, default=int(os.environ.get("GJ_BENCH_ISLANDS", "148")))
     ap.add_argument("--e2e-agents", type=int, default=4)
+    ap.add_argument("--scoring", default="delta", choices=["delta", "full"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -173,7 +177,8 @@ def main():
     spec = inst.tsp(N_CITIES, seed=1)
     prob = gj.Problem(spec, device=local_rank)
     prob.set_exact_sums(False)
-    builder = gj.TabuSearch(NEIGHBOURS, TABU_RATE, True, None, MOVE_PROBAS, MIGRATION_FREQUENCY)
+    SCORING = args.scoring
+    builder = gj.TabuSearch(NEIGHBOURS, TABU_RATE, True, None, MOVE_PROBAS, MIGRATION_FREQUENCY, scoring=SCORING)
     isl = builder.build_agent(prob, n_islands=args.islands, seed=1000 + rank)
     if world > 1:
         isl.set_external_ring(True, rank * args.islands)
@@ -202,6 +207,7 @@ def main():
     sampler.start()
     isl.set_profiling(True)
     c0 = isl.stats()["candidates"]
+    launches0 = gj.load().gj_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     for i in range(args.steps):
@@ -215,7 +221,7 @@ def main():
     clocks = sampler.summary()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     cands = isl.stats()["candidates"] - c0
-    launches_per_step = 5 + (3 if world == 1 else 0) / MIGRATION_FREQUENCY
+    gpu_launches = int(gj.load().gj_launch_count() - launches0)     # counted by the library itself
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -247,12 +253,12 @@ def main():
                    "islands_per_gpu": args.islands, "moves_per_island_step": NEIGHBOURS,
                    "move_probas": MOVE_PROBAS, "tabu_entity_rate": TABU_RATE,
                    "migration_frequency": MIGRATION_FREQUENCY, "score_precision": [3, 3],
-                   "scoring": SCORING_DESC, "float_sums": "tree (gj_problem_set_exact_sums(0))", "l2": "flushed between timed steps (256 MiB write)",
+                   "scoring": SCORING_DESC[SCORING], "float_sums": "tree (gj_problem_set_exact_sums(0))", "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": f"islands x{world}"},
-        "clocks": clocks, "gpu_launches": int(round(launches_per_step * args.steps)),
+        "clocks": clocks, "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": SCORING_KERNEL, "kernel_ms": kernel_ms,
+                     "kernel": SCORING_KERNEL[SCORING], "kernel_ms": kernel_ms,
                      "kernel_share_of_step": kernel_ms / (total_ms / args.steps) if world == 1 else None,
                      "algorithmic_bytes_per_candidate": a_bytes,
                      "candidates_per_launch": per_launch_cands},
@@ -288,7 +294,6 @@ def main():
         line["e2e"] = {"value": A * NEIGHBOURS * args.steps / e2e_s, "unit": UNIT,
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "agents": A, "call": "gj_score_incremental (request_score_incremental), host CSR deltas"}
-        line["gpu_launches"] += 2 * A * args.steps
 
         # ---- cpu_baseline: oracle port on the host cores, bounded sample ------------------------
         if world == 1 and not args.no_cpu_baseline:

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,15 @@ gj_status gj_fail(gj_status code, const std::string& msg);
         cudaError_t _e = (expr);                                                     \
         if (_e != cudaSuccess)                                                       \
             return gj_fail(GJ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// Placed after every kernel launch: counts it (gj_launch_count, bench.py's gpu_launches) and
+// surfaces launch-configuration errors.
+extern std::atomic<long long> gj_launch_counter;
+#define GJ_LAUNCH_CHECK()                                        \
+    do {                                                         \
+        gj_launch_counter.fetch_add(1, std::memory_order_relaxed); \
+        GJ_CUDA_TRY(cudaGetLastError());                         \
     } while (0)
 
 // Grow-only device / pinned-host scratch buffer.

@@ -103,6 +103,158 @@ k_score_moves_vrp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, i
     }
 }
 
+// ---- delta scoring (GJ_SCORING_DELTA) ------------------------------------------------------------
+// One THREAD per neighbour: the move is generated in registers from the counter RNG (never
+// stored), evaluated against the island's cached state (gj_delta.cuh) and its rounded score is
+// written out.  Neighbours whose move the delta evaluator does not cover are queued for
+// k_score_fallback_warp (full evaluator, one warp each).
+struct GjStepCtx {
+    uint64_t seed, step;
+    int I, K, island_base, noop, stride, symmetric;
+    const uint32_t* tabu_bits; int tabu_words_per_island; const int32_t* tabu_word_off;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_score_delta(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
+              const int32_t* __restrict__ cur, GjDeltaState S, double* __restrict__ scores,
+              int* __restrict__ worklist, int* __restrict__ work_count, GjMove* __restrict__ moves_out) {
+    const int64_t total = (int64_t)C.I * C.K;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    const int island = (int)(j / C.K), cand = (int)(j - (int64_t)island * C.K);
+    const uint32_t* bits = C.tabu_bits ? C.tabu_bits + (size_t)island * C.tabu_words_per_island : nullptr;
+    const GjMove m = gj_generate_move(P, G, M, C.seed, (uint32_t)(C.island_base + island), C.step,
+                                      (uint32_t)cand, bits, C.tabu_word_off);
+    if (moves_out) moves_out[j] = m;
+    const int32_t* row = cur + (size_t)island * C.stride;
+    const int32_t* cnt = S.cnt + (size_t)island * S.cnt_stride;
+    const double* raw = S.raw + (size_t)island * GJ_MAX_LEVELS;
+    GjScore s;
+    bool ok;
+    if constexpr (KIND == GJ_NQUEENS) {
+        int d_uniq;
+        ok = gj_nqueens_move_delta(P, G, m, C.noop != 0, row, cnt, d_uniq);
+        // (N - |rows|) + (N - |desc|) + (N - |asc|): integers, exact in f64
+        gj_combine_nqueens(P, raw[0] - (double)d_uniq, s.v);
+    } else {
+        GjTspBase B{row, P.n_vars, P.D, (size_t)P.n_locations};
+        int d_uniq; double d_dist;
+        ok = gj_tsp_move_delta(P, G, m, C.noop != 0, C.symmetric != 0, B, cnt, d_uniq, d_dist);
+        gj_combine_tsp(P, true, raw[0] - (double)d_uniq, raw[1] + d_dist, s.v);
+    }
+    if (!ok) {
+        worklist[atomicAdd(work_count, 1)] = (int)j;
+        return;
+    }
+    gj_score_round(s, P);           // agent_base.rs:311-314
+    for (int l = 0; l < P.levels; ++l) scores[j * P.levels + l] = s.v[l];
+}
+
+// Full evaluation of the queued neighbours: persistent warps walk the worklist.
+template <int KIND>
+__global__ void __launch_bounds__(kWarps * 32)
+k_score_fallback_warp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
+                      const int32_t* __restrict__ cur, const int* __restrict__ worklist,
+                      const int* __restrict__ work_count, double* __restrict__ scores) {
+    extern __shared__ uint32_t smem_u32[];
+    __shared__ GjMove sh_mv[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int words = P.bm_words + P.desc_words + P.asc_words;
+    const int per_warp = words + P.n_vars;
+    uint32_t* bm = smem_u32 + warp * per_warp;
+    int32_t* cand = (int32_t*)(bm + words);
+    const int n_work = *work_count;
+    for (int w = blockIdx.x * kWarps + warp; w < n_work; w += gridDim.x * kWarps) {
+        const int j = worklist[w];
+        const int island = j / C.K, c = j - island * C.K;
+        const int32_t* base = cur + (size_t)island * C.stride;
+        if (lane == 0) {
+            const uint32_t* bits = C.tabu_bits ? C.tabu_bits + (size_t)island * C.tabu_words_per_island : nullptr;
+            sh_mv[warp] = gj_generate_move(P, G, M, C.seed, (uint32_t)(C.island_base + island), C.step,
+                                           (uint32_t)c, bits, C.tabu_word_off);
+        }
+        for (int i = lane; i < P.n_vars; i += 32) cand[i] = base[i];
+        __syncwarp();
+        const GjMove m = sh_mv[warp];
+        gj_apply_move(P, m, G, true, C.noop != 0, lane, 32,
+                      [&](int id) { return base[id]; }, [&](int id, int v) { cand[id] = v; });
+        __syncwarp();
+        GjSrcI32 src{cand};
+        GjScore s;
+        if constexpr (KIND == GJ_NQUEENS) {
+            gj_combine_nqueens(P, gj_nqueens_eval_warp(P, src, bm, lane), s.v);
+        } else {
+            double dup, dist;
+            gj_tsp_eval_warp(P, src, bm, lane, dup, dist);
+            gj_combine_tsp(P, true, dup, dist, s.v);
+        }
+        if (lane == 0) {
+            gj_score_round(s, P);
+            for (int l = 0; l < P.levels; ++l) scores[(size_t)j * P.levels + l] = s.v[l];
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ GjScore gj_load_score(const double* p, int levels);
+__device__ __forceinline__ void gj_update_top(int island, int levels, int stride, int n_vars,
+                                              const int32_t* cur, const double* cur_score,
+                                              int32_t* best, double* best_score, int* dirty);
+
+// Rebuilds the cached state of every island whose current solution changed: value counts, and the
+// FULL evaluation (reference summation order) of the solution -> raw terms; after an accepted
+// neighbour (stale == 2) the stored score is replaced by that full evaluation, rounded, so a
+// current score is always exactly what the reference's scorer returns for the stored vector.
+// Then (update_top) update_top_individual, agent_base.rs:220-224.  One CTA per island.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_refresh(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double* cur_score,
+          GjDeltaState S, int update_top, int32_t* best, double* best_score, int* dirty) {
+    extern __shared__ uint32_t smem_u32[];
+    const int island = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* row = cur + (size_t)island * stride;
+    const int why = S.stale[island];
+    if (why) {
+        int32_t* cnt = S.cnt + (size_t)island * S.cnt_stride;
+        for (int i = tid; i < S.cnt_stride; i += blockDim.x) cnt[i] = 0;
+        __syncthreads();
+        if (warp == 0) {
+            GjSrcI32 src{row};
+            GjScore s;
+            double* raw = S.raw + (size_t)island * GJ_MAX_LEVELS;
+            if constexpr (KIND == GJ_NQUEENS) {
+                const double v = gj_nqueens_eval_warp(P, src, smem_u32, lane);
+                gj_combine_nqueens(P, v, s.v);
+                if (lane == 0) { raw[0] = v; raw[1] = 0.0; raw[2] = 0.0; }
+            } else {
+                double dup, dist;
+                gj_tsp_eval_warp(P, src, smem_u32, lane, dup, dist);
+                gj_combine_tsp(P, true, dup, dist, s.v);
+                if (lane == 0) { raw[0] = dup; raw[1] = dist; raw[2] = 0.0; }
+            }
+            if (lane == 0 && why == 2) {
+                gj_score_round(s, P);
+                for (int l = 0; l < P.levels; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = s.v[l];
+            }
+        } else {
+            for (int i = tid - 32; i < P.n_vars; i += blockDim.x - 32) {
+                const int v = row[i];
+                atomicAdd(&cnt[v - P.val_lo], 1);
+                if constexpr (KIND == GJ_NQUEENS) {
+                    const int col = P.column_id[i];
+                    atomicAdd(&cnt[32 * P.bm_words + (col + v - P.desc_lo)], 1);
+                    atomicAdd(&cnt[32 * (P.bm_words + P.desc_words) + (col - v - P.asc_lo)], 1);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) S.stale[island] = 0;
+    }
+    if (update_top) gj_update_top(island, P.levels, stride, P.n_vars, cur, cur_score, best, best_score, dirty);
+}
+
 // ---- selection ----------------------------------------------------------------------------------
 struct GjSelectArgs {
     int agent;                  // GJ_AGENT_TABU_SEARCH / GJ_AGENT_LATE_ACCEPTANCE
@@ -110,17 +262,21 @@ struct GjSelectArgs {
     int late_size;
     int noop;
     int n_groups;
-    const GjMove* moves;
+    const GjMove* moves;        // stored moves, or nullptr: regenerate from the counter RNG
+    GjMoverParams M; uint64_t seed; uint64_t step; int island_base;
     const double* cand_scores;
     int32_t* cur; double* cur_score;
     int32_t* best; double* best_score;
     int* dirty;
     double* late; int* late_head; int* late_len;      // LA: circular deque per island
     unsigned long long* counters;                     // [0] candidates [1] steps [2] accepted
-    // tabu state
+    // tabu state: rank-indexed deques (slot 0 = newest), read from _old, written to _new
     uint32_t* tabu_bits; int tabu_words_per_island; const int32_t* tabu_word_off;
-    int32_t* tabu_ring; int tabu_ring_per_island; const int32_t* tabu_ring_off;
-    const int32_t* tabu_size; int* tabu_head; int* tabu_fill;
+    const int32_t* tabu_ring_old; int32_t* tabu_ring_new; int tabu_ring_per_island; const int32_t* tabu_ring_off;
+    const int32_t* tabu_size; int* tabu_fill;
+    // delta scoring: the island's cached state goes stale when cur changes; update_top_individual
+    // is deferred to k_refresh (after the exact re-score of the accepted neighbour)
+    int* stale; int defer_top; int* work_count;
     // trace
     long long* selected_out; int* accepted_out;
 };
@@ -140,6 +296,26 @@ __device__ __forceinline__ int gj_move_selected(const GjMove& m, int* out) {
     return k;
 }
 
+// update_top_individual (agent_base.rs:220-224): population[0] <= agent_top -> replace.
+// Cooperative over the CTA; `dirty` marks islands whose population[0] changed.
+__device__ __forceinline__ void gj_update_top(int island, int levels, int stride, int n_vars,
+                                              const int32_t* cur, const double* cur_score,
+                                              int32_t* best, double* best_score, int* dirty) {
+    if (dirty[island]) {
+        GjScore c = gj_load_score(cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        if (gj_score_le(c, top, levels)) {
+            const int32_t* cur_row = cur + (size_t)island * stride;
+            int32_t* best_row = best + (size_t)island * stride;
+            for (int i = threadIdx.x; i < n_vars; i += blockDim.x) best_row[i] = cur_row[i];
+            if (threadIdx.x == 0)
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) best_score[(size_t)island * GJ_MAX_LEVELS + l] = c.v[l];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) dirty[island] = 0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     extern __shared__ int32_t smem_row[];          // [n_vars] copy of the base for in-place apply
@@ -151,9 +327,16 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int K = A.K, levels = A.levels;
     const double* cs = A.cand_scores + (size_t)island * K * levels;
+    const uint32_t* bits_island = A.tabu_bits ? A.tabu_bits + (size_t)island * A.tabu_words_per_island : nullptr;
+    auto load_move = [&](int j) -> GjMove {
+        if (A.moves) return A.moves[(size_t)island * K + j];
+        return gj_generate_move(P, G, A.M, A.seed, (uint32_t)(A.island_base + island), A.step,
+                                (uint32_t)j, bits_island, A.tabu_word_off);
+    };
 
     // first minimum by Ord::cmp (tabu_search_base.rs:166-171: min_by keeps the first)
     GjScore mine; int mine_idx = -1;
+    for (int l = 0; l < GJ_MAX_LEVELS; ++l) mine.v[l] = 0.0;
     for (int j = tid; j < K; j += blockDim.x) {
         GjScore s = gj_load_score(cs + (size_t)j * levels, levels);
         if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = j; }
@@ -206,6 +389,7 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
         atomicAdd(&A.counters[0], (unsigned long long)K);
         if (island == 0) atomicAdd(&A.counters[1], 1ull);
         if (accept) atomicAdd(&A.counters[2], 1ull);
+        if (island == 0 && A.work_count) *A.work_count = 0;
     }
     __syncthreads();
     int32_t* cur_row = A.cur + (size_t)island * A.stride;
@@ -213,80 +397,74 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
         // apply the winning deltas to the stored individual (tabu_search_base.rs:175-178)
         for (int i = tid; i < A.n_vars; i += blockDim.x) smem_row[i] = cur_row[i];
         __syncthreads();
-        const GjMove m = A.moves[(size_t)island * K + sh_best];
+        const GjMove m = load_move(sh_best);
         gj_apply_move(P, m, G, true, A.noop != 0, tid, blockDim.x,
                       [&](int id) { return smem_row[id]; }, [&](int id, int v) { cur_row[id] = v; });
-        if (tid == 0) A.dirty[island] = 1;
-        __syncthreads();
-    }
-    // update_top_individual (agent_base.rs:220-224): population[0] <= agent_top -> replace
-    if (A.dirty[island]) {
-        GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        if (gj_score_le(cur, top, levels)) {
-            int32_t* best_row = A.best + (size_t)island * A.stride;
-            for (int i = tid; i < A.n_vars; i += blockDim.x) best_row[i] = cur_row[i];
-            if (tid == 0)
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
+        if (tid == 0) {
+            A.dirty[island] = 1;
+            if (A.stale) A.stale[island] = 2;
         }
         __syncthreads();
-        if (tid == 0) A.dirty[island] = 0;
     }
+    if (!A.defer_top)
+        gj_update_top(island, levels, A.stride, A.n_vars, A.cur, A.cur_score, A.best, A.best_score, A.dirty);
 
-    // tabu deque update (Mover::select_non_tabu_ids :75-96): every id selected this step is
-    // pushed in candidate order; the oldest ids fall out once the deque exceeds its size.
+    // tabu deque update (Mover::select_non_tabu_ids :75-96): every id selected this step is pushed
+    // to the front in candidate order; ids beyond the deque's size fall off the back.  The deque is
+    // stored by recency rank (slot 0 = newest), so only the newest `size` ids of the step are
+    // needed: walk the candidates backwards and stop once the deque is full.
     if (A.tabu_bits) {
-        uint32_t* bits_island = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
-        int32_t* ring_island = A.tabu_ring + (size_t)island * A.tabu_ring_per_island;
+        uint32_t* bits_rw = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
+        const int32_t* ring_old_island = A.tabu_ring_old + (size_t)island * A.tabu_ring_per_island;
+        int32_t* ring_new_island = A.tabu_ring_new + (size_t)island * A.tabu_ring_per_island;
+        const int n_chunks = (K + blockDim.x - 1) / blockDim.x;
         for (int g = 0; g < A.n_groups; ++g) {
             const int T = A.tabu_size[g];
-            uint32_t* bits = bits_island + A.tabu_word_off[g];
-            int32_t* ring = ring_island + A.tabu_ring_off[g];
+            const int32_t* ring_old = ring_old_island + A.tabu_ring_off[g];
+            int32_t* ring_new = ring_new_island + A.tabu_ring_off[g];
             const int glen = G.offsets[g + 1] - G.offsets[g];
-            // count ids per candidate chunk (blockDim candidates at a time), in order
-            int head = A.tabu_head[island * A.n_groups + g];
-            int fill = A.tabu_fill[island * A.n_groups + g];
-            for (int base = 0; base < K; base += blockDim.x) {
-                const int j = base + tid;
+            const int fill_old = A.tabu_fill[island * A.n_groups + g];
+            int collected = 0;
+            for (int chunk = n_chunks - 1; chunk >= 0 && collected < T; --chunk) {
+                const int j = chunk * blockDim.x + tid;
                 int sel[GJ_MOVE_MAXK]; int cnt = 0;
                 if (j < K) {
-                    const GjMove m = A.moves[(size_t)island * K + j];
+                    const GjMove m = load_move(j);
                     if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
                 }
-                // exclusive scan of cnt over the block
+                // ids pushed by later candidates of this chunk (exclusive suffix sum)
                 sh_scan[tid] = cnt;
                 __syncthreads();
                 for (int o = 1; o < blockDim.x; o <<= 1) {
-                    int x = (tid >= o) ? sh_scan[tid - o] : 0;
+                    const int x = (tid + o < blockDim.x) ? sh_scan[tid + o] : 0;
                     __syncthreads();
                     sh_scan[tid] += x;
                     __syncthreads();
                 }
-                const int total = sh_scan[blockDim.x - 1];
-                const int off = sh_scan[tid] - cnt;
-                // only the last T ids of the chunk can survive
-                const int skip = max(0, total - T);
+                const int total = sh_scan[0];
+                const int after = sh_scan[tid] - cnt;
                 for (int i = 0; i < cnt; ++i) {
-                    const int pos_in_chunk = off + i;
-                    if (pos_in_chunk < skip) continue;
-                    const int slot = (head + (pos_in_chunk - skip)) % T;
-                    ring[slot] = sel[i];
+                    const int rank = collected + after + (cnt - 1 - i);
+                    if (rank < T) ring_new[rank] = sel[i];
                 }
                 __syncthreads();
-                const int pushed = total - skip;
-                head = (head + pushed) % T;
-                fill = min(T, fill + pushed);
+                collected += total;
             }
-            if (tid == 0) {
-                A.tabu_head[island * A.n_groups + g] = head;
-                A.tabu_fill[island * A.n_groups + g] = fill;
+            // older ids keep their order behind the new ones
+            for (int r = collected + tid; r < T; r += blockDim.x) {
+                const int rho = r - collected;
+                if (rho < fill_old) ring_new[r] = ring_old[rho];
             }
-            // rebuild the membership bitmap from the ring
+            const int fill = min(T, fill_old + collected);
+            // rebuild the membership bitmap from the deque
+            uint32_t* bits = bits_rw + A.tabu_word_off[g];
             const int words = (glen + 31) / 32;
+            __syncthreads();
             for (int w = tid; w < words; w += blockDim.x) bits[w] = 0u;
+            if (tid == 0) A.tabu_fill[island * A.n_groups + g] = fill;
             __syncthreads();
             for (int i = tid; i < fill; i += blockDim.x) {
-                const int pos = ring[i];
+                const int pos = ring_new[i];
                 atomicOr(&bits[pos >> 5], 1u << (pos & 31));
             }
             __syncthreads();
@@ -320,7 +498,7 @@ __global__ void k_migrate_wrap(int I, int stride, unsigned char* mailbox) {
 __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, int late_size,
                                const unsigned char* __restrict__ mailbox, int32_t* cur,
                                double* cur_score, int* dirty, double* late, int* late_head,
-                               int* late_len) {
+                               int* late_len, int* stale) {
     __shared__ int sh_take;
     const int island = blockIdx.x;
     const unsigned char* slot = mailbox + (size_t)island * gj_slot_bytes(stride);
@@ -349,6 +527,7 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
         if (take) {
             for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = mig.v[l];
             dirty[island] = 1;
+            if (stale) stale[island] = 1;
         }
         sh_take = take ? 1 : 0;
     }
@@ -383,7 +562,7 @@ __global__ void k_global_adopt(int agent, int compare_to_global, int levels, int
                                int late_size, const int32_t* __restrict__ gbest,
                                const double* __restrict__ gbest_score, const double* __restrict__ best_score,
                                int32_t* cur, double* cur_score, int* dirty, double* late,
-                               int* late_head, int* late_len) {
+                               int* late_head, int* late_len, int* stale) {
     __shared__ int sh_take;
     const int island = blockIdx.x;
     if (threadIdx.x == 0) {
@@ -402,6 +581,7 @@ __global__ void k_global_adopt(int agent, int compare_to_global, int levels, int
         if (take) {
             for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = g.v[l];
             dirty[island] = 1;
+            if (stale) stale[island] = 1;
         }
         sh_take = take ? 1 : 0;
     }
@@ -567,6 +747,29 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
     g->groups.n_groups = (int)p->groups.size();
     if ((rc = dev_upload(g, offs, &g->groups.offsets))) return rc;
     if ((rc = dev_upload(g, ids, &g->groups.ids))) return rc;
+    {
+        // per group {first, step, uniform bounds}: lets the delta evaluator treat a segment of an
+        // affine group as a contiguous run of columns, and skip fix_deltas clamps
+        std::vector<int4> info;
+        const GjProblemDev& P = p->dev;
+        std::vector<int32_t> lbi(P.n_vars), ubi(P.n_vars);
+        GJ_CUDA_TRY(cudaMemcpy(lbi.data(), P.lbi, (size_t)P.n_vars * 4, cudaMemcpyDeviceToHost));
+        GJ_CUDA_TRY(cudaMemcpy(ubi.data(), P.ubi, (size_t)P.n_vars * 4, cudaMemcpyDeviceToHost));
+        for (auto& grp : p->groups) {
+            int4 gi = make_int4(grp.empty() ? 0 : grp[0], 0, 1, 0);
+            if (grp.size() >= 2) {
+                gi.y = grp[1] - grp[0];
+                for (size_t k = 2; k < grp.size() && gi.y != 0; ++k)
+                    if (grp[k] - grp[k - 1] != gi.y) gi.y = 0;
+            } else {
+                gi.y = 1;
+            }
+            for (size_t k = 1; k < grp.size(); ++k)
+                if (lbi[grp[k]] != lbi[grp[0]] || ubi[grp[k]] != ubi[grp[0]]) gi.z = 0;
+            info.push_back(gi);
+        }
+        if ((rc = dev_upload(g, info, &g->groups.info))) return rc;
+    }
 
     // tabu deques: size = max(ceil(rate * group_len), 1) (tabu_search_base.rs:115-121)
     if (prm->tabu_entity_rate != 0.0) {
@@ -586,8 +789,8 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
         if ((rc = dev_upload(g, ring_off, &g->tabu_ring_off))) return rc;
         if ((rc = dev_upload(g, tsize, &g->tabu_size))) return rc;
         if ((rc = dev_alloc(g, (size_t)g->I * words, &g->tabu_bits))) return rc;
-        if ((rc = dev_alloc(g, (size_t)g->I * ring, &g->tabu_ring))) return rc;
-        if ((rc = dev_alloc(g, (size_t)g->I * g->groups.n_groups, &g->tabu_head))) return rc;
+        if ((rc = dev_alloc(g, (size_t)g->I * ring, &g->tabu_ring[0]))) return rc;
+        if ((rc = dev_alloc(g, (size_t)g->I * ring, &g->tabu_ring[1]))) return rc;
         if ((rc = dev_alloc(g, (size_t)g->I * g->groups.n_groups, &g->tabu_fill))) return rc;
     }
     if ((rc = dev_alloc(g, 4, &g->counters))) return rc;
@@ -639,6 +842,8 @@ __global__ void k_init_scores(int I, const double* __restrict__ scored, int leve
             gbest_score[l] = (l < levels) ? 1.7976931348623157e308 : 0.0;   // get_stub_score()
 }
 
+static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top);
+
 static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const double* initial, gj_islands** out) {
     std::unique_ptr<gj_islands> g(new gj_islands());
     gj_status rc;
@@ -678,7 +883,38 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
     cudaStream_t st = p->stream;
     if ((rc = score_cur(g.get(), st))) return rc;
     k_init_scores<<<(I + 127) / 128, 128, 0, st>>>(I, g->cand_scores, g->levels, g->cur_score, g->best_score, g->gbest_score);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
+    // delta scoring: cached per-island state (gj_delta.cuh).  The VRP models are scored by the
+    // full evaluator in either mode for now.
+    if (prm->scoring_mode == GJ_SCORING_DELTA && p->dev.kind <= GJ_TSP) {
+        g->scoring_mode = GJ_SCORING_DELTA;
+        const GjProblemDev& P = p->dev;
+        g->ds.cnt_stride = 32 * (P.bm_words + P.desc_words + P.asc_words);
+        if ((rc = dev_alloc(g.get(), (size_t)I * g->ds.cnt_stride, &g->ds.cnt))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->ds.raw))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.uniq))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.stale))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * g->K, &g->worklist))) return rc;
+        if ((rc = dev_alloc(g.get(), 1, &g->work_count))) return rc;
+        std::vector<int> ones((size_t)I, 1);
+        GJ_CUDA_TRY(cudaMemcpy(g->ds.stale, ones.data(), (size_t)I * sizeof(int), cudaMemcpyHostToDevice));
+        // can a generated move need the full evaluator?  (thresholds are cumulative)
+        const double* thr = g->mover.thresholds;
+        const bool seg_moves = thr[3] < 1.0;                  // insertion / inverse possible
+        const bool inverse = thr[4] < 1.0;
+        bool affine = true;
+        for (auto& grp : p->groups) {
+            bool a = true, u = true;
+            for (size_t k = 1; k < grp.size(); ++k) {
+                if (grp[k] - grp[k - 1] != 1) a = false;
+                if (p->lb[grp[k]] != p->lb[grp[0]] || p->ub[grp[k]] != p->ub[grp[0]]) u = false;
+            }
+            affine = affine && a && u;
+        }
+        if (P.kind == GJ_NQUEENS) g->delta_may_fallback = seg_moves;
+        else g->delta_may_fallback = seg_moves && (!affine || (inverse && !p->symmetric_D));
+        if ((rc = launch_refresh(g.get(), st, false))) return rc;
+    }
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     g->steps_to_send = (int64_t)std::max<int64_t>(1, prm->migration_frequency);
     *out = g.release();
@@ -704,66 +940,152 @@ static gj_status launch_score_moves(gj_islands* g, cudaStream_t st) {
             k_score_moves_warp<GJ_TSP><<<grid, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
         }
     }
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
-static GjSelectArgs make_select_args(gj_islands* g, bool trace) {
+static GjSelectArgs make_select_args(gj_islands* g, bool trace, bool stored_moves) {
     GjSelectArgs A{};
     A.agent = g->prm.agent; A.K = g->K; A.stride = g->stride; A.levels = g->levels; A.n_vars = g->n_vars;
     A.late_size = g->late_size; A.noop = g->noop; A.n_groups = g->groups.n_groups;
-    A.moves = g->moves; A.cand_scores = g->cand_scores;
+    A.moves = stored_moves ? g->moves : nullptr;
+    A.M = g->mover; A.seed = g->prm.seed; A.step = g->step; A.island_base = g->island_base;
+    A.cand_scores = g->cand_scores;
     A.cur = g->cur; A.cur_score = g->cur_score; A.best = g->best; A.best_score = g->best_score;
     A.dirty = g->dirty; A.late = g->late; A.late_head = g->late_head; A.late_len = g->late_len;
     A.counters = g->counters;
     A.tabu_bits = g->tabu_bits; A.tabu_words_per_island = g->tabu_words; A.tabu_word_off = g->tabu_word_off;
-    A.tabu_ring = g->tabu_ring; A.tabu_ring_per_island = g->tabu_ring_len; A.tabu_ring_off = g->tabu_ring_off;
-    A.tabu_size = g->tabu_size; A.tabu_head = g->tabu_head; A.tabu_fill = g->tabu_fill;
+    A.tabu_ring_old = g->tabu_ring[g->step & 1]; A.tabu_ring_new = g->tabu_ring[(g->step + 1) & 1];
+    A.tabu_ring_per_island = g->tabu_ring_len; A.tabu_ring_off = g->tabu_ring_off;
+    A.tabu_size = g->tabu_size; A.tabu_fill = g->tabu_fill;
+    A.stale = g->ds.stale; A.defer_top = g->scoring_mode == GJ_SCORING_DELTA ? 1 : 0;
+    A.work_count = g->work_count;
     A.selected_out = trace ? g->selected : nullptr; A.accepted_out = trace ? g->accepted : nullptr;
     return A;
+}
+
+static GjStepCtx make_step_ctx(gj_islands* g) {
+    GjStepCtx C{};
+    C.seed = g->prm.seed; C.step = g->step; C.I = g->I; C.K = g->K; C.island_base = g->island_base;
+    C.noop = g->noop; C.stride = g->stride; C.symmetric = g->p->symmetric_D ? 1 : 0;
+    C.tabu_bits = g->tabu_bits; C.tabu_words_per_island = g->tabu_words; C.tabu_word_off = g->tabu_word_off;
+    return C;
+}
+
+static size_t warp_eval_smem(const GjProblemDev& P, int warps, bool with_clone) {
+    return (size_t)warps * (size_t)(P.bm_words + P.desc_words + P.asc_words + (with_clone ? P.n_vars : 0)) * 4;
+}
+
+template <class Kern>
+static gj_status opt_in_smem(Kern kernel, size_t bytes) {
+    if (bytes > 48 * 1024)
+        GJ_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return GJ_OK;
+}
+
+// k_refresh for every island (early exit for islands whose state is current)
+static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top) {
+    const GjProblemDev& P = g->p->dev;
+    const size_t smem = warp_eval_smem(P, 1, false);
+    gj_status rc;
+    if (P.kind == GJ_NQUEENS) {
+        if ((rc = opt_in_smem(k_refresh<GJ_NQUEENS>, smem))) return rc;
+        k_refresh<GJ_NQUEENS><<<g->I, 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
+                                                     g->best, g->best_score, g->dirty);
+    } else {
+        if ((rc = opt_in_smem(k_refresh<GJ_TSP>, smem))) return rc;
+        k_refresh<GJ_TSP><<<g->I, 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
+                                                 g->best, g->best_score, g->dirty);
+    }
+    GJ_LAUNCH_CHECK();
+    return GJ_OK;
+}
+
+// Delta scoring of the step's neighbourhood: generation + evaluation fused, then the full
+// evaluator over whatever the delta evaluator queued.
+static gj_status launch_score_delta(gj_islands* g, cudaStream_t st, bool trace) {
+    const GjProblemDev& P = g->p->dev;
+    const int64_t total = (int64_t)g->I * g->K;
+    const GjStepCtx C = make_step_ctx(g);
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    GjMove* moves_out = trace ? g->moves : nullptr;
+    gj_status rc;
+    if (P.kind == GJ_NQUEENS)
+        k_score_delta<GJ_NQUEENS><<<grid, 256, 0, st>>>(P, g->groups, g->mover, C, g->cur, g->ds, g->cand_scores,
+                                                       g->worklist, g->work_count, moves_out);
+    else
+        k_score_delta<GJ_TSP><<<grid, 256, 0, st>>>(P, g->groups, g->mover, C, g->cur, g->ds, g->cand_scores,
+                                                   g->worklist, g->work_count, moves_out);
+    GJ_LAUNCH_CHECK();
+    if (g->delta_may_fallback) {
+        const size_t smem = warp_eval_smem(P, kWarps, true);
+        if (smem > 220 * 1024) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
+        const unsigned fgrid = (unsigned)std::min<int64_t>((total + kWarps - 1) / kWarps, 148 * 4);
+        if (P.kind == GJ_NQUEENS) {
+            if ((rc = opt_in_smem(k_score_fallback_warp<GJ_NQUEENS>, smem))) return rc;
+            k_score_fallback_warp<GJ_NQUEENS><<<fgrid, kWarps * 32, smem, st>>>(P, g->groups, g->mover, C, g->cur,
+                                                                               g->worklist, g->work_count, g->cand_scores);
+        } else {
+            if ((rc = opt_in_smem(k_score_fallback_warp<GJ_TSP>, smem))) return rc;
+            k_score_fallback_warp<GJ_TSP><<<fgrid, kWarps * 32, smem, st>>>(P, g->groups, g->mover, C, g->cur,
+                                                                           g->worklist, g->work_count, g->cand_scores);
+        }
+        GJ_LAUNCH_CHECK();
+    }
+    return GJ_OK;
 }
 
 static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     const GjProblemDev& P = g->p->dev;
     const int64_t total = (int64_t)g->I * g->K;
-    k_gen_moves<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
-        P, g->groups, g->mover, g->prm.seed, g->step, g->I, g->K, g->island_base, g->tabu_bits,
-        g->tabu_words, g->tabu_word_off, g->moves);
-    GJ_CUDA_TRY(cudaGetLastError());
+    const bool delta = g->scoring_mode == GJ_SCORING_DELTA;
     gj_status rc;
-    if ((rc = gj_prof_begin(g, st))) return rc;
-    if ((rc = launch_score_moves(g, st))) return rc;
-    if ((rc = gj_prof_end(g, st))) return rc;
+    if (!delta) {
+        k_gen_moves<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+            P, g->groups, g->mover, g->prm.seed, g->step, g->I, g->K, g->island_base, g->tabu_bits,
+            g->tabu_words, g->tabu_word_off, g->moves);
+        GJ_LAUNCH_CHECK();
+        if ((rc = gj_prof_begin(g, st))) return rc;
+        if ((rc = launch_score_moves(g, st))) return rc;
+        if ((rc = gj_prof_end(g, st))) return rc;
+    } else {
+        if ((rc = gj_prof_begin(g, st))) return rc;
+        if ((rc = launch_score_delta(g, st, trace))) return rc;
+        if ((rc = gj_prof_end(g, st))) return rc;
+    }
     size_t smem = (size_t)g->n_vars * 4;
-    if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_select<<<g->I, 256, smem, st>>>(P, g->groups, make_select_args(g, trace));
-    GJ_CUDA_TRY(cudaGetLastError());
+    if ((rc = opt_in_smem(k_select, smem))) return rc;
+    k_select<<<g->I, 256, smem, st>>>(P, g->groups, make_select_args(g, trace, !delta));
+    GJ_LAUNCH_CHECK();
+    // delta mode: exact re-score of accepted neighbours + state rebuild, then update_top_individual
+    if (delta && (rc = launch_refresh(g, st, true))) return rc;
     g->step += 1;
     return GJ_OK;
 }
 
 gj_status gj_ls_migrate_pack(gj_islands* g, cudaStream_t st) {
     k_migrate_pack<<<g->I, 128, 0, st>>>(g->cur, g->cur_score, g->stride, g->n_vars, g->mailbox);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
 gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
     k_migrate_recv<<<g->I, 128, 0, st>>>(g->prm.agent, g->levels, g->stride, g->n_vars, g->late_size,
                                         g->mailbox, g->cur, g->cur_score, g->dirty, g->late,
-                                        g->late_head, g->late_len);
-    GJ_CUDA_TRY(cudaGetLastError());
+                                        g->late_head, g->late_len, g->ds.stale);
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
     k_global_reduce<<<1, 256, 0, st>>>(g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score,
                                       g->gbest, g->gbest_score);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     k_global_adopt<<<g->I, 128, 0, st>>>(g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
                                         g->n_vars, g->late_size, g->gbest, g->gbest_score, g->best_score,
-                                        g->cur, g->cur_score, g->dirty, g->late, g->late_head, g->late_len);
-    GJ_CUDA_TRY(cudaGetLastError());
+                                        g->cur, g->cur_score, g->dirty, g->late, g->late_head, g->late_len,
+                                        g->ds.stale);
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
@@ -777,12 +1099,14 @@ static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
             if (!g->external_ring) {
                 if ((rc = gj_ls_migrate_pack(g, st))) return rc;
                 k_migrate_wrap<<<8, 256, 0, st>>>(g->I, g->stride, g->mailbox);
-                GJ_CUDA_TRY(cudaGetLastError());
+                GJ_LAUNCH_CHECK();
                 if ((rc = gj_ls_migrate_recv(g, st))) return rc;
             }
             g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
         }
         if ((rc = gj_ls_global_top(g, st))) return rc;      // agent_base.rs:185
+        // delta mode: islands that received a migrant / adopted the global best rebuild their state
+        if (g->scoring_mode == GJ_SCORING_DELTA && (rc = launch_refresh(g, st, false))) return rc;
     }
     return GJ_OK;
 }
@@ -850,6 +1174,7 @@ extern "C" gj_status gj_islands_best(gj_islands* g, int32_t island, double* vars
         gj_status rc = (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) ? gj_ga_global_top(g, g->p->stream)
                                                                    : gj_ls_global_top(g, g->p->stream);
         if (rc) return rc;
+        if (g->scoring_mode == GJ_SCORING_DELTA && (rc = launch_refresh(g, g->p->stream, false))) return rc;
         GJ_CUDA_TRY(cudaStreamSynchronize(g->p->stream));
         return fetch_individual(g, g->gbest, g->gbest_score, vars, score);
     }
@@ -890,7 +1215,10 @@ extern "C" gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buf
     if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_import(g, d_buffer, st);
     const size_t sb = (size_t)g->stride * 4 + GJ_MAX_LEVELS * 8;
     GJ_CUDA_TRY(cudaMemcpyAsync(g->mailbox, d_buffer, sb, cudaMemcpyDeviceToDevice, st));
-    return gj_ls_migrate_recv(g, st);
+    gj_status rc;
+    if ((rc = gj_ls_migrate_recv(g, st))) return rc;
+    if (g->scoring_mode == GJ_SCORING_DELTA) return launch_refresh(g, st, false);
+    return GJ_OK;
 }
 
 extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64_t* offsets,
@@ -937,7 +1265,7 @@ extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64
     GJ_CUDA_TRY(cudaMalloc((void**)&d_vals, (size_t)(offs[K] + 1) * 8));
     GJ_CUDA_TRY(cudaMemcpy(d_offs, offs.data(), (size_t)(K + 1) * 8, cudaMemcpyHostToDevice));
     k_expand_moves<<<K, 128, 0, st>>>(P, g->groups, d_base, g->moves + (size_t)island * K, K, g->noop, d_offs, d_ids, d_vals);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     if (offsets) std::copy(offs.begin(), offs.end(), offsets);
     if (var_ids && offs[K]) GJ_CUDA_TRY(cudaMemcpy(var_ids, d_ids, (size_t)offs[K] * 8, cudaMemcpyDeviceToHost));

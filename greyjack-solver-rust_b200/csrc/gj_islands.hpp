@@ -5,6 +5,7 @@
 
 #include "gj_internal.hpp"
 #include "gj_moves.cuh"
+#include "gj_delta.cuh"
 
 struct gj_islands {
     gj_problem* p = nullptr;
@@ -35,10 +36,17 @@ struct gj_islands {
     double* late = nullptr; int* late_head = nullptr; int* late_len = nullptr;
     long long* selected = nullptr; int* accepted = nullptr;
 
-    // tabu deques
+    // tabu deques: rank-indexed (slot 0 = newest id), double-buffered by step parity
     uint32_t* tabu_bits = nullptr; int tabu_words = 0; const int32_t* tabu_word_off = nullptr;
-    int32_t* tabu_ring = nullptr; int tabu_ring_len = 0; const int32_t* tabu_ring_off = nullptr;
-    const int32_t* tabu_size = nullptr; int* tabu_head = nullptr; int* tabu_fill = nullptr;
+    int32_t* tabu_ring[2] = {nullptr, nullptr}; int tabu_ring_len = 0; const int32_t* tabu_ring_off = nullptr;
+    const int32_t* tabu_size = nullptr; int* tabu_fill = nullptr;
+
+    // delta scoring (GJ_SCORING_DELTA, gj_delta.cuh)
+    int scoring_mode = 0;
+    bool delta_may_fallback = true;      // some generated moves may need the full evaluator
+    GjDeltaState ds{};
+    int* worklist = nullptr;             // [I*K] neighbours queued for the full evaluator
+    int* work_count = nullptr;
 
     unsigned long long* counters = nullptr;
 

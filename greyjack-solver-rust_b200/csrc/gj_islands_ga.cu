@@ -257,10 +257,10 @@ static gj_status ga_sort_and_top(gj_islands* g, cudaStream_t st, bool count) {
     size_t smem = (size_t)pop2 * 4;
     if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_ga_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_ga_sort<<<g->I, 1024, smem, st>>>(g->pop, pop2, g->levels, g->pop_scores, g->order);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     k_ga_top<<<g->I, 128, 0, st>>>(g->pop, g->stride, g->n_vars, g->levels, g->n_cand, g->pop_rows,
                                   g->pop_scores, g->order, g->best, g->best_score, count ? g->counters : nullptr);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
@@ -311,7 +311,7 @@ gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* 
     cudaStream_t st = p->stream;
     if ((rc = gj_launch_score_plain_i32(p, g->pop_rows, stride, (int64_t)I * pop, g->cand_scores, false, st))) return rc;
     k_ga_init_scores<<<148, 256, 0, st>>>(I, pop, g->levels, g->cand_scores, g->pop_scores, g->best_score, g->gbest_score);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     if ((rc = ga_sort_and_top(g.get(), st, false))) return rc;
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     g->steps_to_send = std::max<int64_t>(1, prm->migration_frequency);
@@ -331,14 +331,14 @@ static GjGaArgs ga_args(gj_islands* g) {
 static gj_status ga_migrate_pack(gj_islands* g, cudaStream_t st) {
     k_ga_migrate_pack<<<g->I * (int)g->migrants, 128, 0, st>>>(g->pop, g->stride, (int)g->migrants, g->pop_rows,
                                                              g->pop_scores, g->order, g->mailbox);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
 static gj_status ga_migrate_recv(gj_islands* g, cudaStream_t st) {
     k_ga_migrate_recv<<<g->I * (int)g->migrants, 128, 0, st>>>(g->pop, g->stride, (int)g->migrants, g->levels,
                                                              g->mailbox, g->pop_rows, g->pop_scores, g->order);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     // the next sample_candidates_plain starts with population.sort() (:157)
     return ga_sort_and_top(g, st, false);
 }
@@ -349,16 +349,16 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
     for (int64_t s = 0; s < n_steps; ++s) {
         GjGaArgs A = ga_args(g);
         k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves);
-        GJ_CUDA_TRY(cudaGetLastError());
+        GJ_LAUNCH_CHECK();
         const int64_t S = (int64_t)g->I * g->n_cand;
         if ((rc = gj_prof_begin(g, st))) return rc;
         if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
         if ((rc = gj_prof_end(g, st))) return rc;
         k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
-        GJ_CUDA_TRY(cudaGetLastError());
+        GJ_LAUNCH_CHECK();
         k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,
                                                    g->pop_next, g->pop_scores_next, g->ga_src);
-        GJ_CUDA_TRY(cudaGetLastError());
+        GJ_LAUNCH_CHECK();
         std::swap(g->pop_rows, g->pop_next);
         std::swap(g->pop_scores, g->pop_scores_next);
         if ((rc = ga_sort_and_top(g, st, true))) return rc;
@@ -369,7 +369,7 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
                 if ((rc = ga_migrate_pack(g, st))) return rc;
                 const size_t slot = (size_t)g->migrants * ((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
                 k_copy_bytes<<<64, 256, 0, st>>>(g->mailbox + (size_t)g->I * slot, g->mailbox, slot);
-                GJ_CUDA_TRY(cudaGetLastError());
+                GJ_LAUNCH_CHECK();
                 if ((rc = ga_migrate_recv(g, st))) return rc;
             }
             g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
@@ -386,7 +386,7 @@ __global__ void k_ga_global_reduce(int I, int levels, int stride, int n_vars, co
 
 gj_status gj_ga_global_top(gj_islands* g, cudaStream_t st) {
     k_ga_global_reduce<<<1, 256, 0, st>>>(g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score);
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 

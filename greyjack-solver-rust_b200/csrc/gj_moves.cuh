@@ -24,6 +24,9 @@ struct GjGroups {               // VariablesManager::semantic_groups_map on the 
     int n_groups;
     const int32_t* offsets;     // [n_groups + 1]
     const int32_t* ids;         // variable ids, group after group
+    const int4* info;           // per group {first, step, uniform, 0}: ids[k] == first + k*step when
+                                // step != 0 (affine group); uniform = every column of the group has
+                                // the same integer bounds (moving values inside it never clamps)
 };
 
 enum { GJ_MOVE_NULL = 255 };

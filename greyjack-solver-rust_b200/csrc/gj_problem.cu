@@ -20,6 +20,8 @@ gj_status gj_fail(gj_status code, const std::string& msg) {
 
 extern "C" const char* gj_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t gj_abi_version(void) { return 1; }
+std::atomic<long long> gj_launch_counter{0};
+extern "C" int64_t gj_launch_count(void) { return (int64_t)gj_launch_counter.load(); }
 extern "C" size_t gj_sizeof_problem_desc(void) { return sizeof(gj_problem_desc); }
 extern "C" size_t gj_sizeof_agent_params(void) { return sizeof(gj_agent_params); }
 extern "C" int32_t gj_device_count(void) {
@@ -236,7 +238,7 @@ extern "C" gj_status gj_problem_create(const gj_problem_desc* desc, int32_t devi
             const double* dxy = nullptr;
             if ((st = upload(p.get(), desc->coords, (size_t)L * 2, &dxy))) return st;
             gj_build_distance_matrix_kernel<<<148 * 8, 256>>>(dxy, L, dD);
-            GJ_CUDA_TRY(cudaGetLastError());
+            GJ_LAUNCH_CHECK();
         } else {
             return gj_fail(GJ_ERR_INVALID, "distance_matrix or coords required");
         }
@@ -246,7 +248,7 @@ extern "C" gj_status gj_problem_create(const gj_problem_desc* desc, int32_t devi
         GJ_CUDA_TRY(cudaMalloc((void**)&dflag, sizeof(int)));
         GJ_CUDA_TRY(cudaMemcpy(dflag, &one, sizeof(int), cudaMemcpyHostToDevice));
         gj_check_symmetric_kernel<<<148 * 8, 256>>>(dD, L, dflag);
-        GJ_CUDA_TRY(cudaGetLastError());
+        GJ_LAUNCH_CHECK();
         GJ_CUDA_TRY(cudaMemcpy(&one, dflag, sizeof(int), cudaMemcpyDeviceToHost));
         cudaFree(dflag);
         p->symmetric_D = one != 0;

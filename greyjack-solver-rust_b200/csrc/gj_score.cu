@@ -207,7 +207,7 @@ static gj_status launch_plain(gj_problem* p, const RowT* d_samples, int64_t stri
             k_plain_warp<GJ_TSP, RowT><<<grid, kWarpsPerCta * 32, smem, st>>>(P, d_samples, stride, S, isc, d_scores);
         }
     }
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
@@ -232,7 +232,7 @@ gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32
     gj_status rc;
     if (d_base) {
         k_decode_base<<<std::min(148, (P.n_vars + 255) / 256), 256, 0, st>>>(P, d_base, d_base_i32);
-        GJ_CUDA_TRY(cudaGetLastError());
+        GJ_LAUNCH_CHECK();
     }
     if (P.kind >= GJ_VRP) {
         size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kWarpsPerCta);
@@ -251,7 +251,7 @@ gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32
             k_incr_warp<GJ_TSP><<<grid, kWarpsPerCta * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
         }
     }
-    GJ_CUDA_TRY(cudaGetLastError());
+    GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 

@@ -50,7 +50,7 @@ class AgentParams(C.Structure):
 
 # every symbol include/greyjack_b200.h declares
 EXPORTED = [
-    "gj_last_error", "gj_abi_version", "gj_device_count", "gj_sizeof_problem_desc", "gj_sizeof_agent_params",
+    "gj_last_error", "gj_abi_version", "gj_device_count", "gj_sizeof_problem_desc", "gj_sizeof_agent_params", "gj_launch_count",
     "gj_problem_create", "gj_problem_destroy", "gj_problem_levels", "gj_problem_n_vars",
     "gj_problem_set_constraint_weights", "gj_problem_set_exact_sums", "gj_problem_get_distance_matrix",
     "gj_host_alloc", "gj_host_free",
@@ -75,6 +75,7 @@ def load():
     L.gj_last_error.restype = C.c_char_p
     L.gj_abi_version.restype = C.c_int32
     L.gj_device_count.restype = C.c_int32
+    L.gj_launch_count.restype = C.c_int64
     L.gj_problem_levels.restype = C.c_int32
     L.gj_problem_n_vars.restype = C.c_int32
     L.gj_problem_destroy.restype = None

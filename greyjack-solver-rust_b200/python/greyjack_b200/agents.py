@@ -19,6 +19,7 @@ from . import _lib
 from .problem import Problem, _ptr
 
 TS, LA, GA = 0, 1, 2
+SCORING_FULL, SCORING_DELTA = 0, 1     # GJ_SCORING_* (include/greyjack_b200.h)
 
 
 # ---- termination strategies (TerminationStrategiesVariants::{StL, TSL, SNI, ScL}) ------------
@@ -111,6 +112,8 @@ class _Builder:
                 p.move_probas[i] = float(v)
         p.migration_frequency = int(self.migration_frequency)
         p.reference_noop_moves = int(getattr(self, "reference_noop_moves", True))
+        mode = getattr(self, "scoring", "full")
+        p.scoring_mode = {"full": SCORING_FULL, "delta": SCORING_DELTA}[mode]
         return p
 
     def build_agent(self, problem: Problem, n_islands: int = 1, seed: int = 0, initial=None) -> "Islands":
@@ -121,7 +124,9 @@ class TabuSearch(_Builder):
     agent = TS
 
     def __init__(self, neighbours_count, tabu_entity_rate, compare_to_global, mutation_rate_multiplier,
-                 move_probas, migration_frequency, termination_strategy=None, reference_noop_moves=True):
+                 move_probas, migration_frequency, termination_strategy=None, reference_noop_moves=True,
+                 scoring="full"):
+        self.scoring = scoring
         self.neighbours_count = neighbours_count
         self.tabu_entity_rate = tabu_entity_rate
         self.compare_to_global = compare_to_global
@@ -142,7 +147,8 @@ class LateAcceptance(_Builder):
     agent = LA
 
     def __init__(self, late_acceptance_size, tabu_entity_rate, mutation_rate_multiplier, move_probas,
-                 migration_frequency, termination_strategy=None, reference_noop_moves=True):
+                 migration_frequency, termination_strategy=None, reference_noop_moves=True, scoring="full"):
+        self.scoring = scoring
         self.late_acceptance_size = late_acceptance_size
         self.tabu_entity_rate = tabu_entity_rate
         self.mutation_rate_multiplier = mutation_rate_multiplier

@@ -138,6 +138,8 @@ GJ_API int32_t     gj_device_count(void);
    (Rust #[repr(C)], ctypes) verify its struct layout at start-up.                       */
 GJ_API size_t      gj_sizeof_problem_desc(void);
 GJ_API size_t      gj_sizeof_agent_params(void);
+/* Number of CUDA kernels this library has launched in this process (all handles). */
+GJ_API int64_t     gj_launch_count(void);
 
 /* OOPScoreRequester::new(cotwin) (oop_score_requester.rs:47-83): uploads everything. */
 GJ_API gj_status gj_problem_create(const gj_problem_desc* desc, int32_t device, gj_problem** out);

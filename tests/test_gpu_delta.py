@@ -1,0 +1,172 @@
+"""GPU parity of DELTA scoring (GJ_SCORING_DELTA, csrc/gj_delta.cuh): islands that score a
+neighbour from the O(k) constraint terms its move touches instead of re-scoring the whole vector.
+
+Bar (north_star): integer score levels and integer move deltas bit-exact with the reference's
+scorer (oracle ISC on the same delta lists); the float level (TSP tour length) within a stated
+tolerance: one 10^-3 quantum of ScoreTrait::round after rounding (= 1e-12 relative before it;
+the exact tour length sits ON the truncation boundary, see gj_eval.cuh).  The stored current /
+best scores are re-scored by the full evaluator after every accepted move and must be bit-exact.
+"""
+import numpy as np
+import pytest
+
+from greyjack_b200 import LateAcceptance, Problem, TabuSearch, instances as inst
+from test_gpu_islands import ALL, MIX, _final_state, _oracle_move, _same_score
+
+pytestmark = pytest.mark.gpu
+
+QUANTUM = 1.0e-3 * (1 + 1e-9)
+
+
+def _check_delta_scores(got, want_unrounded, spec, oracle):
+    want = oracle.score_round(want_unrounded, spec.score_precision)
+    L = spec.levels
+    if L == 1:
+        assert np.array_equal(got, want)
+        return
+    for l in range(L - 1):
+        assert np.array_equal(got[:, l], want[:, l]), f"integer level {l} differs"
+    assert np.max(np.abs(got[:, L - 1] - want[:, L - 1])) <= QUANTUM
+    # and before rounding the two sums agree to 1e-12 relative: the rounded values can only
+    # differ when the unrounded oracle value is within 1e-9 of a quantum boundary
+    diff = got[:, L - 1] != want[:, L - 1]
+    frac = np.abs(want_unrounded[diff, L - 1] * 1000.0 - np.rint(want_unrounded[diff, L - 1] * 1000.0))
+    assert np.all(frac < 1e-6)
+
+
+CASES = [
+    ("nq64-swap", lambda: inst.nqueens(64), [0.0, 1.0, 0.0, 0.0, 0.0, 0.0], 0.0, None),
+    ("nq64-all", lambda: inst.nqueens(64), ALL, 0.2, 1.0),
+    ("nq97-small", lambda: inst.nqueens(97), [0.3, 0.3, 0.2, 0.2, 0.0, 0.0], 0.1, 2.0),
+    ("tsp200-mix", lambda: inst.tsp(200, seed=3), MIX, 0.5, None),
+    ("tsp200-all", lambda: inst.tsp(200, seed=3), ALL, 0.0, 1.0),
+    ("tsp131-all-mult", lambda: inst.tsp(131, seed=8), ALL, 0.3, 3.0),
+    ("tsp64-2opt", lambda: inst.tsp(64, seed=5), [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 0.5, None),
+]
+
+
+@pytest.mark.parametrize("noop", [True, False], ids=["refquirk", "plainform"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_delta_step_replay(case, noop, oracle):
+    _, mk, probas, tabu, mult = case
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    K = 160
+    isl = TabuSearch(K, tabu, True, mult, probas, 10, reference_noop_moves=noop,
+                     scoring="delta").build_agent(gp, n_islands=2, seed=4321)
+    for island in (0, 1):
+        for _ in range(5):
+            base, cur_score = isl.current(island)
+            assert _same_score(cur_score, op.score_incremental(base, [[]])[0], spec, oracle)
+            tr = isl.trace_step(island)
+            if noop:
+                for j in range(K):
+                    want = _oracle_move(op, spec, base, tr["desc"][j])
+                    assert _final_state(spec.n_vars, tr["deltas"][j]) == _final_state(spec.n_vars, want)
+            _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+            sel, acc = oracle.ts_select(tr["scores"], cur_score)
+            assert (tr["selected"], tr["accepted"]) == (sel, acc)
+            new, new_score = isl.current(island)
+            want_vec = base.copy()
+            if acc:
+                for c, v in tr["deltas"][sel]:
+                    want_vec[c] = v
+            assert np.array_equal(new, want_vec)
+            # after an accepted move the stored score is the FULL evaluation of the new vector
+            want_score = oracle.score_round(op.score_incremental(new, [[]])[0], spec.score_precision)
+            if acc:
+                assert np.array_equal(new_score, want_score)
+            else:
+                assert np.array_equal(new_score, cur_score)
+    isl.close(); gp.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: inst.tsp(150, seed=2), lambda: inst.nqueens(48)], ids=["tsp", "nqueens"])
+def test_delta_and_full_islands_see_the_same_neighbourhood(mk, oracle):
+    """Same seed -> same moves (the generator is a pure function of seed/island/step/candidate);
+    integer levels identical, float level within one quantum."""
+    spec = mk()
+    gp = Problem(spec)
+    probas = ALL
+    a = TabuSearch(256, 0.2, True, 1.0, probas, 10, scoring="full").build_agent(gp, n_islands=2, seed=77)
+    b = TabuSearch(256, 0.2, True, 1.0, probas, 10, scoring="delta").build_agent(gp, n_islands=2, seed=77)
+    ta, tb = a.trace_step(1), b.trace_step(1)
+    assert np.array_equal(ta["desc"], tb["desc"])
+    L = spec.levels
+    for l in range(max(1, L - 1)):
+        assert np.array_equal(ta["scores"][:, l], tb["scores"][:, l])
+    if L > 1:
+        assert np.max(np.abs(ta["scores"][:, L - 1] - tb["scores"][:, L - 1])) <= QUANTUM
+    a.close(); b.close(); gp.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: inst.tsp(150, seed=2), lambda: inst.nqueens(48)], ids=["tsp", "nqueens"])
+@pytest.mark.parametrize("agent", ["ts", "la"])
+def test_delta_run_is_consistent(mk, agent, oracle):
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    probas = [0.0, 1.0, 0.0, 0.0, 0.0, 0.0] if spec.kind == inst.NQUEENS else [0.1, 0.3, 0.1, 0.1, 0.2, 0.2]
+    if agent == "ts":
+        isl = TabuSearch(128, 0.2, True, None, probas, 5, reference_noop_moves=False,
+                         scoring="delta").build_agent(gp, n_islands=4, seed=5)
+        per_step = 128
+    else:
+        isl = LateAcceptance(8, 0.2, None, probas, 5, reference_noop_moves=False,
+                             scoring="delta").build_agent(gp, n_islands=4, seed=5)
+        per_step = 1
+    _, s0 = isl.best(0)
+    prev = None
+    for _ in range(6):
+        isl.step(25)
+        vec, sc = isl.best(-1)
+        assert _same_score(sc, op.score_incremental(vec, [[]])[0], spec, oracle)
+        if prev is not None:
+            assert oracle.score_cmp(sc, prev) <= 0
+        prev = sc
+        for i in range(4):
+            cv, cs = isl.current(i)
+            assert _same_score(cs, op.score_incremental(cv, [[]])[0], spec, oracle)
+            bv, bs = isl.best(i)
+            assert _same_score(bs, op.score_incremental(bv, [[]])[0], spec, oracle)
+    assert oracle.score_cmp(prev, s0) < 0
+    st = isl.stats()
+    assert st["steps"] == 150 and st["candidates"] == 150 * per_step * 4
+    isl.close(); gp.close()
+
+
+def test_delta_migration_keeps_state_in_sync(oracle):
+    spec = inst.tsp(100, seed=4)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    init = np.stack([spec.initial] + [np.arange(1, 100, dtype=np.float64)] * 3)
+    isl = TabuSearch(64, 0.0, True, None, [0, 0.5, 0, 0, 0, 0.5], 1, scoring="delta").build_agent(
+        gp, n_islands=4, seed=3, initial=init)
+    for _ in range(8):
+        isl.step(1)
+        for i in range(4):
+            base, cur_score = isl.current(i)
+            assert _same_score(cur_score, op.score_incremental(base, [[]])[0], spec, oracle)
+        # the cached state must describe the (possibly migrated / adopted) vector: replay a step
+        base, _ = isl.current(2)
+        tr = isl.trace_step(2)
+        _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+    isl.close(); gp.close()
+
+
+def test_delta_change_moves_track_duplicates(oracle):
+    """change_move introduces / removes duplicate stops: the hard level must follow exactly."""
+    spec = inst.tsp(60, seed=11)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    isl = TabuSearch(512, 0.0, True, 4.0, [1.0, 0, 0, 0, 0, 0], 10, scoring="delta").build_agent(gp, seed=9)
+    seen_hard = set()
+    for _ in range(4):
+        base, _ = isl.current(0)
+        tr = isl.trace_step(0)
+        want = op.score_incremental(base, tr["deltas"])
+        _check_delta_scores(tr["scores"], want, spec, oracle)
+        seen_hard |= set(want[:, 0].tolist())
+    assert len(seen_hard) > 2
+    isl.close(); gp.close()
