@@ -40,10 +40,12 @@ A_FULL = 4 * (N_CITIES - 1) + 8 * N_CITIES + 16     # 12 012 B: full (pseudo-inc
 A_DELTA = 0.5 * 96 + 0.5 * 56                       # swap 96 B / 2-opt 56 B, 50:50 mix
 SCORING_DESC = {
     "full": "full re-evaluation of base+move per candidate (the reference's pseudo-incremental ISC semantics)",
-    "delta": "delta evaluation against the island's cached state (move generated in registers, O(k) edges "
-             "gathered from the L2-resident matrix); accepted neighbours re-scored by the full evaluator",
+    "delta": "fused island step: move generated in registers, delta-scored against the island's state staged in "
+             "shared memory (tour, edge lengths, value counts, tabu table), added edges gathered from the "
+             "L2-resident matrix; selection, apply, full re-score of the accepted neighbour and tabu update in "
+             "the same kernel",
 }
-SCORING_KERNEL = {"full": "k_score_moves_warp<GJ_TSP>", "delta": "k_score_delta<GJ_TSP>"}
+SCORING_KERNEL = {"full": "k_score_moves_warp<GJ_TSP>", "delta": "k_ls_step_fused<GJ_TSP,256>"}
 
 
 def peaks():
@@ -148,7 +150,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--islands", type=int, default=int(os.environ.get("GJ_BENCH_ISLANDS", "148")))
+    ap.add_argument("--islands", type=int, default=int(os.environ.get("GJ_BENCH_ISLANDS", "592")))
     ap.add_argument("--e2e-agents", type=int, default=4)
     ap.add_argument("--scoring", default="delta", choices=["delta", "full"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -46,8 +46,34 @@ __device__ __forceinline__ int gj_uniq_delta(const int32_t* __restrict__ cnt, co
             }
         }
         if (seen || net == 0) continue;
-        const int before = __ldg(&cnt[key]);
+        const int before = cnt[key];
         d += ((before + net) > 0 ? 1 : 0) - (before > 0 ? 1 : 0);
+    }
+    return d;
+}
+
+// Same for exactly two moved occurrences (a swap of two entities), everything in registers.
+__device__ __forceinline__ int gj_uniq_delta2(const int32_t* __restrict__ cnt, int o0, int o1,
+                                              int n0, int n1) {
+    if (o0 == n0 && o1 == n1) return 0;
+    if (o0 == n1 && o1 == n0) return 0;               // the two keys just trade places
+    int key[4] = {o0, o1, n0, n1};
+    int d = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bool seen = false;
+        int net = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (key[q] == key[j]) {
+                if (q < j) seen = true;
+                net += (q < 2) ? -1 : 1;
+            }
+        }
+        if (!seen && net != 0) {
+            const int before = cnt[key[j]];
+            d += ((before + net) > 0 ? 1 : 0) - (before > 0 ? 1 : 0);
+        }
     }
     return d;
 }
@@ -69,7 +95,12 @@ struct GjTspBase {
     int n;
     const double* __restrict__ D;
     size_t L;
-    __device__ __forceinline__ int at(int q) const { return (q < 0 || q >= n) ? 0 : __ldg(&t[q]); }
+    const double* edge;                // optional [n + 1]: edge[i] = D[at(i-1)][at(i)] of the current
+                                       // tour (edge[n] closes it); nullptr -> gathered from D
+    __device__ __forceinline__ double tour_edge(int i) const {
+        return edge ? edge[i] : d(at(i - 1), at(i));
+    }
+    __device__ __forceinline__ int at(int q) const { return (q < 0 || q >= n) ? 0 : t[q]; }
     __device__ __forceinline__ double d(int a, int b) const { return __ldg(&D[(size_t)a * L + (size_t)b]); }
 };
 
@@ -119,42 +150,55 @@ __device__ __forceinline__ bool gj_tsp_move_delta(const GjProblemDev& P, const G
     d_uniq = 0; d_dist = 0.0;
     if (m.kind == GJ_MOVE_NULL) return true;
     const int32_t* g = G.ids + G.offsets[m.group];
+    const int4 gi = G.info[m.group];
+    // Fast path, branch-free over the move kind: a swap of two stops, a 2-opt reversal and an
+    // insertion all replace at most four tour edges by four others.  Needs a group with uniform
+    // bounds (no fix_deltas clamp, stop multiset unchanged); the segment moves also a group of
+    // consecutive columns, the reversal a symmetric matrix (its interior edges then cancel).
+    const bool two_swap = (m.kind == 1 && m.k == 2);
+    const bool seg = (m.kind >= 4) && gi.y == 1 && (m.kind == 4 || symmetric);
+    if (gi.z != 0 && (two_swap || seg)) {
+        const int c0 = (gi.y != 0) ? gi.x + m.a[0] * gi.y : g[m.a[0]];
+        const int c1 = (gi.y != 0) ? gi.x + m.a[1] * gi.y : g[m.a[1]];
+        const int p = min(c0, c1), q = max(c0, c1);
+        const int pm = B.at(p - 1), tp = B.at(p), pn = B.at(p + 1);
+        const int qm = B.at(q - 1), tq = B.at(q), qp = B.at(q + 1);
+        const bool adj = (q == p + 1);
+        const bool inv = (m.kind == 5);
+        const bool ins_l = (m.kind == 4) && (m.a[0] < m.a[1]);     // t[p] travels to the end
+        const bool ins_r = (m.kind == 4) && !ins_l;                 // t[q] travels to the front
+        const bool swp_far = two_swap && !adj;
+        // removed: (pm,tp) (tq,qp) always; third: (tp,pn) [= (tp,tq) when adjacent] or, for a right
+        // insertion, (qm,tq); fourth (far swap): (qm,tq)
+        // added: (pm, x0) (y1, qp) always; third / fourth edge by kind
+        const int x0 = ins_l ? pn : tq;
+        const int y1 = ins_r ? qm : tp;
+        const int a2b = swp_far ? pn : tp;
+        // the removed edges are edges of the current tour: read from the island's edge cache
+        // (the same f64 values the matrix holds); only the added edges gather from D
+        double removed = B.tour_edge(p) + B.tour_edge(q + 1);
+        double added = B.d(pm, x0) + B.d(y1, qp);
+        if (!inv) { removed += B.tour_edge(ins_r ? q : p + 1); added += B.d(tq, a2b); }
+        if (swp_far) { removed += B.tour_edge(q); added += B.d(qm, tp); }
+        d_dist = added - removed;
+        return true;
+    }
     if (m.kind <= 3) {
+        // general small move.  Works on a copy: the expansion indexes the descriptor dynamically,
+        // and the caller's `m` must stay in registers for the fast path above.
+        const GjMove ms = m;
         int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
-        const int np = gj_small_move_pairs(m, g, true, noop_quirk,
-                                           [&](int id) { return __ldg(&B.t[id]); }, cols, vals);
+        const int np = gj_small_move_pairs(ms, g, true, noop_quirk,
+                                           [&](int id) { return B.t[id]; }, cols, vals);
         for (int i = 0; i < np; ++i) vals[i] = gj_fix_column(P, cols[i], vals[i]);
         double removed, added;
         gj_tsp_pairs_delta(P, B, cnt, cols, vals, np, d_uniq, removed, added);
         d_dist = added - removed;
         return true;
     }
-    const int4 gi = G.info[m.group];
-    if (gi.y != 1 || gi.z == 0) return false;          // segment must be contiguous tour positions
-    int lo, hi;
-    gj_segment_bounds(m, lo, hi);
-    const int a = gi.x + lo, b = gi.x + hi;
-    const int ta = B.at(a), tb = B.at(b), pm = B.at(a - 1), pp = B.at(b + 1);
-    if (m.kind == 5) {                                 // inverse_move (2-opt), mover.rs:378-420
-        if (!symmetric) return false;
-        const double removed = B.d(pm, ta) + B.d(tb, pp);
-        const double added = B.d(pm, tb) + B.d(ta, pp);
-        d_dist = added - removed;
-        return true;
-    }
-    // insertion_move, incremental form (mover.rs:339-369): rotate the segment by one
-    if (m.a[0] < m.a[1]) {                             // t[a] travels to the end
-        const int tn = B.at(a + 1);
-        const double removed = B.d(pm, ta) + B.d(ta, tn) + B.d(tb, pp);
-        const double added = B.d(pm, tn) + B.d(tb, ta) + B.d(ta, pp);
-        d_dist = added - removed;
-    } else {                                           // t[b] travels to the front
-        const int tq = B.at(b - 1);
-        const double removed = B.d(pm, ta) + B.d(tq, tb) + B.d(tb, pp);
-        const double added = B.d(pm, tb) + B.d(tb, ta) + B.d(tq, pp);
-        d_dist = added - removed;
-    }
-    return true;
+    // segment move outside the fast path (non-consecutive columns, per-column bounds, or a
+    // reversal on an asymmetric matrix): O(segment) edges change -> full evaluator
+    return false;
 }
 
 // ---- N-Queens --------------------------------------------------------------------------------
@@ -167,9 +211,23 @@ __device__ __forceinline__ bool gj_nqueens_move_delta(const GjProblemDev& P, con
     if (m.kind == GJ_MOVE_NULL) return true;
     if (m.kind > 3) return false;                      // O(segment) changes: full evaluator
     const int32_t* g = G.ids + G.offsets[m.group];
+    const int4 gi = G.info[m.group];
+    if (m.kind == 1 && m.k == 2 && gi.z != 0) {
+        // swap of two queens' rows: the row multiset is unchanged, both diagonals move
+        const int c0 = (gi.y != 0) ? gi.x + m.a[0] * gi.y : g[m.a[0]];
+        const int c1 = (gi.y != 0) ? gi.x + m.a[1] * gi.y : g[m.a[1]];
+        const int r0 = rows[c0], r1 = rows[c1];
+        if (r0 == r1) return true;
+        const int k0 = P.column_id[c0], k1 = P.column_id[c1];
+        const int off_d = 32 * P.bm_words - P.desc_lo, off_a = 32 * (P.bm_words + P.desc_words) - P.asc_lo;
+        d_uniq = gj_uniq_delta2(cnt, off_d + k0 + r0, off_d + k1 + r1, off_d + k0 + r1, off_d + k1 + r0) +
+                 gj_uniq_delta2(cnt, off_a + k0 - r0, off_a + k1 - r1, off_a + k0 - r1, off_a + k1 - r0);
+        return true;
+    }
+    const GjMove ms = m;                               // see gj_tsp_move_delta
     int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
-    const int np = gj_small_move_pairs(m, g, true, noop_quirk,
-                                       [&](int id) { return __ldg(&rows[id]); }, cols, vals);
+    const int np = gj_small_move_pairs(ms, g, true, noop_quirk,
+                                       [&](int id) { return rows[id]; }, cols, vals);
     for (int i = 0; i < np; ++i) vals[i] = gj_fix_column(P, cols[i], vals[i]);
     const unsigned live = gj_live_mask(cols, np);
     const int off_desc = 32 * P.bm_words, off_asc = 32 * (P.bm_words + P.desc_words);
@@ -181,7 +239,7 @@ __device__ __forceinline__ bool gj_nqueens_move_delta(const GjProblemDev& P, con
             ko[i] = -1; kn[i] = -1;
             if (!((live >> i) & 1u)) continue;
             const int c = cols[i], col = __ldg(&P.column_id[c]);
-            const int o = __ldg(&rows[c]), v = vals[i];
+            const int o = rows[c], v = vals[i];
             if (o == v) continue;
             if (space == 0) { ko[i] = o - P.val_lo; kn[i] = v - P.val_lo; }
             else if (space == 1) { ko[i] = off_desc + (col + o - P.desc_lo); kn[i] = off_desc + (col + v - P.desc_lo); }

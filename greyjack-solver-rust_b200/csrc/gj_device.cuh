@@ -186,7 +186,13 @@ __device__ __forceinline__ uint32_t gj_rng_u32(GjPhilox& g) {
         g.c[3] += 1;
         g.have = 4;
     }
-    return g.out[--g.have];
+    // static indices only: the state stays in registers (out[3] is handed out first)
+    g.have -= 1;
+    uint32_t r = g.out[0];
+    if (g.have == 1) r = g.out[1];
+    if (g.have == 2) r = g.out[2];
+    if (g.have == 3) r = g.out[3];
+    return r;
 }
 
 // uniform integer in [0, n) (n > 0); multiply-shift, bias < n / 2^32

@@ -15,6 +15,8 @@
 #include <algorithm>
 #include <cmath>
 #include <memory>
+#include <cstdio>
+#include <cstdlib>
 
 #include "gj_eval.cuh"
 #include "gj_islands.hpp"
@@ -138,7 +140,7 @@ k_score_delta(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
         // (N - |rows|) + (N - |desc|) + (N - |asc|): integers, exact in f64
         gj_combine_nqueens(P, raw[0] - (double)d_uniq, s.v);
     } else {
-        GjTspBase B{row, P.n_vars, P.D, (size_t)P.n_locations};
+        GjTspBase B{row, P.n_vars, P.D, (size_t)P.n_locations, nullptr};
         int d_uniq; double d_dist;
         ok = gj_tsp_move_delta(P, G, m, C.noop != 0, C.symmetric != 0, B, cnt, d_uniq, d_dist);
         gj_combine_tsp(P, true, raw[0] - (double)d_uniq, raw[1] + d_dist, s.v);
@@ -292,7 +294,8 @@ __device__ __forceinline__ int gj_move_selected(const GjMove& m, int* out) {
     if (m.kind == GJ_MOVE_NULL) return 0;
     if (m.kind == 3) { out[0] = m.a[0]; return 1; }
     const int k = (m.kind >= 4) ? 2 : m.k;
-    for (int i = 0; i < k; ++i) out[i] = m.a[i];
+#pragma unroll
+    for (int i = 0; i < GJ_MOVE_MAXK; ++i) out[i] = m.a[i];
     return k;
 }
 
@@ -314,6 +317,47 @@ __device__ __forceinline__ void gj_update_top(int island, int levels, int stride
         __syncthreads();
         if (threadIdx.x == 0) dirty[island] = 0;
     }
+}
+
+// Rebuilds one group's tabu table (membership bits, then the exclusive prefix count of free
+// positions per word; layout in gj_moves.cuh) from its deque.  Cooperative over the CTA;
+// `scan` holds blockDim ints of shared memory.
+__device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen, const int32_t* ring,
+                                                      int fill, int* scan) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int W = (glen + 31) >> 5;
+    int32_t* prefix = (int32_t*)(table + W + 1);
+    __syncthreads();
+    for (int w = tid; w <= W; w += nthr) table[w] = 0u;
+    __syncthreads();
+    for (int i = tid; i < fill; i += nthr) {
+        const int pos = ring[i];
+        atomicOr(&table[pos >> 5], 1u << (pos & 31));
+    }
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < W; base += nthr) {
+        const int w = base + tid;
+        int f = 0;
+        if (w < W) {
+            const int rem = glen - 32 * w;
+            const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+            f = __popc(~table[w] & valid);
+        }
+        scan[tid] = f;
+        __syncthreads();
+        for (int o = 1; o < nthr; o <<= 1) {
+            const int x = (tid >= o) ? scan[tid - o] : 0;
+            __syncthreads();
+            scan[tid] += x;
+            __syncthreads();
+        }
+        if (w < W) prefix[w] = carry + scan[tid] - f;
+        carry += scan[nthr - 1];
+        __syncthreads();
+    }
+    if (tid == 0) prefix[W] = carry;
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256)
@@ -443,9 +487,12 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
                 }
                 const int total = sh_scan[0];
                 const int after = sh_scan[tid] - cnt;
-                for (int i = 0; i < cnt; ++i) {
-                    const int rank = collected + after + (cnt - 1 - i);
-                    if (rank < T) ring_new[rank] = sel[i];
+#pragma unroll
+                for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                    if (i < cnt) {
+                        const int rank = collected + after + (cnt - 1 - i);
+                        if (rank < T) ring_new[rank] = sel[i];
+                    }
                 }
                 __syncthreads();
                 collected += total;
@@ -456,21 +503,13 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
                 if (rho < fill_old) ring_new[r] = ring_old[rho];
             }
             const int fill = min(T, fill_old + collected);
-            // rebuild the membership bitmap from the deque
-            uint32_t* bits = bits_rw + A.tabu_word_off[g];
-            const int words = (glen + 31) / 32;
-            __syncthreads();
-            for (int w = tid; w < words; w += blockDim.x) bits[w] = 0u;
             if (tid == 0) A.tabu_fill[island * A.n_groups + g] = fill;
-            __syncthreads();
-            for (int i = tid; i < fill; i += blockDim.x) {
-                const int pos = ring_new[i];
-                atomicOr(&bits[pos >> 5], 1u << (pos & 31));
-            }
-            __syncthreads();
+            gj_tabu_table_rebuild(bits_rw + A.tabu_word_off[g], glen, ring_new, fill, sh_scan);
         }
     }
 }
+
+#include "gj_islands_fused.cuh"
 
 // ---- migration (ring i -> i+1, solver.rs:85-92) ------------------------------------------------------
 // mailbox slot s: [stride int32][GJ_MAX_LEVELS f64]; slot[i+1] = island i's outgoing migrant,
@@ -537,20 +576,47 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
 }
 
 // ---- global best (update_global_top, agent_base.rs:446-490) ------------------------------------------
-__global__ void k_global_reduce(int I, int levels, int stride, int n_vars,
-                                const int32_t* __restrict__ best, const double* __restrict__ best_score,
-                                int32_t* gbest, double* gbest_score) {
+__global__ void __launch_bounds__(256)
+k_global_reduce(int I, int levels, int stride, int n_vars,
+                const int32_t* __restrict__ best, const double* __restrict__ best_score,
+                int32_t* gbest, double* gbest_score) {
+    // The reference walks the agents one by one replacing the global top whenever an agent's
+    // top is strictly better (:451); the result is the overall minimum, first index on ties,
+    // provided it beats the current global top.  Parallel arg-min with the same tie rule.
+    __shared__ GjScore sh_s[8];
+    __shared__ int sh_i[8];
     __shared__ int sh_win;
-    if (threadIdx.x == 0) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GjScore mine; int mine_idx = -1;
+    mine.v[0] = mine.v[1] = mine.v[2] = 0.0;
+    for (int i = tid; i < I; i += blockDim.x) {
+        GjScore s = gj_load_score(best_score + (size_t)i * GJ_MAX_LEVELS, levels);
+        if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        GjScore other; const int oidx = __shfl_xor_sync(GJ_FULL_MASK, mine_idx, o);
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) other.v[l] = __shfl_xor_sync(GJ_FULL_MASK, mine.v[l], o);
+        if (oidx >= 0) {
+            const int c = (mine_idx < 0) ? 1 : gj_score_cmp(mine, other, levels);
+            if (c > 0 || (c == 0 && oidx < mine_idx)) { mine = other; mine_idx = oidx; }
+        }
+    }
+    if (lane == 0) { sh_s[warp] = mine; sh_i[warp] = mine_idx; }
+    __syncthreads();
+    if (tid == 0) {
+        GjScore b = sh_s[0]; int bi = sh_i[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            if (sh_i[w] < 0) continue;
+            const int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_s[w], levels);
+            if (c > 0 || (c == 0 && sh_i[w] < bi)) { b = sh_s[w]; bi = sh_i[w]; }
+        }
         GjScore g = gj_load_score(gbest_score, levels);
         int win = -1;
-        for (int i = 0; i < I; ++i) {
-            GjScore s = gj_load_score(best_score + (size_t)i * GJ_MAX_LEVELS, levels);
-            // `agent_top.score < global.score` (:451): strict
-            if (!gj_score_le(g, s, levels)) { g = s; win = i; }
+        if (bi >= 0 && !gj_score_le(g, b, levels)) {       // `agent_top.score < global.score`: strict
+            win = bi;
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
         }
-        if (win >= 0)
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = g.v[l];
         sh_win = win;
     }
     __syncthreads();
@@ -588,6 +654,79 @@ __global__ void k_global_adopt(int agent, int compare_to_global, int levels, int
     __syncthreads();
     if (sh_take)
         for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = gbest[i];
+}
+
+// update_global_top (agent_base.rs:446-490) for every island in ONE launch (one CTA per island).
+// Agent tops only ever improve and the global top is refreshed from them after every step, so
+// the new global top is simply the best agent top (first index on ties).  Every CTA finds it
+// redundantly (I is small), CTA 0 publishes it (:451-461), and each island adopts it when it is
+// strictly better than its own top (:465-489; TabuSearch only with compare_to_global).
+__global__ void __launch_bounds__(256)
+k_global_top(int I, int agent, int compare_to_global, int levels, int stride, int n_vars, int late_size,
+             const int32_t* __restrict__ best, const double* __restrict__ best_score,
+             int32_t* gbest, double* gbest_score, int32_t* cur, double* cur_score, int* dirty,
+             double* late, int* late_head, int* late_len, int* stale) {
+    __shared__ GjScore sh_s[8];
+    __shared__ int sh_i[8];
+    __shared__ int sh_take, sh_publish;
+    const int island = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GjScore mine; int mine_idx = -1;
+    mine.v[0] = mine.v[1] = mine.v[2] = 0.0;
+    for (int i = tid; i < I; i += blockDim.x) {
+        GjScore s = gj_load_score(best_score + (size_t)i * GJ_MAX_LEVELS, levels);
+        if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        GjScore other; const int oidx = __shfl_xor_sync(GJ_FULL_MASK, mine_idx, o);
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) other.v[l] = __shfl_xor_sync(GJ_FULL_MASK, mine.v[l], o);
+        if (oidx >= 0) {
+            const int c = (mine_idx < 0) ? 1 : gj_score_cmp(mine, other, levels);
+            if (c > 0 || (c == 0 && oidx < mine_idx)) { mine = other; mine_idx = oidx; }
+        }
+    }
+    if (lane == 0) { sh_s[warp] = mine; sh_i[warp] = mine_idx; }
+    __syncthreads();
+    if (tid == 0) {
+        GjScore b = sh_s[0]; int bi = sh_i[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            if (sh_i[w] < 0) continue;
+            const int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_s[w], levels);
+            if (c > 0 || (c == 0 && sh_i[w] < bi)) { b = sh_s[w]; bi = sh_i[w]; }
+        }
+        sh_s[0] = b; sh_i[0] = bi;
+        sh_publish = 0;
+        if (island == 0) {
+            GjScore g = gj_load_score(gbest_score, levels);
+            if (!gj_score_le(g, b, levels)) {                   // strict: agent_top < global (:451)
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
+                sh_publish = 1;
+            }
+        }
+        GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        bool take = !gj_score_le(top, b, levels);               // global < agent_top (:465)
+        if (agent == GJ_AGENT_TABU_SEARCH) take = take && compare_to_global;
+        if (take && agent == GJ_AGENT_LATE_ACCEPTANCE) {
+            double* lt = late + (size_t)island * late_size * GJ_MAX_LEVELS;
+            const int head = (late_head[island] + late_size - 1) % late_size;
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+                lt[(size_t)head * GJ_MAX_LEVELS + l] = cur_score[(size_t)island * GJ_MAX_LEVELS + l];
+            late_head[island] = head; late_len[island] = min(late_len[island] + 1, late_size);
+        }
+        if (take) {
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = b.v[l];
+            dirty[island] = 1;
+            if (stale) stale[island] = 1;
+        }
+        sh_take = take ? 1 : 0;
+    }
+    __syncthreads();
+    const int32_t* win_row = best + (size_t)sh_i[0] * stride;
+    if (sh_publish)
+        for (int i = tid; i < n_vars; i += blockDim.x) gbest[i] = win_row[i];
+    if (sh_take)
+        for (int i = tid; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = win_row[i];
 }
 
 // Expands move descriptors into the (column, value) lists of the reference's incremental form.
@@ -628,6 +767,18 @@ __global__ void k_i32_to_f64(const int32_t* __restrict__ in, double* __restrict_
 
 gj_islands::~gj_islands() {
     cudaSetDevice(p->device);
+    if (phase_clocks) {
+        // development aid: phase durations (cycles) of the LAST fused step, island 0 and the mean
+        std::vector<long long> h((size_t)I * 8);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), phase_clocks, h.size() * 8, cudaMemcpyDeviceToHost);
+        static const char* names[5] = {"P0 stage", "P1 score", "P2 select", "P3 apply", "P4 tabu"};
+        for (int k = 0; k < 5; ++k) {
+            double mean = 0;
+            for (int i = 0; i < I; ++i) mean += (double)(h[(size_t)i * 8 + k + 1] - h[(size_t)i * 8 + k]);
+            fprintf(stderr, "[gj phase] %-10s island0 %8lld cycles, mean %10.0f\n", names[k], h[k + 1] - h[k], mean / I);
+        }
+    }
     for (void* a : allocs) cudaFree(a);
     for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
 }
@@ -781,7 +932,7 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
             T = std::min(T, std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK));   // keep free ids to draw from
             T = std::max(T, 1);
             tsize.push_back(T);
-            words += (int)((grp.size() + 31) / 32) + 1;
+            words += 2 * ((int)((grp.size() + 31) / 32) + 1);     // bits + free-prefix (gj_moves.cuh)
             ring += T;
         }
         g->tabu_words = words; g->tabu_ring_len = ring;
@@ -789,6 +940,17 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
         if ((rc = dev_upload(g, ring_off, &g->tabu_ring_off))) return rc;
         if ((rc = dev_upload(g, tsize, &g->tabu_size))) return rc;
         if ((rc = dev_alloc(g, (size_t)g->I * words, &g->tabu_bits))) return rc;
+        {
+            // empty deques: every position free
+            std::vector<uint32_t> table((size_t)g->I * words, 0u);
+            for (int i = 0; i < g->I; ++i)
+                for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+                    const int glen = (int)p->groups[gi].size(), W = (glen + 31) / 32;
+                    uint32_t* prefix = table.data() + (size_t)i * words + word_off[gi] + W + 1;
+                    for (int w = 0; w <= W; ++w) prefix[w] = (uint32_t)std::min(32 * w, glen);
+                }
+            GJ_CUDA_TRY(cudaMemcpy(g->tabu_bits, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
+        }
         if ((rc = dev_alloc(g, (size_t)g->I * ring, &g->tabu_ring[0]))) return rc;
         if ((rc = dev_alloc(g, (size_t)g->I * ring, &g->tabu_ring[1]))) return rc;
         if ((rc = dev_alloc(g, (size_t)g->I * g->groups.n_groups, &g->tabu_fill))) return rc;
@@ -886,7 +1048,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
     GJ_LAUNCH_CHECK();
     // delta scoring: cached per-island state (gj_delta.cuh).  The VRP models are scored by the
     // full evaluator in either mode for now.
-    if (prm->scoring_mode == GJ_SCORING_DELTA && p->dev.kind <= GJ_TSP) {
+    if ((prm->scoring_mode == GJ_SCORING_DELTA || prm->scoring_mode == GJ_SCORING_DELTA_UNFUSED) && p->dev.kind <= GJ_TSP) {
         g->scoring_mode = GJ_SCORING_DELTA;
         const GjProblemDev& P = p->dev;
         g->ds.cnt_stride = 32 * (P.bm_words + P.desc_words + P.asc_words);
@@ -913,7 +1075,35 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
         }
         if (P.kind == GJ_NQUEENS) g->delta_may_fallback = seg_moves;
         else g->delta_may_fallback = seg_moves && (!affine || (inverse && !p->symmetric_D));
-        if ((rc = launch_refresh(g.get(), st, false))) return rc;
+        // fused single-kernel step when the island fits in shared memory
+        if (prm->scoring_mode == GJ_SCORING_DELTA) {
+            const int words = P.bm_words + P.desc_words + P.asc_words;
+            // CTA size: an SM holds 1024 threads of this kernel (64 registers each); several
+            // smaller CTAs (islands) per SM overlap one island's serial phases (stage, select,
+            // apply, tabu) with another's scoring loop
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+            int per_sm = std::max(1, std::min(4, (I + sms - 1) / sms));   // 4 x ~50 KB smem per SM
+            int threads = 1024;
+            while (threads > 256 && 1024 / threads < per_sm) threads /= 2;
+            threads = std::min(threads, std::max(32, ((g->K + 31) / 32) * 32));
+            if (const char* e = getenv("GJ_FUSED_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+            g->fused_fold_chunk = 2048;
+            for (int clones = std::min(4, threads / 32); clones >= 0; --clones) {
+                const size_t b = gj_fused_smem_bytes(P.n_vars, g->ds.cnt_stride, g->tabu_words, words, clones,
+                                                     g->fused_fold_chunk);
+                if (b <= 200 * 1024 && (clones > 0 || !g->delta_may_fallback)) {
+                    g->fused = true; g->fused_clones = clones; g->fused_smem = b; g->fused_threads = threads;
+                    break;
+                }
+            }
+        }
+        if (g->fused && getenv("GJ_PHASE_TIMING")) {
+            if ((rc = dev_alloc(g.get(), (size_t)I * 8, &g->phase_clocks))) return rc;
+        }
+        if (g->fused) {
+            // the first step's P0 builds the state (stale == 1)
+        } else if ((rc = launch_refresh(g.get(), st, false))) return rc;
     }
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     g->steps_to_send = (int64_t)std::max<int64_t>(1, prm->migration_frequency);
@@ -978,7 +1168,9 @@ static size_t warp_eval_smem(const GjProblemDev& P, int warps, bool with_clone) 
 
 template <class Kern>
 static gj_status opt_in_smem(Kern kernel, size_t bytes) {
-    if (bytes > 48 * 1024)
+    // static + dynamic shared memory beyond 48 KB needs the opt-in; kernels here carry up to
+    // ~19 KB of static shared memory
+    if (bytes > 24 * 1024)
         GJ_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return GJ_OK;
 }
@@ -1035,11 +1227,56 @@ static gj_status launch_score_delta(gj_islands* g, cudaStream_t st, bool trace) 
     return GJ_OK;
 }
 
+static gj_status launch_fused_step(gj_islands* g, cudaStream_t st, bool trace) {
+    const GjProblemDev& P = g->p->dev;
+    GjFusedArgs F{};
+    F.A = make_select_args(g, trace, false);
+    F.S = g->ds;
+    F.symmetric = g->p->symmetric_D ? 1 : 0;
+    F.n_clone = g->fused_clones;
+    F.fold_chunk = g->fused_fold_chunk;
+    F.scores_out = trace ? g->cand_scores : nullptr;
+    F.moves_out = trace ? g->moves : nullptr;
+    F.worklist = g->worklist;
+    F.phase_clocks = g->phase_clocks;
+    gj_status rc;
+    // registers per thread are capped by the CTA size (64 K registers per SM): 1024 threads -> 64,
+    // 512 -> 128.  The kernel keeps a neighbour's move, its score keys and the RNG in registers.
+#define GJ_LAUNCH_FUSED(KIND, NT)                                                                   \
+    do {                                                                                            \
+        if ((rc = opt_in_smem(k_ls_step_fused<KIND, NT>, g->fused_smem))) return rc;               \
+        k_ls_step_fused<KIND, NT><<<g->I, g->fused_threads, g->fused_smem, st>>>(P, g->groups, F);  \
+    } while (0)
+    const int nt = g->fused_threads;
+    if (P.kind == GJ_NQUEENS) {
+        if (nt > 512) GJ_LAUNCH_FUSED(GJ_NQUEENS, 1024);
+        else if (nt > 256) GJ_LAUNCH_FUSED(GJ_NQUEENS, 512);
+        else if (nt > 128) GJ_LAUNCH_FUSED(GJ_NQUEENS, 256);
+        else GJ_LAUNCH_FUSED(GJ_NQUEENS, 128);
+    } else {
+        if (nt > 512) GJ_LAUNCH_FUSED(GJ_TSP, 1024);
+        else if (nt > 256) GJ_LAUNCH_FUSED(GJ_TSP, 512);
+        else if (nt > 128) GJ_LAUNCH_FUSED(GJ_TSP, 256);
+        else GJ_LAUNCH_FUSED(GJ_TSP, 128);
+    }
+#undef GJ_LAUNCH_FUSED
+    GJ_LAUNCH_CHECK();
+    return GJ_OK;
+}
+
 static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     const GjProblemDev& P = g->p->dev;
     const int64_t total = (int64_t)g->I * g->K;
     const bool delta = g->scoring_mode == GJ_SCORING_DELTA;
     gj_status rc;
+    if (g->fused) {
+        // generation, delta scoring, selection, apply, exact re-score and tabu update in one kernel
+        if ((rc = gj_prof_begin(g, st))) return rc;
+        if ((rc = launch_fused_step(g, st, trace))) return rc;
+        if ((rc = gj_prof_end(g, st))) return rc;
+        g->step += 1;
+        return GJ_OK;
+    }
     if (!delta) {
         k_gen_moves<<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
             P, g->groups, g->mover, g->prm.seed, g->step, g->I, g->K, g->island_base, g->tabu_bits,
@@ -1078,13 +1315,10 @@ gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
 }
 
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
-    k_global_reduce<<<1, 256, 0, st>>>(g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score,
-                                      g->gbest, g->gbest_score);
-    GJ_LAUNCH_CHECK();
-    k_global_adopt<<<g->I, 128, 0, st>>>(g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
-                                        g->n_vars, g->late_size, g->gbest, g->gbest_score, g->best_score,
-                                        g->cur, g->cur_score, g->dirty, g->late, g->late_head, g->late_len,
-                                        g->ds.stale);
+    k_global_top<<<g->I, 256, 0, st>>>(g->I, g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
+                                      g->n_vars, g->late_size, g->best, g->best_score, g->gbest,
+                                      g->gbest_score, g->cur, g->cur_score, g->dirty, g->late, g->late_head,
+                                      g->late_len, g->ds.stale);
     GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
@@ -1106,7 +1340,7 @@ static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         }
         if ((rc = gj_ls_global_top(g, st))) return rc;      // agent_base.rs:185
         // delta mode: islands that received a migrant / adopted the global best rebuild their state
-        if (g->scoring_mode == GJ_SCORING_DELTA && (rc = launch_refresh(g, st, false))) return rc;
+        if (g->scoring_mode == GJ_SCORING_DELTA && !g->fused && (rc = launch_refresh(g, st, false))) return rc;
     }
     return GJ_OK;
 }
@@ -1174,7 +1408,7 @@ extern "C" gj_status gj_islands_best(gj_islands* g, int32_t island, double* vars
         gj_status rc = (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) ? gj_ga_global_top(g, g->p->stream)
                                                                    : gj_ls_global_top(g, g->p->stream);
         if (rc) return rc;
-        if (g->scoring_mode == GJ_SCORING_DELTA && (rc = launch_refresh(g, g->p->stream, false))) return rc;
+        if (g->scoring_mode == GJ_SCORING_DELTA && !g->fused && (rc = launch_refresh(g, g->p->stream, false))) return rc;
         GJ_CUDA_TRY(cudaStreamSynchronize(g->p->stream));
         return fetch_individual(g, g->gbest, g->gbest_score, vars, score);
     }
@@ -1217,7 +1451,7 @@ extern "C" gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buf
     GJ_CUDA_TRY(cudaMemcpyAsync(g->mailbox, d_buffer, sb, cudaMemcpyDeviceToDevice, st));
     gj_status rc;
     if ((rc = gj_ls_migrate_recv(g, st))) return rc;
-    if (g->scoring_mode == GJ_SCORING_DELTA) return launch_refresh(g, st, false);
+    if (g->scoring_mode == GJ_SCORING_DELTA && !g->fused) return launch_refresh(g, st, false);
     return GJ_OK;
 }
 

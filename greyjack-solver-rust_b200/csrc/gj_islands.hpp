@@ -47,6 +47,11 @@ struct gj_islands {
     GjDeltaState ds{};
     int* worklist = nullptr;             // [I*K] neighbours queued for the full evaluator
     int* work_count = nullptr;
+    // fused single-kernel step (gj_islands_fused.cuh)
+    bool fused = false;
+    int fused_threads = 0, fused_clones = 0, fused_fold_chunk = 0;
+    size_t fused_smem = 0;
+    long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid
 
     unsigned long long* counters = nullptr;
 

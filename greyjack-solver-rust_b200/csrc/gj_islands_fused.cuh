@@ -1,0 +1,487 @@
+// gj_islands_fused.cuh -- one TabuSearch / LateAcceptance step of an island as ONE kernel
+// (included by gj_islands.cu).  One CTA owns one island for the whole step:
+//
+//   P0  stage the island in shared memory: current solution, value counts (rebuilt with shared
+//       atomics, one per thread), tabu bitmap; re-score the solution if it was replaced by a
+//       migrant / the global best since the last step
+//   P1  every thread generates + delta-scores K / blockDim neighbours straight from registers
+//       (Mover::do_move -> gj_delta.cuh), keeping its first minimum
+//   P1b neighbours the delta evaluator does not cover: full evaluator, one warp each
+//   P2  CTA arg-min (first minimum, tabu_search_base.rs:166-171), acceptance rule
+//       (tabu_search_base.rs:174 | late_acceptance_base.rs:196-213)
+//   P3  accepted: apply the winning move, write the solution back, full re-score in the
+//       reference's summation order, update_top_individual (agent_base.rs:220-224)
+//   P4  tabu deque update (mover.rs:75-96)
+//
+// Nothing but the winning solution ever leaves the SM: neighbours, their moves and their scores
+// live in registers.  Migration and the global best stay separate (tiny) kernels because they
+// couple islands.
+#pragma once
+
+struct GjFusedArgs {
+    GjSelectArgs A;             // same state as the unfused select
+    GjDeltaState S;
+    int symmetric;
+    int n_clone;                // shared-memory solution clones available to the full evaluator
+    int fold_chunk;             // (unused, kept for layout) 
+    double* scores_out;         // trace only: [I][K][levels]
+    GjMove* moves_out;          // trace only
+    int* worklist;              // [I][K]
+    long long* phase_clocks;    // development aid (GJ_PHASE_TIMING=1): [I][8] clock64 at phase ends
+};
+
+struct GjFusedSmem {
+    int32_t* t;                 // [n_pad] current solution
+    int32_t* cnt;               // [cnt_stride]
+    uint32_t* bits;             // [tabu_words_pad] tabu membership snapshot
+    uint32_t* bm;               // [n_clone][words] bitmaps of the full evaluator
+    int32_t* clone;             // [n_clone][n_pad]
+    double* edge;               // [n + 1] TSP: edge[i] = D[t[i-1]][t[i]], depot at both ends
+};
+
+__host__ __device__ inline size_t gj_fused_smem_bytes(int n_vars, int cnt_stride, int tabu_words,
+                                                      int words, int n_clone, int fold_chunk) {
+    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
+    size_t b = n_pad * 4 + (size_t)cnt_stride * 4 + (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
+    b += (size_t)n_clone * (size_t)words * 4 + (size_t)n_clone * n_pad * 4;
+    b = (b + 15) & ~(size_t)15;
+    b += ((size_t)n_vars + 1) * 8;
+    return b;
+}
+
+__device__ __forceinline__ GjFusedSmem gj_fused_carve(unsigned char* smem, int n_vars, int cnt_stride,
+                                                      int tabu_words, int words, int n_clone) {
+    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
+    GjFusedSmem s;
+    size_t o = 0;
+    s.t = (int32_t*)(smem + o); o += n_pad * 4;
+    s.cnt = (int32_t*)(smem + o); o += (size_t)cnt_stride * 4;
+    s.bits = (uint32_t*)(smem + o); o += (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
+    s.bm = (uint32_t*)(smem + o); o += (size_t)n_clone * (size_t)words * 4;
+    s.clone = (int32_t*)(smem + o); o += (size_t)n_clone * n_pad * 4;
+    o = (o + 15) & ~(size_t)15;
+    s.edge = (double*)(smem + o);
+    return s;
+}
+
+// CTA-wide sums (every thread gets the total).  `scratch` holds 32 entries.
+__device__ __forceinline__ int gj_block_sum(int x, int* scratch) {
+    x = gj_warp_sum(x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < nw; ++w) tot += scratch[w];
+    return tot;
+}
+__device__ __forceinline__ double gj_block_sum(double x, double* scratch) {
+    x = gj_warp_sum(x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < nw; ++w) tot += scratch[w];
+    return tot;
+}
+
+// Value counts of the staged solution (shared atomics), all threads.
+template <int KIND>
+__device__ __forceinline__ void gj_fused_counts(const GjProblemDev& P, const GjFusedSmem& s, int cnt_stride) {
+    for (int i = threadIdx.x; i < cnt_stride; i += blockDim.x) s.cnt[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.n_vars; i += blockDim.x) {
+        const int v = s.t[i];
+        atomicAdd(&s.cnt[v - P.val_lo], 1);
+        if constexpr (KIND == GJ_NQUEENS) {
+            const int col = P.column_id[i];
+            atomicAdd(&s.cnt[32 * P.bm_words + (col + v - P.desc_lo)], 1);
+            atomicAdd(&s.cnt[32 * (P.bm_words + P.desc_words) + (col - v - P.asc_lo)], 1);
+        }
+    }
+    __syncthreads();
+}
+
+// TSP: lengths of the staged tour's n + 1 edges (depot -> s0, s0 -> s1, .., s_last -> depot),
+// one gather per thread.  They serve the full evaluation below and, in P1, every "removed edge"
+// of a neighbour (gj_delta.cuh) -- half of the matrix gathers of a delta evaluation.
+__device__ __forceinline__ void gj_fused_edges(const GjProblemDev& P, const GjFusedSmem& s) {
+    const int n = P.n_vars;
+    const size_t L = (size_t)P.n_locations;
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+        const int a = (i == 0) ? 0 : s.t[i - 1];
+        const int b = (i == n) ? 0 : s.t[i];
+        s.edge[i] = __ldg(&P.D[(size_t)a * L + (size_t)b]);
+    }
+    __syncthreads();
+}
+
+// FULL evaluation of the staged solution by the whole CTA -> unweighted terms raw[0..1]
+// (counts and, for TSP, edges must be current).  TSP: dup count from the counts; tour length
+// either as per-thread partial sums (tree) or, with exact sums, folded by one thread strictly in
+// the reference's order (tsp ISC :76-80): ((0 + D[0][s0]) + D[s_last][0]) + fold_{i>=1} D[s_{i-1}][s_i].
+template <int KIND>
+__device__ __forceinline__ void gj_fused_full_eval(const GjProblemDev& P, const GjFusedSmem& s,
+                                                   int cnt_stride, int* iscratch,
+                                                   double* dscratch, double* raw /*shared [2]*/) {
+    int u = 0;
+    for (int k = threadIdx.x; k < cnt_stride; k += blockDim.x) u += (s.cnt[k] > 0) ? 1 : 0;
+    const int uniq = gj_block_sum(u, iscratch);
+    if constexpr (KIND == GJ_NQUEENS) {
+        // (N - |rows|) + (N - |desc|) + (N - |asc|): integers, exact whatever the grouping
+        if (threadIdx.x == 0) { raw[0] = (double)(3 * P.n_vars - uniq); raw[1] = 0.0; }
+        __syncthreads();
+        return;
+    } else {
+        const int n = P.n_vars;
+        if (!P.exact_sums) {
+            double acc = 0.0;
+            for (int i = threadIdx.x; i <= n; i += blockDim.x) acc += s.edge[i];
+            const double dist = gj_block_sum(acc, dscratch);
+            if (threadIdx.x == 0) { raw[0] = (double)(n - uniq); raw[1] = dist; }
+            __syncthreads();
+            return;
+        }
+        if (threadIdx.x == 0) {
+            double fold = 0.0;
+#pragma unroll 8
+            for (int i = 1; i < n; ++i) fold = fold + s.edge[i];
+            double sample_distance = 0.0;
+            sample_distance += s.edge[0];                 // D[0][s0]
+            sample_distance += s.edge[n];                 // D[s_last][0]
+            sample_distance += fold;
+            raw[0] = (double)(n - uniq); raw[1] = sample_distance;
+        }
+        __syncthreads();
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void gj_fused_combine(const GjProblemDev& P, const double* raw, int d_uniq,
+                                                 double d_dist, GjScore& s) {
+    s.v[0] = 0.0; s.v[1] = 0.0; s.v[2] = 0.0;
+    if constexpr (KIND == GJ_NQUEENS) gj_combine_nqueens(P, raw[0] - (double)d_uniq, s.v);
+    else gj_combine_tsp(P, true, raw[0] - (double)d_uniq, raw[1] + d_dist, s.v);
+}
+
+// Ordering key of a score level under ScoreTrait::round (math_utils.rs:10-13):
+// round(v) = floor(v) + floor((v - floor(v)) * 10^p) / 10^p is strictly increasing in the integer
+// pair (floor(v), floor(frac * 10^p)), so comparing floor(v) * 10^p + floor(frac * 10^p) (exact in
+// f64 for |v| < 2^53 / 10^p) orders neighbours exactly like their rounded scores -- without the
+// two divisions per neighbour.  Only the winner is actually rounded.
+__device__ __forceinline__ double gj_round_key(double v, double mult) {
+    if (mult == 0.0) return v;
+    const double fl = floor(v);
+    return fl * mult + floor((v - fl) * mult);
+}
+
+template <int LV>
+struct GjBest {
+    double key[LV];
+    double val[LV];                 // unrounded score of the same neighbour
+    int idx;
+};
+
+// -1 / 0 / +1: lexicographic order of two key vectors
+template <int LV>
+__device__ __forceinline__ int gj_key_cmp(const double* a, const double* b) {
+    int c = 0;
+#pragma unroll
+    for (int l = LV - 1; l >= 0; --l) {
+        if (a[l] < b[l]) c = -1;
+        else if (a[l] > b[l]) c = 1;
+    }
+    return c;
+}
+
+// keeps the first minimum: replace on strictly smaller key, or equal key and smaller index
+template <int LV>
+__device__ __forceinline__ void gj_best_merge(GjBest<LV>& mine, const GjBest<LV>& o) {
+    const int c = gj_key_cmp<LV>(o.key, mine.key);
+    const bool take = (o.idx >= 0) && (mine.idx < 0 || c < 0 || (c == 0 && o.idx < mine.idx));
+    if (take) {
+#pragma unroll
+        for (int l = 0; l < LV; ++l) { mine.key[l] = o.key[l]; mine.val[l] = o.val[l]; }
+        mine.idx = o.idx;
+    }
+}
+
+template <int LV>
+__device__ __forceinline__ GjBest<LV> gj_best_shfl_xor(const GjBest<LV>& b, int o) {
+    GjBest<LV> r;
+    r.idx = __shfl_xor_sync(GJ_FULL_MASK, b.idx, o);
+#pragma unroll
+    for (int l = 0; l < LV; ++l) {
+        r.key[l] = __shfl_xor_sync(GJ_FULL_MASK, b.key[l], o);
+        r.val[l] = __shfl_xor_sync(GJ_FULL_MASK, b.val[l], o);
+    }
+    return r;
+}
+
+template <int KIND, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 512) ? 1024 / NT : 1)
+k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
+    constexpr int LV = (KIND == GJ_NQUEENS) ? 1 : 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ GjBest<LV> sh_bestw[32];
+    __shared__ int sh_sel0[NT], sh_sel1[NT], sh_selinfo[NT];   // ids the last chunk's moves selected
+    __shared__ int sh_iscratch[32];
+    __shared__ double sh_dscratch[32];
+    __shared__ double sh_raw[2];
+    __shared__ int sh_accept, sh_best, sh_nwork;
+    __shared__ int sh_scan[NT];
+    __shared__ GjMove sh_mv[4];
+
+    const GjSelectArgs& A = F.A;
+    const int island = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int K = A.K, levels = A.levels, n = P.n_vars;
+    const int words = P.bm_words + P.desc_words + P.asc_words;
+    const int cnt_stride = 32 * words;
+    const GjFusedSmem s = gj_fused_carve(smem_raw, n, cnt_stride, A.tabu_words_per_island, words, F.n_clone);
+    int32_t* cur_row = A.cur + (size_t)island * A.stride;
+    double* raw_g = F.S.raw + (size_t)island * GJ_MAX_LEVELS;
+
+    auto stamp = [&](int k) {
+        if (F.phase_clocks && tid == 0) F.phase_clocks[(size_t)island * 8 + k] = clock64();
+    };
+    stamp(0);
+    // ---- P0: stage ---------------------------------------------------------------------------
+    for (int i = tid; i < n; i += blockDim.x) s.t[i] = cur_row[i];
+    if (A.tabu_bits) {
+        const uint32_t* bits_g = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
+        for (int w = tid; w < A.tabu_words_per_island; w += blockDim.x) s.bits[w] = bits_g[w];
+    }
+    if (tid == 0) sh_nwork = 0;
+    __syncthreads();
+    gj_fused_counts<KIND>(P, s, cnt_stride);
+    if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
+    if (F.S.stale[island]) {                       // replaced by a migrant / the global best
+        gj_fused_full_eval<KIND>(P, s, cnt_stride, sh_iscratch, sh_dscratch, sh_raw);
+        if (tid == 0) { raw_g[0] = sh_raw[0]; raw_g[1] = sh_raw[1]; F.S.stale[island] = 0; }
+    } else if (tid == 0) {
+        sh_raw[0] = raw_g[0]; sh_raw[1] = raw_g[1];
+    }
+    __syncthreads();
+    const double raw0 = sh_raw[0], raw1 = sh_raw[1];
+    const double raw[2] = {raw0, raw1};
+    const uint32_t* bits = A.tabu_bits ? s.bits : nullptr;
+    auto make_move = [&](int c) -> GjMove {
+        return gj_generate_move(P, G, A.M, A.seed, (uint32_t)(A.island_base + island), A.step,
+                                (uint32_t)c, bits, A.tabu_word_off);
+    };
+
+    stamp(1);
+    // ---- P1: generate + delta-score ------------------------------------------------------------
+    GjBest<LV> mine;
+    mine.idx = -1;
+#pragma unroll
+    for (int l = 0; l < LV; ++l) { mine.key[l] = 0.0; mine.val[l] = 0.0; }
+    int* worklist = F.worklist + (size_t)island * K;
+    const int n_chunks = (K + blockDim.x - 1) / blockDim.x;
+    sh_selinfo[tid] = 0;
+    auto offer = [&](const GjScore& sc, int c) {
+        GjBest<LV> o;
+        o.idx = c;
+#pragma unroll
+        for (int l = 0; l < LV; ++l) {
+            o.val[l] = sc.v[l];
+            o.key[l] = gj_round_key(sc.v[l], P.round_mult[l]);
+        }
+        if (F.scores_out) {
+            GjScore r = sc;
+            gj_score_round(r, P);                  // agent_base.rs:311-314
+            for (int l = 0; l < levels; ++l) F.scores_out[((size_t)island * K + c) * levels + l] = r.v[l];
+        }
+        gj_best_merge<LV>(mine, o);
+    };
+    for (int c = tid; c < K; c += blockDim.x) {
+        const GjMove m = make_move(c);
+        if (F.moves_out) F.moves_out[(size_t)island * K + c] = m;
+        if (c >= (n_chunks - 1) * (int)blockDim.x && m.kind != GJ_MOVE_NULL) {
+            // remembered for the tabu update (P4): at most two ids, else regenerated there
+            int sel[GJ_MOVE_MAXK];
+            const int cnt = gj_move_selected(m, sel);
+            sh_sel0[tid] = sel[0]; sh_sel1[tid] = sel[1];
+            sh_selinfo[tid] = (cnt + 1) | ((int)m.group << 8);
+        }
+        int d_uniq = 0; double d_dist = 0.0;
+        bool ok;
+        if constexpr (KIND == GJ_NQUEENS) {
+            ok = gj_nqueens_move_delta(P, G, m, A.noop != 0, s.t, s.cnt, d_uniq);
+        } else {
+            GjTspBase B{s.t, n, P.D, (size_t)P.n_locations, s.edge};
+            ok = gj_tsp_move_delta(P, G, m, A.noop != 0, F.symmetric != 0, B, s.cnt, d_uniq, d_dist);
+        }
+        if (!ok) { worklist[atomicAdd(&sh_nwork, 1)] = c; continue; }
+        GjScore sc;
+        gj_fused_combine<KIND>(P, raw, d_uniq, d_dist, sc);
+        offer(sc, c);
+    }
+    __syncthreads();
+
+    // ---- P1b: full evaluator for the queued neighbours (warp per neighbour, smem clone) ---------
+    const int n_work = sh_nwork;
+    if (n_work > 0 && warp < F.n_clone) {
+        const size_t n_pad = ((size_t)n + 3) & ~(size_t)3;
+        uint32_t* bm = s.bm + (size_t)warp * words;
+        int32_t* cand = s.clone + (size_t)warp * n_pad;
+        for (int w = warp; w < n_work; w += F.n_clone) {
+            const int c = worklist[w];
+            if (lane == 0) sh_mv[warp] = make_move(c);
+            for (int i = lane; i < n; i += 32) cand[i] = s.t[i];
+            __syncwarp();
+            const GjMove m = sh_mv[warp];
+            gj_apply_move(P, m, G, true, A.noop != 0, lane, 32,
+                          [&](int id) { return s.t[id]; }, [&](int id, int v) { cand[id] = v; });
+            __syncwarp();
+            GjSrcI32 src{cand};
+            GjScore sc;
+            sc.v[0] = sc.v[1] = sc.v[2] = 0.0;
+            if constexpr (KIND == GJ_NQUEENS) {
+                gj_combine_nqueens(P, gj_nqueens_eval_warp(P, src, bm, lane), sc.v);
+            } else {
+                double dup, dist;
+                gj_tsp_eval_warp(P, src, bm, lane, dup, dist);
+                gj_combine_tsp(P, true, dup, dist, sc.v);
+            }
+            if (lane == 0) offer(sc, c);
+            __syncwarp();
+        }
+    }
+
+    stamp(2);
+    // ---- P2: first minimum + acceptance ------------------------------------------------------------
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gj_best_merge<LV>(mine, gj_best_shfl_xor<LV>(mine, o));
+    if (lane == 0) sh_bestw[warp] = mine;
+    __syncthreads();
+    if (warp == 0) {
+        GjBest<LV> b = sh_bestw[lane < nwarps ? lane : 0];
+        if (lane >= nwarps) b.idx = -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gj_best_merge<LV>(b, gj_best_shfl_xor<LV>(b, o));
+        if (lane == 0) sh_bestw[0] = b;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int bi = sh_bestw[0].idx;
+        GjScore b;
+        b.v[0] = b.v[1] = b.v[2] = 0.0;
+#pragma unroll
+        for (int l = 0; l < LV; ++l) b.v[l] = sh_bestw[0].val[l];
+        gj_score_round(b, P);                       // agent_base.rs:311-314 (the winner only; see gj_round_key)
+        GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
+        bool accept;
+        if (A.agent == GJ_AGENT_TABU_SEARCH) {
+            accept = gj_score_le(b, cur, levels);                       // tabu_search_base.rs:174
+        } else {
+            double* late = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;   // late_acceptance_base.rs:196-213
+            int head = A.late_head[island], len = A.late_len[island];
+            GjScore late_native = cur;
+            if (len > 0) late_native = gj_load_score(late + (size_t)((head + len - 1) % A.late_size) * GJ_MAX_LEVELS, levels);
+            accept = gj_score_le(b, late_native, levels) || gj_score_le(b, cur, levels);
+            if (accept) {
+                head = (head + A.late_size - 1) % A.late_size;
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) late[(size_t)head * GJ_MAX_LEVELS + l] = b.v[l];
+                A.late_head[island] = head; A.late_len[island] = min(len + 1, A.late_size);
+            }
+        }
+        if (accept)
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = b.v[l];
+        sh_accept = accept ? 1 : 0;
+        sh_best = bi;
+        if (accept) sh_mv[0] = make_move(bi);
+        if (A.selected_out) { A.selected_out[island] = bi; A.accepted_out[island] = accept ? 1 : 0; }
+        atomicAdd(&A.counters[0], (unsigned long long)K);
+        if (island == 0) atomicAdd(&A.counters[1], 1ull);
+        if (accept) atomicAdd(&A.counters[2], 1ull);
+    }
+    __syncthreads();
+
+    stamp(3);
+    // ---- P3: apply, write back, exact re-score, update_top_individual ----------------------------------
+    if (sh_accept) {
+        const GjMove m = sh_mv[0];
+        // the global row still holds the base: read it, write the staged copy
+        gj_apply_move(P, m, G, true, A.noop != 0, tid, blockDim.x,
+                      [&](int id) { return cur_row[id]; }, [&](int id, int v) { s.t[id] = v; });
+        __syncthreads();
+        for (int i = tid; i < n; i += blockDim.x) cur_row[i] = s.t[i];
+        gj_fused_counts<KIND>(P, s, cnt_stride);
+        if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
+        gj_fused_full_eval<KIND>(P, s, cnt_stride, sh_iscratch, sh_dscratch, sh_raw);
+        if (tid == 0) {
+            raw_g[0] = sh_raw[0]; raw_g[1] = sh_raw[1];
+            GjScore sc;
+            const double r[2] = {sh_raw[0], sh_raw[1]};
+            gj_fused_combine<KIND>(P, r, 0, 0.0, sc);
+            gj_score_round(sc, P);
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = (l < levels) ? sc.v[l] : 0.0;
+            A.dirty[island] = 1;
+        }
+        __syncthreads();
+    }
+    gj_update_top(island, levels, A.stride, n, A.cur, A.cur_score, A.best, A.best_score, A.dirty);
+
+    stamp(4);
+    // ---- P4: tabu deque update (see k_select) --------------------------------------------------------------
+    if (A.tabu_bits) {
+        uint32_t* bits_rw = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
+        const int32_t* ring_old_island = A.tabu_ring_old + (size_t)island * A.tabu_ring_per_island;
+        int32_t* ring_new_island = A.tabu_ring_new + (size_t)island * A.tabu_ring_per_island;
+        for (int g = 0; g < A.n_groups; ++g) {
+            const int T = A.tabu_size[g];
+            const int32_t* ring_old = ring_old_island + A.tabu_ring_off[g];
+            int32_t* ring_new = ring_new_island + A.tabu_ring_off[g];
+            const int glen = G.offsets[g + 1] - G.offsets[g];
+            const int fill_old = A.tabu_fill[island * A.n_groups + g];
+            int collected = 0;
+            for (int chunk = n_chunks - 1; chunk >= 0 && collected < T; --chunk) {
+                const int j = chunk * blockDim.x + tid;
+                int sel[GJ_MOVE_MAXK]; int cnt = 0;
+                if (j < K) {
+                    const int info = sh_selinfo[tid];
+                    if (chunk == n_chunks - 1 && (info & 0xff) <= 3) {
+                        // remembered from P1 (cnt + 1 in the low byte; 0 = null move)
+                        if ((info & 0xff) != 0 && (info >> 8) == g) {
+                            cnt = (info & 0xff) - 1;
+                            sel[0] = sh_sel0[tid]; sel[1] = sh_sel1[tid];
+                        }
+                    } else {
+                        const GjMove m = make_move(j);
+                        if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
+                    }
+                }
+                sh_scan[tid] = cnt;
+                __syncthreads();
+                for (int o = 1; o < blockDim.x; o <<= 1) {
+                    const int x = (tid + o < blockDim.x) ? sh_scan[tid + o] : 0;
+                    __syncthreads();
+                    sh_scan[tid] += x;
+                    __syncthreads();
+                }
+                const int total = sh_scan[0];
+                const int after = sh_scan[tid] - cnt;
+#pragma unroll
+                for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                    if (i < cnt) {
+                        const int rank = collected + after + (cnt - 1 - i);
+                        if (rank < T) ring_new[rank] = sel[i];
+                    }
+                }
+                __syncthreads();
+                collected += total;
+            }
+            for (int r = collected + tid; r < T; r += blockDim.x) {
+                const int rho = r - collected;
+                if (rho < fill_old) ring_new[r] = ring_old[rho];
+            }
+            const int fill = min(T, fill_old + collected);
+            if (tid == 0) A.tabu_fill[island * A.n_groups + g] = fill;
+            gj_tabu_table_rebuild(bits_rw + A.tabu_word_off[g], glen, ring_new, fill, sh_scan);
+        }
+    }
+    stamp(5);
+}

@@ -199,21 +199,82 @@ __device__ __forceinline__ int gj_binomial_small(GjPhilox& rng, int n, double p,
     return k;
 }
 
-// k distinct positions in [0, right_end), avoiding the island's tabu snapshot
-// (Mover::select_non_tabu_ids :75-96; with tabu_entity_rate == 0 this is
-// math_utils::choice without replacement, :43-45).
+// ---- tabu table ---------------------------------------------------------------------------------
+// Per island and semantic group: W + 1 words of membership bits (bit set = position is in the
+// tabu deque), then W + 1 ints of an exclusive prefix count of FREE positions per word
+// (prefix[W] = all free positions), W = ceil(group_len / 32).  The prefix turns "draw until the
+// id is not tabu" (Mover::select_non_tabu_ids :75-96) into one draw: the r-th free position,
+// r ~ U[0, free) -- the same distribution without a data-dependent retry loop.
+struct GjTabuView {
+    const uint32_t* bits;       // nullptr: no tabu (tabu_entity_rate == 0)
+    const int32_t* prefix;
+    int W;
+};
+
+__device__ __forceinline__ GjTabuView gj_tabu_view(const uint32_t* table, int glen) {
+    GjTabuView v;
+    v.W = (glen + 31) >> 5;
+    v.bits = table;
+    v.prefix = table ? (const int32_t*)(table + v.W + 1) : nullptr;
+    return v;
+}
+
+// position of the r-th (0-based) set bit of v; r < popc(v)
+__device__ __forceinline__ int gj_select_bit(uint32_t v, int r) {
+    int pos = 0, t;
+    t = __popc(v & 0xFFFFu); if (r >= t) { r -= t; pos += 16; v >>= 16; }
+    t = __popc(v & 0xFFu);   if (r >= t) { r -= t; pos += 8;  v >>= 8; }
+    t = __popc(v & 0xFu);    if (r >= t) { r -= t; pos += 4;  v >>= 4; }
+    t = __popc(v & 0x3u);    if (r >= t) { r -= t; pos += 2;  v >>= 2; }
+    t = (int)(v & 1u);       if (r >= t) { pos += 1; }
+    return pos;
+}
+
+__device__ __forceinline__ int gj_tabu_free_below(const GjTabuView& tv, int right_end) {
+    const int w = right_end >> 5, rem = right_end & 31;
+    int f = tv.prefix[w];
+    if (rem) f += __popc(~tv.bits[w] & ((1u << rem) - 1u));
+    return f;
+}
+
+__device__ __forceinline__ int gj_tabu_free_select(const GjTabuView& tv, int r) {
+    int lo = 0, hi = tv.W - 1;
+    while (lo < hi) {                       // largest word whose prefix <= r
+        const int mid = (lo + hi + 1) >> 1;
+        if (tv.prefix[mid] <= r) lo = mid; else hi = mid - 1;
+    }
+    return 32 * lo + gj_select_bit(~tv.bits[lo], r - tv.prefix[lo]);
+}
+
+// k distinct positions in [0, right_end) outside the island's tabu snapshot
+// (Mover::select_non_tabu_ids :75-96; with tabu_entity_rate == 0 this is math_utils::choice
+// without replacement, :43-45): the i-th pick draws a rank among the free positions not yet
+// taken.  Loops are unrolled over the fixed maximum so that everything stays in registers.
 __device__ __forceinline__ void gj_pick_positions(GjPhilox& rng, int right_end, int k,
-                                                  const uint32_t* tabu_bits, int32_t* out) {
-    for (int i = 0; i < k; ++i) {
-        int pos = 0;
-        for (int tries = 0; tries < 64; ++tries) {
-            pos = (int)gj_rng_below(rng, (uint32_t)right_end);
-            bool clash = false;
-            for (int j = 0; j < i; ++j) clash |= (out[j] == pos);
-            if (!clash && tabu_bits && ((tabu_bits[pos >> 5] >> (pos & 31)) & 1u) && tries < 48) clash = true;
-            if (!clash) break;
+                                                  const GjTabuView& tv, int32_t* out) {
+    int F = right_end;
+    bool use_tabu = false;
+    if (tv.bits) {
+        const int f = gj_tabu_free_below(tv, right_end);
+        if (f >= k) { F = f; use_tabu = true; }     // a fully tabu group falls back to plain choice
+    }
+    int sorted[GJ_MOVE_MAXK];
+#pragma unroll
+    for (int i = 0; i < GJ_MOVE_MAXK; ++i) sorted[i] = 0;
+#pragma unroll
+    for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+        if (i < k) {
+            int r = (int)gj_rng_below(rng, (uint32_t)(F - i));
+#pragma unroll
+            for (int j = 0; j < GJ_MOVE_MAXK; ++j)
+                if (j < i && r >= sorted[j]) r += 1;          // skip the ranks already taken (ascending)
+            int ins = r;
+#pragma unroll
+            for (int j = 0; j < GJ_MOVE_MAXK; ++j)
+                if (j < i && sorted[j] > ins) { const int t = sorted[j]; sorted[j] = ins; ins = t; }
+            sorted[i] = ins;
+            out[i] = use_tabu ? gj_tabu_free_select(tv, r) : r;
         }
-        out[i] = pos;
     }
 }
 
@@ -227,15 +288,16 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
     gj_rng_init(rng, seed, island, (uint32_t)step, (uint32_t)(step >> 32), cand);
     GjMove m;
     m.pad = 0;
+#pragma unroll
     for (int i = 0; i < GJ_MOVE_MAXK; ++i) { m.a[i] = 0; m.v[i] = 0; }
-    const double u = gj_rng_f64(rng);
+    const double u = (double)gj_rng_u32(rng) * (1.0 / 4294967296.0);
     int kind = 5;
     for (int i = 0; i < 6; ++i) if (u <= M.thresholds[i]) { kind = i; break; }
     const int grp = (int)gj_rng_below(rng, (uint32_t)G.n_groups);
     const int glen = G.offsets[grp + 1] - G.offsets[grp];
     const int32_t* g = G.ids + G.offsets[grp];
-    const uint32_t* tabu = (M.tabu_entity_rate != 0.0 && tabu_island_bits)
-                               ? tabu_island_bits + tabu_word_off[grp] : nullptr;
+    const GjTabuView tabu = gj_tabu_view((M.tabu_entity_rate != 0.0 && tabu_island_bits)
+                                             ? tabu_island_bits + tabu_word_off[grp] : nullptr, glen);
     m.kind = (uint8_t)kind;
     m.group = (uint8_t)grp;
     m.k = 0;
@@ -247,12 +309,15 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
             if (k < 1) k = 1;
             if (glen < k) { m.kind = GJ_MOVE_NULL; return m; }
             gj_pick_positions(rng, glen, k, tabu, m.a);
-            for (int i = 0; i < k; ++i) {
-                // get_column_random_value: Uniform::new(lb, ub), then fix_deltas (clamp + rint)
-                const int var = g[m.a[i]];
-                const double lb = P.lb[var], ub = P.ub[var];
-                const double x = lb + gj_rng_f64(rng) * (ub - lb);
-                m.v[i] = gj_decode(P, var, x);
+#pragma unroll
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                if (i < k) {
+                    // get_column_random_value: Uniform::new(lb, ub), then fix_deltas (clamp + rint)
+                    const int var = g[m.a[i]];
+                    const double lb = P.lb[var], ub = P.ub[var];
+                    const double x = lb + gj_rng_f64(rng) * (ub - lb);
+                    m.v[i] = gj_decode(P, var, x);
+                }
             }
         } else if (kind == 1) {
             if (k < 2) k = 2;
@@ -270,10 +335,19 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
         const int count = 3 + (int)gj_rng_below(rng, 4);
         if (glen < count - 1 || glen - count <= 0) { m.kind = GJ_MOVE_NULL; return m; }
         gj_pick_positions(rng, glen - count, 1, tabu, m.a);
-        for (int i = 0; i < count; ++i) m.v[i] = i;
-        for (int i = count - 1; i > 0; --i) {          // shuffle
-            const int r = (int)gj_rng_below(rng, (uint32_t)(i + 1));
-            const int t = m.v[i]; m.v[i] = m.v[r]; m.v[r] = t;
+#pragma unroll
+        for (int i = 0; i < GJ_MOVE_MAXK; ++i) m.v[i] = (i < count) ? i : 0;
+#pragma unroll
+        for (int i = GJ_MOVE_MAXK - 1; i > 0; --i) {   // Fisher-Yates over v[0..count)
+            if (i < count) {
+                const int r = (int)gj_rng_below(rng, (uint32_t)(i + 1));
+                const int vi = m.v[i];
+                int vr = vi;
+#pragma unroll
+                for (int j = 0; j < GJ_MOVE_MAXK; ++j)
+                    if (j == r) { vr = m.v[j]; m.v[j] = vi; }
+                m.v[i] = vr;
+            }
         }
         m.k = (uint8_t)count;
     } else {

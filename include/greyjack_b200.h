@@ -72,7 +72,10 @@ enum {
           relative before ScoreTrait::round (one 10^-precision quantum after).  Moves the
           delta evaluator does not cover (listed in DESIGN.md) are re-scored by the FULL
           kernel inside the same step.                                                      */
-enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1 };
+enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1,
+       GJ_SCORING_DELTA_UNFUSED = 2   /* DELTA as separate kernels (generate+score | select |
+                                         refresh); what DELTA falls back to when an island does
+                                         not fit in shared memory.  Exposed for tests / ablation. */ };
 
 /* Agents = AgentBuildersVariants (agents/agent_builders_variants.rs:9-18). */
 enum { GJ_AGENT_TABU_SEARCH = 0, GJ_AGENT_LATE_ACCEPTANCE = 1, GJ_AGENT_GENETIC_ALGORITHM = 2 };

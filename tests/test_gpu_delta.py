@@ -16,6 +16,9 @@ from test_gpu_islands import ALL, MIX, _final_state, _oracle_move, _same_score
 pytestmark = pytest.mark.gpu
 
 QUANTUM = 1.0e-3 * (1 + 1e-9)
+# "delta": the fused single-kernel step (gj_islands_fused.cuh); "delta_unfused": the same
+# arithmetic as separate kernels (what DELTA uses when an island does not fit in shared memory)
+SCORINGS = ["delta", "delta_unfused"]
 
 
 def _check_delta_scores(got, want_unrounded, spec, oracle):
@@ -45,16 +48,17 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("scoring", SCORINGS)
 @pytest.mark.parametrize("noop", [True, False], ids=["refquirk", "plainform"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
-def test_delta_step_replay(case, noop, oracle):
+def test_delta_step_replay(case, noop, scoring, oracle):
     _, mk, probas, tabu, mult = case
     spec = mk()
     op = oracle.OracleProblem(spec)
     gp = Problem(spec)
     K = 160
     isl = TabuSearch(K, tabu, True, mult, probas, 10, reference_noop_moves=noop,
-                     scoring="delta").build_agent(gp, n_islands=2, seed=4321)
+                     scoring=scoring).build_agent(gp, n_islands=2, seed=4321)
     for island in (0, 1):
         for _ in range(5):
             base, cur_score = isl.current(island)
@@ -82,15 +86,16 @@ def test_delta_step_replay(case, noop, oracle):
     isl.close(); gp.close()
 
 
+@pytest.mark.parametrize("scoring", SCORINGS)
 @pytest.mark.parametrize("mk", [lambda: inst.tsp(150, seed=2), lambda: inst.nqueens(48)], ids=["tsp", "nqueens"])
-def test_delta_and_full_islands_see_the_same_neighbourhood(mk, oracle):
+def test_delta_and_full_islands_see_the_same_neighbourhood(mk, scoring, oracle):
     """Same seed -> same moves (the generator is a pure function of seed/island/step/candidate);
     integer levels identical, float level within one quantum."""
     spec = mk()
     gp = Problem(spec)
     probas = ALL
     a = TabuSearch(256, 0.2, True, 1.0, probas, 10, scoring="full").build_agent(gp, n_islands=2, seed=77)
-    b = TabuSearch(256, 0.2, True, 1.0, probas, 10, scoring="delta").build_agent(gp, n_islands=2, seed=77)
+    b = TabuSearch(256, 0.2, True, 1.0, probas, 10, scoring=scoring).build_agent(gp, n_islands=2, seed=77)
     ta, tb = a.trace_step(1), b.trace_step(1)
     assert np.array_equal(ta["desc"], tb["desc"])
     L = spec.levels
@@ -102,19 +107,20 @@ def test_delta_and_full_islands_see_the_same_neighbourhood(mk, oracle):
 
 
 @pytest.mark.parametrize("mk", [lambda: inst.tsp(150, seed=2), lambda: inst.nqueens(48)], ids=["tsp", "nqueens"])
+@pytest.mark.parametrize("scoring", SCORINGS)
 @pytest.mark.parametrize("agent", ["ts", "la"])
-def test_delta_run_is_consistent(mk, agent, oracle):
+def test_delta_run_is_consistent(mk, agent, scoring, oracle):
     spec = mk()
     op = oracle.OracleProblem(spec)
     gp = Problem(spec)
     probas = [0.0, 1.0, 0.0, 0.0, 0.0, 0.0] if spec.kind == inst.NQUEENS else [0.1, 0.3, 0.1, 0.1, 0.2, 0.2]
     if agent == "ts":
         isl = TabuSearch(128, 0.2, True, None, probas, 5, reference_noop_moves=False,
-                         scoring="delta").build_agent(gp, n_islands=4, seed=5)
+                         scoring=scoring).build_agent(gp, n_islands=4, seed=5)
         per_step = 128
     else:
         isl = LateAcceptance(8, 0.2, None, probas, 5, reference_noop_moves=False,
-                             scoring="delta").build_agent(gp, n_islands=4, seed=5)
+                             scoring=scoring).build_agent(gp, n_islands=4, seed=5)
         per_step = 1
     _, s0 = isl.best(0)
     prev = None
@@ -136,12 +142,13 @@ def test_delta_run_is_consistent(mk, agent, oracle):
     isl.close(); gp.close()
 
 
-def test_delta_migration_keeps_state_in_sync(oracle):
+@pytest.mark.parametrize("scoring", SCORINGS)
+def test_delta_migration_keeps_state_in_sync(scoring, oracle):
     spec = inst.tsp(100, seed=4)
     op = oracle.OracleProblem(spec)
     gp = Problem(spec)
     init = np.stack([spec.initial] + [np.arange(1, 100, dtype=np.float64)] * 3)
-    isl = TabuSearch(64, 0.0, True, None, [0, 0.5, 0, 0, 0, 0.5], 1, scoring="delta").build_agent(
+    isl = TabuSearch(64, 0.0, True, None, [0, 0.5, 0, 0, 0, 0.5], 1, scoring=scoring).build_agent(
         gp, n_islands=4, seed=3, initial=init)
     for _ in range(8):
         isl.step(1)
@@ -155,12 +162,13 @@ def test_delta_migration_keeps_state_in_sync(oracle):
     isl.close(); gp.close()
 
 
-def test_delta_change_moves_track_duplicates(oracle):
+@pytest.mark.parametrize("scoring", SCORINGS)
+def test_delta_change_moves_track_duplicates(scoring, oracle):
     """change_move introduces / removes duplicate stops: the hard level must follow exactly."""
     spec = inst.tsp(60, seed=11)
     op = oracle.OracleProblem(spec)
     gp = Problem(spec)
-    isl = TabuSearch(512, 0.0, True, 4.0, [1.0, 0, 0, 0, 0, 0], 10, scoring="delta").build_agent(gp, seed=9)
+    isl = TabuSearch(512, 0.0, True, 4.0, [1.0, 0, 0, 0, 0, 0], 10, scoring=scoring).build_agent(gp, seed=9)
     seen_hard = set()
     for _ in range(4):
         base, _ = isl.current(0)
