@@ -3,7 +3,8 @@
 The product is the shared library (greyjack-solver-rust_b200/csrc, include/greyjack_b200.h);
 this package only mirrors the reference's host-side names for tests, bench.py and demos."""
 from . import instances  # noqa: F401
+
 from ._lib import GjError, LIB_PATH, load  # noqa: F401
-from .problem import Problem, deltas_to_csr  # noqa: F401
+from .problem import PinnedArray, Problem, deltas_to_csr, pinned_copy  # noqa: F401
 from .agents import (GeneticAlgorithm, Islands, LateAcceptance, ScoreLimit, ScoreNoImprovement,  # noqa: F401
                      StepsLimit, TabuSearch, TimeSpentLimit)

@@ -41,6 +41,38 @@ def deltas_to_csr(deltas):
     return offsets, ids, vals
 
 
+class PinnedArray:
+    """numpy view over page-locked host memory from gj_host_alloc (copies to / from it are
+    asynchronous DMA).  Keep the object alive while the array is in use."""
+
+    def __init__(self, shape, dtype):
+        L = _lib.load()
+        self._L = L
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape))
+        self.ptr = C.c_void_p()
+        _lib.check(L.gj_host_alloc(C.c_size_t(max(1, n * dt.itemsize)), C.byref(self.ptr)))
+        buf = (C.c_char * (n * dt.itemsize)).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.array = None
+                self._L.gj_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_copy(a):
+    """Copy of `a` in page-locked host memory; returns (PinnedArray, ndarray view)."""
+    a = np.ascontiguousarray(a)
+    p = PinnedArray(a.shape, a.dtype)
+    p.array[...] = a
+    return p, p.array
+
+
 class Problem:
     """Device-resident Cotwin + score requester."""
 

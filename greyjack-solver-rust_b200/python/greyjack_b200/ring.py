@@ -1,0 +1,74 @@
+"""Cross-GPU island ring: the reference's agent ring `i -> (i + 1) mod n` (solver/solver.rs:85-92,
+AgentToAgentUpdate over crossbeam channels, agent_base.rs:322-444) with one process per GPU.
+
+Each rank owns a group of islands (a gj_islands handle).  Inside a group the ring is handled on
+the device by gj_islands_step; this module closes the ring ACROSS ranks: every
+`migration_frequency` steps the migrants of rank r's last island travel to rank r+1's first
+island (torch.distributed send/recv: NCCL over NVLink on GPUs, gloo in the CPU tests), where the
+reference's acceptance rule (agent_base.rs:414-440) is applied by gj_islands_import_migrants.
+There is no other data-path collective: islands are independent between migrations.
+
+The `islands` object only needs migrant_bytes / export_migrants / import_migrants /
+set_external_ring (greyjack_b200.Islands, or a stand-in in tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def ring_neighbours(rank: int, world: int):
+    """(destination, source) of `rank` in the ring i -> (i + 1) mod world."""
+    return (rank + 1) % world, (rank - 1) % world
+
+
+def global_island_base(rank: int, islands_per_rank: int) -> int:
+    """Global id of a rank's island 0 (RNG key and ring position, solver.rs:92)."""
+    return rank * islands_per_rank
+
+
+class RingMigrator:
+    def __init__(self, islands, rank: int, world: int, islands_per_rank: int, device="cuda", group=None):
+        self.islands, self.rank, self.world, self.group = islands, rank, world, group
+        self.dst, self.src = ring_neighbours(rank, world)
+        islands.set_external_ring(world > 1, global_island_base(rank, islands_per_rank))
+        n = int(islands.migrant_bytes())
+        self.out = torch.empty(n, dtype=torch.uint8, device=device)
+        self.inp = torch.empty(n, dtype=torch.uint8, device=device)
+        self.exchanges = 0
+
+    def exchange(self, stream: int = 0):
+        """One ring exchange; call it every migration_frequency steps on every rank."""
+        if self.world == 1:
+            return
+        # `stream` must be torch's current stream: NCCL orders its send after the work queued on
+        # it (the export kernels), and req.wait() orders the import after the receive
+        self.islands.export_migrants(self.out.data_ptr(), stream)
+        ops = [dist.P2POp(dist.isend, self.out, self.dst, group=self.group),
+               dist.P2POp(dist.irecv, self.inp, self.src, group=self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        self.islands.import_migrants(self.inp.data_ptr(), stream)
+        self.exchanges += 1
+
+
+def run_steps(islands, migrator: RingMigrator, n_steps: int, migration_frequency: int, stream: int = 0,
+              first_step: int = 0):
+    """Agent::solve's loop across ranks: step, and every migration_frequency steps exchange
+    (agent_base.rs:161-183)."""
+    for s in range(first_step, first_step + n_steps):
+        islands.step(1, stream)
+        if (s + 1) % migration_frequency == 0:
+            migrator.exchange(stream)
+
+
+def global_best(score, world: int, device="cpu", group=None):
+    """Lexicographic minimum (lower is better) of every rank's best score -> (score, owner rank).
+    Replaces the Arc<Mutex<global_top_individual>> across processes (agent_base.rs:446-490)."""
+    t = torch.tensor([float(x) for x in score], dtype=torch.float64, device=device)
+    if world == 1:
+        return t.tolist(), 0
+    allv = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allv, t, group=group)
+    rows = [tuple(v.tolist()) for v in allv]
+    owner = min(range(world), key=lambda r: (rows[r], r))
+    return list(rows[owner]), owner
