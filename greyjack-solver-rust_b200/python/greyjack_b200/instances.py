@@ -104,11 +104,14 @@ def nqueens(n: int, seed: int = 45) -> ProblemSpec:
         score_precision=None, name=f"nqueens-{n}")
 
 
-def tsp(n_cities: int, seed: int = 1, greedy: bool = True) -> ProblemSpec:
+def tsp(n_cities: int, seed: int = 1, greedy: bool = True, with_matrix: bool = True) -> ProblemSpec:
     """examples/tsp: n_stops = n_cities-1 variables in [1, n_cities-1], depot = location 0
-    (persistence/cotwin_builder.rs:49-77)."""
+    (persistence/cotwin_builder.rs:49-77).  with_matrix=False leaves distance_matrix None (the
+    device builds it from the coordinates: Problem(spec, use_coords=True)) -- for instances whose
+    matrix is gigabytes."""
     xy = uniform01(seed, 2 * n_cities).reshape(n_cities, 2) * 1000.0
-    D = distance_matrix(xy)
+    D = distance_matrix(xy) if with_matrix else None
+    greedy = greedy and with_matrix
     n = n_cities - 1
     init = np.arange(1, n_cities, dtype=np.float64)
     spec = ProblemSpec(
