@@ -358,6 +358,14 @@ __device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen,
     }
     if (tid == 0) prefix[W] = carry;
     __syncthreads();
+    // compact the free positions, ascending: position p lands at prefix[word] + (free bits below it)
+    int32_t* free_list = (int32_t*)(table + 2 * (W + 1));
+    for (int pos = tid; pos < glen; pos += nthr) {
+        const int w = pos >> 5, b = pos & 31;
+        const uint32_t fm = ~table[w];
+        if ((fm >> b) & 1u) free_list[prefix[w] + __popc(fm & ((1u << b) - 1u))] = pos;
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256)
@@ -932,7 +940,7 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
             T = std::min(T, std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK));   // keep free ids to draw from
             T = std::max(T, 1);
             tsize.push_back(T);
-            words += 2 * ((int)((grp.size() + 31) / 32) + 1);     // bits + free-prefix (gj_moves.cuh)
+            words += gj_tabu_region_words((int)grp.size());       // bits + free-prefix + free list (gj_moves.cuh)
             ring += T;
         }
         g->tabu_words = words; g->tabu_ring_len = ring;
@@ -948,6 +956,8 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
                     const int glen = (int)p->groups[gi].size(), W = (glen + 31) / 32;
                     uint32_t* prefix = table.data() + (size_t)i * words + word_off[gi] + W + 1;
                     for (int w = 0; w <= W; ++w) prefix[w] = (uint32_t)std::min(32 * w, glen);
+                    uint32_t* free_list = prefix + W + 1;
+                    for (int k = 0; k < glen; ++k) free_list[k] = (uint32_t)k;
                 }
             GJ_CUDA_TRY(cudaMemcpy(g->tabu_bits, table.data(), table.size() * 4, cudaMemcpyHostToDevice));
         }

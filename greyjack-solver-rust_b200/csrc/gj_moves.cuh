@@ -200,50 +200,35 @@ __device__ __forceinline__ int gj_binomial_small(GjPhilox& rng, int n, double p,
 }
 
 // ---- tabu table ---------------------------------------------------------------------------------
-// Per island and semantic group: W + 1 words of membership bits (bit set = position is in the
-// tabu deque), then W + 1 ints of an exclusive prefix count of FREE positions per word
-// (prefix[W] = all free positions), W = ceil(group_len / 32).  The prefix turns "draw until the
-// id is not tabu" (Mover::select_non_tabu_ids :75-96) into one draw: the r-th free position,
-// r ~ U[0, free) -- the same distribution without a data-dependent retry loop.
+// Per island and semantic group (W = ceil(group_len / 32)):
+//     bits   [W + 1] words   membership (bit set = position is in the tabu deque)
+//     prefix [W + 1] ints    exclusive count of FREE positions per word; prefix[W] = all of them
+//     free   [group_len] ints the free positions in ascending order (prefix[W] valid entries)
+// The list turns "draw until the id is not tabu" (Mover::select_non_tabu_ids :75-96) into one
+// draw and one load: the r-th free position, r ~ U[0, free) -- the same distribution without a
+// data-dependent retry loop.  bits / prefix are what the list is compacted from once per step.
 struct GjTabuView {
-    const uint32_t* bits;       // nullptr: no tabu (tabu_entity_rate == 0)
-    const int32_t* prefix;
-    int W;
+    const int32_t* free;        // nullptr: no tabu (tabu_entity_rate == 0)
+    int n_free;
 };
+
+__host__ __device__ inline int gj_tabu_region_words(int glen) {
+    return 2 * (((glen + 31) >> 5) + 1) + glen;
+}
 
 __device__ __forceinline__ GjTabuView gj_tabu_view(const uint32_t* table, int glen) {
     GjTabuView v;
-    v.W = (glen + 31) >> 5;
-    v.bits = table;
-    v.prefix = table ? (const int32_t*)(table + v.W + 1) : nullptr;
+    const int W = (glen + 31) >> 5;
+    v.free = table ? (const int32_t*)(table + 2 * (W + 1)) : nullptr;
+    v.n_free = table ? ((const int32_t*)table)[2 * W + 1] : 0;      // prefix[W]
     return v;
 }
 
-// position of the r-th (0-based) set bit of v; r < popc(v)
-__device__ __forceinline__ int gj_select_bit(uint32_t v, int r) {
-    int pos = 0, t;
-    t = __popc(v & 0xFFFFu); if (r >= t) { r -= t; pos += 16; v >>= 16; }
-    t = __popc(v & 0xFFu);   if (r >= t) { r -= t; pos += 8;  v >>= 8; }
-    t = __popc(v & 0xFu);    if (r >= t) { r -= t; pos += 4;  v >>= 4; }
-    t = __popc(v & 0x3u);    if (r >= t) { r -= t; pos += 2;  v >>= 2; }
-    t = (int)(v & 1u);       if (r >= t) { pos += 1; }
-    return pos;
-}
-
+// number of free positions below right_end (right_end is within a few positions of group_len)
 __device__ __forceinline__ int gj_tabu_free_below(const GjTabuView& tv, int right_end) {
-    const int w = right_end >> 5, rem = right_end & 31;
-    int f = tv.prefix[w];
-    if (rem) f += __popc(~tv.bits[w] & ((1u << rem) - 1u));
+    int f = tv.n_free;
+    while (f > 0 && tv.free[f - 1] >= right_end) --f;
     return f;
-}
-
-__device__ __forceinline__ int gj_tabu_free_select(const GjTabuView& tv, int r) {
-    int lo = 0, hi = tv.W - 1;
-    while (lo < hi) {                       // largest word whose prefix <= r
-        const int mid = (lo + hi + 1) >> 1;
-        if (tv.prefix[mid] <= r) lo = mid; else hi = mid - 1;
-    }
-    return 32 * lo + gj_select_bit(~tv.bits[lo], r - tv.prefix[lo]);
 }
 
 // k distinct positions in [0, right_end) outside the island's tabu snapshot
@@ -254,7 +239,7 @@ __device__ __forceinline__ void gj_pick_positions(GjPhilox& rng, int right_end, 
                                                   const GjTabuView& tv, int32_t* out) {
     int F = right_end;
     bool use_tabu = false;
-    if (tv.bits) {
+    if (tv.free) {
         const int f = gj_tabu_free_below(tv, right_end);
         if (f >= k) { F = f; use_tabu = true; }     // a fully tabu group falls back to plain choice
     }
@@ -273,7 +258,7 @@ __device__ __forceinline__ void gj_pick_positions(GjPhilox& rng, int right_end, 
             for (int j = 0; j < GJ_MOVE_MAXK; ++j)
                 if (j < i && sorted[j] > ins) { const int t = sorted[j]; sorted[j] = ins; ins = t; }
             sorted[i] = ins;
-            out[i] = use_tabu ? gj_tabu_free_select(tv, r) : r;
+            out[i] = use_tabu ? tv.free[r] : r;
         }
     }
 }
@@ -301,7 +286,8 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
     m.kind = (uint8_t)kind;
     m.group = (uint8_t)grp;
     m.k = 0;
-    const double rate = (glen > 0) ? M.mutation_rate_multiplier * (1.0 / (double)glen) : 0.0;
+    const double rate = (glen > 0 && M.mutation_rate_multiplier != 0.0)
+                            ? M.mutation_rate_multiplier * (1.0 / (double)glen) : 0.0;
     if (kind <= 2) {
         // get_necessary_info_for_move: change count ~ Binomial(n_vars, group rate)
         int k = gj_binomial_small(rng, P.n_vars, rate, GJ_MOVE_MAXK);
