@@ -312,12 +312,34 @@ def main():
             op = gj_oracle.OracleProblem(spec)
             cores = os.cpu_count() or 1
             n1, s1, _ = op.bench_ts(base, NEIGHBOURS, 1, cores, 3, MOVE_PROBAS, [3, 3])
-            steps = max(2, min(200, int(12.0 / max(s1, 1e-3))))
+            steps = max(2, min(800, int(12.0 / max(s1, 1e-3))))
             n, secs, _ = op.bench_ts(base, NEIGHBOURS, steps, cores, 4, MOVE_PROBAS, [3, 3])
             line["cpu_baseline"] = {
                 "value": n / secs, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{steps} TabuSearch steps x {cores} islands x {NEIGHBOURS} moves ({secs:.1f} s); "
                           "oracle port of the reference ISC path without its Polars marshalling (CPU-favouring)"}
+            # ---- metric (ii): best score at fixed wall time, same instance, same move mix ---------
+            wall = float(os.environ.get("GJ_BENCH_QUALITY_WALL_S", "2.0"))
+            q_isl = builder.build_agent(prob, n_islands=args.islands, seed=4242)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            q_steps = 0
+            while time.perf_counter() - t0 < wall:
+                q_isl.step(MIGRATION_FREQUENCY, stream)
+                torch.cuda.synchronize()
+                q_steps += MIGRATION_FREQUENCY
+            gpu_wall = time.perf_counter() - t0
+            _, gpu_best = q_isl.best(-1)
+            q_isl.close()
+            cpu_steps = max(1, int(wall * (n / secs) / (cores * NEIGHBOURS)))
+            _, cpu_wall, cpu_best = op.bench_ts(base, NEIGHBOURS, cpu_steps, cores, 5, MOVE_PROBAS, [3, 3])
+            line["quality"] = {
+                "metric": "best score (hard, soft) at fixed wall time; lower is better",
+                "start": [float(x) for x in op.score_incremental(base, [[]])[0]],
+                "gpu": {"wall_s": gpu_wall, "best": [float(x) for x in gpu_best], "steps": q_steps,
+                        "islands": args.islands},
+                "cpu": {"wall_s": cpu_wall, "best": [float(x) for x in cpu_best], "steps": cpu_steps,
+                        "islands": cores, "note": "oracle port, one TabuSearch island per host thread"}}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

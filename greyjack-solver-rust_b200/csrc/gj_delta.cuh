@@ -149,6 +149,9 @@ __device__ __forceinline__ bool gj_tsp_move_delta(const GjProblemDev& P, const G
                                                   int& d_uniq, double& d_dist) {
     d_uniq = 0; d_dist = 0.0;
     if (m.kind == GJ_MOVE_NULL) return true;
+    // the reference's incremental scramble / swap_edges(k = 2) assign every column its own value
+    // (SURVEY.md Q8): the neighbour IS the base
+    if (noop_quirk && (m.kind == 3 || (m.kind == 2 && m.k == 2))) return true;
     const int32_t* g = G.ids + G.offsets[m.group];
     const int4 gi = G.info[m.group];
     // Fast path, branch-free over the move kind: a swap of two stops, a 2-opt reversal and an
@@ -209,6 +212,7 @@ __device__ __forceinline__ bool gj_nqueens_move_delta(const GjProblemDev& P, con
                                                       const int32_t* __restrict__ cnt, int& d_uniq) {
     d_uniq = 0;
     if (m.kind == GJ_MOVE_NULL) return true;
+    if (noop_quirk && (m.kind == 3 || (m.kind == 2 && m.k == 2))) return true;   // see gj_tsp_move_delta
     if (m.kind > 3) return false;                      // O(segment) changes: full evaluator
     const int32_t* g = G.ids + G.offsets[m.group];
     const int4 gi = G.info[m.group];

@@ -288,39 +288,48 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
     m.k = 0;
     const double rate = (glen > 0 && M.mutation_rate_multiplier != 0.0)
                             ? M.mutation_rate_multiplier * (1.0 / (double)glen) : 0.0;
+    // Per kind: how many positions to draw and from which range.  ONE gj_pick_positions call site
+    // serves every kind, so a warp whose lanes drew different kinds does not replay the sampler.
+    int k = 2, right_end = glen, count = 0;
+    bool null_move = false;
     if (kind <= 2) {
         // get_necessary_info_for_move: change count ~ Binomial(n_vars, group rate)
-        int k = gj_binomial_small(rng, P.n_vars, rate, GJ_MOVE_MAXK);
-        if (kind == 0) {
+        k = gj_binomial_small(rng, P.n_vars, rate, GJ_MOVE_MAXK);
+        if (kind == 0) {                    // change_move, mover.rs:145-178
             if (k < 1) k = 1;
-            if (glen < k) { m.kind = GJ_MOVE_NULL; return m; }
-            gj_pick_positions(rng, glen, k, tabu, m.a);
-#pragma unroll
-            for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
-                if (i < k) {
-                    // get_column_random_value: Uniform::new(lb, ub), then fix_deltas (clamp + rint)
-                    const int var = g[m.a[i]];
-                    const double lb = P.lb[var], ub = P.ub[var];
-                    const double x = lb + gj_rng_f64(rng) * (ub - lb);
-                    m.v[i] = gj_decode(P, var, x);
-                }
-            }
-        } else if (kind == 1) {
+            null_move = glen < k;
+        } else if (kind == 1) {             // swap_move, :180-219
             if (k < 2) k = 2;
-            if (glen < k) { m.kind = GJ_MOVE_NULL; return m; }
-            gj_pick_positions(rng, glen, k, tabu, m.a);
-        } else {
-            if (glen == 0) { m.kind = GJ_MOVE_NULL; return m; }
+            null_move = glen < k;
+        } else {                            // swap_edges_move, :221-277
             if (k < 2) k = 2;
             if (k > glen - 1) k = glen - 1;
-            if (k < 1) { m.kind = GJ_MOVE_NULL; return m; }
-            gj_pick_positions(rng, glen - 1, k, tabu, m.a);
+            null_move = (glen == 0) || (k < 1);
+            right_end = glen - 1;
         }
-        m.k = (uint8_t)k;
+    } else if (kind == 3) {                 // scramble_move, :279-317: a window of 3..6
+        count = 3 + (int)gj_rng_below(rng, 4);
+        null_move = (glen < count - 1) || (glen - count <= 0);
+        right_end = glen - count;
+        k = 1;
+    } else {                                // insertion_move :319-376 / inverse_move :378-420
+        null_move = glen <= 1;
+    }
+    if (null_move) { m.kind = GJ_MOVE_NULL; return m; }
+    gj_pick_positions(rng, right_end, k, tabu, m.a);
+    m.k = (uint8_t)k;
+    if (kind == 0) {
+#pragma unroll
+        for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+            if (i < k) {
+                // get_column_random_value: Uniform::new(lb, ub), then fix_deltas (clamp + rint)
+                const int var = g[m.a[i]];
+                const double lb = P.lb[var], ub = P.ub[var];
+                const double x = lb + gj_rng_f64(rng) * (ub - lb);
+                m.v[i] = gj_decode(P, var, x);
+            }
+        }
     } else if (kind == 3) {
-        const int count = 3 + (int)gj_rng_below(rng, 4);
-        if (glen < count - 1 || glen - count <= 0) { m.kind = GJ_MOVE_NULL; return m; }
-        gj_pick_positions(rng, glen - count, 1, tabu, m.a);
 #pragma unroll
         for (int i = 0; i < GJ_MOVE_MAXK; ++i) m.v[i] = (i < count) ? i : 0;
 #pragma unroll
@@ -336,10 +345,6 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
             }
         }
         m.k = (uint8_t)count;
-    } else {
-        if (glen <= 1) { m.kind = GJ_MOVE_NULL; return m; }
-        gj_pick_positions(rng, glen, 2, tabu, m.a);
-        m.k = 2;
     }
     return m;
 }
