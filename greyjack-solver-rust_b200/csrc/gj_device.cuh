@@ -138,6 +138,41 @@ __device__ __forceinline__ long long gj_warp_sum(long long x) {
     return x;
 }
 
+// ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------
+// Stages a contiguous table (a solution row, a tabu table, a fact table) from global to shared
+// memory with one instruction issued by one thread; consumers wait on the mbarrier's phase.
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ uint32_t gj_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void gj_mbar_init(uint64_t* mbar, int arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gj_smem_u32(mbar)), "r"(arrivals));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void gj_mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gj_smem_u32(mbar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void gj_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                               uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gj_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(gj_smem_u32(mbar))
+                 : "memory");
+}
+__device__ __forceinline__ void gj_mbar_wait(uint64_t* mbar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n"
+                     "}\n"
+                     : "=r"(done)
+                     : "r"(gj_smem_u32(mbar)), "r"(phase)
+                     : "memory");
+    }
+}
+
 // ---- Philox4x32-10 counter-based RNG -----------------------------------------------
 // key = (seed_lo ^ island, seed_hi); counter = (step, candidate, stream, 0): moves are a
 // pure function of (seed, island, step, candidate) and never visit the host.

@@ -943,6 +943,7 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
             words += gj_tabu_region_words((int)grp.size());       // bits + free-prefix + free list (gj_moves.cuh)
             ring += T;
         }
+        words = (words + 3) & ~3;                     // 16-byte multiple: staged with one TMA bulk copy
         g->tabu_words = words; g->tabu_ring_len = ring;
         if ((rc = dev_upload(g, word_off, &g->tabu_word_off))) return rc;
         if ((rc = dev_upload(g, ring_off, &g->tabu_ring_off))) return rc;

@@ -248,13 +248,23 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     };
     stamp(0);
     // ---- P0: stage ---------------------------------------------------------------------------
-    for (int i = tid; i < n; i += blockDim.x) s.t[i] = cur_row[i];
-    if (A.tabu_bits) {
-        const uint32_t* bits_g = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
-        for (int w = tid; w < A.tabu_words_per_island; w += blockDim.x) s.bits[w] = bits_g[w];
+    // The island's solution row and tabu table travel global -> shared as two TMA bulk copies
+    // issued by one thread (rows and tables are 16-byte aligned and padded, see ls_create).
+    __shared__ __align__(8) uint64_t sh_mbar;
+    if (tid == 0) {
+        gj_mbar_init(&sh_mbar, 1);
+        sh_nwork = 0;
     }
-    if (tid == 0) sh_nwork = 0;
     __syncthreads();
+    if (tid == 0) {
+        const uint32_t row_bytes = (uint32_t)(((n + 3) & ~3) * 4);
+        const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
+        gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes);
+        gj_tma_load_1d(s.t, cur_row, row_bytes, &sh_mbar);
+        if (tabu_bytes)
+            gj_tma_load_1d(s.bits, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
+    }
+    gj_mbar_wait(&sh_mbar, 0);
     gj_fused_counts<KIND>(P, s, cnt_stride);
     if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
     if (F.S.stale[island]) {                       // replaced by a migrant / the global best
