@@ -97,10 +97,14 @@ struct GjTspBase {
     size_t L;
     const double* edge;                // optional [n + 1]: edge[i] = D[at(i-1)][at(i)] of the current
                                        // tour (edge[n] closes it); nullptr -> gathered from D
+    bool padded;                       // t[-1] and t[n] hold the depot (0): no bounds checks
     __device__ __forceinline__ double tour_edge(int i) const {
         return edge ? edge[i] : d(at(i - 1), at(i));
     }
-    __device__ __forceinline__ int at(int q) const { return (q < 0 || q >= n) ? 0 : t[q]; }
+    __device__ __forceinline__ int at(int q) const {
+        if (padded) return t[q];
+        return (q < 0 || q >= n) ? 0 : t[q];
+    }
     __device__ __forceinline__ double d(int a, int b) const { return __ldg(&D[(size_t)a * L + (size_t)b]); }
 };
 

@@ -140,7 +140,7 @@ k_score_delta(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
         // (N - |rows|) + (N - |desc|) + (N - |asc|): integers, exact in f64
         gj_combine_nqueens(P, raw[0] - (double)d_uniq, s.v);
     } else {
-        GjTspBase B{row, P.n_vars, P.D, (size_t)P.n_locations, nullptr};
+        GjTspBase B{row, P.n_vars, P.D, (size_t)P.n_locations, nullptr, false};
         int d_uniq; double d_dist;
         ok = gj_tsp_move_delta(P, G, m, C.noop != 0, C.symmetric != 0, B, cnt, d_uniq, d_dist);
         gj_combine_tsp(P, true, raw[0] - (double)d_uniq, raw[1] + d_dist, s.v);

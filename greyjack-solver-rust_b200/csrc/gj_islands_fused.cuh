@@ -42,7 +42,7 @@ struct GjFusedSmem {
 __host__ __device__ inline size_t gj_fused_smem_bytes(int n_vars, int cnt_stride, int tabu_words,
                                                       int words, int n_clone, int fold_chunk) {
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
-    size_t b = n_pad * 4 + (size_t)cnt_stride * 4 + (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
+    size_t b = (n_pad + 8) * 4 + (size_t)cnt_stride * 4 + (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
     b += (size_t)n_clone * (size_t)words * 4 + (size_t)n_clone * n_pad * 4;
     b = (b + 15) & ~(size_t)15;
     b += ((size_t)n_vars + 1) * 8;
@@ -54,7 +54,8 @@ __device__ __forceinline__ GjFusedSmem gj_fused_carve(unsigned char* smem, int n
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
     GjFusedSmem s;
     size_t o = 0;
-    s.t = (int32_t*)(smem + o); o += n_pad * 4;
+    // the solution sits 16 bytes into its slot: t[-1] and t[n] are sentinels (TSP: the depot)
+    s.t = (int32_t*)(smem + o) + 4; o += (n_pad + 8) * 4;
     s.cnt = (int32_t*)(smem + o); o += (size_t)cnt_stride * 4;
     s.bits = (uint32_t*)(smem + o); o += (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
     s.bm = (uint32_t*)(smem + o); o += (size_t)n_clone * (size_t)words * 4;
@@ -265,6 +266,7 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
             gj_tma_load_1d(s.bits, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
     }
     gj_mbar_wait(&sh_mbar, 0);
+    if (tid == 0) { s.t[-1] = 0; s.t[n] = 0; }     // depot before the first and after the last stop
     gj_fused_counts<KIND>(P, s, cnt_stride);
     if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
     if (F.S.stale[island]) {                       // replaced by a migrant / the global best
@@ -321,7 +323,7 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
         if constexpr (KIND == GJ_NQUEENS) {
             ok = gj_nqueens_move_delta(P, G, m, A.noop != 0, s.t, s.cnt, d_uniq);
         } else {
-            GjTspBase B{s.t, n, P.D, (size_t)P.n_locations, s.edge};
+            GjTspBase B{s.t, n, P.D, (size_t)P.n_locations, s.edge, true};
             ok = gj_tsp_move_delta(P, G, m, A.noop != 0, F.symmetric != 0, B, s.cnt, d_uniq, d_dist);
         }
         if (!ok) { worklist[atomicAdd(&sh_nwork, 1)] = c; continue; }

@@ -243,6 +243,14 @@ __device__ __forceinline__ void gj_pick_positions(GjPhilox& rng, int right_end, 
         const int f = gj_tabu_free_below(tv, right_end);
         if (f >= k) { F = f; use_tabu = true; }     // a fully tabu group falls back to plain choice
     }
+    if (k == 2) {                                  // the common case, straight-line
+        const int r0 = (int)gj_rng_below(rng, (uint32_t)F);
+        int r1 = (int)gj_rng_below(rng, (uint32_t)(F - 1));
+        if (r1 >= r0) r1 += 1;
+        out[0] = use_tabu ? tv.free[r0] : r0;
+        out[1] = use_tabu ? tv.free[r1] : r1;
+        return;
+    }
     int sorted[GJ_MOVE_MAXK];
 #pragma unroll
     for (int i = 0; i < GJ_MOVE_MAXK; ++i) sorted[i] = 0;
@@ -276,8 +284,11 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
 #pragma unroll
     for (int i = 0; i < GJ_MOVE_MAXK; ++i) { m.a[i] = 0; m.v[i] = 0; }
     const double u = (double)gj_rng_u32(rng) * (1.0 / 4294967296.0);
-    int kind = 5;
-    for (int i = 0; i < 6; ++i) if (u <= M.thresholds[i]) { kind = i; break; }
+    // first i with u <= thresholds[i] (mover.rs:105-121); thresholds are cumulative, so that is
+    // the number of thresholds below u -- no branches
+    int kind = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) kind += (u > M.thresholds[i]) ? 1 : 0;
     const int grp = (int)gj_rng_below(rng, (uint32_t)G.n_groups);
     const int glen = G.offsets[grp + 1] - G.offsets[grp];
     const int32_t* g = G.ids + G.offsets[grp];
