@@ -518,6 +518,7 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
 }
 
 #include "gj_islands_fused.cuh"
+#include "gj_islands_chain.cuh"
 
 // ---- migration (ring i -> i+1, solver.rs:85-92) ------------------------------------------------------
 // mailbox slot s: [stride int32][GJ_MAX_LEVELS f64]; slot[i+1] = island i's outgoing migrant,
@@ -1109,6 +1110,29 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
                 }
             }
         }
+        // LateAcceptance (one neighbour per step): chains that run many steps per launch
+        if (prm->scoring_mode == GJ_SCORING_DELTA && prm->agent == GJ_AGENT_LATE_ACCEPTANCE) {
+            const int words = P.bm_words + P.desc_words + P.asc_words;
+            std::vector<int32_t> coff;
+            int cw = 0;
+            for (auto& grp : p->groups) {
+                coff.push_back(cw);
+                const int T = std::max(1, std::min((int)std::ceil(prm->tabu_entity_rate * (double)grp.size()),
+                                                   std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK)));
+                cw += ((int)grp.size() + 31) / 32 + 1 + T + 2;      // bits | ring | head, fill
+            }
+            const size_t per_chain = gj_chain_smem_bytes(P.n_vars, words, cw, g->late_size, P.kind == GJ_TSP);
+            if (per_chain * kChainWarps <= 200 * 1024) {
+                g->chain = true; g->fused = false;
+                g->chain_bytes = per_chain;
+                g->mover.tabu_layout = 1;
+                if (prm->tabu_entity_rate != 0.0) {
+                    g->ctabu_words = cw;
+                    if ((rc = dev_upload(g.get(), coff, &g->ctabu_off))) return rc;
+                    if ((rc = dev_alloc(g.get(), (size_t)I * cw, &g->ctabu))) return rc;
+                }
+            }
+        }
         if (g->fused && getenv("GJ_PHASE_TIMING")) {
             if ((rc = dev_alloc(g.get(), (size_t)I * 8, &g->phase_clocks))) return rc;
         }
@@ -1334,8 +1358,62 @@ gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
     return GJ_OK;
 }
 
+// n consecutive LateAcceptance steps of every chain in one launch
+static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool trace) {
+    const GjProblemDev& P = g->p->dev;
+    GjChainArgs A{};
+    A.I = g->I; A.stride = g->stride; A.n_vars = g->n_vars; A.late_size = g->late_size; A.noop = g->noop;
+    A.n_groups = g->groups.n_groups; A.symmetric = g->p->symmetric_D ? 1 : 0; A.island_base = g->island_base;
+    A.M = g->mover; A.seed = g->prm.seed; A.step0 = g->step; A.n_steps = n;
+    A.cur = g->cur; A.cur_score = g->cur_score; A.best = g->best; A.best_score = g->best_score;
+    A.dirty = g->dirty; A.late = g->late; A.late_head = g->late_head; A.late_len = g->late_len;
+    A.counters = g->counters;
+    A.ctabu = g->ctabu; A.ctabu_words_per_island = g->ctabu_words; A.ctabu_off = g->ctabu_off;
+    A.tabu_size = g->tabu_size;
+    // trace (n == 1): the step's move / score / decision land where the per-step path puts them
+    if (trace) { A.trace_moves = g->moves; A.trace_scores = g->cand_scores; A.trace_accept = g->accepted; }
+    const size_t smem = g->chain_bytes * kChainWarps;
+    const unsigned grid = (unsigned)((g->I + kChainWarps - 1) / kChainWarps);
+    gj_status rc;
+    if (P.kind == GJ_NQUEENS) {
+        if ((rc = opt_in_smem(k_la_chains<GJ_NQUEENS>, smem))) return rc;
+        k_la_chains<GJ_NQUEENS><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);
+    } else {
+        if ((rc = opt_in_smem(k_la_chains<GJ_TSP>, smem))) return rc;
+        k_la_chains<GJ_TSP><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);
+    }
+    GJ_LAUNCH_CHECK();
+    g->step += (uint64_t)n;
+    return GJ_OK;
+}
+
 static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
     gj_status rc;
+    if (g->chain) {
+        // launches of up to steps_to_send steps; migration and the global top between launches
+        int64_t left = n_steps;
+        while (left > 0) {
+            const int per_launch = g->prm.chain_steps_per_launch > 0 ? g->prm.chain_steps_per_launch : 8;
+            const int n = (int)std::min<int64_t>(std::min<int64_t>(left, per_launch),
+                                                 std::max<int64_t>(1, g->steps_to_send));
+            if ((rc = gj_prof_begin(g, st))) return rc;
+            if ((rc = launch_chain_steps(g, n, st, false))) return rc;
+            if ((rc = gj_prof_end(g, st))) return rc;
+            left -= n;
+            g->steps_to_send -= n;
+            if (g->steps_to_send <= 0) {
+                if (!g->external_ring) {
+                    if ((rc = gj_ls_migrate_pack(g, st))) return rc;
+                    k_migrate_wrap<<<8, 256, 0, st>>>(g->I, g->stride, g->mailbox);
+                    GJ_LAUNCH_CHECK();
+                    if ((rc = gj_ls_migrate_recv(g, st))) return rc;
+                }
+                g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
+            }
+            if ((rc = gj_ls_global_top(g, st))) return rc;
+        }
+        return GJ_OK;
+    }
     for (int64_t s = 0; s < n_steps; ++s) {
         if ((rc = ls_one_step(g, st, false))) return rc;
         // agent_base.rs:161-183: every migration_frequency steps send + receive
@@ -1482,7 +1560,7 @@ extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64
     int32_t* d_base = nullptr;
     GJ_CUDA_TRY(cudaMalloc((void**)&d_base, (size_t)g->n_vars * 4));
     GJ_CUDA_TRY(cudaMemcpy(d_base, base.data(), (size_t)g->n_vars * 4, cudaMemcpyHostToDevice));
-    gj_status rc = ls_one_step(g, st, true);
+    gj_status rc = g->chain ? launch_chain_steps(g, 1, st, true) : ls_one_step(g, st, true);
     if (rc) { cudaFree(d_base); return rc; }
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<GjMove> mv(K);

@@ -52,6 +52,11 @@ struct gj_islands {
     int fused_threads = 0, fused_clones = 0, fused_fold_chunk = 0;
     size_t fused_smem = 0;
     long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid
+    // LateAcceptance chains: many steps per launch, one warp per island (gj_islands_chain.cuh)
+    bool chain = false;
+    size_t chain_bytes = 0;              // shared memory per chain
+    uint32_t* ctabu = nullptr; int ctabu_words = 0; const int32_t* ctabu_off = nullptr;
+    GjMove* trace_moves = nullptr; double* trace_scores = nullptr; int* trace_accept = nullptr;
 
     unsigned long long* counters = nullptr;
 

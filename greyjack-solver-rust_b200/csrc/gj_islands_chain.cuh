@@ -1,0 +1,362 @@
+// gj_islands_chain.cuh -- LateAcceptance chains: MANY steps of one island per launch
+// (included by gj_islands.cu).
+//
+// A LateAcceptance agent scores ONE neighbour per step (late_acceptance_base.rs:116-141), so
+// throughput only comes from running thousands of independent chains, and a kernel launch per
+// step would be all overhead.  Here one WARP owns one chain for `n_steps` consecutive steps:
+//
+//   stage   the chain's solution, value counts, edge lengths (TSP), tabu bitmap + deque and
+//           late-score list live in the warp's slice of shared memory for the whole launch
+//   step    move from the counter RNG (same generator as every other path; tabu ids by
+//           rejection against the bitmap, Mover::select_non_tabu_ids :75-96), delta score
+//           (gj_delta.cuh) or -- for moves it does not cover -- apply to a scratch clone + the
+//           warp-wide full evaluator; acceptance rule of late_acceptance_base.rs:196-213;
+//           accepted: apply in shared memory, refresh the touched edges / counts, push the score
+//           to the late list, update_top_individual (agent_base.rs:220-224) straight to HBM
+//   finish  write the chain back; the stored score is re-derived from a FULL evaluation in the
+//           reference's summation order, so float drift is bounded to one launch
+//
+// Chains are independent between migrations (the reference's island model); migration and
+// update_global_top run between launches (every min(migration_frequency, steps) steps -- the
+// reference refreshes the global top after every step of every agent thread, asynchronously; this
+// is the declared relaxation).
+#pragma once
+
+struct GjChainArgs {
+    int I, stride, n_vars, late_size, noop, n_groups, symmetric, island_base;
+    GjMoverParams M;
+    uint64_t seed, step0;
+    int n_steps;
+    int32_t* cur; double* cur_score;
+    int32_t* best; double* best_score;
+    int* dirty;
+    double* late; int* late_head; int* late_len;
+    unsigned long long* counters;
+    // chain tabu state, per island and group (global, persistent):
+    //   bits [W + 1] words | ring [T] ints | head, fill
+    uint32_t* ctabu; int ctabu_words_per_island; const int32_t* ctabu_off; const int32_t* tabu_size;
+    // trace (tests): [n_steps][I]
+    GjMove* trace_moves; double* trace_scores; int* trace_accept;
+};
+
+struct GjChainSmem {
+    int32_t* t;         // [n_pad + 8], solution at +4 (sentinels around it)
+    int32_t* cnt;       // [cnt_stride]
+    int32_t* scratch;   // [n_pad] clone / permutation buffer
+    uint32_t* bm;       // [words] full-evaluator bitmap
+    uint32_t* tabu;     // [ctabu_words] the chain's tabu state
+    double* edge;       // [n + 1] TSP
+    double* late;       // [late_size][GJ_MAX_LEVELS]
+};
+
+__host__ __device__ inline size_t gj_chain_smem_bytes(int n_vars, int words, int ctabu_words, int late_size,
+                                                      bool tsp) {
+    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
+    size_t b = (n_pad + 8) * 4 + (size_t)32 * words * 4 + n_pad * 4 + (size_t)words * 4;
+    b += (((size_t)ctabu_words + 3) & ~(size_t)3) * 4;
+    b = (b + 15) & ~(size_t)15;
+    if (tsp) b += (((size_t)n_vars + 2) & ~(size_t)1) * 8;
+    b += (size_t)late_size * GJ_MAX_LEVELS * 8;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ GjChainSmem gj_chain_carve(unsigned char* smem, int n_vars, int words,
+                                                      int ctabu_words, int late_size, bool tsp) {
+    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
+    GjChainSmem s;
+    size_t o = 0;
+    s.t = (int32_t*)(smem + o) + 4; o += (n_pad + 8) * 4;
+    s.cnt = (int32_t*)(smem + o); o += (size_t)32 * words * 4;
+    s.scratch = (int32_t*)(smem + o); o += n_pad * 4;
+    s.bm = (uint32_t*)(smem + o); o += (size_t)words * 4;
+    s.tabu = (uint32_t*)(smem + o); o += (((size_t)ctabu_words + 3) & ~(size_t)3) * 4;
+    o = (o + 15) & ~(size_t)15;
+    s.edge = (double*)(smem + o);
+    if (tsp) o += (((size_t)n_vars + 2) & ~(size_t)1) * 8;
+    s.late = (double*)(smem + o);
+    return s;
+}
+
+// counts of the chain's solution, one warp
+template <int KIND>
+__device__ __forceinline__ void gj_chain_counts(const GjProblemDev& P, const GjChainSmem& s, int lane) {
+    const int cnt_stride = 32 * (P.bm_words + P.desc_words + P.asc_words);
+    for (int i = lane; i < cnt_stride; i += 32) s.cnt[i] = 0;
+    __syncwarp();
+    for (int i = lane; i < P.n_vars; i += 32) {
+        const int v = s.t[i];
+        atomicAdd(&s.cnt[v - P.val_lo], 1);
+        if constexpr (KIND == GJ_NQUEENS) {
+            const int col = P.column_id[i];
+            atomicAdd(&s.cnt[32 * P.bm_words + (col + v - P.desc_lo)], 1);
+            atomicAdd(&s.cnt[32 * (P.bm_words + P.desc_words) + (col - v - P.asc_lo)], 1);
+        }
+    }
+    __syncwarp();
+}
+
+// edge lengths of tour positions [lo, hi] (inclusive, clamped to [0, n]), one warp
+__device__ __forceinline__ void gj_chain_edges(const GjProblemDev& P, const GjChainSmem& s, int lo, int hi,
+                                               int lane) {
+    const int n = P.n_vars;
+    const size_t L = (size_t)P.n_locations;
+    lo = max(lo, 0); hi = min(hi, n);
+    for (int i = lo + lane; i <= hi; i += 32)
+        s.edge[i] = __ldg(&P.D[(size_t)s.t[i - 1] * L + (size_t)s.t[i]]);     // sentinels: t[-1] = t[n] = 0
+    __syncwarp();
+}
+
+// FULL evaluation of the staged chain by its warp -> unweighted terms (gj_eval.cuh evaluators,
+// reference summation order when exact sums are on)
+template <int KIND>
+__device__ __forceinline__ void gj_chain_full_eval(const GjProblemDev& P, const int32_t* row, uint32_t* bm,
+                                                   int lane, double& r0, double& r1) {
+    GjSrcI32 src{row};
+    if constexpr (KIND == GJ_NQUEENS) {
+        r0 = gj_nqueens_eval_warp(P, src, bm, lane);
+        r1 = 0.0;
+    } else {
+        gj_tsp_eval_warp(P, src, bm, lane, r0, r1);
+        r1 = __shfl_sync(GJ_FULL_MASK, r1, 0);
+        r0 = __shfl_sync(GJ_FULL_MASK, r0, 0);
+    }
+    __syncwarp();
+}
+
+template <int KIND>
+__device__ __forceinline__ void gj_chain_combine(const GjProblemDev& P, double r0, double r1, GjScore& s) {
+    s.v[0] = s.v[1] = s.v[2] = 0.0;
+    if constexpr (KIND == GJ_NQUEENS) gj_combine_nqueens(P, r0, s.v);
+    else gj_combine_tsp(P, true, r0, r1, s.v);
+}
+
+static constexpr int kChainWarps = 4;
+
+template <int KIND>
+__global__ void __launch_bounds__(kChainWarps * 32)
+k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ GjMove sh_mv[kChainWarps];
+    constexpr int LV = (KIND == GJ_NQUEENS) ? 1 : 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int island = blockIdx.x * kChainWarps + warp;
+    if (island >= A.I) return;                       // whole warps only; no CTA-wide barrier below
+    const int n = A.n_vars;
+    const int words = P.bm_words + P.desc_words + P.asc_words;
+    const GjChainSmem s = gj_chain_carve(smem_raw + (size_t)warp * per_chain_bytes, n, words,
+                                         A.ctabu_words_per_island, A.late_size, KIND == GJ_TSP);
+    int32_t* cur_row = A.cur + (size_t)island * A.stride;
+    int32_t* best_row = A.best + (size_t)island * A.stride;
+
+    // ---- stage ---------------------------------------------------------------------------------
+    for (int i = lane; i < n; i += 32) s.t[i] = cur_row[i];
+    if (lane == 0) { s.t[-1] = 0; s.t[n] = 0; }
+    uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
+    if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) s.tabu[w] = tabu_g[w];
+    double* late_g = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
+    for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) s.late[i] = late_g[i];
+    int late_head = A.late_head[island], late_len = A.late_len[island];
+    __syncwarp();
+    gj_chain_counts<KIND>(P, s, lane);
+    if constexpr (KIND == GJ_TSP) gj_chain_edges(P, s, 0, n, lane);
+    double raw0, raw1;
+    gj_chain_full_eval<KIND>(P, s.t, s.bm, lane, raw0, raw1);
+    raw0 = __shfl_sync(GJ_FULL_MASK, raw0, 0);
+    GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    // a migrant / the global best may have replaced the solution since the last launch
+    if (A.dirty[island]) {
+        if (gj_score_le(cur, top, LV)) {
+            for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
+            top = cur;
+        }
+    }
+    int accepted_total = 0;
+    bool cur_from_step = false;                      // cur was produced by an accepted step of this launch
+    bool top_from_step = false;                      // ... and so was the agent's top individual
+
+    for (int it = 0; it < A.n_steps; ++it) {
+        const uint64_t step = A.step0 + (uint64_t)it;
+        // ---- generate (every lane computes the same move: no divergence, no broadcast) ----------
+        GjMoverParams M = A.M;
+        const GjMove m = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
+                                          tabu_g ? s.tabu : nullptr, A.ctabu_off);
+        // ---- score -----------------------------------------------------------------------------
+        int d_uniq = 0; double d_dist = 0.0;
+        bool ok;
+        if constexpr (KIND == GJ_NQUEENS) {
+            ok = gj_nqueens_move_delta(P, G, m, A.noop != 0, s.t, s.cnt, d_uniq);
+        } else {
+            GjTspBase B{s.t, n, P.D, (size_t)P.n_locations, s.edge, true};
+            ok = gj_tsp_move_delta(P, G, m, A.noop != 0, A.symmetric != 0, B, s.cnt, d_uniq, d_dist);
+        }
+        double n0 = raw0 - (double)d_uniq, n1 = raw1 + d_dist;
+        if (!ok) {
+            // scratch clone + full evaluator (a move the delta evaluator does not cover)
+            if (lane == 0) sh_mv[warp] = m;
+            for (int i = lane; i < n; i += 32) s.scratch[i] = s.t[i];
+            __syncwarp();
+            const GjMove ms = sh_mv[warp];
+            gj_apply_move(P, ms, G, true, A.noop != 0, lane, 32,
+                          [&](int id) { return s.t[id]; }, [&](int id, int v) { s.scratch[id] = v; });
+            __syncwarp();
+            gj_chain_full_eval<KIND>(P, s.scratch, s.bm, lane, n0, n1);
+            n0 = __shfl_sync(GJ_FULL_MASK, n0, 0);
+        }
+        GjScore sc;
+        gj_chain_combine<KIND>(P, n0, n1, sc);
+        gj_score_round(sc, P);                          // agent_base.rs:311-314
+        // ---- late acceptance (late_acceptance_base.rs:196-213) -----------------------------------
+        GjScore late_native = cur;
+        if (late_len > 0) late_native = gj_load_score(s.late + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
+        const bool accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
+        if (A.trace_moves) {
+            if (lane == 0) {
+                A.trace_moves[(size_t)it * A.I + island] = m;
+                for (int l = 0; l < LV; ++l) A.trace_scores[((size_t)it * A.I + island) * LV + l] = sc.v[l];
+                A.trace_accept[(size_t)it * A.I + island] = accept ? 1 : 0;
+            }
+        }
+        if (accept) {
+            // ---- apply in shared memory ------------------------------------------------------------
+            if (!ok) {
+                for (int i = lane; i < n; i += 32) s.t[i] = s.scratch[i];
+                __syncwarp();
+                gj_chain_counts<KIND>(P, s, lane);
+                if constexpr (KIND == GJ_TSP) gj_chain_edges(P, s, 0, n, lane);
+            } else if (m.kind != GJ_MOVE_NULL) {
+                if (lane == 0) sh_mv[warp] = m;
+                __syncwarp();
+                const GjMove ms = sh_mv[warp];
+                if (ms.kind <= 3) {
+                    // small move: <= 16 (column, value) pairs, later pairs win
+                    if (lane == 0) {
+                        const int32_t* g = G.ids + G.offsets[ms.group];
+                        int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
+                        const int np = gj_small_move_pairs(ms, g, true, A.noop != 0,
+                                                           [&](int id) { return s.t[id]; }, cols, vals);
+                        s.scratch[0] = np;
+                        for (int i = 0; i < np; ++i) {
+                            const int c = cols[i], v = gj_fix_column(P, c, vals[i]), o = s.t[c];
+                            if (v != o) {
+                                s.cnt[o - P.val_lo] -= 1; s.cnt[v - P.val_lo] += 1;
+                                if constexpr (KIND == GJ_NQUEENS) {
+                                    const int col = P.column_id[c];
+                                    const int od = 32 * P.bm_words - P.desc_lo, oa = 32 * (P.bm_words + P.desc_words) - P.asc_lo;
+                                    s.cnt[od + col + o] -= 1; s.cnt[od + col + v] += 1;
+                                    s.cnt[oa + col - o] -= 1; s.cnt[oa + col - v] += 1;
+                                }
+                                s.t[c] = v;
+                            }
+                            s.scratch[1 + i] = c;
+                        }
+                    }
+                    __syncwarp();
+                    if constexpr (KIND == GJ_TSP) {
+                        // the two edges around every changed stop
+                        const int np = s.scratch[0];
+                        if (lane < np) {
+                            const int c = s.scratch[1 + lane];
+                            const size_t L = (size_t)P.n_locations;
+                            s.edge[c] = __ldg(&P.D[(size_t)s.t[c - 1] * L + (size_t)s.t[c]]);
+                            s.edge[c + 1] = __ldg(&P.D[(size_t)s.t[c] * L + (size_t)s.t[c + 1]]);
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    // segment move on consecutive columns (only those reach the delta path)
+                    const int4 gi = G.info[ms.group];
+                    int plo, phi;
+                    gj_segment_bounds(ms, plo, phi);
+                    const int a = gi.x + plo, len = phi - plo + 1;
+                    for (int t0 = lane; t0 < len; t0 += 32) s.scratch[t0] = s.t[a + t0];
+                    __syncwarp();
+                    for (int t0 = lane; t0 < len; t0 += 32)
+                        s.t[a + t0] = s.scratch[gj_segment_src_slot(ms, true, t0, len)];
+                    __syncwarp();
+                    if constexpr (KIND == GJ_TSP) gj_chain_edges(P, s, a, a + len, lane);
+                    if constexpr (KIND == GJ_NQUEENS) gj_chain_counts<KIND>(P, s, lane);
+                }
+                __syncwarp();
+            }
+            raw0 = n0; raw1 = n1;
+            cur = sc;
+            cur_from_step = true;
+            accepted_total += 1;
+            // push_front; pop_back when longer than late_acceptance_size
+            late_head = (late_head + A.late_size - 1) % A.late_size;
+            if (lane == 0)
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+            late_len = min(late_len + 1, A.late_size);
+            // update_top_individual (agent_base.rs:220-224)
+            if (gj_score_le(cur, top, LV)) {
+                top = cur;
+                top_from_step = true;
+                for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
+            }
+            __syncwarp();
+        }
+        // ---- tabu deque (mover.rs:75-96): every id the move selected enters, the oldest leave ------
+        if (tabu_g && m.kind != GJ_MOVE_NULL && lane == 0) {
+            int sel[GJ_MOVE_MAXK];
+            const int cntsel = gj_move_selected(m, sel);
+            const int glen = G.offsets[m.group + 1] - G.offsets[m.group];
+            const int W = (glen + 31) >> 5;
+            const int T = A.tabu_size[m.group];
+            uint32_t* bits = s.tabu + A.ctabu_off[m.group];
+            int32_t* ring = (int32_t*)(bits + W + 1);
+            int head = ring[T], fill = ring[T + 1];
+#pragma unroll
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                if (i < cntsel) {
+                    const int pos = sel[i];
+                    if (!((bits[pos >> 5] >> (pos & 31)) & 1u)) {
+                        if (fill == T) {
+                            const int old = ring[head];
+                            bits[old >> 5] &= ~(1u << (old & 31));
+                        } else {
+                            fill += 1;
+                        }
+                        ring[head] = pos;
+                        head = (head + 1) % T;
+                        bits[pos >> 5] |= 1u << (pos & 31);
+                    }
+                }
+            }
+            ring[T] = head; ring[T + 1] = fill;
+        }
+        __syncwarp();
+    }
+
+    // ---- finish: write the chain back ---------------------------------------------------------------
+    for (int i = lane; i < n; i += 32) cur_row[i] = s.t[i];
+    if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) tabu_g[w] = s.tabu[w];
+    for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) late_g[i] = s.late[i];
+    __syncwarp();
+    // stored scores are FULL evaluations of the stored vectors (reference summation order): float
+    // drift of the delta sums never outlives a launch
+    if (cur_from_step) {
+        double r0, r1;
+        gj_chain_full_eval<KIND>(P, s.t, s.bm, lane, r0, r1);
+        gj_chain_combine<KIND>(P, r0, r1, cur);
+        gj_score_round(cur, P);
+    }
+    if (top_from_step) {
+        __syncwarp();
+        double r0, r1;
+        gj_chain_full_eval<KIND>(P, best_row, s.bm, lane, r0, r1);
+        gj_chain_combine<KIND>(P, r0, r1, top);
+        gj_score_round(top, P);
+    }
+    if (lane == 0) {
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+            A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = (l < LV) ? cur.v[l] : 0.0;
+            A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = (l < LV) ? top.v[l] : 0.0;
+        }
+        A.late_head[island] = late_head; A.late_len[island] = late_len;
+        A.dirty[island] = 0;
+        atomicAdd(&A.counters[0], (unsigned long long)A.n_steps);
+        if (island == 0) atomicAdd(&A.counters[1], (unsigned long long)A.n_steps);
+        if (accepted_total) atomicAdd(&A.counters[2], (unsigned long long)accepted_total);
+    }
+}

@@ -179,6 +179,8 @@ struct GjMoverParams {
     double thresholds[6];       // cumulative move probabilities (mover.rs:36-62)
     double tabu_entity_rate;
     double mutation_rate_multiplier;   // 0 when None
+    int tabu_layout;            // 0: free-position table (gj_tabu_view), 1: chain bitmap
+    int pad;
 };
 
 // Binomial(n, p) by CDF inversion, truncated at kmax (p*n is O(1) in every configuration:
@@ -208,19 +210,26 @@ __device__ __forceinline__ int gj_binomial_small(GjPhilox& rng, int n, double p,
 // draw and one load: the r-th free position, r ~ U[0, free) -- the same distribution without a
 // data-dependent retry loop.  bits / prefix are what the list is compacted from once per step.
 struct GjTabuView {
-    const int32_t* free;        // nullptr: no tabu (tabu_entity_rate == 0)
+    const int32_t* free;        // free-position list (TabuSearch islands); nullptr otherwise
     int n_free;
+    const uint32_t* bits;       // membership bits only (LateAcceptance chains, whose deque moves
+                                // every step: ids are drawn by rejection); nullptr otherwise
 };
 
 __host__ __device__ inline int gj_tabu_region_words(int glen) {
     return 2 * (((glen + 31) >> 5) + 1) + glen;
 }
 
-__device__ __forceinline__ GjTabuView gj_tabu_view(const uint32_t* table, int glen) {
+__device__ __forceinline__ GjTabuView gj_tabu_view(const uint32_t* table, int glen, int layout) {
     GjTabuView v;
     const int W = (glen + 31) >> 5;
-    v.free = table ? (const int32_t*)(table + 2 * (W + 1)) : nullptr;
-    v.n_free = table ? ((const int32_t*)table)[2 * W + 1] : 0;      // prefix[W]
+    v.free = nullptr; v.n_free = 0; v.bits = nullptr;
+    if (table && layout == 0) {
+        v.free = (const int32_t*)(table + 2 * (W + 1));
+        v.n_free = ((const int32_t*)table)[2 * W + 1];              // prefix[W]
+    } else if (table) {
+        v.bits = table;
+    }
     return v;
 }
 
@@ -237,6 +246,28 @@ __device__ __forceinline__ int gj_tabu_free_below(const GjTabuView& tv, int righ
 // taken.  Loops are unrolled over the fixed maximum so that everything stays in registers.
 __device__ __forceinline__ void gj_pick_positions(GjPhilox& rng, int right_end, int k,
                                                   const GjTabuView& tv, int32_t* out) {
+    if (tv.bits) {
+        // rejection against the bitmap: draw until the id is neither tabu nor already chosen
+        // (select_non_tabu_ids :75-96 verbatim; the tabu test is dropped after 48 tries so that a
+        // nearly-full deque cannot stall the chain)
+#pragma unroll
+        for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+            if (i < k) {
+                int pos = 0;
+                for (int tries = 0; tries < 64; ++tries) {
+                    pos = (int)gj_rng_below(rng, (uint32_t)right_end);
+                    bool clash = false;
+#pragma unroll
+                    for (int j = 0; j < GJ_MOVE_MAXK; ++j)
+                        if (j < i) clash |= (out[j] == pos);
+                    if (!clash && ((tv.bits[pos >> 5] >> (pos & 31)) & 1u) && tries < 48) clash = true;
+                    if (!clash) break;
+                }
+                out[i] = pos;
+            }
+        }
+        return;
+    }
     int F = right_end;
     bool use_tabu = false;
     if (tv.free) {
@@ -293,7 +324,8 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
     const int glen = G.offsets[grp + 1] - G.offsets[grp];
     const int32_t* g = G.ids + G.offsets[grp];
     const GjTabuView tabu = gj_tabu_view((M.tabu_entity_rate != 0.0 && tabu_island_bits)
-                                             ? tabu_island_bits + tabu_word_off[grp] : nullptr, glen);
+                                             ? tabu_island_bits + tabu_word_off[grp] : nullptr, glen,
+                                         M.tabu_layout);
     m.kind = (uint8_t)kind;
     m.group = (uint8_t)grp;
     m.k = 0;

@@ -45,6 +45,7 @@ class AgentParams(C.Structure):
         ("has_move_probas", C.c_int32), ("move_probas", C.c_double * 6),
         ("migration_frequency", C.c_int64),
         ("reference_noop_moves", C.c_int32), ("scoring_mode", C.c_int32),
+        ("chain_steps_per_launch", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -114,6 +114,7 @@ class _Builder:
         p.reference_noop_moves = int(getattr(self, "reference_noop_moves", True))
         mode = getattr(self, "scoring", "full")
         p.scoring_mode = {"full": SCORING_FULL, "delta": SCORING_DELTA, "delta_unfused": SCORING_DELTA_UNFUSED}[mode]
+        p.chain_steps_per_launch = int(getattr(self, "chain_steps_per_launch", 0))
         return p
 
     def build_agent(self, problem: Problem, n_islands: int = 1, seed: int = 0, initial=None) -> "Islands":
@@ -147,8 +148,10 @@ class LateAcceptance(_Builder):
     agent = LA
 
     def __init__(self, late_acceptance_size, tabu_entity_rate, mutation_rate_multiplier, move_probas,
-                 migration_frequency, termination_strategy=None, reference_noop_moves=True, scoring="full"):
+                 migration_frequency, termination_strategy=None, reference_noop_moves=True, scoring="full",
+                 chain_steps_per_launch=0):
         self.scoring = scoring
+        self.chain_steps_per_launch = chain_steps_per_launch
         self.late_acceptance_size = late_acceptance_size
         self.tabu_entity_rate = tabu_entity_rate
         self.mutation_rate_multiplier = mutation_rate_multiplier

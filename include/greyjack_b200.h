@@ -231,6 +231,11 @@ typedef struct gj_agent_params {
                                         no-op scramble / swap_edges(k=2);
                                         0 = apply the plain-form permutation             */
     int32_t scoring_mode;            /* GJ_SCORING_*: how TS / LA islands score a neighbour     */
+    int32_t chain_steps_per_launch;  /* LateAcceptance + GJ_SCORING_DELTA: steps a chain runs between
+                                        two refreshes of the global top (one kernel launch); 0 = 8. 
+                                        The reference refreshes after every step of every agent
+                                        thread (agent_base.rs:185); 1 reproduces that cadence.    */
+    int32_t reserved;
 } gj_agent_params;
 
 /* <Agent>::build_agent + Agent::init_population (agent_base.rs:190-218).  `initial`:

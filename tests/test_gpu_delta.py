@@ -178,3 +178,81 @@ def test_delta_change_moves_track_duplicates(scoring, oracle):
         seen_hard |= set(want[:, 0].tolist())
     assert len(seen_hard) > 2
     isl.close(); gp.close()
+
+
+# ---- LateAcceptance chains (gj_islands_chain.cuh): many steps per launch, one warp per chain --------
+LA_CASES = [
+    ("tsp120-mix", lambda: inst.tsp(120, seed=9), MIX, 0.2, None),
+    ("tsp97-all", lambda: inst.tsp(97, seed=2), ALL, 0.3, 2.0),
+    ("tsp64-notabu", lambda: inst.tsp(64, seed=5), [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 0.0, None),
+    ("nq64-swap", lambda: inst.nqueens(64), [0.0, 1.0, 0.0, 0.0, 0.0, 0.0], 0.2, None),
+    ("nq48-all", lambda: inst.nqueens(48), ALL, 0.2, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", LA_CASES, ids=lambda c: c[0])
+def test_la_chain_step_replay(case, oracle):
+    """Every step of a chain replayed through the oracle: move expansion (mover.rs), candidate score
+    (ISC scorer), acceptance rule with the late list (late_acceptance_base.rs:188-241), tabu ids."""
+    _, mk, probas, tabu, mult = case
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    size = 5
+    isl = LateAcceptance(size, tabu, mult, probas, 10000, scoring="delta").build_agent(gp, n_islands=3, seed=99)
+    late = []
+    recent = []
+    T = max(1, int(np.ceil(tabu * spec.n_vars))) if tabu else 0
+    for step in range(60):
+        base, cur_score = isl.current(1)
+        tr = isl.trace_step(1)
+        d = tr["desc"][0]
+        want = _oracle_move(op, spec, base, d)
+        assert _final_state(spec.n_vars, tr["deltas"][0]) == _final_state(spec.n_vars, want)
+        _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+        acc, late = oracle.la_accept(tr["scores"][0], cur_score, late, size)
+        assert tr["accepted"] == acc, step
+        new, new_score = isl.current(1)
+        want_vec = base.copy()
+        if acc:
+            for c, v in tr["deltas"][0]:
+                want_vec[c] = v
+        assert np.array_equal(new, want_vec)
+        # stored score: the full evaluation of the stored vector (bit-exact), or untouched
+        if acc:
+            assert np.array_equal(new_score, oracle.score_round(op.score_incremental(new, [[]])[0], spec.score_precision))
+            late[0] = tr["scores"][0]                    # the late list keeps the step's own score
+        else:
+            assert np.array_equal(new_score, cur_score)
+        # tabu: a move never selects an id that one of the last T selections holds
+        if tabu and d[0] != 255:
+            k = 1 if d[0] == 3 else (2 if d[0] >= 4 else d[2])
+            sel = [int(x) for x in d[4:4 + k]]
+            assert not (set(sel) & set(recent[-T:])), (step, sel, recent[-T:])
+            recent += sel
+    isl.close(); gp.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: inst.tsp(150, seed=2), lambda: inst.nqueens(48)], ids=["tsp", "nqueens"])
+def test_la_chain_many_steps_per_launch_equal_single_steps(mk, oracle):
+    """The state carried in shared memory across the steps of one launch is the state single-step
+    launches rebuild from HBM: same seed -> same chain, whatever the launch granularity."""
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    probas = [0.0, 1.0, 0.0, 0.0, 0.0, 0.0] if spec.kind == inst.NQUEENS else [0.1, 0.3, 0.1, 0.1, 0.2, 0.2]
+    gp = Problem(spec)
+    a = LateAcceptance(8, 0.2, None, probas, 1000, scoring="delta").build_agent(gp, n_islands=1, seed=5)
+    b = LateAcceptance(8, 0.2, None, probas, 1000, scoring="delta").build_agent(gp, n_islands=1, seed=5)
+    a.step(64)
+    for _ in range(64):
+        b.trace_step(0)
+    va, sa = a.current(0)
+    vb, sb = b.current(0)
+    assert np.array_equal(va, vb)
+    assert np.array_equal(sa, sb)
+    ba, bsa = a.best(0)
+    bb, bsb = b.best(0)
+    assert np.array_equal(ba, bb) and np.array_equal(bsa, bsb)
+    assert _same_score(bsa, op.score_incremental(ba, [[]])[0], spec, oracle)
+    assert a.stats()["candidates"] == 64 and a.stats()["accepted"] == b.stats()["accepted"]
+    a.close(); b.close(); gp.close()

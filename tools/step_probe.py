@@ -43,3 +43,14 @@ if __name__ == "__main__":
         run("nq256 TS K=4096 I=148 delta", spec, gj.TabuSearch(4096, 0.2, True, None, SW, 10, scoring="delta"), 148)
         run("nq256 LA I=4096 delta", spec, gj.LateAcceptance(32, 0.2, None, SW, 100, scoring="delta"), 4096, steps=200)
         run("nq256 LA I=4096 full", spec, gj.LateAcceptance(32, 0.2, None, SW, 100, scoring="full"), 4096, steps=200)
+    if "vrp" in which:
+        spec = inst.cvrp(2000, 50, seed=2, greedy=False)
+        import numpy as np
+        spec.initial = np.full(spec.n_vars, np.nan)
+        run("cvrp2000x50 GA pop=8192 I=1", spec, gj.GeneticAlgorithm(8192, 0.5, 0.2, 0.05, 1.0, None, 0.00001, 10), 1, steps=20)
+        run("cvrp2000x50 GA pop=8192 I=8", spec, gj.GeneticAlgorithm(8192, 0.5, 0.2, 0.05, 1.0, None, 0.00001, 10), 8, steps=10)
+        spec = inst.cvrp(2000, 50, seed=2, greedy=True)
+        run("cvrp2000x50 TS K=4096 I=8 full", spec, gj.TabuSearch(4096, 0.2, True, None, [0.5, 0.5, 0, 0, 0, 0], 10), 8, steps=10)
+        spec = inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False)
+        run("vrptw5000 LA I=592 full", spec, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50), 592, steps=50)
+        run("vrptw5000 LA I=4096 full", spec, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50), 4096, steps=20)
