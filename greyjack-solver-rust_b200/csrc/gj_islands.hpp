@@ -74,6 +74,7 @@ struct gj_islands {
     int32_t* cand_rows = nullptr;  // [I][n_cand][stride]
     int* order = nullptr;          // [I][pop] rank -> row index after the sort
     int* ga_src = nullptr;         // [I][pop] replacement source (trace)
+    int* ga_rank = nullptr;        // [I][pop] rank scratch of the counting sort (kept zeroed)
 
     ~gj_islands();
 };

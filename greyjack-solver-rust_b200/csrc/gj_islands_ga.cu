@@ -5,7 +5,7 @@
 //   k_ga_offspring  select_p_best x2, cross, Mover::do_move(plain) x2, fix_variables (:141-187)
 //   plain scorer    request_score_plain on the offspring (PSC semantics) + round
 //   k_ga_replace    build_updated_population: candidate i vs random p-worst native (:198-213)
-//   k_ga_sort       population.sort() (agent_base.rs:149-151) -> rank table
+//   k_ga_rank       population.sort() (agent_base.rs:149-151) by counting -> rank table
 //   k_ga_top        update_top_individual (agent_base.rs:220-224)
 //   k_ga_migrate_*  send_updates / receive_updates for Population agents (:337-341, 405-412)
 #include <algorithm>
@@ -115,37 +115,59 @@ k_ga_replace(GjGaArgs A, const int32_t* __restrict__ pop_rows, const double* __r
     for (int k = threadIdx.x; k < A.stride / 4; k += blockDim.x) d4[k] = s4[k];
 }
 
-// population.sort(): stable order by Ord::cmp == bitonic sort on (score, index).  One CTA per
-// island; the rank table lives in shared memory, scores are read through L1/L2.
-__global__ void __launch_bounds__(1024)
-k_ga_sort(int pop, int pop2, int levels, const double* __restrict__ pop_scores, int* __restrict__ order) {
-    extern __shared__ int sh_ord[];
-    const int island = blockIdx.x;
+// population.sort() by counting: rank(i) = #{ j : (score_j, j) < (score_i, i) } under Ord::cmp --
+// a strict total order, so the ranks are a permutation and order[rank(i)] = i is the stable sort.
+// O(pop^2) comparisons, but embarrassingly parallel: the (i-tile, j-slice) grid fills every SM,
+// where a single-CTA sorting network leaves 147 of them idle.
+static constexpr int kRankTile = 256;
+
+// f64 -> int64 whose signed order is f64::total_cmp's order (the transform inside gj_total_cmp)
+__device__ __forceinline__ long long gj_total_order_key(double x) {
+    long long l = __double_as_longlong(x);
+    return l ^ (long long)(((unsigned long long)(l >> 63)) >> 1);
+}
+
+__global__ void __launch_bounds__(kRankTile)
+k_ga_rank(int pop, int levels, int j_slices, const double* __restrict__ pop_scores, int* __restrict__ rank) {
+    __shared__ long long sh[kRankTile * GJ_MAX_LEVELS];
+    const int island = blockIdx.z;
     const double* sc = pop_scores + (size_t)island * pop * GJ_MAX_LEVELS;
-    for (int i = threadIdx.x; i < pop2; i += blockDim.x) sh_ord[i] = (i < pop) ? i : -1;
-    __syncthreads();
-    auto greater = [&](int a, int b) {      // a sorts after b ?  (-1 = padding, sorts last)
-        if (a < 0) return b >= 0;
-        if (b < 0) return false;
-        GjScore sa = {}, sb = {};
-        for (int l = 0; l < levels; ++l) { sa.v[l] = sc[(size_t)a * GJ_MAX_LEVELS + l]; sb.v[l] = sc[(size_t)b * GJ_MAX_LEVELS + l]; }
-        const int c = gj_score_cmp(sa, sb, levels);
-        return c > 0 || (c == 0 && a > b);
-    };
-    for (int k = 2; k <= pop2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < pop2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int a = sh_ord[i], b = sh_ord[ixj];
-                    const bool up = (i & k) == 0;
-                    if (greater(a, b) == up) { sh_ord[i] = b; sh_ord[ixj] = a; }
-                }
+    const int i = blockIdx.x * kRankTile + threadIdx.x;
+    // unused levels hold 0.0 in pop_scores: they compare equal and drop out
+    long long m0 = 0, m1 = 0, m2 = 0;
+    if (i < pop) {
+        m0 = gj_total_order_key(sc[(size_t)i * GJ_MAX_LEVELS + 0]);
+        m1 = gj_total_order_key(sc[(size_t)i * GJ_MAX_LEVELS + 1]);
+        m2 = gj_total_order_key(sc[(size_t)i * GJ_MAX_LEVELS + 2]);
+    }
+    const int per = (pop + j_slices - 1) / j_slices;
+    const int j0 = blockIdx.y * per, j1 = min(pop, j0 + per);
+    int below = 0;
+    for (int base = j0; base < j1; base += kRankTile) {
+        const int m = min(kRankTile, j1 - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < m * GJ_MAX_LEVELS; k += kRankTile)
+            sh[k] = gj_total_order_key(sc[(size_t)base * GJ_MAX_LEVELS + k]);
+        __syncthreads();
+        if (i < pop) {
+#pragma unroll 4
+            for (int k = 0; k < m; ++k) {
+                const long long o0 = sh[k * GJ_MAX_LEVELS], o1 = sh[k * GJ_MAX_LEVELS + 1], o2 = sh[k * GJ_MAX_LEVELS + 2];
+                const bool lt = (o0 < m0) || (o0 == m0 && ((o1 < m1) || (o1 == m1 && ((o2 < m2) || (o2 == m2 && base + k < i)))));
+                below += lt ? 1 : 0;
             }
-            __syncthreads();
         }
     }
-    for (int i = threadIdx.x; i < pop; i += blockDim.x) order[(size_t)island * pop + i] = sh_ord[i];
+    if (i < pop && below) atomicAdd(&rank[(size_t)island * pop + i], below);
+}
+
+__global__ void k_ga_order_from_rank(int pop, int I, int* __restrict__ rank, int* __restrict__ order) {
+    const int64_t n = (int64_t)pop * I;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int island = (int)(t / pop), i = (int)(t % pop);
+        order[(size_t)island * pop + rank[t]] = i;
+        rank[t] = 0;                                   // ready for the next generation
+    }
 }
 
 // update_top_individual: population[0] <= agent_top -> replace (agent_base.rs:220-224)
@@ -250,13 +272,13 @@ static gj_status ga_alloc(gj_islands* g, size_t n, T** out) {
     return GJ_OK;
 }
 
-static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
-
 static gj_status ga_sort_and_top(gj_islands* g, cudaStream_t st, bool count) {
-    const int pop2 = next_pow2(g->pop);
-    size_t smem = (size_t)pop2 * 4;
-    if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_ga_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ga_sort<<<g->I, 1024, smem, st>>>(g->pop, pop2, g->levels, g->pop_scores, g->order);
+    const int i_tiles = (g->pop + kRankTile - 1) / kRankTile;
+    int j_slices = std::max(1, std::min((g->pop + kRankTile - 1) / kRankTile, (148 * 8) / std::max(1, i_tiles * g->I)));
+    k_ga_rank<<<dim3(i_tiles, j_slices, g->I), kRankTile, 0, st>>>(g->pop, g->levels, j_slices, g->pop_scores, g->ga_rank);
+    GJ_LAUNCH_CHECK();
+    k_ga_order_from_rank<<<(unsigned)std::min<int64_t>(((int64_t)g->pop * g->I + 255) / 256, 1184), 256, 0, st>>>(
+        g->pop, g->I, g->ga_rank, g->order);
     GJ_LAUNCH_CHECK();
     k_ga_top<<<g->I, 128, 0, st>>>(g->pop, g->stride, g->n_vars, g->levels, g->n_cand, g->pop_rows,
                                   g->pop_scores, g->order, g->best, g->best_score, count ? g->counters : nullptr);
@@ -286,6 +308,7 @@ gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* 
     if ((rc = ga_alloc(g.get(), (size_t)I * std::max(g->n_cand, pop) * GJ_MAX_LEVELS, &g->cand_scores))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->moves))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->order))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_rank))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_src))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->best_score))) return rc;
