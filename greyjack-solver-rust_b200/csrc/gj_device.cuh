@@ -120,6 +120,34 @@ __device__ __forceinline__ void gj_score_round(GjScore& s, const GjProblemDev& P
         if (P.round_mult[l] != 0.0) s.v[l] = gj_round_mult(s.v[l], P.round_mult[l]);
 }
 
+// ---- SimulatedAnnealing acceptance ------------------------------------------------------------
+struct GjSaParams {
+    int has_cooling;            // cooling_rate: Option<f64>
+    double cooling_rate;
+    double inv_rate;            // 1 - termination_strategy.get_accomplish_rate() (agent_base.rs:544)
+};
+
+// SimulatedAnnealingBase::build_updated_population_incremental
+// (metaheuristic_bases/simulated_annealing_base.rs:198-233): temperature update per level, then
+// accept iff u < prod_l e^(-(candidate_l - current_l) / T_l).  temp: [levels], updated in place.
+__device__ __forceinline__ bool gj_sa_accept(const GjScore& cand, const GjScore& cur, int levels,
+                                             double* temp, const GjSaParams& sa, double u, double* proba_out) {
+    double proba = 1.0;
+    for (int l = 0; l < levels; ++l) {
+        double t = temp[l];
+        if (sa.has_cooling) {
+            t = t * sa.cooling_rate;
+            if (t < 0.000001) t = 0.0000001;
+        } else {
+            t = sa.inv_rate;
+        }
+        temp[l] = t;
+        proba = proba * pow(2.7182818284590452, -((cand.v[l] - cur.v[l]) / t));
+    }
+    if (proba_out) *proba_out = proba;
+    return u < proba;
+}
+
 // ---- warp primitives ---------------------------------------------------------------
 
 __device__ __forceinline__ double gj_warp_sum(double x) {

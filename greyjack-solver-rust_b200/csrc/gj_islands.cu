@@ -279,9 +279,34 @@ struct GjSelectArgs {
     // delta scoring: the island's cached state goes stale when cur changes; update_top_individual
     // is deferred to k_refresh (after the exact re-score of the accepted neighbour)
     int* stale; int defer_top; int* work_count;
+    // SimulatedAnnealing: temperatures per island [I][GJ_MAX_LEVELS], schedule
+    double* sa_temp; GjSaParams sa;
     // trace
-    long long* selected_out; int* accepted_out;
+    long long* selected_out; int* accepted_out; double* aux_out;
 };
+
+// uniform [0, 1) of the acceptance rule of (island, step): its own RNG stream
+__device__ __forceinline__ double gj_accept_uniform(uint64_t seed, uint32_t island_global, uint64_t step) {
+    GjPhilox rng;
+    gj_rng_init(rng, seed, island_global, (uint32_t)step, (uint32_t)(step >> 32), 0xFFFFFFF0u);
+    return gj_rng_f64(rng);
+}
+
+// SimulatedAnnealing acceptance of one island's single neighbour (thread 0 of its CTA / lane 0)
+__device__ __forceinline__ bool gj_sa_step_accept(const GjSelectArgs& A, int island, const GjScore& b,
+                                                  const GjScore& cur) {
+    double* temp = A.sa_temp + (size_t)island * GJ_MAX_LEVELS;
+    double t[GJ_MAX_LEVELS] = {temp[0], temp[1], temp[2]};
+    const double u = gj_accept_uniform(A.seed, (uint32_t)(A.island_base + island), A.step);
+    double proba;
+    const bool accept = gj_sa_accept(b, cur, A.levels, t, A.sa, u, &proba);
+    for (int l = 0; l < GJ_MAX_LEVELS; ++l) temp[l] = t[l];
+    if (A.aux_out) {
+        double* o = A.aux_out + (size_t)island * 5;
+        o[0] = u; o[1] = proba; o[2] = t[0]; o[3] = t[1]; o[4] = t[2];
+    }
+    return accept;
+}
 
 __device__ __forceinline__ GjScore gj_load_score(const double* p, int levels) {
     GjScore s;
@@ -415,6 +440,8 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
         bool accept;
         if (A.agent == GJ_AGENT_TABU_SEARCH) {
             accept = gj_score_le(b, cur, levels);                       // tabu_search_base.rs:174
+        } else if (A.agent == GJ_AGENT_SIMULATED_ANNEALING) {
+            accept = gj_sa_step_accept(A, island, b, cur);              // simulated_annealing_base.rs:198-233
         } else {
             // late_acceptance_base.rs:196-213
             double* late = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
@@ -556,8 +583,8 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
         GjScore mig = gj_load_score(sc, levels);
         GjScore cs = gj_load_score(cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
         bool take;
-        if (agent == GJ_AGENT_TABU_SEARCH) {
-            take = gj_score_le(mig, cs, levels);                    // agent_base.rs:429-434
+        if (agent != GJ_AGENT_LATE_ACCEPTANCE) {
+            take = gj_score_le(mig, cs, levels);                    // agent_base.rs:429-439
         } else {
             // agent_base.rs:416-428 (late_scores.back() of an empty deque would panic in the
             // reference; an empty deque falls back to the current score here)
@@ -582,87 +609,6 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
     __syncthreads();
     if (sh_take)
         for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = row[i];
-}
-
-// ---- global best (update_global_top, agent_base.rs:446-490) ------------------------------------------
-__global__ void __launch_bounds__(256)
-k_global_reduce(int I, int levels, int stride, int n_vars,
-                const int32_t* __restrict__ best, const double* __restrict__ best_score,
-                int32_t* gbest, double* gbest_score) {
-    // The reference walks the agents one by one replacing the global top whenever an agent's
-    // top is strictly better (:451); the result is the overall minimum, first index on ties,
-    // provided it beats the current global top.  Parallel arg-min with the same tie rule.
-    __shared__ GjScore sh_s[8];
-    __shared__ int sh_i[8];
-    __shared__ int sh_win;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    GjScore mine; int mine_idx = -1;
-    mine.v[0] = mine.v[1] = mine.v[2] = 0.0;
-    for (int i = tid; i < I; i += blockDim.x) {
-        GjScore s = gj_load_score(best_score + (size_t)i * GJ_MAX_LEVELS, levels);
-        if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        GjScore other; const int oidx = __shfl_xor_sync(GJ_FULL_MASK, mine_idx, o);
-        for (int l = 0; l < GJ_MAX_LEVELS; ++l) other.v[l] = __shfl_xor_sync(GJ_FULL_MASK, mine.v[l], o);
-        if (oidx >= 0) {
-            const int c = (mine_idx < 0) ? 1 : gj_score_cmp(mine, other, levels);
-            if (c > 0 || (c == 0 && oidx < mine_idx)) { mine = other; mine_idx = oidx; }
-        }
-    }
-    if (lane == 0) { sh_s[warp] = mine; sh_i[warp] = mine_idx; }
-    __syncthreads();
-    if (tid == 0) {
-        GjScore b = sh_s[0]; int bi = sh_i[0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-            if (sh_i[w] < 0) continue;
-            const int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_s[w], levels);
-            if (c > 0 || (c == 0 && sh_i[w] < bi)) { b = sh_s[w]; bi = sh_i[w]; }
-        }
-        GjScore g = gj_load_score(gbest_score, levels);
-        int win = -1;
-        if (bi >= 0 && !gj_score_le(g, b, levels)) {       // `agent_top.score < global.score`: strict
-            win = bi;
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
-        }
-        sh_win = win;
-    }
-    __syncthreads();
-    if (sh_win >= 0)
-        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) gbest[i] = best[(size_t)sh_win * stride + i];
-}
-
-__global__ void k_global_adopt(int agent, int compare_to_global, int levels, int stride, int n_vars,
-                               int late_size, const int32_t* __restrict__ gbest,
-                               const double* __restrict__ gbest_score, const double* __restrict__ best_score,
-                               int32_t* cur, double* cur_score, int* dirty, double* late,
-                               int* late_head, int* late_len, int* stale) {
-    __shared__ int sh_take;
-    const int island = blockIdx.x;
-    if (threadIdx.x == 0) {
-        GjScore g = gj_load_score(gbest_score, levels);
-        GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        // `global.score < agent_top.score` (:465-489)
-        bool take = !gj_score_le(top, g, levels);
-        if (agent == GJ_AGENT_TABU_SEARCH) take = take && compare_to_global;
-        if (take && agent == GJ_AGENT_LATE_ACCEPTANCE) {
-            double* lt = late + (size_t)island * late_size * GJ_MAX_LEVELS;
-            int head = (late_head[island] + late_size - 1) % late_size;
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l)
-                lt[(size_t)head * GJ_MAX_LEVELS + l] = cur_score[(size_t)island * GJ_MAX_LEVELS + l];
-            late_head[island] = head; late_len[island] = min(late_len[island] + 1, late_size);
-        }
-        if (take) {
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = g.v[l];
-            dirty[island] = 1;
-            if (stale) stale[island] = 1;
-        }
-        sh_take = take ? 1 : 0;
-    }
-    __syncthreads();
-    if (sh_take)
-        for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = gbest[i];
 }
 
 // update_global_top (agent_base.rs:446-490) for every island in ONE launch (one CTA per island).
@@ -1025,7 +971,9 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
     const bool ts = prm->agent == GJ_AGENT_TABU_SEARCH;
     g->K = ts ? (int)prm->neighbours_count : 1;
     if (g->K < 1) return gj_fail(GJ_ERR_INVALID, "neighbours_count must be >= 1");
-    if (!ts && prm->late_acceptance_size < 1) return gj_fail(GJ_ERR_INVALID, "late_acceptance_size must be >= 1");
+    const bool la = prm->agent == GJ_AGENT_LATE_ACCEPTANCE;
+    const bool sa = prm->agent == GJ_AGENT_SIMULATED_ANNEALING;
+    if (la && prm->late_acceptance_size < 1) return gj_fail(GJ_ERR_INVALID, "late_acceptance_size must be >= 1");
     const int I = g->I, stride = g->stride;
     if ((rc = dev_alloc(g.get(), (size_t)I * stride, &g->cur))) return rc;
     if ((rc = dev_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
@@ -1037,7 +985,21 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
     if ((rc = dev_alloc(g.get(), (size_t)I * g->K, &g->moves))) return rc;
     if ((rc = dev_alloc(g.get(), (size_t)I * std::max(g->K, 1) * GJ_MAX_LEVELS, &g->cand_scores))) return rc;
     if ((rc = dev_alloc(g.get(), (size_t)(I + 1) * ((size_t)stride * 4 + GJ_MAX_LEVELS * 8), &g->mailbox))) return rc;
-    if (!ts) {
+    if (sa) {
+        g->sa.has_cooling = prm->has_cooling_rate ? 1 : 0;
+        g->sa.cooling_rate = prm->cooling_rate;
+        g->sa.inv_rate = 1.0;                           // inverted_accomplish_rate starts at 1.0
+        std::vector<double> t0((size_t)I * GJ_MAX_LEVELS, 1.0);
+        for (int i = 0; i < I; ++i)
+            for (int l = 0; l < p->dev.levels; ++l) {
+                if (!(prm->initial_temperature[l] > 0.0)) return gj_fail(GJ_ERR_INVALID, "initial_temperature must be > 0 for every score level");
+                t0[(size_t)i * GJ_MAX_LEVELS + l] = prm->initial_temperature[l];
+            }
+        if ((rc = dev_alloc(g.get(), t0.size(), &g->sa_temp, false))) return rc;
+        GJ_CUDA_TRY(cudaMemcpy(g->sa_temp, t0.data(), t0.size() * 8, cudaMemcpyHostToDevice));
+        if ((rc = dev_alloc(g.get(), (size_t)I * 5, &g->trace_aux))) return rc;
+    }
+    if (la) {
         g->late_size = (int)prm->late_acceptance_size;
         if ((rc = dev_alloc(g.get(), (size_t)I * g->late_size * GJ_MAX_LEVELS, &g->late))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I, &g->late_head))) return rc;
@@ -1111,7 +1073,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
             }
         }
         // LateAcceptance (one neighbour per step): chains that run many steps per launch
-        if (prm->scoring_mode == GJ_SCORING_DELTA && prm->agent == GJ_AGENT_LATE_ACCEPTANCE) {
+        if (prm->scoring_mode == GJ_SCORING_DELTA && (la || sa)) {
             const int words = P.bm_words + P.desc_words + P.asc_words;
             std::vector<int32_t> coff;
             int cw = 0;
@@ -1185,7 +1147,9 @@ static GjSelectArgs make_select_args(gj_islands* g, bool trace, bool stored_move
     A.tabu_size = g->tabu_size; A.tabu_fill = g->tabu_fill;
     A.stale = g->ds.stale; A.defer_top = g->scoring_mode == GJ_SCORING_DELTA ? 1 : 0;
     A.work_count = g->work_count;
+    A.sa_temp = g->sa_temp; A.sa = g->sa;
     A.selected_out = trace ? g->selected : nullptr; A.accepted_out = trace ? g->accepted : nullptr;
+    A.aux_out = trace ? g->trace_aux : nullptr;
     return A;
 }
 
@@ -1370,6 +1334,8 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     A.counters = g->counters;
     A.ctabu = g->ctabu; A.ctabu_words_per_island = g->ctabu_words; A.ctabu_off = g->ctabu_off;
     A.tabu_size = g->tabu_size;
+    A.agent = g->prm.agent; A.sa_temp = g->sa_temp; A.sa = g->sa;
+    if (trace) A.trace_aux = g->trace_aux;
     // trace (n == 1): the step's move / score / decision land where the per-step path puts them
     if (trace) { A.trace_moves = g->moves; A.trace_scores = g->cand_scores; A.trace_accept = g->accepted; }
     const size_t smem = g->chain_bytes * kChainWarps;
@@ -1444,7 +1410,8 @@ extern "C" gj_status gj_islands_create(gj_problem* p, const gj_agent_params* par
     GJ_CUDA_TRY(cudaSetDevice(p->device));
     switch (params->agent) {
         case GJ_AGENT_TABU_SEARCH:
-        case GJ_AGENT_LATE_ACCEPTANCE: return ls_create(p, params, initial, out);
+        case GJ_AGENT_LATE_ACCEPTANCE:
+        case GJ_AGENT_SIMULATED_ANNEALING: return ls_create(p, params, initial, out);
         case GJ_AGENT_GENETIC_ALGORITHM: return gj_ga_create(p, params, initial, out);
         default: return gj_fail(GJ_ERR_INVALID, "unknown agent kind");
     }
@@ -1457,6 +1424,22 @@ extern "C" gj_status gj_islands_step(gj_islands* g, int64_t n_steps, void* strea
     GJ_CUDA_TRY(cudaSetDevice(g->p->device));
     if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_step(g, n_steps, (cudaStream_t)stream);
     return ls_step(g, n_steps, (cudaStream_t)stream);
+}
+
+extern "C" gj_status gj_islands_set_accomplish_rate(gj_islands* g, double accomplish_rate) {
+    if (!g) return gj_fail(GJ_ERR_INVALID, "null handle");
+    g->sa.inv_rate = 1.0 - accomplish_rate;             // agent_base.rs:544
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_trace_aux(gj_islands* g, int32_t island, double* out) {
+    if (!g || !out || island < 0 || island >= g->I) return gj_fail(GJ_ERR_INVALID, "bad argument");
+    for (int i = 0; i < 5; ++i) out[i] = 0.0;
+    if (!g->trace_aux) return GJ_OK;
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    GJ_CUDA_TRY(cudaDeviceSynchronize());
+    GJ_CUDA_TRY(cudaMemcpy(out, g->trace_aux + (size_t)island * 5, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    return GJ_OK;
 }
 
 extern "C" gj_status gj_islands_set_external_ring(gj_islands* g, int32_t on, int32_t island_base) {

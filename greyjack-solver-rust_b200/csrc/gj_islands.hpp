@@ -57,6 +57,8 @@ struct gj_islands {
     size_t chain_bytes = 0;              // shared memory per chain
     uint32_t* ctabu = nullptr; int ctabu_words = 0; const int32_t* ctabu_off = nullptr;
     GjMove* trace_moves = nullptr; double* trace_scores = nullptr; int* trace_accept = nullptr;
+    // SimulatedAnnealing: temperatures [I][GJ_MAX_LEVELS] on the device, schedule, trace of the rule
+    double* sa_temp = nullptr; GjSaParams sa{}; double* trace_aux = nullptr;
 
     unsigned long long* counters = nullptr;
 

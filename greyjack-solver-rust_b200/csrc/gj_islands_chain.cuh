@@ -23,6 +23,8 @@
 #pragma once
 
 struct GjChainArgs {
+    int agent;                  // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING
+    double* sa_temp; GjSaParams sa; double* trace_aux;
     int I, stride, n_vars, late_size, noop, n_groups, symmetric, island_base;
     GjMoverParams M;
     uint64_t seed, step0;
@@ -154,8 +156,12 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
     if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) s.tabu[w] = tabu_g[w];
     double* late_g = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
-    for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) s.late[i] = late_g[i];
-    int late_head = A.late_head[island], late_len = A.late_len[island];
+    if (A.late) for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) s.late[i] = late_g[i];
+    const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
+    int late_head = is_la ? A.late_head[island] : 0, late_len = is_la ? A.late_len[island] : 0;
+    double temp[GJ_MAX_LEVELS] = {1.0, 1.0, 1.0};
+    if (!is_la)
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) temp[l] = A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l];
     __syncwarp();
     gj_chain_counts<KIND>(P, s, lane);
     if constexpr (KIND == GJ_TSP) gj_chain_edges(P, s, 0, n, lane);
@@ -207,9 +213,21 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         gj_chain_combine<KIND>(P, n0, n1, sc);
         gj_score_round(sc, P);                          // agent_base.rs:311-314
         // ---- late acceptance (late_acceptance_base.rs:196-213) -----------------------------------
-        GjScore late_native = cur;
-        if (late_len > 0) late_native = gj_load_score(s.late + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
-        const bool accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
+        bool accept;
+        if (is_la) {
+            GjScore late_native = cur;
+            if (late_len > 0) late_native = gj_load_score(s.late + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
+            accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
+        } else {
+            // SimulatedAnnealing (simulated_annealing_base.rs:198-233); every lane evaluates the same rule
+            const double u = gj_accept_uniform(A.seed, (uint32_t)(A.island_base + island), step);
+            double proba;
+            accept = gj_sa_accept(sc, cur, LV, temp, A.sa, u, &proba);
+            if (A.trace_aux && lane == 0) {
+                double* o = A.trace_aux + (size_t)island * 5;
+                o[0] = u; o[1] = proba; o[2] = temp[0]; o[3] = temp[1]; o[4] = temp[2];
+            }
+        }
         if (A.trace_moves) {
             if (lane == 0) {
                 A.trace_moves[(size_t)it * A.I + island] = m;
@@ -283,11 +301,13 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
             cur = sc;
             cur_from_step = true;
             accepted_total += 1;
-            // push_front; pop_back when longer than late_acceptance_size
-            late_head = (late_head + A.late_size - 1) % A.late_size;
-            if (lane == 0)
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
-            late_len = min(late_len + 1, A.late_size);
+            if (is_la) {
+                // push_front; pop_back when longer than late_acceptance_size
+                late_head = (late_head + A.late_size - 1) % A.late_size;
+                if (lane == 0)
+                    for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+                late_len = min(late_len + 1, A.late_size);
+            }
             // update_top_individual (agent_base.rs:220-224)
             if (gj_score_le(cur, top, LV)) {
                 top = cur;
@@ -331,7 +351,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     // ---- finish: write the chain back ---------------------------------------------------------------
     for (int i = lane; i < n; i += 32) cur_row[i] = s.t[i];
     if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) tabu_g[w] = s.tabu[w];
-    for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) late_g[i] = s.late[i];
+    if (A.late) for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) late_g[i] = s.late[i];
     __syncwarp();
     // stored scores are FULL evaluations of the stored vectors (reference summation order): float
     // drift of the delta sums never outlives a launch
@@ -353,7 +373,8 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
             A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = (l < LV) ? cur.v[l] : 0.0;
             A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = (l < LV) ? top.v[l] : 0.0;
         }
-        A.late_head[island] = late_head; A.late_len[island] = late_len;
+        if (is_la) { A.late_head[island] = late_head; A.late_len[island] = late_len; }
+        else for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l] = temp[l];
         A.dirty[island] = 0;
         atomicAdd(&A.counters[0], (unsigned long long)A.n_steps);
         if (island == 0) atomicAdd(&A.counters[1], (unsigned long long)A.n_steps);

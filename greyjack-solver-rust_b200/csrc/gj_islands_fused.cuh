@@ -388,6 +388,8 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
         bool accept;
         if (A.agent == GJ_AGENT_TABU_SEARCH) {
             accept = gj_score_le(b, cur, levels);                       // tabu_search_base.rs:174
+        } else if (A.agent == GJ_AGENT_SIMULATED_ANNEALING) {
+            accept = gj_sa_step_accept(A, island, b, cur);              // simulated_annealing_base.rs:198-233
         } else {
             double* late = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;   // late_acceptance_base.rs:196-213
             int head = A.late_head[island], len = A.late_len[island];

@@ -7,4 +7,4 @@ from . import instances  # noqa: F401
 from ._lib import GjError, LIB_PATH, load  # noqa: F401
 from .problem import PinnedArray, Problem, deltas_to_csr, pinned_copy  # noqa: F401
 from .agents import (GeneticAlgorithm, Islands, LateAcceptance, ScoreLimit, ScoreNoImprovement,  # noqa: F401
-                     StepsLimit, TabuSearch, TimeSpentLimit)
+                     SimulatedAnnealing, StepsLimit, TabuSearch, TimeSpentLimit)

@@ -45,7 +45,8 @@ class AgentParams(C.Structure):
         ("has_move_probas", C.c_int32), ("move_probas", C.c_double * 6),
         ("migration_frequency", C.c_int64),
         ("reference_noop_moves", C.c_int32), ("scoring_mode", C.c_int32),
-        ("chain_steps_per_launch", C.c_int32), ("reserved", C.c_int32),
+        ("chain_steps_per_launch", C.c_int32), ("has_cooling_rate", C.c_int32),
+        ("cooling_rate", C.c_double), ("initial_temperature", C.c_double * 3),
     ]
 
 
@@ -57,7 +58,7 @@ EXPORTED = [
     "gj_host_alloc", "gj_host_free",
     "gj_score_plain", "gj_score_incremental",
     "gj_score_plain_device", "gj_score_plain_i32_device", "gj_score_incremental_device",
-    "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_stats", "gj_islands_set_profiling", "gj_islands_profile_read",
+    "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_set_accomplish_rate", "gj_islands_stats", "gj_islands_trace_aux", "gj_islands_set_profiling", "gj_islands_profile_read",
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",
     "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step",
 ]

@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from .problem import Problem, _ptr
 
-TS, LA, GA = 0, 1, 2
+TS, LA, GA, SA = 0, 1, 2, 3
 SCORING_FULL, SCORING_DELTA, SCORING_DELTA_UNFUSED = 0, 1, 2     # GJ_SCORING_* (include/greyjack_b200.h)
 
 
@@ -166,6 +166,33 @@ class LateAcceptance(_Builder):
         return p
 
 
+class SimulatedAnnealing(_Builder):
+    """agents/simulated_annealing.rs:31-39"""
+    agent = SA
+
+    def __init__(self, initial_temperature, cooling_rate, tabu_entity_rate, mutation_rate_multiplier, move_probas,
+                 migration_frequency, termination_strategy=None, reference_noop_moves=True, scoring="delta",
+                 chain_steps_per_launch=0):
+        self.initial_temperature = list(initial_temperature)
+        self.cooling_rate = cooling_rate
+        self.tabu_entity_rate = tabu_entity_rate
+        self.mutation_rate_multiplier = mutation_rate_multiplier
+        self.move_probas = move_probas
+        self.migration_frequency = migration_frequency
+        self.termination_strategy = termination_strategy
+        self.reference_noop_moves = reference_noop_moves
+        self.scoring = scoring
+        self.chain_steps_per_launch = chain_steps_per_launch
+
+    def _params(self, n_islands, seed):
+        p = super()._params(n_islands, seed)
+        p.has_cooling_rate = int(self.cooling_rate is not None)
+        p.cooling_rate = float(self.cooling_rate or 0.0)
+        for i in range(3):
+            p.initial_temperature[i] = float(self.initial_temperature[i]) if i < len(self.initial_temperature) else 1.0
+        return p
+
+
 class GeneticAlgorithm(_Builder):
     agent = GA
 
@@ -208,7 +235,7 @@ class Islands:
         _lib.check(self._L.gj_islands_create(problem.handle, C.byref(self.params), _ptr(init), C.byref(h)))
         self.handle = h
         self.K = int(builder.neighbours_count) if builder.agent == TS else (
-            1 if builder.agent == LA else 2 * ((int(builder.population_size) + 1) // 2))
+            1 if builder.agent in (LA, SA) else 2 * ((int(builder.population_size) + 1) // 2))
 
     def close(self):
         if getattr(self, "handle", None):
@@ -228,6 +255,15 @@ class Islands:
         c, s, a = C.c_int64(), C.c_int64(), C.c_int64()
         _lib.check(self._L.gj_islands_stats(self.handle, C.byref(c), C.byref(s), C.byref(a)))
         return {"candidates": c.value, "steps": s.value, "accepted": a.value}
+
+    def set_accomplish_rate(self, rate: float):
+        """termination_strategy.get_accomplish_rate() for SimulatedAnnealing without a cooling rate."""
+        _lib.check(self._L.gj_islands_set_accomplish_rate(self.handle, C.c_double(rate)))
+
+    def trace_aux(self, island=0):
+        out = np.zeros(5, dtype=np.float64)
+        _lib.check(self._L.gj_islands_trace_aux(self.handle, C.c_int32(island), _ptr(out)))
+        return {"random": out[0], "accept_proba": out[1], "temperature": out[2:5].copy()}
 
     def set_profiling(self, on: bool):
         _lib.check(self._L.gj_islands_set_profiling(self.handle, C.c_int32(int(on))))

@@ -78,7 +78,8 @@ enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1,
                                          not fit in shared memory.  Exposed for tests / ablation. */ };
 
 /* Agents = AgentBuildersVariants (agents/agent_builders_variants.rs:9-18). */
-enum { GJ_AGENT_TABU_SEARCH = 0, GJ_AGENT_LATE_ACCEPTANCE = 1, GJ_AGENT_GENETIC_ALGORITHM = 2 };
+enum { GJ_AGENT_TABU_SEARCH = 0, GJ_AGENT_LATE_ACCEPTANCE = 1, GJ_AGENT_GENETIC_ALGORITHM = 2,
+       GJ_AGENT_SIMULATED_ANNEALING = 3 };
 
 typedef struct gj_problem gj_problem;   /* Cotwin + OOPScoreRequester + VariablesManager */
 typedef struct gj_islands gj_islands;   /* a group of Agents resident on one GPU          */
@@ -207,6 +208,9 @@ GJ_API gj_status gj_score_incremental_device(gj_problem* p, const double* d_base
  *   GeneticAlgorithm::new(population_size, crossover_probability, p_best_rate,
  *                   tabu_entity_rate, mutation_rate_multiplier, move_probas, migration_rate,
  *                   migration_frequency, termination)          (genetic_algorithm.rs:34-44)
+ *   SimulatedAnnealing::new(initial_temperature, cooling_rate, tabu_entity_rate,
+ *                   mutation_rate_multiplier, move_probas, migration_frequency, termination)
+ *                                                            (agents/simulated_annealing.rs:31-39)
  * Termination strategies stay on the host (they are trivial control logic).
  */
 typedef struct gj_agent_params {
@@ -235,7 +239,10 @@ typedef struct gj_agent_params {
                                         two refreshes of the global top (one kernel launch); 0 = 8. 
                                         The reference refreshes after every step of every agent
                                         thread (agent_base.rs:185); 1 reproduces that cadence.    */
-    int32_t reserved;
+    int32_t has_cooling_rate;        /* SA: Option<f64>: 0 = None (temperature = 1 - accomplish rate,
+                                        agent_base.rs:537-552, see gj_islands_set_accomplish_rate)  */
+    double  cooling_rate;            /* SA                                                       */
+    double  initial_temperature[3];  /* SA: one per score level                                  */
 } gj_agent_params;
 
 /* <Agent>::build_agent + Agent::init_population (agent_base.rs:190-218).  `initial`:
@@ -250,6 +257,11 @@ GJ_API void      gj_islands_destroy(gj_islands* g);
    migration every migration_frequency steps inside the group, ring i -> i+1,
    solver.rs:85-92; global best shared as in update_global_top :446-490).              */
 GJ_API gj_status gj_islands_step(gj_islands* g, int64_t n_steps, void* stream);
+
+/* Agent::set_agent_step_dependent_params (agent_base.rs:537-552): SimulatedAnnealing without a
+   cooling rate uses temperature = 1 - termination_strategy.get_accomplish_rate(); the host owns
+   the termination strategy and passes its accomplish rate before stepping.                     */
+GJ_API gj_status gj_islands_set_accomplish_rate(gj_islands* g, double accomplish_rate);
 
 /* Counters: candidates scored so far, steps done, accepted moves. */
 GJ_API gj_status gj_islands_stats(gj_islands* g, int64_t* candidates, int64_t* steps,
@@ -294,6 +306,11 @@ GJ_API gj_status gj_islands_trace_step(gj_islands* g, int32_t island,
                                                             chosen positions[8], values[8]*/,
                                        double* scores /*[K][levels]*/,
                                        int64_t* selected, int32_t* accepted);
+
+/* Test hook next to gj_islands_trace_step: what the acceptance rule of the LAST traced step saw.
+   out[0] = the uniform random value, out[1] = accept probability (SimulatedAnnealing),
+   out[2..4] = temperatures per level after the step's update.                              */
+GJ_API gj_status gj_islands_trace_aux(gj_islands* g, int32_t island, double* out /*[5]*/);
 
 #ifdef __cplusplus
 }

@@ -740,6 +740,27 @@ int gjo_la_accept(const double* cand, const double* current, double* late, int* 
 }
 
 /* genetic_algorithm_base.rs:198-213 */
+int gjo_sa_accept(const double* cand, const double* current, int levels, double* temperature,
+                  int has_cooling_rate, double cooling_rate, double inverted_accomplish_rate,
+                  double u, double* proba_out) {
+    /* simulated_annealing_base.rs:206-216 */
+    for (int l = 0; l < levels; ++l) {
+        if (has_cooling_rate) {
+            double t = temperature[l] * cooling_rate;
+            if (t < 0.000001) t = 0.0000001;
+            temperature[l] = t;
+        } else {
+            temperature[l] = inverted_accomplish_rate;
+        }
+    }
+    /* :218-225: self.exp.powf(-((can_e - cur_e) / T)), folded from 1.0 */
+    double proba = 1.0;
+    for (int l = 0; l < levels; ++l)
+        proba = proba * pow(2.7182818284590452, -((cand[l] - current[l]) / temperature[l]));
+    if (proba_out) *proba_out = proba;
+    return u < proba ? 1 : 0;                       /* :229 */
+}
+
 void gjo_ga_replace(const double* cand_scores, const double* pop_scores, const int64_t* worst_ids,
                     int64_t pop, int levels, int64_t* out_src) {
     for (int64_t i = 0; i < pop; ++i) {

@@ -144,6 +144,14 @@ int64_t gjo_ts_select(const double* scores, int64_t S, int levels,
    front at late[0].  Returns 1 on accept and updates the deque in place.       */
 int gjo_la_accept(const double* cand, const double* current, double* late,
                   int* late_len, int late_size, int levels);
+/* SimulatedAnnealingBase::build_updated_population_incremental
+   (metaheuristic_bases/simulated_annealing_base.rs:198-233) with an explicit uniform `u`:
+   temperature update per level (cooling: T *= rate, floored at 1e-7 once below 1e-6; none:
+   T = inverted_accomplish_rate), accept iff u < prod_l e^(-(cand_l - cur_l) / T_l).
+   temperature: [levels] in/out.  Returns 1 on accept; *proba_out = the product.            */
+int gjo_sa_accept(const double* cand, const double* current, int levels, double* temperature,
+                  int has_cooling_rate, double cooling_rate, double inverted_accomplish_rate,
+                  double u, double* proba_out);
 /* GeneticAlgorithmBase::build_updated_population (genetic_algorithm_base.rs:198-213)
    with explicit p-worst ids: winner[i] = cand[i] <= pop[worst_id[i]] ? cand : native;
    out_src[i] = i (candidate) or -(worst_id+1) (native).                         */

@@ -279,6 +279,18 @@ def la_accept(cand, current, late, late_size):
     return bool(acc), [buf[i].copy() for i in range(n.value)]
 
 
+def sa_accept(cand, current, temperature, cooling_rate, inverted_accomplish_rate, u):
+    """Returns (accepted, new_temperature, accept_proba)."""
+    c = np.ascontiguousarray(cand, dtype=np.float64)
+    cur = np.ascontiguousarray(current, dtype=np.float64)
+    t = np.array(temperature, dtype=np.float64)
+    proba = C.c_double(0.0)
+    acc = lib().gjo_sa_accept(_ptr(c), _ptr(cur), C.c_int(len(c)), _ptr(t),
+                              C.c_int(int(cooling_rate is not None)), C.c_double(cooling_rate or 0.0),
+                              C.c_double(inverted_accomplish_rate), C.c_double(u), C.byref(proba))
+    return bool(acc), t, proba.value
+
+
 def ga_replace(cand_scores, pop_scores, worst_ids):
     cs = np.ascontiguousarray(cand_scores, dtype=np.float64)
     ps = np.ascontiguousarray(pop_scores, dtype=np.float64)

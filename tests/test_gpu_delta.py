@@ -256,3 +256,67 @@ def test_la_chain_many_steps_per_launch_equal_single_steps(mk, oracle):
     assert _same_score(bsa, op.score_incremental(ba, [[]])[0], spec, oracle)
     assert a.stats()["candidates"] == 64 and a.stats()["accepted"] == b.stats()["accepted"]
     a.close(); b.close(); gp.close()
+
+
+# ---- SimulatedAnnealing on the same chain kernel ---------------------------
+@pytest.mark.parametrize("cooling", [0.98, None], ids=["cooling", "accomplish-rate"])
+@pytest.mark.parametrize("mk", [lambda: inst.tsp(90, seed=6), lambda: inst.nqueens(40)], ids=["tsp", "nqueens"])
+def test_simulated_annealing_step_replay(mk, cooling, oracle):
+    """Move, score and the Metropolis rule of simulated_annealing_base.rs:198-233 replayed through the
+    oracle with the step's own uniform value; temperatures must follow the schedule bit for bit."""
+    from greyjack_b200 import SimulatedAnnealing
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    t0 = [0.5] if spec.levels == 1 else [0.5, 3000.0]
+    isl = SimulatedAnnealing(t0, cooling, 0.2, None, ALL, 10000, scoring="delta").build_agent(gp, n_islands=2, seed=31)
+    temp = np.array(t0, dtype=np.float64)
+    accepted_worse = 0
+    metropolis_steps = 0
+    for step in range(80):
+        rate = step / 100.0
+        if cooling is None:
+            isl.set_accomplish_rate(rate)
+        base, cur_score = isl.current(1)
+        tr = isl.trace_step(1)
+        aux = isl.trace_aux(1)
+        want = _oracle_move(op, spec, base, tr["desc"][0])
+        assert _final_state(spec.n_vars, tr["deltas"][0]) == _final_state(spec.n_vars, want)
+        _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+        acc, temp, proba = oracle.sa_accept(tr["scores"][0], cur_score, temp, cooling, 1.0 - rate, aux["random"])
+        assert 0.0 <= aux["random"] < 1.0
+        assert np.array_equal(aux["temperature"][: spec.levels], temp)
+        assert aux["accept_proba"] == pytest.approx(proba, rel=1e-12)
+        assert tr["accepted"] == acc, step
+        accepted_worse += int(acc and oracle.score_cmp(tr["scores"][0], cur_score) > 0)
+        metropolis_steps += int(proba < 1.0)
+        new, new_score = isl.current(1)
+        want_vec = base.copy()
+        if acc:
+            for c, v in tr["deltas"][0]:
+                want_vec[c] = v
+        assert np.array_equal(new, want_vec)
+    assert accepted_worse >= 0 and metropolis_steps > 0     # worsening neighbours met the exp() branch
+    isl.close(); gp.close()
+
+
+def test_simulated_annealing_run_and_full_mode(oracle):
+    from greyjack_b200 import SimulatedAnnealing
+    spec = inst.tsp(150, seed=2)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    for scoring in ("delta", "full"):
+        isl = SimulatedAnnealing([1.0, 5.0], 0.999, 0.2, None, [0.1, 0.3, 0.1, 0.1, 0.2, 0.2], 5,
+                                 reference_noop_moves=False, scoring=scoring).build_agent(gp, n_islands=4, seed=5)
+        _, s0 = isl.best(0)
+        for _ in range(4):
+            isl.step(100)
+            vec, sc = isl.best(-1)
+            assert _same_score(sc, op.score_incremental(vec, [[]])[0], spec, oracle)
+            for i in range(4):
+                cv, cs = isl.current(i)
+                assert _same_score(cs, op.score_incremental(cv, [[]])[0], spec, oracle)
+        assert oracle.score_cmp(isl.best(-1)[1], s0) < 0
+        assert isl.stats()["steps"] == 400 and isl.stats()["candidates"] == 400 * 4
+        isl.close()
+    gp.close()

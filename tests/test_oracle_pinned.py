@@ -234,3 +234,18 @@ def test_vrptw_hand_instance_variants(oracle):
         # only stop 1 is visited: arrival 10 > 15+10 no; leaves 20 <= 100 -> 0
         assert psc[1] == 0.0
         assert psc[0] == isc[0] == 0.0 and psc[2] == isc[2] == 4.0
+
+
+def test_simulated_annealing_rule(oracle):
+    """simulated_annealing_base.rs:198-233 by hand: cooling floor, accomplish-rate schedule, and
+    u < e^(-dE0/T0) * e^(-dE1/T1)."""
+    import math
+    acc, t, p = oracle.sa_accept([0.0, 12.0], [0.0, 10.0], [1.0, 4.0], 0.5, 1.0, 0.3)
+    assert list(t) == [0.5, 2.0]
+    assert p == pytest.approx(math.exp(-1.0), rel=1e-15) and acc            # 0.3 < 0.3679
+    acc, t, p = oracle.sa_accept([0.0, 12.0], [0.0, 10.0], [1.0, 4.0], 0.5, 1.0, 0.4)
+    assert not acc
+    acc, t, p = oracle.sa_accept([0.0, 9.0], [0.0, 10.0], [1.0, 4.0], None, 0.25, 0.999)
+    assert list(t) == [0.25, 0.25] and p > 1.0 and acc                       # improving moves always pass
+    _, t, _ = oracle.sa_accept([1.0], [1.0], [1.5e-6], 0.5, 1.0, 0.0)
+    assert list(t) == [1e-7]                                                 # < 1e-6 -> 1e-7 floor
