@@ -8,3 +8,4 @@ from ._lib import GjError, LIB_PATH, load  # noqa: F401
 from .problem import PinnedArray, Problem, deltas_to_csr, pinned_copy  # noqa: F401
 from .agents import (GeneticAlgorithm, Islands, LateAcceptance, ScoreLimit, ScoreNoImprovement,  # noqa: F401
                      SimulatedAnnealing, StepsLimit, TabuSearch, TimeSpentLimit)
+from .solver import Solver  # noqa: F401,E402

@@ -1,0 +1,47 @@
+"""Solver.solve host loop (termination strategies, observers) over device-resident islands."""
+import numpy as np
+import pytest
+
+from greyjack_b200 import (LateAcceptance, Problem, ScoreLimit, SimulatedAnnealing, Solver, StepsLimit,
+                           TabuSearch, TimeSpentLimit, instances as inst)
+
+pytestmark = pytest.mark.gpu
+
+
+class Collect:
+    def __init__(self):
+        self.updates = []
+
+    def update(self, payload):
+        self.updates.append(payload)
+
+
+def test_solve_nqueens_to_zero_conflicts(oracle):
+    spec = inst.nqueens(64, seed=45)
+    gp = Problem(spec)
+    obs = Collect()
+    vars_, score = Solver.solve(gp, TabuSearch(256, 0.2, True, None, [0, 1.0, 0, 0, 0, 0], 10, scoring="delta"),
+                                n_jobs=16, termination_strategy=ScoreLimit((0.0,)), observers=[obs], seed=3)
+    assert score[0] == 0.0
+    assert np.array_equal(oracle.OracleProblem(spec).score_incremental(vars_, [[]])[0], score)
+    assert obs.updates and obs.updates[-1]["score"] == [0.0]
+    scores = [u["score"][0] for u in obs.updates]
+    assert scores == sorted(scores, reverse=True)           # observers only see improvements
+    gp.close()
+
+
+@pytest.mark.parametrize("builder", [
+    LateAcceptance(16, 0.2, None, [0, 0.5, 0, 0, 0, 0.5], 10, scoring="delta"),
+    SimulatedAnnealing([1.0, 50.0], None, 0.2, None, [0, 0.5, 0, 0, 0, 0.5], 10),
+], ids=["la", "sa-accomplish-rate"])
+def test_solve_steps_limit_and_time_limit(builder, oracle):
+    spec = inst.tsp(120, seed=5)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    start = op.score_incremental(spec.initial, [[]])[0]
+    vars_, score = Solver.solve(gp, builder, n_jobs=32, termination_strategy=StepsLimit(400), seed=1)
+    assert oracle.score_cmp(score, start) < 0
+    assert np.array_equal(oracle.score_round(op.score_incremental(vars_, [[]])[0], spec.score_precision), score)
+    vars2, score2 = Solver.solve(gp, builder, n_jobs=32, termination_strategy=TimeSpentLimit(200), seed=1)
+    assert oracle.score_cmp(score2, start) < 0
+    gp.close()
