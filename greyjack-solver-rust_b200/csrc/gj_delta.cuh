@@ -105,7 +105,11 @@ struct GjTspBase {
         if (padded) return t[q];
         return (q < 0 || q >= n) ? 0 : t[q];
     }
-    __device__ __forceinline__ double d(int a, int b) const { return __ldg(&D[(size_t)a * L + (size_t)b]); }
+    __device__ __forceinline__ double d(int a, int b) const {
+        // 32-bit index arithmetic while the matrix has fewer than 2^31 entries (L <= 46340)
+        if (L <= 46340) return __ldg(&D[(unsigned)(a * (int)L + b)]);
+        return __ldg(&D[(size_t)a * L + (size_t)b]);
+    }
 };
 
 // (column, value) pairs of a small move -> change of the tour length and of the distinct count.

@@ -212,6 +212,7 @@ __device__ __forceinline__ int gj_binomial_small(GjPhilox& rng, int n, double p,
 struct GjTabuView {
     const int32_t* free;        // free-position list (TabuSearch islands); nullptr otherwise
     int n_free;
+    int glen;
     const uint32_t* bits;       // membership bits only (LateAcceptance chains, whose deque moves
                                 // every step: ids are drawn by rejection); nullptr otherwise
 };
@@ -223,7 +224,7 @@ __host__ __device__ inline int gj_tabu_region_words(int glen) {
 __device__ __forceinline__ GjTabuView gj_tabu_view(const uint32_t* table, int glen, int layout) {
     GjTabuView v;
     const int W = (glen + 31) >> 5;
-    v.free = nullptr; v.n_free = 0; v.bits = nullptr;
+    v.free = nullptr; v.n_free = 0; v.bits = nullptr; v.glen = glen;
     if (table && layout == 0) {
         v.free = (const int32_t*)(table + 2 * (W + 1));
         v.n_free = ((const int32_t*)table)[2 * W + 1];              // prefix[W]
@@ -236,6 +237,7 @@ __device__ __forceinline__ GjTabuView gj_tabu_view(const uint32_t* table, int gl
 // number of free positions below right_end (right_end is within a few positions of group_len)
 __device__ __forceinline__ int gj_tabu_free_below(const GjTabuView& tv, int right_end) {
     int f = tv.n_free;
+    if (right_end >= tv.glen) return f;           // the whole group: nothing to trim
     while (f > 0 && tv.free[f - 1] >= right_end) --f;
     return f;
 }
