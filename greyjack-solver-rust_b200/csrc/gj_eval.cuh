@@ -145,6 +145,12 @@ __device__ __forceinline__ void gj_tsp_eval_warp(const GjProblemDev& P, const Sr
 // examples/vrp/src/score/plain_score_calculator.rs:51-233 (PSC)
 enum { GJ_TW_ISC_FILE = 0, GJ_TW_ISC_SERVICE = 1, GJ_TW_PSC = 2 };
 
+// warps of the CTA that evaluates one VRP candidate (k_plain_vrp / k_incr_vrp / k_score_moves_vrp)
+#ifndef GJ_VRP_WARPS
+#define GJ_VRP_WARPS 8
+#endif
+static constexpr int kVrpWarps = GJ_VRP_WARPS;
+
 // Shared-memory plan of one VRP candidate (one CTA).
 struct GjVrpSmem {
     uint32_t* bm;            // customer-id bitmap, P.bm_words

@@ -74,13 +74,13 @@ k_score_moves_warp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, 
     }
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kVrpWarps * 32)
 k_score_moves_vrp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, int stride,
                   const GjMove* __restrict__ moves, int K, int64_t total, int incremental,
                   int noop, int isc, double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kWarps);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
     const int64_t j = blockIdx.x;
     const int32_t* base = cur + (size_t)(j / K) * stride;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -1112,9 +1112,9 @@ static gj_status launch_score_moves(gj_islands* g, cudaStream_t st) {
     const GjProblemDev& P = g->p->dev;
     const int64_t total = (int64_t)g->I * g->K;
     if (P.kind >= GJ_VRP) {
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kWarps);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
         if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_score_moves_vrp<<<(unsigned)total, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
+        k_score_moves_vrp<<<(unsigned)total, kVrpWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
     } else {
         size_t smem = (size_t)kWarps * (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
         if (smem > 220 * 1024) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
@@ -1540,11 +1540,16 @@ extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64
     // base of the island BEFORE the step
     std::vector<int32_t> base(g->n_vars);
     GJ_CUDA_TRY(cudaMemcpy(base.data(), g->cur + (size_t)island * g->stride, (size_t)g->n_vars * 4, cudaMemcpyDeviceToHost));
-    int32_t* d_base = nullptr;
-    GJ_CUDA_TRY(cudaMalloc((void**)&d_base, (size_t)g->n_vars * 4));
+    // scratch buffers are grow-only members of nothing: scoped holders free them on every return path
+    struct DevBuf {
+        void* p = nullptr;
+        ~DevBuf() { if (p) cudaFree(p); }
+    } b_base, b_offs, b_ids, b_vals;
+    GJ_CUDA_TRY(cudaMalloc(&b_base.p, (size_t)g->n_vars * 4));
+    int32_t* d_base = (int32_t*)b_base.p;
     GJ_CUDA_TRY(cudaMemcpy(d_base, base.data(), (size_t)g->n_vars * 4, cudaMemcpyHostToDevice));
     gj_status rc = g->chain ? launch_chain_steps(g, 1, st, true) : ls_one_step(g, st, true);
-    if (rc) { cudaFree(d_base); return rc; }
+    if (rc) return rc;
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<GjMove> mv(K);
     GJ_CUDA_TRY(cudaMemcpy(mv.data(), g->moves + (size_t)island * K, (size_t)K * sizeof(GjMove), cudaMemcpyDeviceToHost));
@@ -1564,11 +1569,11 @@ extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64
             for (int i = 0; i < GJ_MOVE_MAXK; ++i) { d[4 + i] = m.a[i]; d[12 + i] = m.v[i]; }
         }
     }
-    if ((int64_t)offs[K] > delta_capacity) { cudaFree(d_base); return gj_fail(GJ_ERR_INVALID, "delta_capacity too small"); }
-    uint64_t *d_offs = nullptr, *d_ids = nullptr; double* d_vals = nullptr;
-    GJ_CUDA_TRY(cudaMalloc((void**)&d_offs, (size_t)(K + 1) * 8));
-    GJ_CUDA_TRY(cudaMalloc((void**)&d_ids, (size_t)(offs[K] + 1) * 8));
-    GJ_CUDA_TRY(cudaMalloc((void**)&d_vals, (size_t)(offs[K] + 1) * 8));
+    if ((int64_t)offs[K] > delta_capacity) return gj_fail(GJ_ERR_INVALID, "delta_capacity too small");
+    GJ_CUDA_TRY(cudaMalloc(&b_offs.p, (size_t)(K + 1) * 8));
+    GJ_CUDA_TRY(cudaMalloc(&b_ids.p, (size_t)(offs[K] + 1) * 8));
+    GJ_CUDA_TRY(cudaMalloc(&b_vals.p, (size_t)(offs[K] + 1) * 8));
+    uint64_t* d_offs = (uint64_t*)b_offs.p; uint64_t* d_ids = (uint64_t*)b_ids.p; double* d_vals = (double*)b_vals.p;
     GJ_CUDA_TRY(cudaMemcpy(d_offs, offs.data(), (size_t)(K + 1) * 8, cudaMemcpyHostToDevice));
     k_expand_moves<<<K, 128, 0, st>>>(P, g->groups, d_base, g->moves + (size_t)island * K, K, g->noop, d_offs, d_ids, d_vals);
     GJ_LAUNCH_CHECK();
@@ -1582,7 +1587,6 @@ extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64
     GJ_CUDA_TRY(cudaMemcpy(&acc, g->accepted + island, 4, cudaMemcpyDeviceToHost));
     if (selected) *selected = sel;
     if (accepted) *accepted = acc;
-    cudaFree(d_base); cudaFree(d_offs); cudaFree(d_ids); cudaFree(d_vals);
     // the trace bypasses migration / global-top bookkeeping of gj_islands_step on purpose
     return GJ_OK;
 }

@@ -50,12 +50,12 @@ k_plain_warp(GjProblemDev P, const RowT* __restrict__ samples, int64_t stride, i
 
 // ---- plain: one CTA per candidate (VRP) -------------------------------------------------
 template <class RowT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kVrpWarps * 32)
 k_plain_vrp(GjProblemDev P, const RowT* __restrict__ samples, int64_t stride, int64_t S,
             int isc, double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kWarpsPerCta);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
     const int64_t j = blockIdx.x;
     const RowT* row = samples + j * stride;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -143,13 +143,13 @@ k_incr_warp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __
         for (int l = 0; l < P.levels; ++l) scores[j * P.levels + l] = out[l];
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kVrpWarps * 32)
 k_incr_vrp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __restrict__ offsets,
            const uint64_t* __restrict__ ids, const double* __restrict__ vals, int64_t S,
            double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kWarpsPerCta);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
     const int64_t j = blockIdx.x;
     // clones of candidate_vehicle_ids / candidate_customer_ids (vrp ISC :63-64)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -193,9 +193,9 @@ static gj_status launch_plain(gj_problem* p, const RowT* d_samples, int64_t stri
     const GjProblemDev& P = p->dev;
     gj_status rc;
     if (P.kind >= GJ_VRP) {
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kWarpsPerCta);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
         if ((rc = set_smem(k_plain_vrp<RowT>, smem))) return rc;
-        k_plain_vrp<RowT><<<(unsigned)S, kWarpsPerCta * 32, smem, st>>>(P, d_samples, stride, S, isc, d_scores);
+        k_plain_vrp<RowT><<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_samples, stride, S, isc, d_scores);
     } else {
         size_t smem = (size_t)kWarpsPerCta * (size_t)(P.bm_words + P.desc_words + P.asc_words) * 4;
         unsigned grid = (unsigned)((S + kWarpsPerCta - 1) / kWarpsPerCta);
@@ -235,9 +235,9 @@ gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32
         GJ_LAUNCH_CHECK();
     }
     if (P.kind >= GJ_VRP) {
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kWarpsPerCta);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
         if ((rc = set_smem(k_incr_vrp, smem))) return rc;
-        k_incr_vrp<<<(unsigned)S, kWarpsPerCta * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
+        k_incr_vrp<<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
     } else {
         size_t per_warp = (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
         size_t smem = per_warp * kWarpsPerCta;
