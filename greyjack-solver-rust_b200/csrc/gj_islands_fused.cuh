@@ -293,18 +293,31 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     int* worklist = F.worklist + (size_t)island * K;
     const int n_chunks = (K + blockDim.x - 1) / blockDim.x;
     sh_selinfo[tid] = 0;
-    auto offer = [&](const GjScore& sc, int c) {
+    // `in_order`: neighbours offered in increasing index order (the main loop).  ScoreTrait::round is
+    // monotone, so a neighbour whose UNROUNDED score is not below the thread's best cannot round to a
+    // smaller key, and on a tie the earlier index stays: the key arithmetic is only needed for the
+    // (rare) improving neighbours.
+    auto offer = [&](const GjScore& sc, int c, bool in_order) {
+        if (F.scores_out) {
+            GjScore r = sc;
+            gj_score_round(r, P);                  // agent_base.rs:311-314
+            for (int l = 0; l < levels; ++l) F.scores_out[((size_t)island * K + c) * levels + l] = r.v[l];
+        }
+        if (in_order && mine.idx >= 0) {
+            bool below = false, decided = false;
+#pragma unroll
+            for (int l = 0; l < LV; ++l) {
+                if (!decided && sc.v[l] < mine.val[l]) { below = true; decided = true; }
+                if (!decided && sc.v[l] > mine.val[l]) { decided = true; }
+            }
+            if (!below) return;
+        }
         GjBest<LV> o;
         o.idx = c;
 #pragma unroll
         for (int l = 0; l < LV; ++l) {
             o.val[l] = sc.v[l];
             o.key[l] = gj_round_key(sc.v[l], P.round_mult[l]);
-        }
-        if (F.scores_out) {
-            GjScore r = sc;
-            gj_score_round(r, P);                  // agent_base.rs:311-314
-            for (int l = 0; l < levels; ++l) F.scores_out[((size_t)island * K + c) * levels + l] = r.v[l];
         }
         gj_best_merge<LV>(mine, o);
     };
@@ -329,7 +342,7 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
         if (!ok) { worklist[atomicAdd(&sh_nwork, 1)] = c; continue; }
         GjScore sc;
         gj_fused_combine<KIND>(P, raw, d_uniq, d_dist, sc);
-        offer(sc, c);
+        offer(sc, c, true);
     }
     __syncthreads();
 
@@ -358,7 +371,7 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
                 gj_tsp_eval_warp(P, src, bm, lane, dup, dist);
                 gj_combine_tsp(P, true, dup, dist, sc.v);
             }
-            if (lane == 0) offer(sc, c);
+            if (lane == 0) offer(sc, c, false);
             __syncwarp();
         }
     }
