@@ -320,3 +320,57 @@ def test_simulated_annealing_run_and_full_mode(oracle):
         assert isl.stats()["steps"] == 400 and isl.stats()["candidates"] == 400 * 4
         isl.close()
     gp.close()
+
+
+# ---- several semantic groups, non-consecutive groups, frozen variables ---------------------------------
+def _grouped_specs():
+    t = inst.tsp(90, seed=12)
+    n = t.n_vars
+    t.groups = {"front": np.arange(0, n // 2, dtype=np.int32), "back": np.arange(n // 2, n, dtype=np.int32)}
+    t.name = "tsp90-two-groups"
+    u = inst.tsp(70, seed=13)
+    u.groups = {"even": np.arange(0, u.n_vars, 2, dtype=np.int32), "odd": np.arange(1, u.n_vars, 2, dtype=np.int32)}
+    u.name = "tsp70-strided-groups"          # segment moves are NOT runs of consecutive stops: full evaluator
+    f = inst.tsp(60, seed=14)
+    f.frozen = np.zeros(f.n_vars, dtype=np.uint8)
+    f.frozen[[3, 4, 17, 40]] = 1              # frozen stops drop out of the group (variables_manager.rs:76-106)
+    f.name = "tsp60-frozen"
+    q = inst.nqueens(50)
+    q.groups = {"left": np.arange(0, 20, dtype=np.int32), "right": np.arange(20, 50, dtype=np.int32)}
+    q.name = "nq50-two-groups"
+    return [t, u, f, q]
+
+
+@pytest.mark.parametrize("scoring", SCORINGS + ["full"])
+@pytest.mark.parametrize("spec", _grouped_specs(), ids=lambda s: s.name)
+def test_groups_and_frozen_variables_step_replay(spec, scoring, oracle):
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    if spec.frozen is not None:
+        # the mover only ever sees the unfrozen members of a group (variables_manager.rs:76-106)
+        import copy
+        spec = copy.copy(spec)
+        spec.groups = {k: np.asarray([v for v in ids if not spec.frozen[v]], dtype=np.int32)
+                       for k, ids in spec.groups.items()}
+    K = 192
+    isl = TabuSearch(K, 0.3, True, 1.5, ALL, 10, scoring=scoring).build_agent(gp, n_islands=2, seed=77)
+    for _ in range(4):
+        base, cur_score = isl.current(1)
+        tr = isl.trace_step(1)
+        groups_seen = set()
+        for j in range(K):
+            d = tr["desc"][j]
+            want = _oracle_move(op, spec, base, d)
+            assert _final_state(spec.n_vars, tr["deltas"][j]) == _final_state(spec.n_vars, want)
+            groups_seen.add(int(d[1]))
+            if spec.frozen is not None:
+                assert not any(spec.frozen[c] for c, _ in tr["deltas"][j])      # frozen columns never move
+        assert groups_seen == set(range(len(spec.groups)))
+        want = op.score_incremental(base, tr["deltas"])
+        if scoring == "full":
+            assert np.array_equal(tr["scores"], oracle.score_round(want, spec.score_precision))
+        else:
+            _check_delta_scores(tr["scores"], want, spec, oracle)
+        sel, acc = oracle.ts_select(tr["scores"], cur_score)
+        assert (tr["selected"], tr["accepted"]) == (sel, acc)
+    isl.close(); gp.close()
