@@ -26,6 +26,7 @@ struct GjDeltaState {
     double* raw;         // [I][GJ_MAX_LEVELS] unrounded, unweighted terms of the current solution
     int* uniq;           // [I]
     int* stale;          // [I] 1 = cur changed since the state was built
+    double* edge;        // [I][n + 1] TSP: scratch for the exact-order fold of k_refresh
 };
 
 // Change of the number of distinct keys when, for every i < m with ko[i] != kn[i], one

@@ -166,6 +166,28 @@ __device__ __forceinline__ long long gj_warp_sum(long long x) {
     return x;
 }
 
+// CTA-wide sums (every thread gets the total).  `scratch` holds 32 entries.
+__device__ __forceinline__ int gj_block_sum(int x, int* scratch) {
+    x = gj_warp_sum(x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < nw; ++w) tot += scratch[w];
+    return tot;
+}
+__device__ __forceinline__ double gj_block_sum(double x, double* scratch) {
+    x = gj_warp_sum(x);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = x;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < nw; ++w) tot += scratch[w];
+    return tot;
+}
+
 // ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------
 // Stages a contiguous table (a solution row, a tabu table, a fact table) from global to shared
 // memory with one instruction issued by one thread; consumers wait on the mbarrier's phase.

@@ -50,7 +50,7 @@ k_score_moves_warp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, 
     const int per_warp = words + P.n_vars;
     uint32_t* bm = smem_u32 + warp * per_warp;
     int32_t* cand = (int32_t*)(bm + words);
-    const int64_t j = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;      // 1..kWarps warps per CTA
     if (j >= total) return;
     const int32_t* base = cur + (size_t)(j / K) * stride;
     for (int i = lane; i < P.n_vars; i += 32) cand[i] = base[i];
@@ -167,7 +167,8 @@ k_score_fallback_warp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
     uint32_t* bm = smem_u32 + warp * per_warp;
     int32_t* cand = (int32_t*)(bm + words);
     const int n_work = *work_count;
-    for (int w = blockIdx.x * kWarps + warp; w < n_work; w += gridDim.x * kWarps) {
+    const int cta_warps = blockDim.x >> 5;
+    for (int w = blockIdx.x * cta_warps + warp; w < n_work; w += gridDim.x * cta_warps) {
         const int j = worklist[w];
         const int island = j / C.K, c = j - island * C.K;
         const int32_t* base = cur + (size_t)island * C.stride;
@@ -213,46 +214,79 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
 k_refresh(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double* cur_score,
           GjDeltaState S, int update_top, int32_t* best, double* best_score, int* dirty) {
-    extern __shared__ uint32_t smem_u32[];
+    __shared__ int sh_i[32];
+    __shared__ double sh_d[32];
     const int island = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int32_t* row = cur + (size_t)island * stride;
     const int why = S.stale[island];
     if (why) {
+        // value counts, then the FULL evaluation by the whole CTA: distinct count from the counts;
+        // TSP edges gathered in parallel (tree: CTA-wide sum; exact: staged in HBM scratch and
+        // folded by one thread strictly in the reference's order, tsp ISC :76-80)
         int32_t* cnt = S.cnt + (size_t)island * S.cnt_stride;
         for (int i = tid; i < S.cnt_stride; i += blockDim.x) cnt[i] = 0;
         __syncthreads();
-        if (warp == 0) {
-            GjSrcI32 src{row};
-            GjScore s;
-            double* raw = S.raw + (size_t)island * GJ_MAX_LEVELS;
+        const int n = P.n_vars;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const int v = row[i];
+            atomicAdd(&cnt[v - P.val_lo], 1);
             if constexpr (KIND == GJ_NQUEENS) {
-                const double v = gj_nqueens_eval_warp(P, src, smem_u32, lane);
-                gj_combine_nqueens(P, v, s.v);
-                if (lane == 0) { raw[0] = v; raw[1] = 0.0; raw[2] = 0.0; }
-            } else {
-                double dup, dist;
-                gj_tsp_eval_warp(P, src, smem_u32, lane, dup, dist);
-                gj_combine_tsp(P, true, dup, dist, s.v);
-                if (lane == 0) { raw[0] = dup; raw[1] = dist; raw[2] = 0.0; }
-            }
-            if (lane == 0 && why == 2) {
-                gj_score_round(s, P);
-                for (int l = 0; l < P.levels; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = s.v[l];
-            }
-        } else {
-            for (int i = tid - 32; i < P.n_vars; i += blockDim.x - 32) {
-                const int v = row[i];
-                atomicAdd(&cnt[v - P.val_lo], 1);
-                if constexpr (KIND == GJ_NQUEENS) {
-                    const int col = P.column_id[i];
-                    atomicAdd(&cnt[32 * P.bm_words + (col + v - P.desc_lo)], 1);
-                    atomicAdd(&cnt[32 * (P.bm_words + P.desc_words) + (col - v - P.asc_lo)], 1);
-                }
+                const int col = P.column_id[i];
+                atomicAdd(&cnt[32 * P.bm_words + (col + v - P.desc_lo)], 1);
+                atomicAdd(&cnt[32 * (P.bm_words + P.desc_words) + (col - v - P.asc_lo)], 1);
             }
         }
         __syncthreads();
-        if (tid == 0) S.stale[island] = 0;
+        int u = 0;
+        for (int k = tid; k < S.cnt_stride; k += blockDim.x) u += (cnt[k] > 0) ? 1 : 0;
+        const int uniq = gj_block_sum(u, sh_i);
+        double r0, r1 = 0.0;
+        if constexpr (KIND == GJ_NQUEENS) {
+            r0 = (double)(3 * n - uniq);
+        } else {
+            r0 = (double)(n - uniq);
+            const size_t L = (size_t)P.n_locations;
+            double* edge = S.edge + (size_t)island * (size_t)(n + 1);
+            double acc = 0.0;
+            for (int i = tid; i <= n; i += blockDim.x) {
+                const int a = (i == 0) ? 0 : row[i - 1];
+                const int b = (i == n) ? 0 : row[i];
+                const double d = __ldg(&P.D[(size_t)a * L + (size_t)b]);
+                if (P.exact_sums) edge[i] = d; else acc += d;
+            }
+            if (!P.exact_sums) {
+                r1 = gj_block_sum(acc, sh_d);
+            } else {
+                __syncthreads();
+                if (tid == 0) {
+                    double fold = 0.0;
+#pragma unroll 8
+                    for (int i = 1; i < n; ++i) fold = fold + edge[i];
+                    double sample_distance = 0.0;
+                    sample_distance += edge[0];
+                    sample_distance += edge[n];
+                    sample_distance += fold;
+                    sh_d[0] = sample_distance;
+                }
+                __syncthreads();
+                r1 = sh_d[0];
+            }
+        }
+        if (tid == 0) {
+            double* raw = S.raw + (size_t)island * GJ_MAX_LEVELS;
+            raw[0] = r0; raw[1] = r1; raw[2] = 0.0;
+            if (why == 2) {
+                GjScore s;
+                s.v[0] = s.v[1] = s.v[2] = 0.0;
+                if constexpr (KIND == GJ_NQUEENS) gj_combine_nqueens(P, r0, s.v);
+                else gj_combine_tsp(P, true, r0, r1, s.v);
+                gj_score_round(s, P);
+                for (int l = 0; l < P.levels; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = s.v[l];
+            }
+            S.stale[island] = 0;
+        }
+        __syncthreads();
     }
     if (update_top) gj_update_top(island, P.levels, stride, P.n_vars, cur, cur_score, best, best_score, dirty);
 }
@@ -1029,6 +1063,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
         if ((rc = dev_alloc(g.get(), (size_t)I * g->ds.cnt_stride, &g->ds.cnt))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->ds.raw))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.uniq))) return rc;
+        if (P.kind == GJ_TSP && (rc = dev_alloc(g.get(), (size_t)I * (size_t)(P.n_vars + 1), &g->ds.edge, false))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.stale))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I * g->K, &g->worklist))) return rc;
         if ((rc = dev_alloc(g.get(), 1, &g->work_count))) return rc;
@@ -1116,15 +1151,18 @@ static gj_status launch_score_moves(gj_islands* g, cudaStream_t st) {
         if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_moves_vrp<<<(unsigned)total, kVrpWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
     } else {
-        size_t smem = (size_t)kWarps * (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
-        if (smem > 220 * 1024) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
-        unsigned grid = (unsigned)((total + kWarps - 1) / kWarps);
+        // one shared-memory clone per warp: fewer warps per CTA for large instances
+        const size_t per_warp = (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
+        const int warps = (int)std::min<size_t>(kWarps, (220 * 1024) / per_warp);
+        if (warps < 1) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
+        const size_t smem = per_warp * warps;
+        unsigned grid = (unsigned)((total + warps - 1) / warps);
         if (P.kind == GJ_NQUEENS) {
             if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_warp<GJ_NQUEENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_score_moves_warp<GJ_NQUEENS><<<grid, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
+            k_score_moves_warp<GJ_NQUEENS><<<grid, warps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
         } else {
             if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_warp<GJ_TSP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_score_moves_warp<GJ_TSP><<<grid, kWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
+            k_score_moves_warp<GJ_TSP><<<grid, warps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
         }
     }
     GJ_LAUNCH_CHECK();
@@ -1177,7 +1215,7 @@ static gj_status opt_in_smem(Kern kernel, size_t bytes) {
 // k_refresh for every island (early exit for islands whose state is current)
 static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top) {
     const GjProblemDev& P = g->p->dev;
-    const size_t smem = warp_eval_smem(P, 1, false);
+    const size_t smem = 0;
     gj_status rc;
     if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_refresh<GJ_NQUEENS>, smem))) return rc;
@@ -1209,16 +1247,17 @@ static gj_status launch_score_delta(gj_islands* g, cudaStream_t st, bool trace) 
                                                    g->worklist, g->work_count, moves_out);
     GJ_LAUNCH_CHECK();
     if (g->delta_may_fallback) {
-        const size_t smem = warp_eval_smem(P, kWarps, true);
-        if (smem > 220 * 1024) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
-        const unsigned fgrid = (unsigned)std::min<int64_t>((total + kWarps - 1) / kWarps, 148 * 4);
+        const int warps = (int)std::min<size_t>(kWarps, (220 * 1024) / warp_eval_smem(P, 1, true));
+        if (warps < 1) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
+        const size_t smem = warp_eval_smem(P, warps, true);
+        const unsigned fgrid = (unsigned)std::min<int64_t>((total + warps - 1) / warps, 148 * 4);
         if (P.kind == GJ_NQUEENS) {
             if ((rc = opt_in_smem(k_score_fallback_warp<GJ_NQUEENS>, smem))) return rc;
-            k_score_fallback_warp<GJ_NQUEENS><<<fgrid, kWarps * 32, smem, st>>>(P, g->groups, g->mover, C, g->cur,
+            k_score_fallback_warp<GJ_NQUEENS><<<fgrid, warps * 32, smem, st>>>(P, g->groups, g->mover, C, g->cur,
                                                                                g->worklist, g->work_count, g->cand_scores);
         } else {
             if ((rc = opt_in_smem(k_score_fallback_warp<GJ_TSP>, smem))) return rc;
-            k_score_fallback_warp<GJ_TSP><<<fgrid, kWarps * 32, smem, st>>>(P, g->groups, g->mover, C, g->cur,
+            k_score_fallback_warp<GJ_TSP><<<fgrid, warps * 32, smem, st>>>(P, g->groups, g->mover, C, g->cur,
                                                                            g->worklist, g->work_count, g->cand_scores);
         }
         GJ_LAUNCH_CHECK();

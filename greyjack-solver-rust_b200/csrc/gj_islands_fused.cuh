@@ -65,28 +65,6 @@ __device__ __forceinline__ GjFusedSmem gj_fused_carve(unsigned char* smem, int n
     return s;
 }
 
-// CTA-wide sums (every thread gets the total).  `scratch` holds 32 entries.
-__device__ __forceinline__ int gj_block_sum(int x, int* scratch) {
-    x = gj_warp_sum(x);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    if (lane == 0) scratch[warp] = x;
-    __syncthreads();
-    int tot = 0;
-    for (int w = 0; w < nw; ++w) tot += scratch[w];
-    return tot;
-}
-__device__ __forceinline__ double gj_block_sum(double x, double* scratch) {
-    x = gj_warp_sum(x);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    if (lane == 0) scratch[warp] = x;
-    __syncthreads();
-    double tot = 0.0;
-    for (int w = 0; w < nw; ++w) tot += scratch[w];
-    return tot;
-}
-
 // Value counts of the staged solution (shared atomics), all threads.
 template <int KIND>
 __device__ __forceinline__ void gj_fused_counts(const GjProblemDev& P, const GjFusedSmem& s, int cnt_stride) {

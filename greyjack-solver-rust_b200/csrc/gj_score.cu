@@ -123,7 +123,7 @@ k_incr_warp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __
     const int per_warp = words + P.n_vars;
     uint32_t* bm = smem_u32 + warp * per_warp;
     int32_t* cand = (int32_t*)(bm + words);
-    const int64_t j = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;      // 1..kWarpsPerCta warps per CTA
     if (j >= S) return;
     // clone of the planning ids (tsp ISC :64, nqueens ISC :42)
     for (int i = lane; i < P.n_vars; i += 32) cand[i] = base[i];
@@ -239,16 +239,18 @@ gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32
         if ((rc = set_smem(k_incr_vrp, smem))) return rc;
         k_incr_vrp<<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
     } else {
+        // one shared-memory clone per warp: fewer warps per CTA for large instances
         size_t per_warp = (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
-        size_t smem = per_warp * kWarpsPerCta;
-        if (smem > 220 * 1024) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
-        unsigned grid = (unsigned)((S + kWarpsPerCta - 1) / kWarpsPerCta);
+        const int warps = (int)std::min<size_t>(kWarpsPerCta, (220 * 1024) / per_warp);
+        if (warps < 1) return gj_fail(GJ_ERR_UNSUPPORTED, "instance too large for the shared-memory candidate clone");
+        size_t smem = per_warp * warps;
+        unsigned grid = (unsigned)((S + warps - 1) / warps);
         if (P.kind == GJ_NQUEENS) {
             if ((rc = set_smem(k_incr_warp<GJ_NQUEENS>, smem))) return rc;
-            k_incr_warp<GJ_NQUEENS><<<grid, kWarpsPerCta * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
+            k_incr_warp<GJ_NQUEENS><<<grid, warps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
         } else {
             if ((rc = set_smem(k_incr_warp<GJ_TSP>, smem))) return rc;
-            k_incr_warp<GJ_TSP><<<grid, kWarpsPerCta * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
+            k_incr_warp<GJ_TSP><<<grid, warps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
         }
     }
     GJ_LAUNCH_CHECK();

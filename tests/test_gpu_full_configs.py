@@ -100,6 +100,14 @@ def test_c5_tsp20000_ga_and_tabu_islands(oracle):
     want = oracle.score_round(op.score_incremental(base, tr["deltas"][:64]), spec.score_precision)
     assert np.array_equal(tr["scores"][:64, 0], want[:, 0])
     assert np.max(np.abs(tr["scores"][:64, 1] - want[:, 1])) <= 1.001e-3
+    # the reference-facing incremental call and the full-evaluation islands at this size (one
+    # 80 KB shared-memory clone per warp: the kernels drop to two warps per CTA)
+    got = gp.request_score_incremental(base, tr["deltas"][:48])
+    assert np.array_equal(got, op.score_incremental(base, tr["deltas"][:48]))
+    tf = TabuSearch(64, 0.2, True, None, [0, 0.5, 0, 0, 0, 0.5], 10, scoring="full").build_agent(gp, n_islands=2, seed=4)
+    trf = tf.trace_step(1)
+    assert np.array_equal(trf["scores"], oracle.score_round(op.score_incremental(base, trf["deltas"]), spec.score_precision))
+    tf.close()
     s0 = ts.best(-1)[1]
     ts.step(20)
     v, s = ts.best(-1)
