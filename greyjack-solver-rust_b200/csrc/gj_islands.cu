@@ -211,7 +211,7 @@ __device__ __forceinline__ void gj_update_top(int island, int levels, int stride
 // current score is always exactly what the reference's scorer returns for the stored vector.
 // Then (update_top) update_top_individual, agent_base.rs:220-224.  One CTA per island.
 template <int KIND>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_refresh(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double* cur_score,
           GjDeltaState S, int update_top, int32_t* best, double* best_score, int* dirty) {
     __shared__ int sh_i[32];
@@ -427,13 +427,13 @@ __device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen,
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     extern __shared__ int32_t smem_row[];          // [n_vars] copy of the base for in-place apply
-    __shared__ GjScore sh_score[8];
-    __shared__ int sh_idx[8];
+    __shared__ GjScore sh_score[32];
+    __shared__ int sh_idx[32];
     __shared__ int sh_accept, sh_best;
-    __shared__ int sh_scan[256];
+    __shared__ int sh_scan[1024];
     const int island = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int K = A.K, levels = A.levels;
@@ -650,13 +650,13 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
 // the new global top is simply the best agent top (first index on ties).  Every CTA finds it
 // redundantly (I is small), CTA 0 publishes it (:451-461), and each island adopts it when it is
 // strictly better than its own top (:465-489; TabuSearch only with compare_to_global).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_global_top(int I, int agent, int compare_to_global, int levels, int stride, int n_vars, int late_size,
              const int32_t* __restrict__ best, const double* __restrict__ best_score,
              int32_t* gbest, double* gbest_score, int32_t* cur, double* cur_score, int* dirty,
              double* late, int* late_head, int* late_len, int* stale) {
-    __shared__ GjScore sh_s[8];
-    __shared__ int sh_i[8];
+    __shared__ GjScore sh_s[32];
+    __shared__ int sh_i[32];
     __shared__ int sh_take, sh_publish;
     const int island = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1219,11 +1219,11 @@ static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top)
     gj_status rc;
     if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_refresh<GJ_NQUEENS>, smem))) return rc;
-        k_refresh<GJ_NQUEENS><<<g->I, 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
+        k_refresh<GJ_NQUEENS><<<g->I, g->n_vars > 4096 ? 1024 : 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
                                                      g->best, g->best_score, g->dirty);
     } else {
         if ((rc = opt_in_smem(k_refresh<GJ_TSP>, smem))) return rc;
-        k_refresh<GJ_TSP><<<g->I, 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
+        k_refresh<GJ_TSP><<<g->I, g->n_vars > 4096 ? 1024 : 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
                                                  g->best, g->best_score, g->dirty);
     }
     GJ_LAUNCH_CHECK();
@@ -1330,7 +1330,8 @@ static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     }
     size_t smem = (size_t)g->n_vars * 4;
     if ((rc = opt_in_smem(k_select, smem))) return rc;
-    k_select<<<g->I, 256, smem, st>>>(P, g->groups, make_select_args(g, trace, !delta));
+    // row copies dominate for long solutions: a wider CTA then
+    k_select<<<g->I, g->n_vars > 4096 ? 1024 : 256, smem, st>>>(P, g->groups, make_select_args(g, trace, !delta));
     GJ_LAUNCH_CHECK();
     // delta mode: exact re-score of accepted neighbours + state rebuild, then update_top_individual
     if (delta && (rc = launch_refresh(g, st, true))) return rc;
@@ -1353,7 +1354,7 @@ gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
 }
 
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
-    k_global_top<<<g->I, 256, 0, st>>>(g->I, g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
+    k_global_top<<<g->I, g->n_vars > 4096 ? 1024 : 256, 0, st>>>(g->I, g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
                                       g->n_vars, g->late_size, g->best, g->best_score, g->gbest,
                                       g->gbest_score, g->cur, g->cur_score, g->dirty, g->late, g->late_head,
                                       g->late_len, g->ds.stale);
