@@ -144,6 +144,55 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def other_configs(gj, inst, torch):
+    """BASELINE.json's other configurations (parity-test cases, not bench lines): device-timed
+    candidates/s of the agent each one names, islands resident in HBM, no L2 flush.  Reported for
+    context next to the headline; a failure here never touches the headline numbers."""
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def timed(name, make, steps):
+        try:
+            prob, isl = make()
+            isl.step(max(1, steps // 10), stream)
+            torch.cuda.synchronize()
+            c0 = isl.stats()["candidates"]
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); isl.step(steps, stream); b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            out[name] = {"candidates_per_s": (isl.stats()["candidates"] - c0) / (ms * 1e-3),
+                         "us_per_step": 1e3 * ms / steps, "best": [float(x) for x in isl.best(-1)[1]]}
+            isl.close(); prob.close()
+        except Exception as e:                      # noqa: BLE001
+            out[name] = {"error": str(e)[:200]}
+
+    def c1():
+        p = gj.Problem(inst.nqueens(256, seed=45))
+        return p, gj.LateAcceptance(32, 0.2, None, [0, 1.0, 0, 0, 0, 0], 100, scoring="delta").build_agent(p, n_islands=4096, seed=1)
+
+    def c3():
+        spec = inst.cvrp(2000, 50, seed=2, greedy=False)
+        spec.initial = np.full(spec.n_vars, np.nan)
+        p = gj.Problem(spec)
+        return p, gj.GeneticAlgorithm(8192, 0.5, 0.2, 0.05, 1.0, None, 0.00001, 10).build_agent(p, n_islands=1, seed=2)
+
+    def c4():
+        p = gj.Problem(inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False))
+        return p, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50).build_agent(p, n_islands=592, seed=3)
+
+    def c5():
+        p = gj.Problem(inst.tsp(20000, seed=4, with_matrix=False), use_coords=True)
+        p.set_exact_sums(False)
+        return p, gj.TabuSearch(4096, 0.2, True, None, MOVE_PROBAS, 10, scoring="delta").build_agent(p, n_islands=148, seed=4)
+
+    timed("C1 nqueens-256 LateAcceptance x4096 chains (k_la_chains)", c1, 1000)
+    timed("C3 cvrp-2000x50 GeneticAlgorithm pop 8192 x1 island", c3, 10)
+    timed("C4 vrptw-5000 (vrp_service) LateAcceptance x592 islands", c4, 40)
+    timed("C5 tsp-20000 TabuSearch 4096 moves x148 islands (unfused delta)", c5, 20)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,6 +389,8 @@ def main():
                         "islands": args.islands},
                 "cpu": {"wall_s": cpu_wall, "best": [float(x) for x in cpu_best], "steps": cpu_steps,
                         "islands": cores, "note": "oracle port, one TabuSearch island per host thread"}}
+        if world == 1 and os.environ.get("GJ_BENCH_EXTRAS", "1") != "0":
+            line["other_configs"] = other_configs(gj, inst, torch)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
