@@ -54,7 +54,8 @@ struct GjChainSmem {
 __host__ __device__ inline size_t gj_chain_smem_bytes(int n_vars, int words, int ctabu_words, int late_size,
                                                       bool tsp) {
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
-    size_t b = (n_pad + 8) * 4 + (size_t)32 * words * 4 + n_pad * 4 + (size_t)words * 4;
+    const size_t scratch = n_pad < 32 ? 32 : n_pad;      // also holds <= 17 ints of a small move's columns
+    size_t b = (n_pad + 8) * 4 + (size_t)32 * words * 4 + scratch * 4 + (size_t)words * 4;
     b += (((size_t)ctabu_words + 3) & ~(size_t)3) * 4;
     b = (b + 15) & ~(size_t)15;
     if (tsp) b += (((size_t)n_vars + 2) & ~(size_t)1) * 8;
@@ -69,7 +70,7 @@ __device__ __forceinline__ GjChainSmem gj_chain_carve(unsigned char* smem, int n
     size_t o = 0;
     s.t = (int32_t*)(smem + o) + 4; o += (n_pad + 8) * 4;
     s.cnt = (int32_t*)(smem + o); o += (size_t)32 * words * 4;
-    s.scratch = (int32_t*)(smem + o); o += n_pad * 4;
+    s.scratch = (int32_t*)(smem + o); o += (n_pad < 32 ? 32 : n_pad) * 4;
     s.bm = (uint32_t*)(smem + o); o += (size_t)words * 4;
     s.tabu = (uint32_t*)(smem + o); o += (((size_t)ctabu_words + 3) & ~(size_t)3) * 4;
     o = (o + 15) & ~(size_t)15;

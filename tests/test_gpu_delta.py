@@ -374,3 +374,29 @@ def test_groups_and_frozen_variables_step_replay(spec, scoring, oracle):
         sel, acc = oracle.ts_select(tr["scores"], cur_score)
         assert (tr["selected"], tr["accepted"]) == (sel, acc)
     isl.close(); gp.close()
+
+
+def test_tiny_instances_all_paths(oracle):
+    """n = 6..9 variables: every buffer-size corner (padding, scratch, tabu tables) in all scoring modes."""
+    for spec in (inst.nqueens(6), inst.tsp(8, seed=3), inst.nqueens(9)):
+        op = oracle.OracleProblem(spec)
+        gp = Problem(spec)
+        for scoring in ("full", "delta", "delta_unfused"):
+            ts = TabuSearch(40, 0.3, True, 1.0, ALL, 2, scoring=scoring).build_agent(gp, n_islands=3, seed=1)
+            base, _ = ts.current(0)
+            tr = ts.trace_step(0)
+            _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+            ts.step(10)
+            v, s = ts.best(-1)
+            assert _same_score(s, op.score_incremental(v, [[]])[0], spec, oracle)
+            ts.close()
+            la = LateAcceptance(3, 0.3, None, ALL, 2, scoring=scoring).build_agent(gp, n_islands=3, seed=2)
+            for _ in range(12):
+                base, _ = la.current(1)
+                tr = la.trace_step(1)
+                _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+            la.step(20)
+            v, s = la.best(-1)
+            assert _same_score(s, op.score_incremental(v, [[]])[0], spec, oracle)
+            la.close()
+        gp.close()
