@@ -315,6 +315,9 @@ struct GjSelectArgs {
     int* stale; int defer_top; int* work_count;
     // SimulatedAnnealing: temperatures per island [I][GJ_MAX_LEVELS], schedule
     double* sa_temp; GjSaParams sa;
+    // fused islands adopt the published global top at the START of their next step (P0)
+    int compare_to_global;
+    int32_t* gbest; double* gbest_score; int* gver; int* gseen;
     // trace
     long long* selected_out; int* accepted_out; double* aux_out;
 };
@@ -578,6 +581,42 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     }
 }
 
+// update_global_top, adopt half (agent_base.rs:465-489), for fused islands: once per published
+// version of the global top, an island whose own top is strictly worse takes it over (TabuSearch:
+// only with compare_to_global).  Decision and bookkeeping (score, late list, flags) by ONE thread;
+// returns whether the island's solution is to be replaced by the gbest row.
+__device__ __forceinline__ bool gj_adopt_decide(const GjSelectArgs& A, int island) {
+    const int ver = *A.gver;
+    if (ver == A.gseen[island]) return false;
+    A.gseen[island] = ver;
+    const GjScore g = gj_load_score(A.gbest_score, A.levels);
+    const GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, A.levels);
+    const bool take = !gj_score_le(top, g, A.levels) && A.compare_to_global;     // global < agent_top
+    if (!take) return false;
+    if (A.agent == GJ_AGENT_LATE_ACCEPTANCE) {
+        double* lt = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
+        const int head = (A.late_head[island] + A.late_size - 1) % A.late_size;
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+            lt[(size_t)head * GJ_MAX_LEVELS + l] = A.cur_score[(size_t)island * GJ_MAX_LEVELS + l];
+        A.late_head[island] = head; A.late_len[island] = min(A.late_len[island] + 1, A.late_size);
+    }
+    for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = g.v[l];
+    A.dirty[island] = 1;
+    if (A.stale) A.stale[island] = 1;
+    return true;
+}
+
+// Applies pending adoptions outside a step (before the host reads / exports current solutions).
+__global__ void __launch_bounds__(128)
+k_apply_adoption(GjSelectArgs A) {
+    __shared__ int sh_take;
+    const int island = blockIdx.x;
+    if (threadIdx.x == 0) sh_take = gj_adopt_decide(A, island) ? 1 : 0;
+    __syncthreads();
+    if (sh_take)
+        for (int i = threadIdx.x; i < A.n_vars; i += blockDim.x) A.cur[(size_t)island * A.stride + i] = A.gbest[i];
+}
+
 #include "gj_islands_fused.cuh"
 #include "gj_islands_chain.cuh"
 
@@ -654,7 +693,7 @@ __global__ void __launch_bounds__(1024)
 k_global_top(int I, int agent, int compare_to_global, int levels, int stride, int n_vars, int late_size,
              const int32_t* __restrict__ best, const double* __restrict__ best_score,
              int32_t* gbest, double* gbest_score, int32_t* cur, double* cur_score, int* dirty,
-             double* late, int* late_head, int* late_len, int* stale) {
+             double* late, int* late_head, int* late_len, int* stale, int adopt, int* gver) {
     __shared__ GjScore sh_s[32];
     __shared__ int sh_i[32];
     __shared__ int sh_take, sh_publish;
@@ -691,10 +730,11 @@ k_global_top(int I, int agent, int compare_to_global, int levels, int stride, in
             if (!gj_score_le(g, b, levels)) {                   // strict: agent_top < global (:451)
                 for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
                 sh_publish = 1;
+                if (gver) *gver += 1;
             }
         }
         GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        bool take = !gj_score_le(top, b, levels);               // global < agent_top (:465)
+        bool take = adopt && !gj_score_le(top, b, levels);      // global < agent_top (:465)
         if (agent == GJ_AGENT_TABU_SEARCH) take = take && compare_to_global;
         if (take && agent == GJ_AGENT_LATE_ACCEPTANCE) {
             double* lt = late + (size_t)island * late_size * GJ_MAX_LEVELS;
@@ -1039,6 +1079,8 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
         if ((rc = dev_alloc(g.get(), (size_t)I, &g->late_head))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I, &g->late_len))) return rc;
     }
+    if ((rc = dev_alloc(g.get(), 1, &g->gver))) return rc;
+    if ((rc = dev_alloc(g.get(), (size_t)I, &g->gseen))) return rc;
     if ((rc = dev_alloc(g.get(), (size_t)I, &g->selected))) return rc;
     if ((rc = dev_alloc(g.get(), (size_t)I, &g->accepted))) return rc;
 
@@ -1186,6 +1228,8 @@ static GjSelectArgs make_select_args(gj_islands* g, bool trace, bool stored_move
     A.stale = g->ds.stale; A.defer_top = g->scoring_mode == GJ_SCORING_DELTA ? 1 : 0;
     A.work_count = g->work_count;
     A.sa_temp = g->sa_temp; A.sa = g->sa;
+    A.compare_to_global = g->prm.agent == GJ_AGENT_TABU_SEARCH ? g->prm.compare_to_global : 1;
+    A.gbest = g->gbest; A.gbest_score = g->gbest_score; A.gver = g->gver; A.gseen = g->gseen;
     A.selected_out = trace ? g->selected : nullptr; A.accepted_out = trace ? g->accepted : nullptr;
     A.aux_out = trace ? g->trace_aux : nullptr;
     return A;
@@ -1354,10 +1398,22 @@ gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
 }
 
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
-    k_global_top<<<g->I, g->n_vars > 4096 ? 1024 : 256, 0, st>>>(g->I, g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
+    // fused islands: ONE CTA publishes (gbest row + score + version); every island adopts at the
+    // start of its next step (k_ls_step_fused P0).  Other paths: publish + adopt, one CTA per island.
+    const int adopt = g->fused ? 0 : 1;
+    const int grid = g->fused ? 1 : g->I;
+    k_global_top<<<grid, g->n_vars > 4096 ? 1024 : 256, 0, st>>>(g->I, g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
                                       g->n_vars, g->late_size, g->best, g->best_score, g->gbest,
                                       g->gbest_score, g->cur, g->cur_score, g->dirty, g->late, g->late_head,
-                                      g->late_len, g->ds.stale);
+                                      g->late_len, g->ds.stale, adopt, g->gver);
+    GJ_LAUNCH_CHECK();
+    return GJ_OK;
+}
+
+// fused islands: pending adoptions must land before anyone looks at (or exports) current solutions
+static gj_status apply_pending_adoption(gj_islands* g, cudaStream_t st) {
+    if (!g->fused) return GJ_OK;
+    k_apply_adoption<<<g->I, 128, 0, st>>>(make_select_args(g, false, false));
     GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
@@ -1533,6 +1589,11 @@ extern "C" gj_status gj_islands_current(gj_islands* g, int32_t island, double* v
     GJ_CUDA_TRY(cudaSetDevice(g->p->device));
     GJ_CUDA_TRY(cudaDeviceSynchronize());
     if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_current(g, island, vars, score);
+    {
+        gj_status rc = apply_pending_adoption(g, g->p->stream);
+        if (rc) return rc;
+        GJ_CUDA_TRY(cudaStreamSynchronize(g->p->stream));
+    }
     return fetch_individual(g, g->cur + (size_t)island * g->stride,
                             g->cur_score + (size_t)island * GJ_MAX_LEVELS, vars, score);
 }
@@ -1548,6 +1609,7 @@ extern "C" gj_status gj_islands_export_migrants(gj_islands* g, void* d_buffer, v
     cudaStream_t st = (cudaStream_t)stream;
     gj_status rc;
     if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_export(g, d_buffer, st);
+    if ((rc = apply_pending_adoption(g, st))) return rc;
     if ((rc = gj_ls_migrate_pack(g, st))) return rc;
     const size_t sb = (size_t)g->stride * 4 + GJ_MAX_LEVELS * 8;
     GJ_CUDA_TRY(cudaMemcpyAsync(d_buffer, g->mailbox + (size_t)g->I * sb, sb, cudaMemcpyDeviceToDevice, st));
@@ -1578,6 +1640,11 @@ extern "C" gj_status gj_islands_trace_step(gj_islands* g, int32_t island, uint64
     const GjProblemDev& P = g->p->dev;
     const int K = g->K;
     // base of the island BEFORE the step
+    {
+        gj_status rc0 = apply_pending_adoption(g, st);
+        if (rc0) return rc0;
+        GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     std::vector<int32_t> base(g->n_vars);
     GJ_CUDA_TRY(cudaMemcpy(base.data(), g->cur + (size_t)island * g->stride, (size_t)g->n_vars * 4, cudaMemcpyDeviceToHost));
     // scratch buffers are grow-only members of nothing: scoped holders free them on every return path

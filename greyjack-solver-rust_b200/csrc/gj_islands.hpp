@@ -30,6 +30,8 @@ struct gj_islands {
     int32_t* best = nullptr; double* best_score = nullptr;      // agent_top_individual
     int32_t* gbest = nullptr; double* gbest_score = nullptr;    // global_top_individual
     int* dirty = nullptr;
+    int* gver = nullptr;         // version of the published global top
+    int* gseen = nullptr;        // [I] last version every island has looked at (fused islands)
     GjMove* moves = nullptr;
     double* cand_scores = nullptr;
     unsigned char* mailbox = nullptr;

@@ -230,21 +230,28 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     // The island's solution row and tabu table travel global -> shared as two TMA bulk copies
     // issued by one thread (rows and tables are 16-byte aligned and padded, see ls_create).
     __shared__ __align__(8) uint64_t sh_mbar;
+    __shared__ int sh_adopt;
     if (tid == 0) {
         gj_mbar_init(&sh_mbar, 1);
         sh_nwork = 0;
+        // update_global_top, adopt half: the global top published after the previous step replaces
+        // this island's solution when it beats the island's own top
+        sh_adopt = gj_adopt_decide(A, island) ? 1 : 0;
     }
     __syncthreads();
+    const bool adopted = sh_adopt != 0;
     if (tid == 0) {
         const uint32_t row_bytes = (uint32_t)(((n + 3) & ~3) * 4);
         const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
         gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes);
-        gj_tma_load_1d(s.t, cur_row, row_bytes, &sh_mbar);
+        gj_tma_load_1d(s.t, adopted ? A.gbest : cur_row, row_bytes, &sh_mbar);
         if (tabu_bytes)
             gj_tma_load_1d(s.bits, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
     }
     gj_mbar_wait(&sh_mbar, 0);
     if (tid == 0) { s.t[-1] = 0; s.t[n] = 0; }     // depot before the first and after the last stop
+    if (adopted)
+        for (int i = tid; i < n; i += blockDim.x) cur_row[i] = s.t[i];
     gj_fused_counts<KIND>(P, s, cnt_stride);
     if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
     if (F.S.stale[island]) {                       // replaced by a migrant / the global best
