@@ -5,7 +5,6 @@
 // island keeps, next to its current solution,
 //     cnt[key]  occurrence count of every counted value (TSP: location ids; N-Queens: rows,
 //               col+row and col-row diagonals in three disjoint key ranges),
-//     uniq      number of keys with cnt > 0,
 //     raw[]     the unrounded constraint terms of the current solution (TSP: dup count, tour
 //               length), produced by the FULL evaluator in the reference's summation order,
 // and one thread scores one neighbour from the O(k) terms its move touches:
@@ -24,7 +23,6 @@ struct GjDeltaState {
     int32_t* cnt;        // [I][cnt_stride]
     int cnt_stride;
     double* raw;         // [I][GJ_MAX_LEVELS] unrounded, unweighted terms of the current solution
-    int* uniq;           // [I]
     int* stale;          // [I] 1 = cur changed since the state was built
     double* edge;        // [I][n + 1] TSP: scratch for the exact-order fold of k_refresh
 };

@@ -1104,7 +1104,6 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
         g->ds.cnt_stride = 32 * (P.bm_words + P.desc_words + P.asc_words);
         if ((rc = dev_alloc(g.get(), (size_t)I * g->ds.cnt_stride, &g->ds.cnt))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->ds.raw))) return rc;
-        if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.uniq))) return rc;
         if (P.kind == GJ_TSP && (rc = dev_alloc(g.get(), (size_t)I * (size_t)(P.n_vars + 1), &g->ds.edge, false))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.stale))) return rc;
         if ((rc = dev_alloc(g.get(), (size_t)I * g->K, &g->worklist))) return rc;
@@ -1139,10 +1138,8 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
             while (threads > 256 && 1024 / threads < per_sm) threads /= 2;
             threads = std::min(threads, std::max(32, ((g->K + 31) / 32) * 32));
             if (const char* e = getenv("GJ_FUSED_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
-            g->fused_fold_chunk = 2048;
             for (int clones = std::min(4, threads / 32); clones >= 0; --clones) {
-                const size_t b = gj_fused_smem_bytes(P.n_vars, g->ds.cnt_stride, g->tabu_words, words, clones,
-                                                     g->fused_fold_chunk);
+                const size_t b = gj_fused_smem_bytes(P.n_vars, g->ds.cnt_stride, g->tabu_words, words, clones);
                 if (b <= 200 * 1024 && (clones > 0 || !g->delta_may_fallback)) {
                     g->fused = true; g->fused_clones = clones; g->fused_smem = b; g->fused_threads = threads;
                     break;
@@ -1316,7 +1313,6 @@ static gj_status launch_fused_step(gj_islands* g, cudaStream_t st, bool trace) {
     F.S = g->ds;
     F.symmetric = g->p->symmetric_D ? 1 : 0;
     F.n_clone = g->fused_clones;
-    F.fold_chunk = g->fused_fold_chunk;
     F.scores_out = trace ? g->cand_scores : nullptr;
     F.moves_out = trace ? g->moves : nullptr;
     F.worklist = g->worklist;

@@ -51,7 +51,7 @@ struct gj_islands {
     int* work_count = nullptr;
     // fused single-kernel step (gj_islands_fused.cuh)
     bool fused = false;
-    int fused_threads = 0, fused_clones = 0, fused_fold_chunk = 0;
+    int fused_threads = 0, fused_clones = 0;
     size_t fused_smem = 0;
     long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid
     // LateAcceptance chains: many steps per launch, one warp per island (gj_islands_chain.cuh)

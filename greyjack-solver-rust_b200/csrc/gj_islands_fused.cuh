@@ -23,7 +23,6 @@ struct GjFusedArgs {
     GjDeltaState S;
     int symmetric;
     int n_clone;                // shared-memory solution clones available to the full evaluator
-    int fold_chunk;             // (unused, kept for layout) 
     double* scores_out;         // trace only: [I][K][levels]
     GjMove* moves_out;          // trace only
     int* worklist;              // [I][K]
@@ -40,7 +39,7 @@ struct GjFusedSmem {
 };
 
 __host__ __device__ inline size_t gj_fused_smem_bytes(int n_vars, int cnt_stride, int tabu_words,
-                                                      int words, int n_clone, int fold_chunk) {
+                                                      int words, int n_clone) {
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
     size_t b = (n_pad + 8) * 4 + (size_t)cnt_stride * 4 + (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
     b += (size_t)n_clone * (size_t)words * 4 + (size_t)n_clone * n_pad * 4;
