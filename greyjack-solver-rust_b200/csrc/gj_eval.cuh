@@ -192,11 +192,19 @@ __device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_sto
     return s;
 }
 
+// Optional per-route by-products of an evaluation (global memory; the delta evaluator's base state).
+struct GjVrpOut {
+    int32_t* bstop;              // [n_stops] stop index of every bucket slot
+    unsigned long long* rload;   // [K] demand carried per vehicle
+    unsigned long long* rlate;   // [K] lateness per vehicle
+};
+
 // Evaluates the candidate whose decoded (vehicle, customer) columns already sit in
 // s.veh / s.cust.  All threads of the CTA must call it.  Results valid in thread 0.
 __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjVrpSmem& s,
                                                 int tw_mode, double& dup1000, double& cap,
-                                                double& dist, double& late) {
+                                                double& dist, double& late,
+                                                const GjVrpOut* out = nullptr) {
     const int n = P.n_entities;
     const int K = P.n_vehicles;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -270,6 +278,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         __syncwarp();
         if (on) {
             s.bucket[slot + rank] = s.cust[i];
+            if (out) out->bstop[slot + rank] = i;
             if (rank == 0) mycnt[v] = slot + __popc(grp);
         }
         __syncwarp();
@@ -282,6 +291,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         const int b = s.start[v], e = s.start[v + 1];
         const int len = e - b;
         double current_distance = 0.0;
+        unsigned long long route_load = 0ull, route_late = 0ull;
         if (len != 0) {
             const int32_t* st = s.bucket + b;
             const size_t depot = (size_t)P.veh_depot[v];
@@ -297,6 +307,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
             current_distance += fold;
             const unsigned long long capv = P.veh_capacity[v];
             if (load > capv) my_cap += load - capv;
+            route_load = load;
 
             if (P.time_windowed) {
                 unsigned long long arrival = P.day_start[v];
@@ -307,16 +318,18 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
                     const unsigned long long ws = c.y, we = c.z, sv = c.w;
                     if (arrival < ws) arrival = ws;
                     if (tw_mode == GJ_TW_ISC_FILE) {
-                        if (arrival + sv > we) my_late += (arrival + sv) - we;
+                        if (arrival + sv > we) route_late += (arrival + sv) - we;
                     } else {
-                        if (arrival > we + sv) my_late += arrival - (we + sv);
+                        if (arrival > we + sv) route_late += arrival - (we + sv);
                     }
                     arrival += sv;
                 }
-                if (arrival > day_end) my_late += arrival - day_end;
+                if (arrival > day_end) route_late += arrival - day_end;
+                my_late += route_late;
             }
         }
         s.vdist[v] = current_distance;
+        if (out) { out->rload[v] = route_load; out->rlate[v] = route_late; }
     }
     if (my_cap) atomicAdd(&s.acc[0], my_cap);
     if (my_late) atomicAdd(&s.acc[1], my_late);

@@ -200,6 +200,84 @@ k_score_fallback_warp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
     }
 }
 
+// ---- VRP delta scoring (gj_vrp_delta.cuh) -------------------------------------------------------
+__device__ __forceinline__ int gj_vrp_tw_mode(const GjProblemDev& P) {
+    return P.kind == GJ_VRP_SERVICE ? GJ_TW_ISC_SERVICE : GJ_TW_ISC_FILE;      // islands score with the ISC
+}
+
+// one thread per neighbour: generate the move, re-walk the routes it touches
+__global__ void __launch_bounds__(128)
+k_score_delta_vrp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C, const int32_t* __restrict__ cur,
+                  GjDeltaState S, GjVrpState V, double* __restrict__ scores, int* __restrict__ worklist,
+                  int* __restrict__ work_count, GjMove* __restrict__ moves_out) {
+    const int64_t total = (int64_t)C.I * C.K;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    const int island = (int)(j / C.K), cand = (int)(j - (int64_t)island * C.K);
+    const uint32_t* bits = C.tabu_bits ? C.tabu_bits + (size_t)island * C.tabu_words_per_island : nullptr;
+    const GjMove m = gj_generate_move(P, G, M, C.seed, (uint32_t)(C.island_base + island), C.step,
+                                      (uint32_t)cand, bits, C.tabu_word_off);
+    if (moves_out) moves_out[j] = m;
+    const int n = P.n_entities, K = P.n_vehicles;
+    double dup1000, cap, dist, late;
+    const bool ok = gj_vrp_move_delta(P, G, m, C.noop != 0, gj_vrp_tw_mode(P), cur + (size_t)island * C.stride,
+                                      V.bucket + (size_t)island * n, V.bstop + (size_t)island * n,
+                                      V.start + (size_t)island * (K + 1), V.rdist + (size_t)island * K,
+                                      V.rload + (size_t)island * K, V.rlate + (size_t)island * K,
+                                      V.tot + (size_t)island * 4, S.cnt + (size_t)island * S.cnt_stride,
+                                      dup1000, cap, dist, late);
+    if (!ok) {
+        worklist[atomicAdd(work_count, 1)] = (int)j;
+        return;
+    }
+    GjScore s;
+    gj_combine_vrp(P, true, dup1000, cap, dist, late, s.v);
+    gj_score_round(s, P);
+    for (int l = 0; l < 3; ++l) scores[j * 3 + l] = s.v[l];
+}
+
+// the queued neighbours (segment moves): full evaluator, one CTA each, persistent over the worklist
+__global__ void __launch_bounds__(kVrpWarps * 32)
+k_score_fallback_vrp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C, const int32_t* __restrict__ cur,
+                     const int* __restrict__ worklist, const int* __restrict__ work_count,
+                     double* __restrict__ scores) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ GjMove sh_mv;
+    const int n = P.n_entities;
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
+    const int n_work = *work_count;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int j = worklist[w];
+        const int island = j / C.K, c = j - island * C.K;
+        const int32_t* base = cur + (size_t)island * C.stride;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t* bits = C.tabu_bits ? C.tabu_bits + (size_t)island * C.tabu_words_per_island : nullptr;
+            sh_mv = gj_generate_move(P, G, M, C.seed, (uint32_t)(C.island_base + island), C.step, (uint32_t)c,
+                                     bits, C.tabu_word_off);
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int2 pr = *reinterpret_cast<const int2*>(base + 2 * i);
+            s.veh[i] = (uint16_t)pr.x;
+            s.cust[i] = pr.y;
+        }
+        __syncthreads();
+        const GjMove m = sh_mv;
+        gj_apply_move(P, m, G, true, C.noop != 0, threadIdx.x, blockDim.x,
+                      [&](int id) { return base[id]; },
+                      [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; });
+        __syncthreads();
+        double dup1000 = 0, cap = 0, dist = 0, late = 0;
+        gj_vrp_eval_cta(P, s, gj_vrp_tw_mode(P), dup1000, cap, dist, late);
+        if (threadIdx.x == 0) {
+            GjScore sc;
+            gj_combine_vrp(P, true, dup1000, cap, dist, late, sc.v);
+            gj_score_round(sc, P);
+            for (int l = 0; l < 3; ++l) scores[(size_t)j * 3 + l] = sc.v[l];
+        }
+    }
+}
+
 __device__ __forceinline__ GjScore gj_load_score(const double* p, int levels);
 __device__ __forceinline__ void gj_update_top(int island, int levels, int stride, int n_vars,
                                               const int32_t* cur, const double* cur_score,
@@ -283,6 +361,55 @@ k_refresh(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double* c
                 else gj_combine_tsp(P, true, r0, r1, s.v);
                 gj_score_round(s, P);
                 for (int l = 0; l < P.levels; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = s.v[l];
+            }
+            S.stale[island] = 0;
+        }
+        __syncthreads();
+    }
+    if (update_top) gj_update_top(island, P.levels, stride, P.n_vars, cur, cur_score, best, best_score, dirty);
+}
+
+// Rebuilds the VRP base state of every island whose solution changed: one FULL evaluation by the
+// CTA (the same evaluator that scores plain candidates) whose by-products -- bucketed stops, route
+// boundaries, per-route distance / demand / lateness, customer counts -- are kept in HBM.  After an
+// accepted neighbour (stale == 2) the stored score is re-derived from that evaluation.  Then
+// update_top_individual.
+__global__ void __launch_bounds__(kVrpWarps * 32)
+k_vrp_state(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double* cur_score, GjDeltaState S,
+            GjVrpState V, int update_top, int32_t* best, double* best_score, int* dirty) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int island = blockIdx.x;
+    const int n = P.n_entities, K = P.n_vehicles;
+    const int why = S.stale[island];
+    if (why) {
+        GjVrpSmem s = gj_vrp_carve(smem_raw, n, K, P.bm_words, kVrpWarps);
+        const int32_t* row = cur + (size_t)island * stride;
+        int32_t* cnt = S.cnt + (size_t)island * S.cnt_stride;
+        for (int i = threadIdx.x; i < S.cnt_stride; i += blockDim.x) cnt[i] = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int2 pr = *reinterpret_cast<const int2*>(row + 2 * i);
+            s.veh[i] = (uint16_t)pr.x;
+            s.cust[i] = pr.y;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cnt[s.cust[i] - P.val_lo], 1);
+        GjVrpOut out{V.bstop + (size_t)island * n, V.rload + (size_t)island * K, V.rlate + (size_t)island * K};
+        double dup1000 = 0, cap = 0, dist = 0, late = 0;
+        gj_vrp_eval_cta(P, s, gj_vrp_tw_mode(P), dup1000, cap, dist, late, &out);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) V.bucket[(size_t)island * n + i] = s.bucket[i];
+        for (int v = threadIdx.x; v <= K; v += blockDim.x) V.start[(size_t)island * (K + 1) + v] = s.start[v];
+        for (int v = threadIdx.x; v < K; v += blockDim.x) V.rdist[(size_t)island * K + v] = s.vdist[v];
+        if (threadIdx.x == 0) {
+            unsigned long long* tot = V.tot + (size_t)island * 4;
+            tot[0] = (unsigned long long)llrint(dup1000 / 1000.0);
+            tot[1] = s.acc[0];
+            tot[2] = s.acc[1];
+            if (why == 2) {
+                GjScore sc;
+                gj_combine_vrp(P, true, dup1000, cap, dist, late, sc.v);
+                gj_score_round(sc, P);
+                for (int l = 0; l < 3; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = sc.v[l];
             }
             S.stale[island] = 0;
         }
@@ -1098,6 +1225,33 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
     GJ_LAUNCH_CHECK();
     // delta scoring: cached per-island state (gj_delta.cuh).  The VRP models are scored by the
     // full evaluator in either mode for now.
+    // VRP models: route-level delta evaluation (gj_vrp_delta.cuh), separate kernels per step.  The base
+    // state is rebuilt (one full evaluation per island) after every accepted neighbour, which only
+    // pays off when a step scores several neighbours: single-neighbour agents (LateAcceptance,
+    // SimulatedAnnealing) keep the full evaluator.
+    if ((prm->scoring_mode == GJ_SCORING_DELTA || prm->scoring_mode == GJ_SCORING_DELTA_UNFUSED) &&
+        p->dev.kind >= GJ_VRP && g->K >= 8) {
+        g->scoring_mode = GJ_SCORING_DELTA;
+        const GjProblemDev& P = p->dev;
+        const int n = P.n_entities, K = P.n_vehicles;
+        g->ds.cnt_stride = 32 * P.bm_words;
+        if ((rc = dev_alloc(g.get(), (size_t)I * g->ds.cnt_stride, &g->ds.cnt))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->ds.raw))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.stale))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * g->K, &g->worklist))) return rc;
+        if ((rc = dev_alloc(g.get(), 1, &g->work_count))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * n, &g->vs.bucket))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * n, &g->vs.bstop))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * (K + 1), &g->vs.start))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * K, &g->vs.rdist))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * K, &g->vs.rload))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * K, &g->vs.rlate))) return rc;
+        if ((rc = dev_alloc(g.get(), (size_t)I * 4, &g->vs.tot))) return rc;
+        std::vector<int> ones((size_t)I, 1);
+        GJ_CUDA_TRY(cudaMemcpy(g->ds.stale, ones.data(), (size_t)I * sizeof(int), cudaMemcpyHostToDevice));
+        g->delta_may_fallback = g->mover.thresholds[3] < 1.0;      // insertion / inverse possible
+        if ((rc = launch_refresh(g.get(), st, false))) return rc;
+    }
     if ((prm->scoring_mode == GJ_SCORING_DELTA || prm->scoring_mode == GJ_SCORING_DELTA_UNFUSED) && p->dev.kind <= GJ_TSP) {
         g->scoring_mode = GJ_SCORING_DELTA;
         const GjProblemDev& P = p->dev;
@@ -1258,6 +1412,14 @@ static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top)
     const GjProblemDev& P = g->p->dev;
     const size_t smem = 0;
     gj_status rc;
+    if (P.kind >= GJ_VRP) {
+        const size_t vsmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+        if ((rc = opt_in_smem(k_vrp_state, vsmem))) return rc;
+        k_vrp_state<<<g->I, kVrpWarps * 32, vsmem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, g->vs,
+                                                         update_top ? 1 : 0, g->best, g->best_score, g->dirty);
+        GJ_LAUNCH_CHECK();
+        return GJ_OK;
+    }
     if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_refresh<GJ_NQUEENS>, smem))) return rc;
         k_refresh<GJ_NQUEENS><<<g->I, g->n_vars > 4096 ? 1024 : 256, smem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, update_top ? 1 : 0,
@@ -1280,6 +1442,20 @@ static gj_status launch_score_delta(gj_islands* g, cudaStream_t st, bool trace) 
     const unsigned grid = (unsigned)((total + 255) / 256);
     GjMove* moves_out = trace ? g->moves : nullptr;
     gj_status rc;
+    if (P.kind >= GJ_VRP) {
+        k_score_delta_vrp<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, C, g->cur, g->ds, g->vs,
+                                                                           g->cand_scores, g->worklist, g->work_count, moves_out);
+        GJ_LAUNCH_CHECK();
+        if (g->delta_may_fallback) {
+            const size_t vsmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+            if ((rc = opt_in_smem(k_score_fallback_vrp, vsmem))) return rc;
+            const unsigned fgrid = (unsigned)std::min<int64_t>(total, 148 * 4);
+            k_score_fallback_vrp<<<fgrid, kVrpWarps * 32, vsmem, st>>>(P, g->groups, g->mover, C, g->cur, g->worklist,
+                                                                      g->work_count, g->cand_scores);
+            GJ_LAUNCH_CHECK();
+        }
+        return GJ_OK;
+    }
     if (P.kind == GJ_NQUEENS)
         k_score_delta<GJ_NQUEENS><<<grid, 256, 0, st>>>(P, g->groups, g->mover, C, g->cur, g->ds, g->cand_scores,
                                                        g->worklist, g->work_count, moves_out);

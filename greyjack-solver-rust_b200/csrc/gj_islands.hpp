@@ -6,6 +6,7 @@
 #include "gj_internal.hpp"
 #include "gj_moves.cuh"
 #include "gj_delta.cuh"
+#include "gj_vrp_delta.cuh"
 
 struct gj_islands {
     gj_problem* p = nullptr;
@@ -47,6 +48,7 @@ struct gj_islands {
     int scoring_mode = 0;
     bool delta_may_fallback = true;      // some generated moves may need the full evaluator
     GjDeltaState ds{};
+    GjVrpState vs{};                     // VRP route-level base state (gj_vrp_delta.cuh)
     int* worklist = nullptr;             // [I*K] neighbours queued for the full evaluator
     int* work_count = nullptr;
     // fused single-kernel step (gj_islands_fused.cuh)

@@ -66,12 +66,14 @@ enum {
    FULL : every candidate is materialised and fully re-scored -- the reference's own
           pseudo-incremental ISC semantics, bit-exact incl. the float level
           when exact sums are on.
-   DELTA: the island keeps per-solution state on the device (value counts, exact base score)
-          and a candidate's score is base + the change over the O(k) constraint terms the move
-          touches.  Integer levels are bit-exact with FULL; the float level agrees to 1e-12
-          relative before ScoreTrait::round (one 10^-precision quantum after).  Moves the
-          delta evaluator does not cover (listed in DESIGN.md) are re-scored by the FULL
-          kernel inside the same step.                                                      */
+   DELTA: the island keeps per-solution state on the device and a candidate is scored from
+          the constraint terms its move touches.  N-Queens / TSP: value counts + exact base
+          score; integer levels bit-exact with FULL, the float level agrees to 1e-12 relative
+          before ScoreTrait::round (one 10^-precision quantum after).  VRP models: the routes
+          a move touches are re-walked in the reference's order -- every level bit-exact with
+          FULL (used by agents that score >= 8 neighbours per step).  Moves the delta evaluator
+          does not cover (listed in DESIGN.md) are re-scored by the FULL kernel inside the
+          same step.                                                                        */
 enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1,
        GJ_SCORING_DELTA_UNFUSED = 2   /* DELTA as separate kernels (generate+score | select |
                                          refresh); what DELTA falls back to when an island does

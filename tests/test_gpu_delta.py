@@ -400,3 +400,80 @@ def test_tiny_instances_all_paths(oracle):
             assert _same_score(s, op.score_incremental(v, [[]])[0], spec, oracle)
             la.close()
         gp.close()
+
+
+# ---- VRP models: route-level delta evaluation (gj_vrp_delta.cuh) -- every level BIT-exact ---------------
+VRP_CASES = [
+    ("cvrp60", lambda: inst.cvrp(60, 6, seed=2), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.8, None),
+    ("cvrp60-all", lambda: inst.cvrp(60, 6, seed=2), ALL, 0.2, 1.0),
+    ("cvrp45-mult", lambda: inst.cvrp(45, 5, seed=7), [0.3, 0.3, 0.2, 0.2, 0.0, 0.0], 0.1, 3.0),
+    ("vrpsvc80", lambda: inst.vrptw(80, 6, n_depots=2, seed=3), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.2, None),
+    ("vrptw80-all", lambda: inst.vrptw(80, 6, n_depots=2, seed=3, service_variant=False), ALL, 0.2, 1.0),
+    ("vrpsvc50-mult", lambda: inst.vrptw(50, 7, n_depots=3, seed=9), [0.3, 0.3, 0.2, 0.2, 0.0, 0.0], 0.0, 4.0),
+]
+
+
+@pytest.mark.parametrize("noop", [True, False], ids=["refquirk", "plainform"])
+@pytest.mark.parametrize("case", VRP_CASES, ids=lambda c: c[0])
+def test_vrp_delta_step_replay(case, noop, oracle):
+    _, mk, probas, tabu, mult = case
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    K = 160
+    isl = TabuSearch(K, tabu, True, mult, probas, 10, reference_noop_moves=noop,
+                     scoring="delta").build_agent(gp, n_islands=2, seed=4321)
+    for island in (0, 1):
+        for _ in range(5):
+            base, cur_score = isl.current(island)
+            assert _same_score(cur_score, op.score_incremental(base, [[]])[0], spec, oracle)
+            tr = isl.trace_step(island)
+            if noop:
+                for j in range(K):
+                    want = _oracle_move(op, spec, base, tr["desc"][j])
+                    assert _final_state(spec.n_vars, tr["deltas"][j]) == _final_state(spec.n_vars, want)
+            want = oracle.score_round(op.score_incremental(base, tr["deltas"]), spec.score_precision)
+            assert np.array_equal(tr["scores"], want)          # hard, medium AND the float soft level
+            sel, acc = oracle.ts_select(tr["scores"], cur_score)
+            assert (tr["selected"], tr["accepted"]) == (sel, acc)
+            new, new_score = isl.current(island)
+            want_vec = base.copy()
+            if acc:
+                for c, v in tr["deltas"][sel]:
+                    want_vec[c] = v
+                assert np.array_equal(new_score, tr["scores"][sel])
+            else:
+                assert np.array_equal(new_score, cur_score)
+            assert np.array_equal(new, want_vec)
+    isl.close(); gp.close()
+
+
+@pytest.mark.parametrize("mk", [lambda: inst.cvrp(50, 5, seed=6), lambda: inst.vrptw(50, 5, n_depots=2, seed=6)],
+                         ids=["cvrp", "vrpsvc"])
+@pytest.mark.parametrize("agent", ["ts", "la"])
+def test_vrp_delta_run_is_consistent(mk, agent, oracle):
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    probas = [0.3, 0.3, 0.1, 0.1, 0.1, 0.1]
+    if agent == "ts":
+        isl = TabuSearch(128, 0.2, True, None, probas, 5, reference_noop_moves=False, scoring="delta").build_agent(gp, n_islands=4, seed=5)
+        per_step = 128
+    else:
+        isl = LateAcceptance(8, 0.2, None, probas, 5, reference_noop_moves=False, scoring="delta").build_agent(gp, n_islands=4, seed=5)
+        per_step = 1
+    _, s0 = isl.best(0)
+    prev = None
+    for _ in range(5):
+        isl.step(20)
+        vec, sc = isl.best(-1)
+        assert _same_score(sc, op.score_incremental(vec, [[]])[0], spec, oracle)
+        if prev is not None:
+            assert oracle.score_cmp(sc, prev) <= 0
+        prev = sc
+        for i in range(4):
+            cv, cs = isl.current(i)
+            assert _same_score(cs, op.score_incremental(cv, [[]])[0], spec, oracle)
+    assert oracle.score_cmp(prev, s0) < 0
+    assert isl.stats()["candidates"] == 100 * per_step * 4
+    isl.close(); gp.close()
