@@ -57,40 +57,46 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons during the timed regions (B200_PROFILING.md): one
+    `nvidia-smi -lms 50` process streams samples while the bench runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self.stop_flag = threading.Event()
+        self.proc = None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                line = line.strip()
+                if line:
+                    self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
 
     def summary(self):
-        self.stop_flag.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         self.join(timeout=6)
-        if not self.rows:
+        rows = [r for r in self.rows if len(r) >= 6]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "sm_max_mhz": int(rows[0][1]) if rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(rows)}
 
 
 def host_moves(base, n_moves, rng):
@@ -263,7 +269,6 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.summary()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     cands = isl.stats()["candidates"] - c0
     gpu_launches = int(gj.load().gj_launch_count() - launches0)     # counted by the library itself
@@ -300,7 +305,7 @@ def main():
                    "migration_frequency": MIGRATION_FREQUENCY, "score_precision": [3, 3],
                    "scoring": SCORING_DESC[SCORING], "float_sums": "tree (gj_problem_set_exact_sums(0))", "l2": "flushed between timed steps (256 MiB write)",
                    "parallelism": f"islands x{world}"},
-        "clocks": clocks, "gpu_launches": gpu_launches,
+        "clocks": None, "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": SCORING_KERNEL[SCORING], "kernel_ms": kernel_ms,
@@ -309,6 +314,8 @@ def main():
                      "candidates_per_launch": per_launch_cands},
     }
 
+    if rank != 0:
+        sampler.summary()
     if rank == 0:
         # ---- e2e: reference-facing call, host buffers, H2D + D2H inside the timed region ------
         A = args.e2e_agents
@@ -348,6 +355,8 @@ def main():
         run_agents(args.steps)
         e2e_s = time.perf_counter() - t0
         e2e_launches = int(gj.load().gj_launch_count() - l0)
+        # the sampler has been running since before the device-timed region: both timed regions
+        line["clocks"] = sampler.summary()
         line["e2e"] = {"value": A * NEIGHBOURS * args.steps / e2e_s, "unit": UNIT,
                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "agents": A, "host_memory": "pinned (gj_host_alloc)",
