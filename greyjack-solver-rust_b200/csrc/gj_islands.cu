@@ -811,20 +811,16 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
         for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = row[i];
 }
 
-// update_global_top (agent_base.rs:446-490) for every island in ONE launch (one CTA per island).
-// Agent tops only ever improve and the global top is refreshed from them after every step, so
-// the new global top is simply the best agent top (first index on ties).  Every CTA finds it
-// redundantly (I is small), CTA 0 publishes it (:451-461), and each island adopts it when it is
-// strictly better than its own top (:465-489; TabuSearch only with compare_to_global).
+// update_global_top, publish half (agent_base.rs:451-461), ONE CTA.  Agent tops only ever improve
+// and the global top is refreshed from them after every step, so the new global top is simply the
+// best agent top (first index on ties); it replaces the published one when strictly better (:451)
+// and bumps the version that gj_adopt_decide (the adopt half) watches.
 __global__ void __launch_bounds__(1024)
-k_global_top(int I, int agent, int compare_to_global, int levels, int stride, int n_vars, int late_size,
-             const int32_t* __restrict__ best, const double* __restrict__ best_score,
-             int32_t* gbest, double* gbest_score, int32_t* cur, double* cur_score, int* dirty,
-             double* late, int* late_head, int* late_len, int* stale, int adopt, int* gver) {
+k_global_top(int I, int levels, int stride, int n_vars, const int32_t* __restrict__ best,
+             const double* __restrict__ best_score, int32_t* gbest, double* gbest_score, int* gver) {
     __shared__ GjScore sh_s[32];
     __shared__ int sh_i[32];
-    __shared__ int sh_take, sh_publish;
-    const int island = blockIdx.x;
+    __shared__ int sh_publish;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     GjScore mine; int mine_idx = -1;
     mine.v[0] = mine.v[1] = mine.v[2] = 0.0;
@@ -850,39 +846,20 @@ k_global_top(int I, int agent, int compare_to_global, int levels, int stride, in
             const int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_s[w], levels);
             if (c > 0 || (c == 0 && sh_i[w] < bi)) { b = sh_s[w]; bi = sh_i[w]; }
         }
-        sh_s[0] = b; sh_i[0] = bi;
+        sh_i[0] = bi;
         sh_publish = 0;
-        if (island == 0) {
-            GjScore g = gj_load_score(gbest_score, levels);
-            if (!gj_score_le(g, b, levels)) {                   // strict: agent_top < global (:451)
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
-                sh_publish = 1;
-                if (gver) *gver += 1;
-            }
+        const GjScore g = gj_load_score(gbest_score, levels);
+        if (bi >= 0 && !gj_score_le(g, b, levels)) {            // strict: agent_top < global (:451)
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
+            sh_publish = 1;
+            *gver += 1;
         }
-        GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        bool take = adopt && !gj_score_le(top, b, levels);      // global < agent_top (:465)
-        if (agent == GJ_AGENT_TABU_SEARCH) take = take && compare_to_global;
-        if (take && agent == GJ_AGENT_LATE_ACCEPTANCE) {
-            double* lt = late + (size_t)island * late_size * GJ_MAX_LEVELS;
-            const int head = (late_head[island] + late_size - 1) % late_size;
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l)
-                lt[(size_t)head * GJ_MAX_LEVELS + l] = cur_score[(size_t)island * GJ_MAX_LEVELS + l];
-            late_head[island] = head; late_len[island] = min(late_len[island] + 1, late_size);
-        }
-        if (take) {
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) cur_score[(size_t)island * GJ_MAX_LEVELS + l] = b.v[l];
-            dirty[island] = 1;
-            if (stale) stale[island] = 1;
-        }
-        sh_take = take ? 1 : 0;
     }
     __syncthreads();
-    const int32_t* win_row = best + (size_t)sh_i[0] * stride;
-    if (sh_publish)
+    if (sh_publish) {
+        const int32_t* win_row = best + (size_t)sh_i[0] * stride;
         for (int i = tid; i < n_vars; i += blockDim.x) gbest[i] = win_row[i];
-    if (sh_take)
-        for (int i = tid; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = win_row[i];
+    }
 }
 
 // Expands move descriptors into the (column, value) lists of the reference's incremental form.
@@ -1569,22 +1546,26 @@ gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
     return GJ_OK;
 }
 
+static gj_status apply_pending_adoption(gj_islands* g, cudaStream_t st);
+
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
-    // fused islands: ONE CTA publishes (gbest row + score + version); every island adopts at the
-    // start of its next step (k_ls_step_fused P0).  Other paths: publish + adopt, one CTA per island.
-    const int adopt = g->fused ? 0 : 1;
-    const int grid = g->fused ? 1 : g->I;
-    k_global_top<<<grid, g->n_vars > 4096 ? 1024 : 256, 0, st>>>(g->I, g->prm.agent, g->prm.compare_to_global, g->levels, g->stride,
-                                      g->n_vars, g->late_size, g->best, g->best_score, g->gbest,
-                                      g->gbest_score, g->cur, g->cur_score, g->dirty, g->late, g->late_head,
-                                      g->late_len, g->ds.stale, adopt, g->gver);
+    // update_global_top (agent_base.rs:446-490).  Publish half: ONE CTA (arg-min over the agent tops
+    // -> gbest row, score, version).  Adopt half: once per published version and island
+    // (gj_adopt_decide) -- inside the next launch for fused islands and chains (staging phase),
+    // right away by k_apply_adoption for the other paths.  O(I) work in total.
+    k_global_top<<<1, (g->n_vars > 4096 || g->I > 2048) ? 1024 : 256, 0, st>>>(
+        g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score, g->gver);
     GJ_LAUNCH_CHECK();
+    if (!g->fused && !g->chain) {
+        k_apply_adoption<<<g->I, 128, 0, st>>>(make_select_args(g, false, false));
+        GJ_LAUNCH_CHECK();
+    }
     return GJ_OK;
 }
 
 // fused islands: pending adoptions must land before anyone looks at (or exports) current solutions
 static gj_status apply_pending_adoption(gj_islands* g, cudaStream_t st) {
-    if (!g->fused) return GJ_OK;
+    if (!g->fused && !g->chain) return GJ_OK;          // the other paths adopt right after publishing
     k_apply_adoption<<<g->I, 128, 0, st>>>(make_select_args(g, false, false));
     GJ_LAUNCH_CHECK();
     return GJ_OK;
@@ -1603,6 +1584,7 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     A.ctabu = g->ctabu; A.ctabu_words_per_island = g->ctabu_words; A.ctabu_off = g->ctabu_off;
     A.tabu_size = g->tabu_size;
     A.agent = g->prm.agent; A.sa_temp = g->sa_temp; A.sa = g->sa;
+    A.gbest = g->gbest; A.gbest_score = g->gbest_score; A.gver = g->gver; A.gseen = g->gseen;
     if (trace) A.trace_aux = g->trace_aux;
     // trace (n == 1): the step's move / score / decision land where the per-step path puts them
     if (trace) { A.trace_moves = g->moves; A.trace_scores = g->cand_scores; A.trace_accept = g->accepted; }

@@ -37,6 +37,8 @@ struct GjChainArgs {
     // chain tabu state, per island and group (global, persistent):
     //   bits [W + 1] words | ring [T] ints | head, fill
     uint32_t* ctabu; int ctabu_words_per_island; const int32_t* ctabu_off; const int32_t* tabu_size;
+    // published global top (one-CTA k_global_top); adopted here, at the start of a launch
+    const int32_t* gbest; const double* gbest_score; const int* gver; int* gseen;
     // trace (tests): [n_steps][I]
     GjMove* trace_moves; double* trace_scores; int* trace_accept;
 };
@@ -152,7 +154,21 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     int32_t* best_row = A.best + (size_t)island * A.stride;
 
     // ---- stage ---------------------------------------------------------------------------------
-    for (int i = lane; i < n; i += 32) s.t[i] = cur_row[i];
+    // update_global_top, adopt half (agent_base.rs:465-489): a newly published global top that beats
+    // this chain's own top replaces its solution (once per published version)
+    int adopted = 0;
+    if (lane == 0 && A.gver) {
+        const int ver = *A.gver;
+        if (ver != A.gseen[island]) {
+            A.gseen[island] = ver;
+            const GjScore g = gj_load_score(A.gbest_score, LV);
+            const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+            adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
+        }
+    }
+    adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
+    const int32_t* src_row = adopted ? A.gbest : cur_row;
+    for (int i = lane; i < n; i += 32) s.t[i] = src_row[i];
     if (lane == 0) { s.t[-1] = 0; s.t[n] = 0; }
     uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
     if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) s.tabu[w] = tabu_g[w];
@@ -171,8 +187,18 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     raw0 = __shfl_sync(GJ_FULL_MASK, raw0, 0);
     GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
     GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    if (adopted) {
+        if (is_la) {          // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
+            late_head = (late_head + A.late_size - 1) % A.late_size;
+            if (lane == 0)
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = cur.v[l];
+            late_len = min(late_len + 1, A.late_size);
+            __syncwarp();
+        }
+        cur = gj_load_score(A.gbest_score, LV);
+    }
     // a migrant / the global best may have replaced the solution since the last launch
-    if (A.dirty[island]) {
+    if (A.dirty[island] || adopted) {
         if (gj_score_le(cur, top, LV)) {
             for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
             top = cur;
