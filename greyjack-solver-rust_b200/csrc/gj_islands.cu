@@ -1276,6 +1276,19 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
                     break;
                 }
             }
+            // long solutions (TSP-20000): lean layout -- only the solution in shared memory -- when
+            // every move the mover can generate takes the delta fast path (two-stop swaps, 2-opt,
+            // insertions on consecutive uniform columns; the reference's no-op scramble / swap_edges)
+            if (!g->fused && P.kind == GJ_TSP && !g->delta_may_fallback) {
+                const bool quirk_only = prm->reference_noop_moves != 0;
+                const bool need_cnt = thr[0] > 0.0 || g->mover.mutation_rate_multiplier != 0.0 || !affine ||
+                                      ((thr[2] - thr[1] > 0.0 || thr[3] - thr[2] > 0.0) && !quirk_only);
+                const size_t b = gj_fused_smem_bytes_lean(P.n_vars, words);
+                if (!need_cnt && b <= 110 * 1024) {
+                    g->fused = true; g->fused_lean = true; g->fused_clones = 0; g->fused_smem = b;
+                    g->fused_threads = std::max(threads, 512);      // at most two CTAs per SM fit
+                }
+            }
         }
         // LateAcceptance (one neighbour per step): chains that run many steps per launch
         if (prm->scoring_mode == GJ_SCORING_DELTA && (la || sa)) {
@@ -1466,6 +1479,7 @@ static gj_status launch_fused_step(gj_islands* g, cudaStream_t st, bool trace) {
     F.S = g->ds;
     F.symmetric = g->p->symmetric_D ? 1 : 0;
     F.n_clone = g->fused_clones;
+    F.lean = g->fused_lean ? 1 : 0;
     F.scores_out = trace ? g->cand_scores : nullptr;
     F.moves_out = trace ? g->moves : nullptr;
     F.worklist = g->worklist;

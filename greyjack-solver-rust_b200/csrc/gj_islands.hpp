@@ -53,6 +53,7 @@ struct gj_islands {
     int* work_count = nullptr;
     // fused single-kernel step (gj_islands_fused.cuh)
     bool fused = false;
+    bool fused_lean = false;             // long solutions: only the solution is staged in shared memory
     int fused_threads = 0, fused_clones = 0;
     size_t fused_smem = 0;
     long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid

@@ -23,6 +23,9 @@ struct GjFusedArgs {
     GjDeltaState S;
     int symmetric;
     int n_clone;                // shared-memory solution clones available to the full evaluator
+    int lean;                   // 1: long solutions -- only the solution itself is staged in shared
+                                // memory; edge lengths and the tabu table stay in HBM / L2 and there are
+                                // no value counts (the host guarantees every move takes the fast path)
     double* scores_out;         // trace only: [I][K][levels]
     GjMove* moves_out;          // trace only
     int* worklist;              // [I][K]
@@ -38,6 +41,11 @@ struct GjFusedSmem {
     double* edge;               // [n + 1] TSP: edge[i] = D[t[i-1]][t[i]], depot at both ends
 };
 
+__host__ __device__ inline size_t gj_fused_smem_bytes_lean(int n_vars, int words) {
+    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
+    return (((n_pad + 8) * 4 + (size_t)words * 4) + 15) & ~(size_t)15;
+}
+
 __host__ __device__ inline size_t gj_fused_smem_bytes(int n_vars, int cnt_stride, int tabu_words,
                                                       int words, int n_clone) {
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
@@ -49,10 +57,16 @@ __host__ __device__ inline size_t gj_fused_smem_bytes(int n_vars, int cnt_stride
 }
 
 __device__ __forceinline__ GjFusedSmem gj_fused_carve(unsigned char* smem, int n_vars, int cnt_stride,
-                                                      int tabu_words, int words, int n_clone) {
+                                                      int tabu_words, int words, int n_clone, bool lean) {
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
     GjFusedSmem s;
     size_t o = 0;
+    if (lean) {                 // solution + one distinct-count bitmap; the caller points edge / bits at HBM
+        s.t = (int32_t*)(smem + o) + 4; o += (n_pad + 8) * 4;
+        s.bm = (uint32_t*)(smem + o);
+        s.cnt = nullptr; s.bits = nullptr; s.clone = nullptr; s.edge = nullptr;
+        return s;
+    }
     // the solution sits 16 bytes into its slot: t[-1] and t[n] are sentinels (TSP: the depot)
     s.t = (int32_t*)(smem + o) + 4; o += (n_pad + 8) * 4;
     s.cnt = (int32_t*)(smem + o); o += (size_t)cnt_stride * 4;
@@ -67,6 +81,7 @@ __device__ __forceinline__ GjFusedSmem gj_fused_carve(unsigned char* smem, int n
 // Value counts of the staged solution (shared atomics), all threads.
 template <int KIND>
 __device__ __forceinline__ void gj_fused_counts(const GjProblemDev& P, const GjFusedSmem& s, int cnt_stride) {
+    if (!s.cnt) return;                              // lean layout: no move needs them
     for (int i = threadIdx.x; i < cnt_stride; i += blockDim.x) s.cnt[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < P.n_vars; i += blockDim.x) {
@@ -95,6 +110,41 @@ __device__ __forceinline__ void gj_fused_edges(const GjProblemDev& P, const GjFu
     __syncthreads();
 }
 
+// Lean layout (edges persistent in HBM): after an accepted fast-path move only the edges it touched
+// are refreshed -- a two-stop swap gathers its <= 4 edges, a 2-opt reverses the interior edge run
+// in place (symmetric matrix: the same lengths in reverse order) and gathers the two boundary edges,
+// an insertion re-gathers its segment -- instead of all n + 1 random matrix reads.
+__device__ __forceinline__ void gj_fused_edges_after_move(const GjProblemDev& P, const GjFusedSmem& s,
+                                                          const GjGroups& G, const GjMove& m, bool noop_quirk) {
+    if (m.kind == GJ_MOVE_NULL) return;
+    if (noop_quirk && (m.kind == 3 || (m.kind == 2 && m.k == 2))) return;
+    const int n = P.n_vars;
+    const size_t L = (size_t)P.n_locations;
+    const int4 gi = G.info[m.group];
+    const int c0 = gi.x + m.a[0] * gi.y, c1 = gi.x + m.a[1] * gi.y;
+    const int p = min(c0, c1), q = max(c0, c1);
+    auto regather = [&](int i) {                    // s.t carries the sentinels t[-1] = t[n] = 0
+        if (i >= 0 && i <= n) s.edge[i] = __ldg(&P.D[(size_t)s.t[i - 1] * L + (size_t)s.t[i]]);
+    };
+    if (m.kind == 1) {
+        if (threadIdx.x == 0) regather(p);
+        if (threadIdx.x == 1) regather(p + 1);
+        if (threadIdx.x == 2) regather(q);
+        if (threadIdx.x == 3) regather(q + 1);
+    } else if (m.kind == 5) {
+        const int len = q - p;                      // interior edges p+1 .. q
+        for (int j = threadIdx.x; j < len / 2; j += blockDim.x) {
+            const double x = s.edge[p + 1 + j], y = s.edge[q - j];
+            s.edge[p + 1 + j] = y; s.edge[q - j] = x;
+        }
+        if (threadIdx.x == 0) regather(p);
+        if (threadIdx.x == 1) regather(q + 1);
+    } else {
+        for (int i = p + (int)threadIdx.x; i <= q + 1; i += blockDim.x) regather(i);
+    }
+    __syncthreads();
+}
+
 // FULL evaluation of the staged solution by the whole CTA -> unweighted terms raw[0..1]
 // (counts and, for TSP, edges must be current).  TSP: dup count from the counts; tour length
 // either as per-thread partial sums (tree) or, with exact sums, folded by one thread strictly in
@@ -104,7 +154,20 @@ __device__ __forceinline__ void gj_fused_full_eval(const GjProblemDev& P, const 
                                                    int cnt_stride, int* iscratch,
                                                    double* dscratch, double* raw /*shared [2]*/) {
     int u = 0;
-    for (int k = threadIdx.x; k < cnt_stride; k += blockDim.x) u += (s.cnt[k] > 0) ? 1 : 0;
+    if (s.cnt) {
+        for (int k = threadIdx.x; k < cnt_stride; k += blockDim.x) u += (s.cnt[k] > 0) ? 1 : 0;
+    } else {
+        // lean layout: distinct values through a bitmap (as the warp evaluators do)
+        const int words = cnt_stride >> 5;
+        for (int w = threadIdx.x; w < words; w += blockDim.x) s.bm[w] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.n_vars; i += blockDim.x) {
+            const unsigned b = (unsigned)(s.t[i] - P.val_lo);
+            atomicOr(&s.bm[b >> 5], 1u << (b & 31));
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < words; w += blockDim.x) u += __popc(s.bm[w]);
+    }
     const int uniq = gj_block_sum(u, iscratch);
     if constexpr (KIND == GJ_NQUEENS) {
         // (N - |rows|) + (N - |desc|) + (N - |asc|): integers, exact whatever the grouping
@@ -217,7 +280,11 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     const int K = A.K, levels = A.levels, n = P.n_vars;
     const int words = P.bm_words + P.desc_words + P.asc_words;
     const int cnt_stride = 32 * words;
-    const GjFusedSmem s = gj_fused_carve(smem_raw, n, cnt_stride, A.tabu_words_per_island, words, F.n_clone);
+    GjFusedSmem s = gj_fused_carve(smem_raw, n, cnt_stride, A.tabu_words_per_island, words, F.n_clone, F.lean != 0);
+    if (F.lean) {
+        s.edge = F.S.edge + (size_t)island * (size_t)(n + 1);
+        s.bits = A.tabu_bits ? A.tabu_bits + (size_t)island * A.tabu_words_per_island : nullptr;
+    }
     int32_t* cur_row = A.cur + (size_t)island * A.stride;
     double* raw_g = F.S.raw + (size_t)island * GJ_MAX_LEVELS;
 
@@ -241,7 +308,7 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     const bool adopted = sh_adopt != 0;
     if (tid == 0) {
         const uint32_t row_bytes = (uint32_t)(((n + 3) & ~3) * 4);
-        const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
+        const uint32_t tabu_bytes = (A.tabu_bits && !F.lean) ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
         gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes);
         gj_tma_load_1d(s.t, adopted ? A.gbest : cur_row, row_bytes, &sh_mbar);
         if (tabu_bytes)
@@ -252,8 +319,11 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     if (adopted)
         for (int i = tid; i < n; i += blockDim.x) cur_row[i] = s.t[i];
     gj_fused_counts<KIND>(P, s, cnt_stride);
-    if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
-    if (F.S.stale[island]) {                       // replaced by a migrant / the global best
+    const int state_stale = F.S.stale[island];
+    // edge lengths: shared memory does not outlive the launch, so they are re-gathered every step;
+    // the lean layout keeps them in HBM, where they stay valid until the solution changes
+    if constexpr (KIND == GJ_TSP) if (!F.lean || state_stale) gj_fused_edges(P, s);
+    if (state_stale) {                             // replaced by a migrant / the global best
         gj_fused_full_eval<KIND>(P, s, cnt_stride, sh_iscratch, sh_dscratch, sh_raw);
         if (tid == 0) { raw_g[0] = sh_raw[0]; raw_g[1] = sh_raw[1]; F.S.stale[island] = 0; }
     } else if (tid == 0) {
@@ -421,7 +491,10 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
         __syncthreads();
         for (int i = tid; i < n; i += blockDim.x) cur_row[i] = s.t[i];
         gj_fused_counts<KIND>(P, s, cnt_stride);
-        if constexpr (KIND == GJ_TSP) gj_fused_edges(P, s);
+        if constexpr (KIND == GJ_TSP) {
+            if (F.lean) gj_fused_edges_after_move(P, s, G, m, A.noop != 0);
+            else gj_fused_edges(P, s);
+        }
         gj_fused_full_eval<KIND>(P, s, cnt_stride, sh_iscratch, sh_dscratch, sh_raw);
         if (tid == 0) {
             raw_g[0] = sh_raw[0]; raw_g[1] = sh_raw[1];
