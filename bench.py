@@ -364,6 +364,33 @@ def main():
                                "one call per agent per step, agents on separate host threads / CUDA streams"}
         line["gpu_launches"] = gpu_launches + e2e_launches      # both timed regions, counted by the library
 
+        # ---- additional figure: the same call with the packed wire format (u32 ids, i32 values) ----
+        psets = []
+        for o, i, v in sets:
+            psets.append((o, pin(i.astype(np.uint32)), pin(np.rint(v).astype(np.int32))))
+        ph2d = sum(base.nbytes + o.nbytes + i.nbytes + v.nbytes for o, i, v in psets)
+
+        def agent_packed(a, n):
+            o, i, v = psets[a]
+            for _ in range(n):
+                probs[a].request_score_incremental_packed(base, o, i, v, out=outs[a])
+
+        def run_packed(n):
+            th = [threading.Thread(target=agent_packed, args=(a, n)) for a in range(A)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        run_packed(args.warmup)
+        t0 = time.perf_counter()
+        run_packed(args.steps)
+        p_s = time.perf_counter() - t0
+        line["e2e"]["packed"] = {"value": A * NEIGHBOURS * args.steps / p_s, "unit": UNIT,
+                                 "h2d_bytes_per_step": int(ph2d),
+                                 "call": "gj_score_incremental_packed: 8 B per delta instead of the "
+                                         "reference layout's 16 B (not the headline)"}
+
         # ---- cpu_baseline: oracle port on the host cores, bounded sample ------------------------
         if world == 1 and not args.no_cpu_baseline:
             from oracle import gj_oracle

@@ -95,27 +95,35 @@ __global__ void k_decode_base(GjProblemDev P, const double* __restrict__ base,
 // time, in emission order: when several deltas of one chunk hit the same variable the
 // last one wins (the stored individual is updated the same way,
 // tabu_search_base.rs:175-178).  Must be called by a full warp.
-template <class StoreFn>
+// A delta value on the wire: the reference's f64 (decoded like any variable) or, in the packed
+// form, an int32 that is already an inverse-transformed value (clamped into the bounds again).
+__device__ __forceinline__ int gj_decode_delta(const GjProblemDev& P, int id, double v) { return gj_decode(P, id, v); }
+__device__ __forceinline__ int gj_decode_delta(const GjProblemDev& P, int id, int32_t v) {
+    if (P.frozen[id]) return (int)P.initial[id];
+    return min(max(v, P.lbi[id]), P.ubi[id]);
+}
+
+template <class IdT, class ValT, class StoreFn>
 __device__ __forceinline__ void gj_apply_deltas_warp(const GjProblemDev& P, int lane,
-                                                     const uint64_t* __restrict__ ids,
-                                                     const double* __restrict__ vals,
+                                                     const IdT* __restrict__ ids,
+                                                     const ValT* __restrict__ vals,
                                                      uint64_t b, uint64_t e, StoreFn store) {
     for (uint64_t k0 = b; k0 < e; k0 += 32) {
         const uint64_t k = k0 + lane;
         const bool on = k < e;
-        uint64_t id64 = on ? ids[k] : 0;
+        uint64_t id64 = on ? (uint64_t)ids[k] : 0;
         const bool valid = on && id64 < (uint64_t)P.n_vars;
         const int id = valid ? (int)id64 : -1 - lane;
         const unsigned grp = __match_any_sync(GJ_FULL_MASK, id);
-        if (valid && lane == 31 - __clz(grp)) store(id, gj_decode(P, id, vals[k]));
+        if (valid && lane == 31 - __clz(grp)) store(id, gj_decode_delta(P, id, vals[k]));
         __syncwarp();
     }
 }
 
-template <int KIND>
+template <int KIND, class IdT, class ValT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_incr_warp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __restrict__ offsets,
-            const uint64_t* __restrict__ ids, const double* __restrict__ vals, int64_t S,
+            const IdT* __restrict__ ids, const ValT* __restrict__ vals, int64_t S,
             double* __restrict__ scores) {
     extern __shared__ uint32_t smem_u32[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,9 +151,10 @@ k_incr_warp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __
         for (int l = 0; l < P.levels; ++l) scores[j * P.levels + l] = out[l];
 }
 
+template <class IdT, class ValT>
 __global__ void __launch_bounds__(kVrpWarps * 32)
 k_incr_vrp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __restrict__ offsets,
-           const uint64_t* __restrict__ ids, const double* __restrict__ vals, int64_t S,
+           const IdT* __restrict__ ids, const ValT* __restrict__ vals, int64_t S,
            double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
@@ -223,10 +232,10 @@ gj_status gj_launch_score_plain_i32(gj_problem* p, const int32_t* d_samples, int
     return launch_plain<int32_t>(p, d_samples, stride, S, d_scores, isc, st);
 }
 
-gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32_t* d_base_i32,
-                                      const uint64_t* d_offsets, const uint64_t* d_ids,
-                                      const double* d_vals, int64_t S, double* d_scores,
-                                      cudaStream_t st) {
+template <class IdT, class ValT>
+static gj_status launch_incremental(gj_problem* p, const double* d_base, int32_t* d_base_i32,
+                                    const uint64_t* d_offsets, const IdT* d_ids, const ValT* d_vals,
+                                    int64_t S, double* d_scores, cudaStream_t st) {
     if (S <= 0) return GJ_OK;
     const GjProblemDev& P = p->dev;
     gj_status rc;
@@ -236,8 +245,8 @@ gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32
     }
     if (P.kind >= GJ_VRP) {
         size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
-        if ((rc = set_smem(k_incr_vrp, smem))) return rc;
-        k_incr_vrp<<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
+        if ((rc = set_smem(k_incr_vrp<IdT, ValT>, smem))) return rc;
+        k_incr_vrp<IdT, ValT><<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
     } else {
         // one shared-memory clone per warp: fewer warps per CTA for large instances
         size_t per_warp = (size_t)(P.bm_words + P.desc_words + P.asc_words + P.n_vars) * 4;
@@ -246,15 +255,22 @@ gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32
         size_t smem = per_warp * warps;
         unsigned grid = (unsigned)((S + warps - 1) / warps);
         if (P.kind == GJ_NQUEENS) {
-            if ((rc = set_smem(k_incr_warp<GJ_NQUEENS>, smem))) return rc;
-            k_incr_warp<GJ_NQUEENS><<<grid, warps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
+            if ((rc = set_smem(k_incr_warp<GJ_NQUEENS, IdT, ValT>, smem))) return rc;
+            k_incr_warp<GJ_NQUEENS, IdT, ValT><<<grid, warps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
         } else {
-            if ((rc = set_smem(k_incr_warp<GJ_TSP>, smem))) return rc;
-            k_incr_warp<GJ_TSP><<<grid, warps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
+            if ((rc = set_smem(k_incr_warp<GJ_TSP, IdT, ValT>, smem))) return rc;
+            k_incr_warp<GJ_TSP, IdT, ValT><<<grid, warps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
         }
     }
     GJ_LAUNCH_CHECK();
     return GJ_OK;
+}
+
+gj_status gj_launch_score_incremental(gj_problem* p, const double* d_base, int32_t* d_base_i32,
+                                      const uint64_t* d_offsets, const uint64_t* d_ids,
+                                      const double* d_vals, int64_t S, double* d_scores,
+                                      cudaStream_t st) {
+    return launch_incremental<uint64_t, double>(p, d_base, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores, st);
 }
 
 // ---- C ABI ------------------------------------------------------------------------------------
@@ -329,6 +345,41 @@ extern "C" gj_status gj_score_incremental(gj_problem* p, const double* base, con
     if ((rc = gj_launch_score_incremental(p, (const double*)p->d_base.ptr, (int32_t*)p->d_base_i32.ptr,
                                           (const uint64_t*)p->d_offsets.ptr, (const uint64_t*)p->d_ids.ptr,
                                           (const double*)p->d_vals.ptr, S, (double*)p->d_scores.ptr, st))) return rc;
+    GJ_CUDA_TRY(cudaMemcpyAsync(scores, p->d_scores.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
+    GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    return GJ_OK;
+}
+
+// Packed wire format of the same call: 8 bytes per delta instead of 16.  The Rust shim that flattens
+// Vec<Vec<(usize, f64)>> into CSR walks every pair anyway; narrowing the column id to u32 and the
+// (already inverse-transformed, integer) value to i32 in that loop halves the bytes that cross PCIe,
+// which is what bounds this call.
+extern "C" gj_status gj_score_incremental_packed(gj_problem* p, const double* base, const uint64_t* offsets,
+                                                 const uint32_t* var_ids, const int32_t* values, int64_t S,
+                                                 double* scores) {
+    if (!p || !base || !offsets || !scores || S < 0) return gj_fail(GJ_ERR_INVALID, "bad argument");
+    if (S == 0) return GJ_OK;
+    const uint64_t total = offsets[S];
+    if (total > 0 && (!var_ids || !values)) return gj_fail(GJ_ERR_INVALID, "delta arrays missing");
+    GJ_CUDA_TRY(cudaSetDevice(p->device));
+    const size_t out_bytes = (size_t)S * (size_t)p->dev.levels * 8;
+    gj_status rc;
+    if ((rc = p->d_base.reserve((size_t)p->dev.n_vars * 8))) return rc;
+    if ((rc = p->d_base_i32.reserve((size_t)p->dev.n_vars * 4))) return rc;
+    if ((rc = p->d_offsets.reserve((size_t)(S + 1) * 8))) return rc;
+    if ((rc = p->d_ids.reserve((size_t)(total + 1) * 4))) return rc;
+    if ((rc = p->d_vals.reserve((size_t)(total + 1) * 4))) return rc;
+    if ((rc = p->d_scores.reserve(out_bytes))) return rc;
+    cudaStream_t st = p->stream;
+    GJ_CUDA_TRY(cudaMemcpyAsync(p->d_base.ptr, base, (size_t)p->dev.n_vars * 8, cudaMemcpyHostToDevice, st));
+    GJ_CUDA_TRY(cudaMemcpyAsync(p->d_offsets.ptr, offsets, (size_t)(S + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) {
+        GJ_CUDA_TRY(cudaMemcpyAsync(p->d_ids.ptr, var_ids, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+        GJ_CUDA_TRY(cudaMemcpyAsync(p->d_vals.ptr, values, (size_t)total * 4, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = launch_incremental<uint32_t, int32_t>(p, (const double*)p->d_base.ptr, (int32_t*)p->d_base_i32.ptr,
+                                                    (const uint64_t*)p->d_offsets.ptr, (const uint32_t*)p->d_ids.ptr,
+                                                    (const int32_t*)p->d_vals.ptr, S, (double*)p->d_scores.ptr, st))) return rc;
     GJ_CUDA_TRY(cudaMemcpyAsync(scores, p->d_scores.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
     GJ_CUDA_TRY(cudaStreamSynchronize(st));
     return GJ_OK;

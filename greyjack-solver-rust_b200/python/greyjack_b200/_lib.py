@@ -56,7 +56,7 @@ EXPORTED = [
     "gj_problem_create", "gj_problem_destroy", "gj_problem_levels", "gj_problem_n_vars",
     "gj_problem_set_constraint_weights", "gj_problem_set_exact_sums", "gj_problem_get_distance_matrix",
     "gj_host_alloc", "gj_host_free",
-    "gj_score_plain", "gj_score_incremental",
+    "gj_score_plain", "gj_score_incremental", "gj_score_incremental_packed",
     "gj_score_plain_device", "gj_score_plain_i32_device", "gj_score_incremental_device",
     "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_set_accomplish_rate", "gj_islands_stats", "gj_islands_trace_aux", "gj_islands_set_profiling", "gj_islands_profile_read",
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",

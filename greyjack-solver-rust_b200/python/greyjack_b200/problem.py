@@ -157,6 +157,16 @@ class Problem:
                                                 _ptr(vals), C.c_int64(S), _ptr(out)))
         return out
 
+    def request_score_incremental_packed(self, sample, offsets, ids_u32, vals_i32, out=None) -> np.ndarray:
+        """Packed wire format (gj_score_incremental_packed): u32 ids, i32 already-decoded values."""
+        b = np.ascontiguousarray(sample, dtype=np.float64)
+        S = len(offsets) - 1
+        if out is None:
+            out = np.empty((S, self.levels), dtype=np.float64)
+        _lib.check(self._L.gj_score_incremental_packed(self.handle, _ptr(b), _ptr(offsets), _ptr(ids_u32),
+                                                       _ptr(vals_i32), C.c_int64(S), _ptr(out)))
+        return out
+
     def set_constraint_weights(self, weights):
         w = np.ascontiguousarray(weights, dtype=np.float64)
         _lib.check(self._L.gj_problem_set_constraint_weights(self.handle, _ptr(w), C.c_int32(len(w))))

@@ -188,6 +188,15 @@ GJ_API gj_status gj_score_incremental(gj_problem* p, const double* base,
                                       const uint64_t* offsets, const uint64_t* var_ids,
                                       const double* values, int64_t S, double* scores);
 
+/* request_score_incremental with a packed wire format: u32 column ids and i32 values that are
+   ALREADY inverse-transformed (what VariablesManager::inverse_transform_deltas yields for
+   GJInteger variables, variables_manager.rs:165-185) -- 8 bytes per delta instead of 16.  The
+   binding's flatten loop narrows the pairs while it builds the CSR arrays; the call is bound by
+   the bytes that cross PCIe.  Integer variables only (all the reference's examples).            */
+GJ_API gj_status gj_score_incremental_packed(gj_problem* p, const double* base,
+                                             const uint64_t* offsets, const uint32_t* var_ids,
+                                             const int32_t* values, int64_t S, double* scores);
+
 /* Same two calls with every buffer already resident in device memory (HBM) and an
    explicit cudaStream_t (NULL = default stream); asynchronous.                          */
 GJ_API gj_status gj_score_plain_device(gj_problem* p, const double* d_samples, int64_t S,

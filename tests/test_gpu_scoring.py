@@ -78,6 +78,24 @@ def test_incremental_repeated_ids_last_wins(triple):
                         soft_exact=spec.kind >= inst.VRP)
 
 
+def test_incremental_packed_equals_reference_layout(triple):
+    """gj_score_incremental_packed (u32 ids, i32 decoded values) == gj_score_incremental, bit for bit,
+    and == the oracle; repeated ids and out-of-bounds values included."""
+    from greyjack_b200.problem import deltas_to_csr
+    spec, op, gp = triple
+    rng = np.random.default_rng(29)
+    base = spec.initial.copy()
+    deltas, _ = random_moves(op, spec, base, 120, rng)
+    deltas.append([])
+    ids = rng.integers(0, min(spec.n_vars, 6), size=70)
+    deltas.append([(int(i), float(rng.integers(spec.lower_bounds[i] - 3, spec.upper_bounds[i] + 4))) for i in ids])
+    o, i, v = deltas_to_csr(deltas)
+    got = gp.request_score_incremental_packed(base, o, i.astype(np.uint32), np.rint(v).astype(np.int32))
+    ref = gp.request_score_incremental_csr(base, o, i, v)
+    assert np.array_equal(got, ref)
+    assert_scores_match(got, op.score_incremental(base, deltas), spec, soft_exact=True)
+
+
 def test_fast_sums_within_tolerance(triple):
     """gj_problem_set_exact_sums(0): tree-reduced distance sums, stated tolerance 1e-12 rel."""
     spec, op, gp = triple
