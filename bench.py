@@ -195,7 +195,7 @@ def other_configs(gj, inst, torch):
     timed("C1 nqueens-256 LateAcceptance x4096 chains (k_la_chains)", c1, 1000)
     timed("C3 cvrp-2000x50 GeneticAlgorithm pop 8192 x1 island", c3, 10)
     timed("C4 vrptw-5000 (vrp_service) LateAcceptance x592 islands", c4, 40)
-    timed("C5 tsp-20000 TabuSearch 4096 moves x148 islands (unfused delta)", c5, 20)
+    timed("C5 tsp-20000 TabuSearch 4096 moves x148 islands (fused step, lean layout)", c5, 20)
     return out
 
 
