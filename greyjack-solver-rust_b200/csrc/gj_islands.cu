@@ -746,6 +746,7 @@ k_apply_adoption(GjSelectArgs A) {
 
 #include "gj_islands_fused.cuh"
 #include "gj_islands_chain.cuh"
+#include "gj_islands_vrp_chain.cuh"
 
 // ---- migration (ring i -> i+1, solver.rs:85-92) ------------------------------------------------------
 // mailbox slot s: [stride int32][GJ_MAX_LEVELS f64]; slot[i+1] = island i's outgoing migrant,
@@ -1229,6 +1230,49 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
         g->delta_may_fallback = g->mover.thresholds[3] < 1.0;      // insertion / inverse possible
         if ((rc = launch_refresh(g.get(), st, false))) return rc;
     }
+    // VRP models, single-neighbour agents (LateAcceptance / SimulatedAnnealing): chains that run many
+    // steps per launch over a route index kept in HBM (gj_islands_vrp_chain.cuh).  Needs move_probas
+    // without segment moves (insertion / inverse re-label O(segment) stops) and room for the index.
+    if (prm->scoring_mode == GJ_SCORING_DELTA && p->dev.kind >= GJ_VRP && (la || sa) &&
+        g->mover.thresholds[3] >= 1.0) {
+        const GjProblemDev& P = p->dev;
+        const size_t n = (size_t)P.n_entities, K = (size_t)P.n_vehicles;
+        size_t free_b = 0, total_b = 0;
+        GJ_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)I * (K * n + n) * 4;
+        if (need <= free_b / 2) {
+            g->scoring_mode = GJ_SCORING_DELTA;
+            g->chain = true; g->vrp_chain = true;
+            g->mover.tabu_layout = 1;
+            GjVrpChainState& V = g->vcs;
+            V.cnt_stride = 32 * P.bm_words;
+            if ((rc = dev_alloc(g.get(), (size_t)I * K * n, &V.rs, false))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rlen))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rdist))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rload))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rlate))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * 4, &V.tot))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * n, &V.spare, false))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * V.cnt_stride, &V.cnt))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.stale))) return rc;
+            V.stale = g->ds.stale;
+            std::vector<int> ones((size_t)I, 1);
+            GJ_CUDA_TRY(cudaMemcpy(g->ds.stale, ones.data(), (size_t)I * sizeof(int), cudaMemcpyHostToDevice));
+            if (prm->tabu_entity_rate != 0.0) {
+                std::vector<int32_t> coff;
+                int cw = 0;
+                for (auto& grp : p->groups) {
+                    coff.push_back(cw);
+                    const int T = std::max(1, std::min((int)std::ceil(prm->tabu_entity_rate * (double)grp.size()),
+                                                       std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK)));
+                    cw += ((int)grp.size() + 31) / 32 + 1 + T + 2;      // bits | ring | head, fill
+                }
+                g->ctabu_words = cw;
+                if ((rc = dev_upload(g.get(), coff, &g->ctabu_off))) return rc;
+                if ((rc = dev_alloc(g.get(), (size_t)I * cw, &g->ctabu))) return rc;
+            }
+        }
+    }
     if ((prm->scoring_mode == GJ_SCORING_DELTA || prm->scoring_mode == GJ_SCORING_DELTA_UNFUSED) && p->dev.kind <= GJ_TSP) {
         g->scoring_mode = GJ_SCORING_DELTA;
         const GjProblemDev& P = p->dev;
@@ -1399,6 +1443,7 @@ static gj_status opt_in_smem(Kern kernel, size_t bytes) {
 
 // k_refresh for every island (early exit for islands whose state is current)
 static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top) {
+    if (g->vrp_chain) return GJ_OK;        // the chain kernel rebuilds its own route index (stale flag)
     const GjProblemDev& P = g->p->dev;
     const size_t smem = 0;
     gj_status rc;
@@ -1605,7 +1650,10 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     const size_t smem = g->chain_bytes * kChainWarps;
     const unsigned grid = (unsigned)((g->I + kChainWarps - 1) / kChainWarps);
     gj_status rc;
-    if (P.kind == GJ_NQUEENS) {
+    if (g->vrp_chain) {
+        k_vrp_chains<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(
+            P, g->groups, A, g->vcs);
+    } else if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_la_chains<GJ_NQUEENS>, smem))) return rc;
         k_la_chains<GJ_NQUEENS><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);
     } else {
@@ -1704,6 +1752,18 @@ extern "C" gj_status gj_islands_trace_aux(gj_islands* g, int32_t island, double*
     GJ_CUDA_TRY(cudaDeviceSynchronize());
     GJ_CUDA_TRY(cudaMemcpy(out, g->trace_aux + (size_t)island * 5, 5 * sizeof(double), cudaMemcpyDeviceToHost));
     return GJ_OK;
+}
+
+// Which kernels a step of this group runs (decided at creation from the agent, the model, the
+// instance size and move_probas); for logs and tests.
+extern "C" const char* gj_islands_step_path(const gj_islands* g) {
+    if (!g) return "";
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return "ga";
+    if (g->vrp_chain) return "vrp_chain";
+    if (g->chain) return "chain";
+    if (g->fused) return g->fused_lean ? "fused_lean" : "fused";
+    if (g->scoring_mode == GJ_SCORING_DELTA) return g->p->dev.kind >= GJ_VRP ? "vrp_delta" : "delta";
+    return "full";
 }
 
 extern "C" gj_status gj_islands_set_external_ring(gj_islands* g, int32_t on, int32_t island_base) {

@@ -59,6 +59,8 @@ struct gj_islands {
     long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid
     // LateAcceptance chains: many steps per launch, one warp per island (gj_islands_chain.cuh)
     bool chain = false;
+    bool vrp_chain = false;              // ... on a VRP model: route index in HBM (gj_islands_vrp_chain.cuh)
+    GjVrpChainState vcs{};
     size_t chain_bytes = 0;              // shared memory per chain
     uint32_t* ctabu = nullptr; int ctabu_words = 0; const int32_t* ctabu_off = nullptr;
     GjMove* trace_moves = nullptr; double* trace_scores = nullptr; int* trace_accept = nullptr;

@@ -1,0 +1,464 @@
+// gj_islands_vrp_chain.cuh -- LateAcceptance / SimulatedAnnealing chains on the VRP models: many
+// steps per launch, one warp per chain, route-level delta evaluation (included by gj_islands.cu).
+//
+// A single-neighbour agent on VRPTW-5000 (BASELINE config C4) used to pay one 5000-stop full
+// evaluation per step (late_acceptance_base.rs:116-141 -> vrp_service ISC :32-143).  A change / swap
+// move re-labels a handful of stops, i.e. touches 2-4 of the 125 routes.  Every chain therefore keeps
+// a ROUTE INDEX of its current solution in HBM (L2-resident between the steps of a launch):
+//     rs   [K][n]     the stop indices of every route, ascending (= the reference's visiting order:
+//                     stops are bucketed by vehicle in stop order, ISC :87-98)
+//     rlen / rdist / rload / rlate [K]   length, distance, demand, lateness of every route
+//     cnt  [locations]                   customer occurrence counts;  tot: duplicates, capacity, lateness
+// and a step re-walks only the touched routes: the warp loads 32 stops of the old route at a time,
+// drops the departures, merges the arrivals (both sorted by stop index), gathers customer facts and
+// leg lengths for the merged run in parallel, and folds them in order -- the reference's own
+// summation order, so hard, medium AND the float soft level are bit-identical to the full
+// evaluation.  The merged stop lists go to a spare buffer and are copied over the route slots only
+// when the neighbour is accepted.  Segment moves (insertion / inverse) are not generated on this
+// path (gj_islands_create picks it only when move_probas excludes them).
+#pragma once
+
+
+static constexpr int kVrpChainWarps = 4;
+#define GJ_VRPC_Q 48             // 32 stops of the old route + <= 16 arrivals
+
+struct GjVrpcScratch {
+    uint4 qf[GJ_VRPC_Q];         // customer facts of the merged run
+    double qd[GJ_VRPC_Q];        // leg into every stop of the run
+    int32_t qc[GJ_VRPC_Q];       // customers
+    int32_t qs[GJ_VRPC_Q];       // stop indices
+    // the move: changed stops (new / old labels), arrivals of the route being walked
+    int cs_stop[GJ_VRP_MAXCS], cs_v[GJ_VRP_MAXCS], cs_c[GJ_VRP_MAXCS], cs_ov[GJ_VRP_MAXCS], cs_oc[GJ_VRP_MAXCS];
+    int arr_stop[GJ_VRP_MAXCS], arr_c[GJ_VRP_MAXCS];
+    int av[GJ_VRP_MAXAV], noff[GJ_VRP_MAXAV], nlen[GJ_VRP_MAXAV];
+    double nd[GJ_VRP_MAXAV];
+    unsigned long long nl[GJ_VRP_MAXAV], nt[GJ_VRP_MAXAV];
+    int ncs, nav, na, d_uniq;
+    GjMove mv;
+};
+
+struct GjRouteStat { double dist; unsigned long long load, late; int len; };
+
+// Walks route v of the chain: old stop list `rs_v[len]` minus the changed stops that leave, plus the
+// arrivals q.arr_* (sorted by stop), changed stops that stay take their new customer.  Every lane
+// returns the same result.  `out` (nullable) receives the merged stop list.
+__device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int tw_mode, int v, const int32_t* row,
+                                                    const int32_t* rs_v, int len, int ncs, int na,
+                                                    int32_t* out, GjVrpcScratch& q, int lane) {
+    const size_t L = (size_t)P.n_locations;
+    const double* __restrict__ D = P.D;
+    int first = -1, last = -1, outn = 0, ia = 0;
+    double fold = 0.0;
+    unsigned long long load = 0ull, lateness = 0ull, arrival = P.day_start[v];
+    const int nchunks = max(1, (len + 31) >> 5);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int idx = (ch << 5) + lane;
+        bool keep = idx < len;
+        const int s = keep ? rs_v[idx] : 0x7fffffff;
+        int c = keep ? row[2 * s + 1] : 0;
+        for (int j = 0; j < ncs; ++j)
+            if (q.cs_stop[j] == s) {
+                if (q.cs_v[j] != v) keep = false; else c = q.cs_c[j];
+            }
+        // arrivals that belong before the next chunk's first stop
+        const int limit = (ch == nchunks - 1) ? 0x7fffffff : __shfl_sync(GJ_FULL_MASK, s, 31);
+        int ib = ia;
+        while (ib < na && q.arr_stop[ib] < limit) ++ib;
+        const unsigned keepmask = __ballot_sync(GJ_FULL_MASK, keep);
+        int pos = __popc(keepmask & ((1u << lane) - 1u));
+        for (int a = ia; a < ib; ++a) {
+            const int st = q.arr_stop[a];
+            if (st < s) ++pos;
+            const unsigned before = __ballot_sync(GJ_FULL_MASK, keep && s < st);
+            if (lane == 0) {
+                const int p = __popc(before) + (a - ia);
+                q.qc[p] = q.arr_c[a]; q.qs[p] = st;
+            }
+        }
+        if (keep) { q.qc[pos] = c; q.qs[pos] = s; }
+        const int m = __popc(keepmask) + (ib - ia);
+        ia = ib;
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            const int ci = q.qc[i];
+            const int prev = i > 0 ? q.qc[i - 1] : last;
+            q.qf[i] = P.cust[ci];
+            q.qd[i] = prev >= 0 ? __ldg(&D[(size_t)prev * L + (size_t)ci]) : 0.0;
+            if (out) out[outn + i] = q.qs[i];
+        }
+        __syncwarp();
+        for (int i = 0; i < m; ++i) {
+            const int ci = q.qc[i];
+            if (first < 0) first = ci; else fold = fold + q.qd[i];
+            last = ci;
+            const uint4 f = q.qf[i];
+            load += (unsigned long long)f.x;
+            if (P.time_windowed) {
+                const unsigned long long ws = f.y, we = f.z, sv = f.w;
+                if (arrival < ws) arrival = ws;
+                if (tw_mode == GJ_TW_ISC_FILE) {
+                    if (arrival + sv > we) lateness += (arrival + sv) - we;
+                } else {
+                    if (arrival > we + sv) lateness += arrival - (we + sv);
+                }
+                arrival += sv;
+            }
+        }
+        outn += m;
+        __syncwarp();
+    }
+    GjRouteStat r;
+    double current_distance = 0.0;
+    if (first >= 0) {
+        const size_t depot = (size_t)P.veh_depot[v];
+        current_distance += __ldg(&D[depot * L + (size_t)first]);
+        current_distance += __ldg(&D[(size_t)last * L + depot]);
+        current_distance += fold;
+        if (P.time_windowed && arrival > P.day_end[v]) lateness += arrival - P.day_end[v];
+    }
+    r.dist = current_distance; r.load = load; r.late = lateness; r.len = outn;
+    return r;
+}
+
+// sum over the K routes in the reference's order (vehicle_distances.iter().sum()), touched routes
+// substituted by their re-walked value
+__device__ __forceinline__ double gj_vrpc_sum_routes(const double* rdist, int K, const GjVrpcScratch& q, int nav, int lane) {
+    double sum = 0.0;
+    for (int v0 = 0; v0 < K; v0 += 32) {
+        const int v = v0 + lane;
+        double x = v < K ? rdist[v] : 0.0;
+        for (int a = 0; a < nav; ++a) if (q.av[a] == v) x = q.nd[a];
+        const int m = min(32, K - v0);
+        for (int i = 0; i < m; ++i) sum += __shfl_sync(GJ_FULL_MASK, x, i);
+    }
+    return sum;
+}
+
+// Rebuilds the route index of a chain from its solution row (creation, migrant, adopted global top).
+__device__ __forceinline__ void gj_vrpc_rebuild(const GjProblemDev& P, int tw_mode, const int32_t* row,
+                                                const GjVrpChainState& V, int island, GjVrpcScratch& q, int lane) {
+    const int n = P.n_entities, K = P.n_vehicles;
+    int32_t* rs = V.rs + (size_t)island * K * n;
+    int32_t* rlen = V.rlen + (size_t)island * K;
+    int32_t* cnt = V.cnt + (size_t)island * V.cnt_stride;
+    for (int i = lane; i < V.cnt_stride; i += 32) cnt[i] = 0;
+    for (int v = lane; v < K; v += 32) rlen[v] = 0;
+    __syncwarp();
+    // bucket the stops by vehicle, stop order kept: rank among the same-vehicle lanes of the chunk
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        const int s = s0 + lane;
+        const bool on = s < n;
+        const int v = on ? row[2 * s] : -1 - lane;
+        const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
+        if (on) {
+            const int rank = __popc(grp & ((1u << lane) - 1u));
+            const int base = rlen[v];
+            rs[(size_t)v * n + base + rank] = s;
+            atomicAdd(&cnt[row[2 * s + 1] - P.val_lo], 1);
+        }
+        __syncwarp();
+        if (on && lane == 31 - __clz(grp)) rlen[v] += __popc(grp);
+        __syncwarp();
+    }
+    unsigned long long cap_pen = 0ull, late_pen = 0ull;
+    for (int v = 0; v < K; ++v) {
+        const GjRouteStat r = gj_vrpc_walk(P, tw_mode, v, row, rs + (size_t)v * n, rlen[v], 0, 0, nullptr, q, lane);
+        if (lane == 0) {
+            V.rdist[(size_t)island * K + v] = r.dist;
+            V.rload[(size_t)island * K + v] = r.load;
+            V.rlate[(size_t)island * K + v] = r.late;
+        }
+        const unsigned long long capv = P.veh_capacity[v];
+        if (r.load > capv) cap_pen += r.load - capv;
+        late_pen += r.late;
+    }
+    int distinct = 0;
+    for (int i = lane; i < V.cnt_stride; i += 32) distinct += cnt[i] > 0 ? 1 : 0;
+    distinct = gj_warp_sum(distinct);
+    distinct = __shfl_sync(GJ_FULL_MASK, distinct, 0);
+    if (lane == 0) {
+        unsigned long long* tot = V.tot + (size_t)island * 4;
+        tot[0] = (unsigned long long)(n - distinct);
+        tot[1] = cap_pen;
+        tot[2] = late_pen;
+        V.stale[island] = 0;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kVrpChainWarps * 32)
+k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
+    __shared__ GjVrpcScratch sh_q[kVrpChainWarps];
+    constexpr int LV = 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int island = blockIdx.x * kVrpChainWarps + warp;
+    if (island >= A.I) return;                       // whole warps only; no CTA-wide barrier below
+    GjVrpcScratch& q = sh_q[warp];
+    const int n = P.n_entities, K = P.n_vehicles;
+    const int tw_mode = gj_vrp_tw_mode(P);
+    int32_t* row = A.cur + (size_t)island * A.stride;
+    int32_t* best_row = A.best + (size_t)island * A.stride;
+    int32_t* rs = V.rs + (size_t)island * K * n;
+    int32_t* rlen = V.rlen + (size_t)island * K;
+    double* rdist = V.rdist + (size_t)island * K;
+    unsigned long long* rload = V.rload + (size_t)island * K;
+    unsigned long long* rlate = V.rlate + (size_t)island * K;
+    unsigned long long* tot = V.tot + (size_t)island * 4;
+    int32_t* cnt = V.cnt + (size_t)island * V.cnt_stride;
+    int32_t* spare = V.spare + (size_t)island * n;
+    uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
+    double* late_g = A.late ? A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS : nullptr;
+    const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
+
+    // ---- stage: update_global_top adopt half (agent_base.rs:465-489), route index ----------------------
+    int adopted = 0;
+    if (lane == 0 && A.gver) {
+        const int ver = *A.gver;
+        if (ver != A.gseen[island]) {
+            A.gseen[island] = ver;
+            const GjScore g = gj_load_score(A.gbest_score, LV);
+            const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+            adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
+        }
+    }
+    adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
+    int late_head = is_la ? A.late_head[island] : 0, late_len = is_la ? A.late_len[island] : 0;
+    double temp[GJ_MAX_LEVELS] = {1.0, 1.0, 1.0};
+    if (!is_la)
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) temp[l] = A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l];
+    GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    if (adopted) {
+        for (int i = lane; i < A.n_vars; i += 32) row[i] = A.gbest[i];
+        if (is_la) {          // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
+            late_head = (late_head + A.late_size - 1) % A.late_size;
+            if (lane == 0)
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)late_head * GJ_MAX_LEVELS + l] = cur.v[l];
+            late_len = min(late_len + 1, A.late_size);
+        }
+        cur = gj_load_score(A.gbest_score, LV);
+        __syncwarp();
+    }
+    if (V.stale[island] || adopted) gj_vrpc_rebuild(P, tw_mode, row, V, island, q, lane);
+    if (A.dirty[island] || adopted) {
+        if (gj_score_le(cur, top, LV)) {
+            for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+            top = cur;
+        }
+    }
+    __syncwarp();
+    int accepted_total = 0;
+    // update_top_individual copies are lazy: while the top IS the current solution, best_row is only
+    // written when the chain is about to leave it (or at the end of the launch)
+    bool top_pending = false;
+
+    for (int it = 0; it < A.n_steps; ++it) {
+        const uint64_t step = A.step0 + (uint64_t)it;
+        // ---- generate (every lane computes the same move) -----------------------------------------------
+        GjMoverParams M = A.M;
+        const GjMove m = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
+                                          tabu_g, A.ctabu_off);
+        const bool identity = m.kind == GJ_MOVE_NULL || (A.noop != 0 && (m.kind == 3 || (m.kind == 2 && m.k == 2)));
+        // ---- changed stops, touched routes (lane 0) --------------------------------------------------
+        if (lane == 0) {
+            int ncs = 0, nav = 0, d_uniq = 0;
+            if (!identity) {
+                q.mv = m;
+                const GjMove ms = q.mv;
+                const int32_t* g = G.ids + G.offsets[ms.group];
+                int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
+                const int np = gj_small_move_pairs(ms, g, true, A.noop != 0, [&](int id) { return row[id]; }, cols, vals);
+                for (int i = 0; i < np; ++i) {
+                    const int col = cols[i], val = gj_fix_column(P, col, vals[i]);
+                    const int stop = col >> 1;
+                    int j = 0;
+                    for (; j < ncs; ++j) if (q.cs_stop[j] == stop) break;
+                    if (j == ncs) {
+                        q.cs_stop[j] = stop;
+                        q.cs_v[j] = q.cs_ov[j] = row[2 * stop];
+                        q.cs_c[j] = q.cs_oc[j] = row[2 * stop + 1];
+                        ++ncs;
+                    }
+                    if (col & 1) q.cs_c[j] = val; else q.cs_v[j] = val;
+                }
+                // customer multiset -> duplicates
+                for (int j = 0; j < ncs; ++j) {
+                    if (q.cs_oc[j] == q.cs_c[j]) continue;
+                    for (int side = 0; side < 2; ++side) {
+                        const int key = (side ? q.cs_c[j] : q.cs_oc[j]) - P.val_lo;
+                        bool seen = false;
+                        int net = 0;
+                        for (int t = 0; t < ncs; ++t) {
+                            if (q.cs_oc[t] == q.cs_c[t]) continue;
+                            for (int ts = 0; ts < 2; ++ts) {
+                                const int other = (ts ? q.cs_c[t] : q.cs_oc[t]) - P.val_lo;
+                                if (other != key) continue;
+                                if (t < j || (t == j && ts < side)) seen = true;
+                                net += ts ? 1 : -1;
+                            }
+                        }
+                        if (seen || net == 0) continue;
+                        const int before = cnt[key];
+                        d_uniq += ((before + net) > 0 ? 1 : 0) - (before > 0 ? 1 : 0);
+                    }
+                }
+                // routes that gain, lose or re-label a stop
+                for (int j = 0; j < ncs; ++j) {
+                    if (q.cs_ov[j] == q.cs_v[j] && q.cs_oc[j] == q.cs_c[j]) continue;
+                    for (int side = 0; side < 2; ++side) {
+                        const int v = side ? q.cs_v[j] : q.cs_ov[j];
+                        int a = 0;
+                        for (; a < nav; ++a) if (q.av[a] == v) break;
+                        if (a == nav) q.av[nav++] = v;
+                    }
+                }
+            }
+            q.ncs = ncs; q.nav = nav; q.d_uniq = d_uniq;
+        }
+        __syncwarp();
+        const int ncs = q.ncs, nav = q.nav;
+        // ---- re-walk the touched routes -----------------------------------------------------------------
+        int off = 0;
+        for (int a = 0; a < nav; ++a) {
+            const int v = q.av[a];
+            if (lane == 0) {
+                int na = 0;                                  // arrivals, sorted by stop index
+                for (int j = 0; j < ncs; ++j)
+                    if (q.cs_v[j] == v && q.cs_ov[j] != v) {
+                        int p = na++;
+                        while (p > 0 && q.arr_stop[p - 1] > q.cs_stop[j]) {
+                            q.arr_stop[p] = q.arr_stop[p - 1]; q.arr_c[p] = q.arr_c[p - 1]; --p;
+                        }
+                        q.arr_stop[p] = q.cs_stop[j]; q.arr_c[p] = q.cs_c[j];
+                    }
+                q.na = na;
+            }
+            __syncwarp();
+            const GjRouteStat r = gj_vrpc_walk(P, tw_mode, v, row, rs + (size_t)v * n, rlen[v], ncs, q.na,
+                                               spare + off, q, lane);
+            if (lane == 0) { q.nd[a] = r.dist; q.nl[a] = r.load; q.nt[a] = r.late; q.noff[a] = off; q.nlen[a] = r.len; }
+            off += r.len;
+            __syncwarp();
+        }
+        // ---- totals -----------------------------------------------------------------------------------
+        unsigned long long cap_pen = tot[1], late_pen = tot[2];
+        for (int a = 0; a < nav; ++a) {
+            const int v = q.av[a];
+            const unsigned long long capv = P.veh_capacity[v];
+            const unsigned long long ol = rload[v], nl = q.nl[a];
+            if (ol > capv) cap_pen -= ol - capv;
+            if (nl > capv) cap_pen += nl - capv;
+            late_pen -= rlate[v];
+            late_pen += q.nt[a];
+        }
+        const double sum_distance = gj_vrpc_sum_routes(rdist, K, q, nav, lane);
+        const long long dups = (long long)tot[0] - (long long)q.d_uniq;
+        GjScore sc;
+        gj_combine_vrp(P, true, 1000.0 * (double)dups, (double)cap_pen, sum_distance, (double)late_pen, sc.v);
+        gj_score_round(sc, P);                          // agent_base.rs:311-314
+        // ---- acceptance ---------------------------------------------------------------------------------
+        bool accept;
+        if (is_la) {
+            GjScore late_native = cur;                  // late_acceptance_base.rs:196-213
+            if (late_len > 0) late_native = gj_load_score(late_g + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
+            accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
+        } else {
+            const double u = gj_accept_uniform(A.seed, (uint32_t)(A.island_base + island), step);
+            double proba;
+            accept = gj_sa_accept(sc, cur, LV, temp, A.sa, u, &proba);      // simulated_annealing_base.rs:198-233
+            if (A.trace_aux && lane == 0) {
+                double* o = A.trace_aux + (size_t)island * 5;
+                o[0] = u; o[1] = proba; o[2] = temp[0]; o[3] = temp[1]; o[4] = temp[2];
+            }
+        }
+        if (A.trace_moves && lane == 0) {
+            A.trace_moves[(size_t)it * A.I + island] = m;
+            for (int l = 0; l < LV; ++l) A.trace_scores[((size_t)it * A.I + island) * LV + l] = sc.v[l];
+            A.trace_accept[(size_t)it * A.I + island] = accept ? 1 : 0;
+        }
+        if (accept) {
+            if (top_pending && !gj_score_le(sc, top, LV)) {
+                for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+                top_pending = false;
+                __syncwarp();
+            }
+            // ---- apply: labels, counts, route slots, totals ------------------------------------------------
+            if (lane == 0) {
+                for (int j = 0; j < ncs; ++j) {
+                    const int stop = q.cs_stop[j];
+                    row[2 * stop] = q.cs_v[j];
+                    if (q.cs_oc[j] != q.cs_c[j]) {
+                        row[2 * stop + 1] = q.cs_c[j];
+                        cnt[q.cs_oc[j] - P.val_lo] -= 1;
+                        cnt[q.cs_c[j] - P.val_lo] += 1;
+                    }
+                }
+                tot[0] = (unsigned long long)dups; tot[1] = cap_pen; tot[2] = late_pen;
+            }
+            for (int a = 0; a < nav; ++a) {
+                const int v = q.av[a], len = q.nlen[a];
+                const int32_t* src = spare + q.noff[a];
+                int32_t* dst = rs + (size_t)v * n;
+                for (int i = lane; i < len; i += 32) dst[i] = src[i];
+                if (lane == 0) { rlen[v] = len; rdist[v] = q.nd[a]; rload[v] = q.nl[a]; rlate[v] = q.nt[a]; }
+            }
+            cur = sc;
+            accepted_total += 1;
+            if (is_la) {
+                late_head = (late_head + A.late_size - 1) % A.late_size;
+                if (lane == 0)
+                    for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+                late_len = min(late_len + 1, A.late_size);
+            }
+            __syncwarp();
+            // update_top_individual (agent_base.rs:220-224)
+            if (gj_score_le(cur, top, LV)) { top = cur; top_pending = true; }
+        }
+        // ---- tabu deque (mover.rs:75-96): every id the move selected enters, the oldest leave ------
+        if (tabu_g && m.kind != GJ_MOVE_NULL && lane == 0) {
+            int sel[GJ_MOVE_MAXK];
+            const int cntsel = gj_move_selected(m, sel);
+            const int glen = G.offsets[m.group + 1] - G.offsets[m.group];
+            const int W = (glen + 31) >> 5;
+            const int T = A.tabu_size[m.group];
+            uint32_t* bits = tabu_g + A.ctabu_off[m.group];
+            int32_t* ring = (int32_t*)(bits + W + 1);
+            int head = ring[T], fill = ring[T + 1];
+#pragma unroll
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                if (i < cntsel) {
+                    const int pos = sel[i];
+                    if (!((bits[pos >> 5] >> (pos & 31)) & 1u)) {
+                        if (fill == T) {
+                            const int old = ring[head];
+                            bits[old >> 5] &= ~(1u << (old & 31));
+                        } else {
+                            fill += 1;
+                        }
+                        ring[head] = pos;
+                        head = (head + 1) % T;
+                        bits[pos >> 5] |= 1u << (pos & 31);
+                    }
+                }
+            }
+            ring[T] = head; ring[T + 1] = fill;
+        }
+        __syncwarp();
+    }
+
+    // ---- finish -----------------------------------------------------------------------------------------
+    if (top_pending)
+        for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+    if (lane == 0) {
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+            A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
+            A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = top.v[l];
+        }
+        if (is_la) { A.late_head[island] = late_head; A.late_len[island] = late_len; }
+        else for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l] = temp[l];
+        A.dirty[island] = 0;
+        atomicAdd(&A.counters[0], (unsigned long long)A.n_steps);
+        if (island == 0) atomicAdd(&A.counters[1], (unsigned long long)A.n_steps);
+        if (accepted_total) atomicAdd(&A.counters[2], (unsigned long long)accepted_total);
+    }
+}

@@ -25,6 +25,19 @@ struct GjVrpState {
     unsigned long long* tot;         // [I][4]: duplicates, capacity penalty, lateness, -
 };
 
+// Route index of a single-neighbour chain (gj_islands_vrp_chain.cuh)
+struct GjVrpChainState {
+    int32_t* rs;                 // [I][K][n]
+    int32_t* rlen;               // [I][K]
+    double* rdist;               // [I][K]
+    unsigned long long* rload;   // [I][K]
+    unsigned long long* rlate;   // [I][K]
+    unsigned long long* tot;     // [I][4]: duplicates, capacity penalty, lateness, -
+    int32_t* spare;              // [I][n]
+    int32_t* cnt; int cnt_stride;
+    int* stale;                  // [I] route index out of date (creation, migrant, adopted global top)
+};
+
 #define GJ_VRP_MAXCS 16              // changed stops of a small move
 #define GJ_VRP_MAXAV 32              // routes they can touch
 

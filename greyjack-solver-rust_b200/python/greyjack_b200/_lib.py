@@ -58,7 +58,7 @@ EXPORTED = [
     "gj_host_alloc", "gj_host_free",
     "gj_score_plain", "gj_score_incremental", "gj_score_incremental_packed",
     "gj_score_plain_device", "gj_score_plain_i32_device", "gj_score_incremental_device",
-    "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_set_accomplish_rate", "gj_islands_stats", "gj_islands_trace_aux", "gj_islands_set_profiling", "gj_islands_profile_read",
+    "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_set_accomplish_rate", "gj_islands_stats", "gj_islands_trace_aux", "gj_islands_step_path", "gj_islands_set_profiling", "gj_islands_profile_read",
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",
     "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step",
 ]
@@ -75,6 +75,8 @@ def load():
                       "(python __graft_entry__.py build); there is no CPU fallback")
     L = C.CDLL(LIB_PATH)
     L.gj_last_error.restype = C.c_char_p
+    L.gj_islands_step_path.restype = C.c_char_p
+    L.gj_islands_step_path.argtypes = [C.c_void_p]
     L.gj_abi_version.restype = C.c_int32
     L.gj_device_count.restype = C.c_int32
     L.gj_launch_count.restype = C.c_int64

@@ -265,6 +265,11 @@ class Islands:
         _lib.check(self._L.gj_islands_trace_aux(self.handle, C.c_int32(island), _ptr(out)))
         return {"random": out[0], "accept_proba": out[1], "temperature": out[2:5].copy()}
 
+    @property
+    def step_path(self) -> str:
+        """Kernel path of a step: fused / fused_lean / chain / vrp_chain / delta / vrp_delta / full / ga."""
+        return self._L.gj_islands_step_path(self.handle).decode()
+
     def set_profiling(self, on: bool):
         _lib.check(self._L.gj_islands_set_profiling(self.handle, C.c_int32(int(on))))
 

@@ -323,6 +323,10 @@ GJ_API gj_status gj_islands_trace_step(gj_islands* g, int32_t island,
    out[2..4] = temperatures per level after the step's update.                              */
 GJ_API gj_status gj_islands_trace_aux(gj_islands* g, int32_t island, double* out /*[5]*/);
 
+/* Name of the kernel path a step of this group takes, chosen at creation: "fused", "fused_lean",
+   "chain", "vrp_chain", "delta", "vrp_delta", "full" or "ga" (static string).                     */
+GJ_API const char* gj_islands_step_path(const gj_islands* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ best scores are re-scored by the full evaluator after every accepted move and mu
 import numpy as np
 import pytest
 
-from greyjack_b200 import LateAcceptance, Problem, TabuSearch, instances as inst
+from greyjack_b200 import LateAcceptance, Problem, SimulatedAnnealing, TabuSearch, instances as inst
 from test_gpu_islands import ALL, MIX, _final_state, _oracle_move, _same_score
 
 pytestmark = pytest.mark.gpu
@@ -476,4 +476,116 @@ def test_vrp_delta_run_is_consistent(mk, agent, oracle):
             assert _same_score(cs, op.score_incremental(cv, [[]])[0], spec, oracle)
     assert oracle.score_cmp(prev, s0) < 0
     assert isl.stats()["candidates"] == 100 * per_step * 4
+    isl.close(); gp.close()
+
+
+# ---- VRP models, single-neighbour agents: chains over a route index (gj_islands_vrp_chain.cuh) ----------
+VRP_CHAIN_CASES = [
+    ("cvrp60", lambda: inst.cvrp(60, 6, seed=2), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.3, None),
+    ("cvrp45-small-moves", lambda: inst.cvrp(45, 5, seed=7), [0.3, 0.3, 0.2, 0.2, 0.0, 0.0], 0.1, 3.0),
+    ("vrpsvc80", lambda: inst.vrptw(80, 6, n_depots=2, seed=3), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.2, None),
+    ("vrptw80-file", lambda: inst.vrptw(80, 6, n_depots=2, seed=3, service_variant=False), [0.4, 0.4, 0.1, 0.1, 0.0, 0.0], 0.2, 2.0),
+    ("vrpsvc70-long-routes", lambda: inst.vrptw(70, 2, n_depots=1, seed=9), [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 0.0, 4.0),
+]
+
+
+@pytest.mark.parametrize("noop", [True, False], ids=["refquirk", "plainform"])
+@pytest.mark.parametrize("case", VRP_CHAIN_CASES, ids=lambda c: c[0])
+def test_vrp_chain_step_replay(case, noop, oracle):
+    """Every step of a LateAcceptance chain on a VRP model replayed through the oracle: the move, the
+    candidate score (all three levels bit-exact: the route re-walk keeps the reference's summation
+    order), the acceptance rule, the stored vector and score."""
+    _, mk, probas, tabu, mult = case
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    size = 4
+    isl = LateAcceptance(size, tabu, mult, probas, 10000, reference_noop_moves=noop,
+                         scoring="delta").build_agent(gp, n_islands=3, seed=77)
+    assert isl.step_path == "vrp_chain"
+    late = []
+    for step in range(70):
+        base, cur_score = isl.current(2)
+        tr = isl.trace_step(2)
+        if noop:
+            want = _oracle_move(op, spec, base, tr["desc"][0])
+            assert _final_state(spec.n_vars, tr["deltas"][0]) == _final_state(spec.n_vars, want)
+        want_sc = oracle.score_round(op.score_incremental(base, tr["deltas"]), spec.score_precision)
+        assert np.array_equal(tr["scores"], want_sc), step
+        acc, late = oracle.la_accept(tr["scores"][0], cur_score, late, size)
+        assert tr["accepted"] == acc, step
+        new, new_score = isl.current(2)
+        want_vec = base.copy()
+        if acc:
+            for c, v in tr["deltas"][0]:
+                want_vec[c] = v
+            assert np.array_equal(new_score, tr["scores"][0])
+        else:
+            assert np.array_equal(new_score, cur_score)
+        assert np.array_equal(new, want_vec)
+    vec, sc = isl.best(2)
+    assert np.array_equal(sc, oracle.score_round(op.score_incremental(vec, [[]])[0], spec.score_precision))
+    isl.close(); gp.close()
+
+
+@pytest.mark.parametrize("agent", ["la", "sa"])
+@pytest.mark.parametrize("mk", [lambda: inst.cvrp(90, 7, seed=6), lambda: inst.vrptw(90, 7, n_depots=2, seed=6)],
+                         ids=["cvrp", "vrpsvc"])
+def test_vrp_chain_many_steps_per_launch_equal_single_steps(mk, agent, oracle):
+    """The route index carried across steps and launches == the one rebuilt from the solution row:
+    same seed -> same chain whatever the launch granularity, and every stored score is the full
+    evaluation of its vector."""
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    probas = [0.4, 0.4, 0.1, 0.1, 0.0, 0.0]
+
+    def build():
+        if agent == "la":
+            b = LateAcceptance(8, 0.2, None, probas, 100000, reference_noop_moves=False, scoring="delta")
+        else:
+            b = SimulatedAnnealing([1.0, 1.0, 50.0], 0.999, 0.2, None, probas, 100000,
+                                   reference_noop_moves=False, scoring="delta")
+        return b.build_agent(gp, n_islands=1, seed=11)        # one chain: no global-top adoption
+
+    a, b = build(), build()
+    assert a.step_path == "vrp_chain"
+    a.step(200)
+    for _ in range(200):
+        b.trace_step(0)
+    for i in (0,):
+        va, sa_ = a.current(i)
+        vb, sb = b.current(i)
+        assert np.array_equal(va, vb) and np.array_equal(sa_, sb)
+        assert np.array_equal(sa_, oracle.score_round(op.score_incremental(va, [[]])[0], spec.score_precision))
+        ba, bsa = a.best(i)
+        bb, bsb = b.best(i)
+        assert np.array_equal(ba, bb) and np.array_equal(bsa, bsb)
+        assert np.array_equal(bsa, oracle.score_round(op.score_incremental(ba, [[]])[0], spec.score_precision))
+    assert a.stats()["candidates"] == 200 and a.stats()["accepted"] == b.stats()["accepted"] > 0
+    a.close(); b.close(); gp.close()
+
+
+def test_vrp_chain_migration_and_global_top_keep_the_index_in_sync(oracle):
+    """Migrants and adopted global tops replace a chain's solution between launches: the route index
+    is rebuilt (stale flag) and every stored score stays the full evaluation of its vector."""
+    spec = inst.vrptw(60, 5, n_depots=2, seed=4)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    isl = LateAcceptance(6, 0.2, None, [0.5, 0.5, 0.0, 0.0, 0.0, 0.0], 3, reference_noop_moves=False,
+                         scoring="delta", chain_steps_per_launch=4).build_agent(gp, n_islands=6, seed=3)
+    assert isl.step_path == "vrp_chain"
+    _, s0 = isl.best(-1)
+    prev = None
+    for _ in range(8):
+        isl.step(25)
+        vec, sc = isl.best(-1)
+        assert np.array_equal(sc, oracle.score_round(op.score_incremental(vec, [[]])[0], spec.score_precision))
+        if prev is not None:
+            assert oracle.score_cmp(sc, prev) <= 0
+        prev = sc
+        for i in range(6):
+            cv, cs = isl.current(i)
+            assert np.array_equal(cs, oracle.score_round(op.score_incremental(cv, [[]])[0], spec.score_precision))
+    assert oracle.score_cmp(prev, s0) < 0
     isl.close(); gp.close()
