@@ -232,6 +232,8 @@ struct GjPhilox {
     uint32_t k[2];
     uint32_t out[4];
     int have;
+    int compact;      // 1: refill through ONE out-of-line Philox block (latency-bound kernels where the
+                      // instruction footprint matters more than the call)
 };
 
 __device__ __forceinline__ void gj_philox_round(uint32_t* c, const uint32_t* k) {
@@ -256,6 +258,13 @@ __device__ __forceinline__ void gj_philox_block(const uint32_t* ctr, const uint3
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 
+static __device__ __noinline__ uint4 gj_philox_block_call(uint4 c, uint2 k) {
+    const uint32_t cc[4] = {c.x, c.y, c.z, c.w}, kk[2] = {k.x, k.y};
+    uint32_t o[4];
+    gj_philox_block(cc, kk, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __device__ __forceinline__ void gj_rng_init(GjPhilox& g, uint64_t seed, uint32_t island,
                                             uint32_t step_lo, uint32_t step_hi,
                                             uint32_t candidate) {
@@ -263,11 +272,17 @@ __device__ __forceinline__ void gj_rng_init(GjPhilox& g, uint64_t seed, uint32_t
     g.k[1] = (uint32_t)(seed >> 32) + island;
     g.c[0] = step_lo; g.c[1] = candidate; g.c[2] = step_hi; g.c[3] = 0;
     g.have = 0;
+    g.compact = 0;
 }
 
 __device__ __forceinline__ uint32_t gj_rng_u32(GjPhilox& g) {
     if (g.have == 0) {
-        gj_philox_block(g.c, g.k, g.out);
+        if (g.compact) {
+            const uint4 o = gj_philox_block_call(make_uint4(g.c[0], g.c[1], g.c[2], g.c[3]), make_uint2(g.k[0], g.k[1]));
+            g.out[0] = o.x; g.out[1] = o.y; g.out[2] = o.z; g.out[3] = o.w;
+        } else {
+            gj_philox_block(g.c, g.k, g.out);
+        }
         g.c[3] += 1;
         g.have = 4;
     }

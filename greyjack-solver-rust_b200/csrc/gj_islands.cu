@@ -1239,22 +1239,28 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
         const size_t n = (size_t)P.n_entities, K = (size_t)P.n_vehicles;
         size_t free_b = 0, total_b = 0;
         GJ_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need = (size_t)I * (K * n + n) * 4;
-        if (need <= free_b / 2) {
+        const size_t need = ((size_t)I + 1) * (K * n + n) * 4;
+        if (need <= free_b / 2 && K * n < ((size_t)1 << 31)) {
             g->scoring_mode = GJ_SCORING_DELTA;
             g->chain = true; g->vrp_chain = true;
             g->mover.tabu_layout = 1;
             GjVrpChainState& V = g->vcs;
             V.cnt_stride = 32 * P.bm_words;
-            if ((rc = dev_alloc(g.get(), (size_t)I * K * n, &V.rs, false))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rlen))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rdist))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rload))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I * K, &V.rlate))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I * 4, &V.tot))) return rc;
+            const size_t I1 = (size_t)I + 1;            // slot I: the published global top's index
+            if ((rc = dev_alloc(g.get(), I1 * K * n, &V.rs, false))) return rc;
+            if ((rc = dev_alloc(g.get(), I1 * K, &V.rlen))) return rc;
+            if ((rc = dev_alloc(g.get(), I1 * K, &V.rdist))) return rc;
+            if ((rc = dev_alloc(g.get(), I1 * K, &V.rload))) return rc;
+            if ((rc = dev_alloc(g.get(), I1 * K, &V.rlate))) return rc;
+            if ((rc = dev_alloc(g.get(), I1 * 4, &V.tot))) return rc;
             if ((rc = dev_alloc(g.get(), (size_t)I * n, &V.spare, false))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I * V.cnt_stride, &V.cnt))) return rc;
-            if ((rc = dev_alloc(g.get(), (size_t)I, &g->ds.stale))) return rc;
+            if ((rc = dev_alloc(g.get(), I1 * V.cnt_stride, &V.cnt))) return rc;
+            if ((rc = dev_alloc(g.get(), n, &V.gstop))) return rc;
+            if ((rc = dev_alloc(g.get(), n, &V.gdst))) return rc;
+            if ((rc = dev_alloc(g.get(), 1, &V.gidx_ver))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I * GJ_VRPC_DIFF, &V.diff))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I, &V.ndiff))) return rc;
+            if ((rc = dev_alloc(g.get(), I1, &g->ds.stale))) return rc;
             V.stale = g->ds.stale;
             std::vector<int> ones((size_t)I, 1);
             GJ_CUDA_TRY(cudaMemcpy(g->ds.stale, ones.data(), (size_t)I * sizeof(int), cudaMemcpyHostToDevice));
@@ -1619,6 +1625,10 @@ gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
         k_apply_adoption<<<g->I, 128, 0, st>>>(make_select_args(g, false, false));
         GJ_LAUNCH_CHECK();
     }
+    if (g->vrp_chain) {
+        k_vrp_chain_gindex<<<1, 32, 0, st>>>(g->p->dev, g->I, g->gbest, g->gver, g->vcs);
+        GJ_LAUNCH_CHECK();
+    }
     return GJ_OK;
 }
 
@@ -1651,6 +1661,8 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     const unsigned grid = (unsigned)((g->I + kChainWarps - 1) / kChainWarps);
     gj_status rc;
     if (g->vrp_chain) {
+        k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
+        GJ_LAUNCH_CHECK();
         k_vrp_chains<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(
             P, g->groups, A, g->vcs);
     } else if (P.kind == GJ_NQUEENS) {

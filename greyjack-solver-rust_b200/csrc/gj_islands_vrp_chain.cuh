@@ -21,10 +21,9 @@
 
 static constexpr int kVrpChainWarps = 4;
 #define GJ_VRPC_Q 48             // 32 stops of the old route + <= 16 arrivals
+#define GJ_VRPC_DIFF 512          // stops the agent's top may trail the chain by before a whole-row copy
 
 struct GjVrpcScratch {
-    uint4 qf[GJ_VRPC_Q];         // customer facts of the merged run
-    double qd[GJ_VRPC_Q];        // leg into every stop of the run
     int32_t qc[GJ_VRPC_Q];       // customers
     int32_t qs[GJ_VRPC_Q];       // stop indices
     // the move: changed stops (new / old labels), arrivals of the route being walked
@@ -79,30 +78,53 @@ __device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int t
         const int m = __popc(keepmask) + (ib - ia);
         ia = ib;
         __syncwarp();
-        for (int i = lane; i < m; i += 32) {
-            const int ci = q.qc[i];
-            const int prev = i > 0 ? q.qc[i - 1] : last;
-            q.qf[i] = P.cust[ci];
-            q.qd[i] = prev >= 0 ? __ldg(&D[(size_t)prev * L + (size_t)ci]) : 0.0;
-            if (out) out[outn + i] = q.qs[i];
-        }
-        __syncwarp();
-        for (int i = 0; i < m; ++i) {
-            const int ci = q.qc[i];
-            if (first < 0) first = ci; else fold = fold + q.qd[i];
-            last = ci;
-            const uint4 f = q.qf[i];
-            load += (unsigned long long)f.x;
+        // the merged run, 32 stops at a time: facts and legs gathered in parallel; demand and lateness
+        // are integer sums (order-free), the arrival-time recurrence arrival' = max(arrival, start) +
+        // service is a max-plus map a -> max(a + A, B) and composes associatively (warp scan); only the
+        // float distance fold stays sequential, in the reference's order
+        for (int b2 = 0; b2 < m; b2 += 32) {
+            const int i = b2 + lane;
+            const bool on = i < m;
+            const int ci = on ? q.qc[i] : 0;
+            const int prev = i > 0 ? q.qc[on ? i - 1 : 0] : last;
+            uint4 f = make_uint4(0u, 0u, 0u, 0u);
+            double d = 0.0;
+            if (on) {
+                f = P.cust[ci];
+                if (prev >= 0) d = __ldg(&D[(size_t)prev * L + (size_t)ci]);
+                if (out) out[outn + i] = q.qs[i];
+            }
+            load += (unsigned long long)__reduce_add_sync(GJ_FULL_MASK, f.x & 0xffffu) +
+                    ((unsigned long long)__reduce_add_sync(GJ_FULL_MASK, f.x >> 16) << 16);
             if (P.time_windowed) {
                 const unsigned long long ws = f.y, we = f.z, sv = f.w;
-                if (arrival < ws) arrival = ws;
-                if (tw_mode == GJ_TW_ISC_FILE) {
-                    if (arrival + sv > we) lateness += (arrival + sv) - we;
-                } else {
-                    if (arrival > we + sv) lateness += arrival - (we + sv);
+                unsigned long long SA = sv, SB = on ? ws + sv : 0ull;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long pa = __shfl_up_sync(GJ_FULL_MASK, SA, o);
+                    const unsigned long long pb = __shfl_up_sync(GJ_FULL_MASK, SB, o);
+                    if (lane >= o) { SB = max(pb + SA, SB); SA = pa + SA; }
                 }
-                arrival += sv;
+                const unsigned long long after = max(arrival + SA, SB);         // leaving stop i
+                unsigned long long before = __shfl_up_sync(GJ_FULL_MASK, after, 1);
+                if (lane == 0) before = arrival;
+                const unsigned long long t = max(before, ws);                    // service start at stop i
+                unsigned long long lt = 0ull;
+                if (on) {
+                    if (tw_mode == GJ_TW_ISC_FILE) { if (t + sv > we) lt = (t + sv) - we; }
+                    else { if (t > we + sv) lt = t - (we + sv); }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) lt += __shfl_xor_sync(GJ_FULL_MASK, lt, o);
+                lateness += lt;
+                arrival = __shfl_sync(GJ_FULL_MASK, after, 31);
             }
+            const int cntk = min(32, m - b2);
+            for (int k = 0; k < cntk; ++k) fold = fold + __shfl_sync(GJ_FULL_MASK, d, k);
+        }
+        if (m > 0) {
+            if (first < 0) first = q.qc[0];
+            last = q.qc[m - 1];
         }
         outn += m;
         __syncwarp();
@@ -186,7 +208,106 @@ __device__ __forceinline__ void gj_vrpc_rebuild(const GjProblemDev& P, int tw_mo
     __syncwarp();
 }
 
+// Route index of the published global top (slot I), once per published version; one warp.
+__global__ void __launch_bounds__(32)
+k_vrp_chain_gindex(GjProblemDev P, int I, const int32_t* gbest, const int* gver, GjVrpChainState V) {
+    __shared__ GjVrpcScratch q;
+    const int lane = threadIdx.x;
+    const int ver = *gver;
+    if (ver == *V.gidx_ver) return;
+    gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), gbest, V, I, q, lane);
+    const int n = P.n_entities, K = P.n_vehicles;
+    const int32_t* rs = V.rs + (size_t)I * K * n;
+    const int32_t* rlen = V.rlen + (size_t)I * K;
+    int p = 0;
+    for (int v = 0; v < K; ++v) {
+        const int len = rlen[v];
+        for (int i = lane; i < len; i += 32) { V.gstop[p + i] = rs[(size_t)v * n + i]; V.gdst[p + i] = v * n + i; }
+        p += len;
+    }
+    __syncwarp();
+    if (lane == 0) *V.gidx_ver = ver;
+}
+
+// Between launches (cold path): update_global_top adopt half (agent_base.rs:465-489), route index of
+// chains whose solution was replaced (adopted global top: copy of slot I; migrant / creation:
+// rebuild), update_top_individual for the replaced solution.  One warp per chain; chains with
+// nothing pending leave after three loads.
 __global__ void __launch_bounds__(kVrpChainWarps * 32)
+k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
+    __shared__ GjVrpcScratch sh_q[kVrpChainWarps];
+    constexpr int LV = 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int island = blockIdx.x * kVrpChainWarps + warp;
+    if (island >= A.I) return;
+    GjVrpcScratch& q = sh_q[warp];
+    const int n = P.n_entities, K = P.n_vehicles;
+    int32_t* row = A.cur + (size_t)island * A.stride;
+    int32_t* best_row = A.best + (size_t)island * A.stride;
+    const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
+    int adopted = 0;
+    if (lane == 0 && A.gver) {
+        const int ver = *A.gver;
+        if (ver != A.gseen[island]) {
+            A.gseen[island] = ver;
+            const GjScore g = gj_load_score(A.gbest_score, LV);
+            const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+            adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
+            if (adopted && *V.gidx_ver == ver) adopted = 2;              // ... and its route index is ready
+        }
+    }
+    adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
+    const int stale = V.stale[island], dirty = A.dirty[island];
+    if (!adopted && !stale && !dirty) return;
+    GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    if (adopted) {
+        for (int i = lane; i < A.n_vars; i += 32) row[i] = A.gbest[i];
+        if (is_la && lane == 0) {   // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
+            double* late_g = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
+            const int head = (A.late_head[island] + A.late_size - 1) % A.late_size;
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)head * GJ_MAX_LEVELS + l] = cur.v[l];
+            A.late_head[island] = head;
+            A.late_len[island] = min(A.late_len[island] + 1, A.late_size);
+        }
+        cur = gj_load_score(A.gbest_score, LV);
+        if (lane == 0)
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
+        __syncwarp();
+    }
+    if (adopted == 2) {
+        // copy the global top's route index (slot I) instead of re-walking all K routes
+        const size_t gI = (size_t)A.I;
+        int32_t* rs = V.rs + (size_t)island * K * n;
+        for (int p = lane; p < n; p += 32) rs[V.gdst[p]] = V.gstop[p];
+        for (int v = lane; v < K; v += 32) {
+            V.rlen[(size_t)island * K + v] = V.rlen[gI * K + v]; V.rdist[(size_t)island * K + v] = V.rdist[gI * K + v];
+            V.rload[(size_t)island * K + v] = V.rload[gI * K + v]; V.rlate[(size_t)island * K + v] = V.rlate[gI * K + v];
+        }
+        for (int i = lane; i < V.cnt_stride; i += 32)
+            V.cnt[(size_t)island * V.cnt_stride + i] = V.cnt[gI * V.cnt_stride + i];
+        if (lane < 3) V.tot[(size_t)island * 4 + lane] = V.tot[gI * 4 + lane];
+        if (lane == 0) V.stale[island] = 0;
+    } else if (stale || adopted) {
+        gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, lane);
+    }
+    // the replaced solution against the agent's top (update_top_individual)
+    if (gj_score_le(cur, top, LV)) {
+        for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+        if (lane == 0) {
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
+            V.ndiff[island] = 0;
+        }
+    } else if (lane == 0) {
+        V.ndiff[island] = -1;                       // row and best_row are unrelated vectors now
+    }
+    if (lane == 0) A.dirty[island] = 0;
+}
+
+#ifndef GJ_VRPC_MINBLOCKS
+#define GJ_VRPC_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(kVrpChainWarps * 32, GJ_VRPC_MINBLOCKS)
 k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     __shared__ GjVrpcScratch sh_q[kVrpChainWarps];
     constexpr int LV = 3;
@@ -206,47 +327,32 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     unsigned long long* tot = V.tot + (size_t)island * 4;
     int32_t* cnt = V.cnt + (size_t)island * V.cnt_stride;
     int32_t* spare = V.spare + (size_t)island * n;
+    int32_t* diff = V.diff + (size_t)island * GJ_VRPC_DIFF;
     uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
     double* late_g = A.late ? A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS : nullptr;
     const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
-
-    // ---- stage: update_global_top adopt half (agent_base.rs:465-489), route index ----------------------
-    int adopted = 0;
-    if (lane == 0 && A.gver) {
-        const int ver = *A.gver;
-        if (ver != A.gseen[island]) {
-            A.gseen[island] = ver;
-            const GjScore g = gj_load_score(A.gbest_score, LV);
-            const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
-            adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
-        }
-    }
-    adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
     int late_head = is_la ? A.late_head[island] : 0, late_len = is_la ? A.late_len[island] : 0;
     double temp[GJ_MAX_LEVELS] = {1.0, 1.0, 1.0};
     if (!is_la)
         for (int l = 0; l < GJ_MAX_LEVELS; ++l) temp[l] = A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l];
     GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
     GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
-    if (adopted) {
-        for (int i = lane; i < A.n_vars; i += 32) row[i] = A.gbest[i];
-        if (is_la) {          // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
-            late_head = (late_head + A.late_size - 1) % A.late_size;
-            if (lane == 0)
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)late_head * GJ_MAX_LEVELS + l] = cur.v[l];
-            late_len = min(late_len + 1, A.late_size);
-        }
-        cur = gj_load_score(A.gbest_score, LV);
-        __syncwarp();
-    }
-    if (V.stale[island] || adopted) gj_vrpc_rebuild(P, tw_mode, row, V, island, q, lane);
-    if (A.dirty[island] || adopted) {
-        if (gj_score_le(cur, top, LV)) {
+    // best_row (the agent's top) trails the chain: `diff` lists the stops whose labels changed since
+    // best_row last equalled the solution row (ndiff < 0: too many -> whole-row copy)
+    int ndiff = V.ndiff[island];
+    auto materialize_top = [&]() {
+        if (ndiff < 0) {
             for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
-            top = cur;
+        } else {
+            for (int i = lane; i < ndiff; i += 32) {
+                const int st = diff[i];
+                best_row[2 * st] = row[2 * st];
+                best_row[2 * st + 1] = row[2 * st + 1];
+            }
         }
-    }
-    __syncwarp();
+        ndiff = 0;
+        __syncwarp();
+    };
     int accepted_total = 0;
     // update_top_individual copies are lazy: while the top IS the current solution, best_row is only
     // written when the chain is about to leave it (or at the end of the launch)
@@ -256,8 +362,8 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
         const uint64_t step = A.step0 + (uint64_t)it;
         // ---- generate (every lane computes the same move) -----------------------------------------------
         GjMoverParams M = A.M;
-        const GjMove m = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
-                                          tabu_g, A.ctabu_off);
+        const GjMove m = gj_generate_move<true>(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
+                                                tabu_g, A.ctabu_off);
         const bool identity = m.kind == GJ_MOVE_NULL || (A.noop != 0 && (m.kind == 3 || (m.kind == 2 && m.k == 2)));
         // ---- changed stops, touched routes (lane 0) --------------------------------------------------
         if (lane == 0) {
@@ -378,9 +484,16 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
         }
         if (accept) {
             if (top_pending && !gj_score_le(sc, top, LV)) {
-                for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+                materialize_top();
                 top_pending = false;
-                __syncwarp();
+            }
+            if (ndiff >= 0) {
+                if (ndiff + ncs <= GJ_VRPC_DIFF) {
+                    if (lane < ncs) diff[ndiff + lane] = q.cs_stop[lane];
+                    ndiff += ncs;
+                } else {
+                    ndiff = -1;
+                }
             }
             // ---- apply: labels, counts, route slots, totals ------------------------------------------------
             if (lane == 0) {
@@ -424,7 +537,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             uint32_t* bits = tabu_g + A.ctabu_off[m.group];
             int32_t* ring = (int32_t*)(bits + W + 1);
             int head = ring[T], fill = ring[T + 1];
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
                 if (i < cntsel) {
                     const int pos = sel[i];
@@ -447,16 +560,15 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     }
 
     // ---- finish -----------------------------------------------------------------------------------------
-    if (top_pending)
-        for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+    if (top_pending) materialize_top();
     if (lane == 0) {
+        V.ndiff[island] = ndiff;
         for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
             A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
             A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = top.v[l];
         }
         if (is_la) { A.late_head[island] = late_head; A.late_len[island] = late_len; }
         else for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l] = temp[l];
-        A.dirty[island] = 0;
         atomicAdd(&A.counters[0], (unsigned long long)A.n_steps);
         if (island == 0) atomicAdd(&A.counters[1], (unsigned long long)A.n_steps);
         if (accepted_total) atomicAdd(&A.counters[2], (unsigned long long)accepted_total);

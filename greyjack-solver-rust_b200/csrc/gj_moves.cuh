@@ -305,6 +305,8 @@ __device__ __forceinline__ void gj_pick_positions(GjPhilox& rng, int right_end, 
 }
 
 // Mover::do_move (mover.rs:98-128) for candidate `cand` of island `island` at step `step`.
+// COMPACT_RNG: same stream, Philox refills out of line (smaller code; see GjPhilox::compact).
+template <bool COMPACT_RNG = false>
 __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const GjGroups& G,
                                                    const GjMoverParams& M, uint64_t seed,
                                                    uint32_t island, uint64_t step, uint32_t cand,
@@ -312,6 +314,7 @@ __device__ __forceinline__ GjMove gj_generate_move(const GjProblemDev& P, const 
                                                    const int32_t* tabu_word_off) {
     GjPhilox rng;
     gj_rng_init(rng, seed, island, (uint32_t)step, (uint32_t)(step >> 32), cand);
+    rng.compact = COMPACT_RNG ? 1 : 0;
     GjMove m;
     m.pad = 0;
 #pragma unroll

@@ -27,7 +27,7 @@ struct GjVrpState {
 
 // Route index of a single-neighbour chain (gj_islands_vrp_chain.cuh)
 struct GjVrpChainState {
-    int32_t* rs;                 // [I][K][n]
+    int32_t* rs;                 // [I + 1][K][n]
     int32_t* rlen;               // [I][K]
     double* rdist;               // [I][K]
     unsigned long long* rload;   // [I][K]
@@ -35,7 +35,12 @@ struct GjVrpChainState {
     unsigned long long* tot;     // [I][4]: duplicates, capacity penalty, lateness, -
     int32_t* spare;              // [I][n]
     int32_t* cnt; int cnt_stride;
-    int* stale;                  // [I] route index out of date (creation, migrant, adopted global top)
+    int* stale;                  // [I + 1] route index out of date (creation, migrant)
+    // slot I of every array above = the route index of the published global top, built once per
+    // published version (k_vrp_chain_gindex); adopting chains copy it instead of re-walking K routes
+    int32_t* gstop; int32_t* gdst;   // [n] its stop lists flattened: rs[gdst[p]] = gstop[p]
+    int* gidx_ver;
+    int32_t* diff; int* ndiff;       // [I][GJ_VRPC_DIFF], [I]: stops where the chain differs from its top row
 };
 
 #define GJ_VRP_MAXCS 16              // changed stops of a small move
