@@ -185,7 +185,8 @@ def other_configs(gj, inst, torch):
 
     def c4():
         p = gj.Problem(inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False))
-        return p, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50).build_agent(p, n_islands=592, seed=3)
+        return p, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50, scoring="delta",
+                                    chain_steps_per_launch=32).build_agent(p, n_islands=4096, seed=3)
 
     def c5():
         p = gj.Problem(inst.tsp(20000, seed=4, with_matrix=False), use_coords=True)
@@ -194,7 +195,7 @@ def other_configs(gj, inst, torch):
 
     timed("C1 nqueens-256 LateAcceptance x4096 chains (k_la_chains)", c1, 1000)
     timed("C3 cvrp-2000x50 GeneticAlgorithm pop 8192 x1 island", c3, 10)
-    timed("C4 vrptw-5000 (vrp_service) LateAcceptance x592 islands", c4, 40)
+    timed("C4 vrptw-5000 (vrp_service) LateAcceptance x4096 chains (k_vrp_chains, route-level delta)", c4, 640)
     timed("C5 tsp-20000 TabuSearch 4096 moves x148 islands (fused step, lean layout)", c5, 20)
     return out
 

@@ -71,7 +71,8 @@ enum {
           score; integer levels bit-exact with FULL, the float level agrees to 1e-12 relative
           before ScoreTrait::round (one 10^-precision quantum after).  VRP models: the routes
           a move touches are re-walked in the reference's order -- every level bit-exact with
-          FULL (used by agents that score >= 8 neighbours per step).  Moves the delta evaluator
+          FULL (agents that score >= 8 neighbours per step; LateAcceptance / SimulatedAnnealing
+          chains when move_probas has no insertion / inverse).  Moves the delta evaluator
           does not cover (listed in DESIGN.md) are re-scored by the FULL kernel inside the
           same step.                                                                        */
 enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1,
