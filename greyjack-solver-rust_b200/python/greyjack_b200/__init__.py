@@ -9,3 +9,4 @@ from .problem import PinnedArray, Problem, deltas_to_csr, pinned_copy  # noqa: F
 from .agents import (GeneticAlgorithm, Islands, LateAcceptance, ScoreLimit, ScoreNoImprovement,  # noqa: F401
                      SimulatedAnnealing, StepsLimit, TabuSearch, TimeSpentLimit)
 from .solver import Solver  # noqa: F401,E402
+from . import wire  # noqa: F401,E402

@@ -22,6 +22,10 @@ from .problem import Problem
 SILENT, INFO, TRACE = 0, 1, 2
 
 
+def _is_number_vector(x) -> bool:
+    return not isinstance(x, str) and len(x) > 0 and all(isinstance(v, (int, float, np.floating, np.integer)) for v in x)
+
+
 class Solver:
     @staticmethod
     def solve(problem: Problem, agent_builder: _Builder, n_jobs: int = 1,
@@ -31,13 +35,20 @@ class Solver:
         """n_jobs = islands on this GPU (the reference: one agent per rayon worker, solver.rs:58-64).
         observers: objects with update(dict) (ObserverTrait::update), called whenever the global best
         improves with {"score": [...], "variable_values": [...], "step": n}.
-        Returns (variable_values, score) of the global best individual."""
+        initial_solution: a variable vector, or the reference's solution Value / JSON text
+        (InitialSolutionVariants::CotwinValuesVector, solver.rs:108-119; see wire.py) -- every island
+        starts from it.
+        Returns (variable_values, score) of the global best individual; wire.solution_to_value turns
+        that into the Value the reference's Solver::solve returns."""
         term = copy.deepcopy(termination_strategy if termination_strategy is not None
                              else getattr(agent_builder, "termination_strategy", None))
         if term is None:
             raise ValueError("a termination strategy is required")
         init = None
         if initial_solution is not None:
+            if isinstance(initial_solution, (str, list, tuple)) and not _is_number_vector(initial_solution):
+                from . import wire
+                initial_solution, _ = wire.solution_from_value(problem.spec, initial_solution)
             init = np.tile(np.asarray(initial_solution, dtype=np.float64), (n_jobs, 1))
         islands = Islands(problem, agent_builder, n_islands=n_jobs, seed=seed, initial=init)
         chunk = int(steps_per_call or max(1, int(getattr(agent_builder, "migration_frequency", 1))))

@@ -45,3 +45,20 @@ def test_solve_steps_limit_and_time_limit(builder, oracle):
     vars2, score2 = Solver.solve(gp, builder, n_jobs=32, termination_strategy=TimeSpentLimit(200), seed=1)
     assert oracle.score_cmp(score2, start) < 0
     gp.close()
+
+
+def test_warm_start_from_the_reference_solution_value(oracle):
+    """Multi-stage solving as in the reference: the Value of one solve (Agent::convert_to_json) goes
+    back in as InitialSolutionVariants::CotwinValuesVector (solver.rs:108-119)."""
+    from greyjack_b200 import wire
+    spec = inst.cvrp(40, 4, seed=8)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    builder = TabuSearch(128, 0.2, True, None, [0.5, 0.5, 0, 0, 0, 0], 5, scoring="delta")
+    v1, s1 = Solver.solve(gp, builder, n_jobs=4, termination_strategy=StepsLimit(30), seed=1)
+    text = wire.solution_to_json(spec, v1, s1)
+    v2, s2 = Solver.solve(gp, builder, n_jobs=4, termination_strategy=StepsLimit(30), seed=2,
+                          initial_solution=text)
+    assert oracle.score_cmp(s2, s1) <= 0                     # the second stage starts where the first ended
+    assert np.array_equal(oracle.score_round(op.score_incremental(v2, [[]])[0], spec.score_precision), s2)
+    gp.close()
