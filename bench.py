@@ -186,7 +186,7 @@ def other_configs(gj, inst, torch):
     def c4():
         p = gj.Problem(inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False))
         return p, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50, scoring="delta",
-                                    chain_steps_per_launch=32).build_agent(p, n_islands=4096, seed=3)
+                                    chain_steps_per_launch=64).build_agent(p, n_islands=4096, seed=3)
 
     def c5():
         p = gj.Problem(inst.tsp(20000, seed=4, with_matrix=False), use_coords=True)

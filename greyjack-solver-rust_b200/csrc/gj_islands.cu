@@ -1258,6 +1258,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
             if ((rc = dev_alloc(g.get(), n, &V.gstop))) return rc;
             if ((rc = dev_alloc(g.get(), n, &V.gdst))) return rc;
             if ((rc = dev_alloc(g.get(), 1, &V.gidx_ver))) return rc;
+            if ((rc = dev_alloc(g.get(), K, &V.goff))) return rc;
             if ((rc = dev_alloc(g.get(), (size_t)I * GJ_VRPC_DIFF, &V.diff))) return rc;
             if ((rc = dev_alloc(g.get(), (size_t)I, &V.ndiff))) return rc;
             if ((rc = dev_alloc(g.get(), I1, &g->ds.stale))) return rc;
@@ -1626,7 +1627,7 @@ gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
         GJ_LAUNCH_CHECK();
     }
     if (g->vrp_chain) {
-        k_vrp_chain_gindex<<<1, 32, 0, st>>>(g->p->dev, g->I, g->gbest, g->gver, g->vcs);
+        k_vrp_chain_gindex<<<1, kGindexWarps * 32, 0, st>>>(g->p->dev, g->I, g->gbest, g->gver, g->vcs);
         GJ_LAUNCH_CHECK();
     }
     return GJ_OK;
@@ -1683,7 +1684,7 @@ static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         // launches of up to steps_to_send steps; migration and the global top between launches
         int64_t left = n_steps;
         while (left > 0) {
-            const int per_launch = g->prm.chain_steps_per_launch > 0 ? g->prm.chain_steps_per_launch : 8;
+            const int per_launch = g->prm.chain_steps_per_launch > 0 ? g->prm.chain_steps_per_launch : (g->vrp_chain ? 32 : 8);
             const int n = (int)std::min<int64_t>(std::min<int64_t>(left, per_launch),
                                                  std::max<int64_t>(1, g->steps_to_send));
             if ((rc = gj_prof_begin(g, st))) return rc;

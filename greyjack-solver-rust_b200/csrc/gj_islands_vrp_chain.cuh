@@ -36,14 +36,22 @@ struct GjVrpcScratch {
     GjMove mv;
 };
 
+// what a walk without a move needs (rebuilds): the merged-run buffers only
+struct GjVrpcScratchLite {
+    int32_t qc[GJ_VRPC_Q];
+    int32_t qs[GJ_VRPC_Q];
+    int cs_stop[1], cs_v[1], cs_c[1], arr_stop[1], arr_c[1];
+};
+
 struct GjRouteStat { double dist; unsigned long long load, late; int len; };
 
 // Walks route v of the chain: old stop list `rs_v[len]` minus the changed stops that leave, plus the
 // arrivals q.arr_* (sorted by stop), changed stops that stay take their new customer.  Every lane
 // returns the same result.  `out` (nullable) receives the merged stop list.
+template <class Scratch>
 __device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int tw_mode, int v, const int32_t* row,
                                                     const int32_t* rs_v, int len, int ncs, int na,
-                                                    int32_t* out, GjVrpcScratch& q, int lane) {
+                                                    int32_t* out, Scratch& q, int lane) {
     const size_t L = (size_t)P.n_locations;
     const double* __restrict__ D = P.D;
     int first = -1, last = -1, outn = 0, ia = 0;
@@ -156,32 +164,51 @@ __device__ __forceinline__ double gj_vrpc_sum_routes(const double* rdist, int K,
     return sum;
 }
 
-// Rebuilds the route index of a chain from its solution row (creation, migrant, adopted global top).
-__device__ __forceinline__ void gj_vrpc_rebuild(const GjProblemDev& P, int tw_mode, const int32_t* row,
-                                                const GjVrpChainState& V, int island, GjVrpcScratch& q, int lane) {
+#define GJ_VRPC_KSM 512           // route-length counters kept in shared memory while bucketing
+
+// Bucket phase of a rebuild, one warp: stop lists rs[K][n] (stop order kept: rank among the
+// same-vehicle lanes of every 32-stop chunk), route lengths, customer counts.  `sh_rlen`: K <= 
+// GJ_VRPC_KSM counters in shared memory (nullptr: the counters in HBM are used directly).
+__device__ __forceinline__ void gj_vrpc_bucket(const GjProblemDev& P, const int32_t* row, const GjVrpChainState& V,
+                                               int island, int* sh_rlen, int lane) {
     const int n = P.n_entities, K = P.n_vehicles;
     int32_t* rs = V.rs + (size_t)island * K * n;
-    int32_t* rlen = V.rlen + (size_t)island * K;
+    int32_t* rlen_g = V.rlen + (size_t)island * K;
     int32_t* cnt = V.cnt + (size_t)island * V.cnt_stride;
+    int* rlen = sh_rlen ? sh_rlen : rlen_g;
     for (int i = lane; i < V.cnt_stride; i += 32) cnt[i] = 0;
     for (int v = lane; v < K; v += 32) rlen[v] = 0;
     __syncwarp();
-    // bucket the stops by vehicle, stop order kept: rank among the same-vehicle lanes of the chunk
+    int2 nxt = lane < n ? *reinterpret_cast<const int2*>(row + 2 * lane) : make_int2(0, 0);
     for (int s0 = 0; s0 < n; s0 += 32) {
         const int s = s0 + lane;
         const bool on = s < n;
-        const int v = on ? row[2 * s] : -1 - lane;
+        const int2 vc = nxt;
+        if (s + 32 < n) nxt = *reinterpret_cast<const int2*>(row + 2 * (s + 32));     // next chunk in flight
+        const int v = on ? vc.x : -1 - lane;
         const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
         if (on) {
             const int rank = __popc(grp & ((1u << lane) - 1u));
-            const int base = rlen[v];
-            rs[(size_t)v * n + base + rank] = s;
-            atomicAdd(&cnt[row[2 * s + 1] - P.val_lo], 1);
+            rs[(size_t)v * n + rlen[v] + rank] = s;
+            atomicAdd(&cnt[vc.y - P.val_lo], 1);
         }
         __syncwarp();
         if (on && lane == 31 - __clz(grp)) rlen[v] += __popc(grp);
         __syncwarp();
     }
+    if (sh_rlen) for (int v = lane; v < K; v += 32) rlen_g[v] = sh_rlen[v];
+    __syncwarp();
+}
+
+// Rebuilds the route index of a chain from its solution row (creation, migrant), one warp.
+__device__ __forceinline__ void gj_vrpc_rebuild(const GjProblemDev& P, int tw_mode, const int32_t* row,
+                                                const GjVrpChainState& V, int island, GjVrpcScratchLite& q,
+                                                int* sh_rlen, int lane) {
+    const int n = P.n_entities, K = P.n_vehicles;
+    const int32_t* rs = V.rs + (size_t)island * K * n;
+    const int32_t* rlen = V.rlen + (size_t)island * K;
+    const int32_t* cnt = V.cnt + (size_t)island * V.cnt_stride;
+    gj_vrpc_bucket(P, row, V, island, K <= GJ_VRPC_KSM ? sh_rlen : nullptr, lane);
     unsigned long long cap_pen = 0ull, late_pen = 0ull;
     for (int v = 0; v < K; ++v) {
         const GjRouteStat r = gj_vrpc_walk(P, tw_mode, v, row, rs + (size_t)v * n, rlen[v], 0, 0, nullptr, q, lane);
@@ -208,25 +235,73 @@ __device__ __forceinline__ void gj_vrpc_rebuild(const GjProblemDev& P, int tw_mo
     __syncwarp();
 }
 
-// Route index of the published global top (slot I), once per published version; one warp.
-__global__ void __launch_bounds__(32)
+// Route index of the published global top (slot I), once per published version.  One CTA: warp 0
+// buckets the stops, then the warps share the K route walks and the flattening of the stop lists.
+static constexpr int kGindexWarps = 32;
+__global__ void __launch_bounds__(kGindexWarps * 32)
 k_vrp_chain_gindex(GjProblemDev P, int I, const int32_t* gbest, const int* gver, GjVrpChainState V) {
-    __shared__ GjVrpcScratch q;
-    const int lane = threadIdx.x;
+    __shared__ GjVrpcScratchLite sh_q[kGindexWarps];
+    __shared__ int sh_rlen[GJ_VRPC_KSM];
+    __shared__ unsigned long long sh_pen[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ver = *gver;
-    if (ver == *V.gidx_ver) return;
-    gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), gbest, V, I, q, lane);
+    if (ver == *V.gidx_ver) return;                   // uniform over the CTA
     const int n = P.n_entities, K = P.n_vehicles;
+    const int tw_mode = gj_vrp_tw_mode(P);
     const int32_t* rs = V.rs + (size_t)I * K * n;
-    const int32_t* rlen = V.rlen + (size_t)I * K;
-    int p = 0;
-    for (int v = 0; v < K; ++v) {
-        const int len = rlen[v];
-        for (int i = lane; i < len; i += 32) { V.gstop[p + i] = rs[(size_t)v * n + i]; V.gdst[p + i] = v * n + i; }
-        p += len;
+    int32_t* rlen = V.rlen + (size_t)I * K;
+    if (threadIdx.x < 2) sh_pen[threadIdx.x] = 0ull;
+    if (warp == 0) gj_vrpc_bucket(P, gbest, V, I, K <= GJ_VRPC_KSM ? sh_rlen : nullptr, lane);
+    __syncthreads();
+    unsigned long long cap_pen = 0ull, late_pen = 0ull;
+    for (int v = warp; v < K; v += kGindexWarps) {
+        const GjRouteStat r = gj_vrpc_walk(P, tw_mode, v, gbest, rs + (size_t)v * n, rlen[v], 0, 0, nullptr, sh_q[warp], lane);
+        if (lane == 0) {
+            V.rdist[(size_t)I * K + v] = r.dist;
+            V.rload[(size_t)I * K + v] = r.load;
+            V.rlate[(size_t)I * K + v] = r.late;
+        }
+        const unsigned long long capv = P.veh_capacity[v];
+        if (r.load > capv) cap_pen += r.load - capv;
+        late_pen += r.late;
     }
-    __syncwarp();
-    if (lane == 0) *V.gidx_ver = ver;
+    if (lane == 0) { atomicAdd(&sh_pen[0], cap_pen); atomicAdd(&sh_pen[1], late_pen); }
+    // flattened stop lists: offsets = exclusive prefix of the route lengths (warp 0, into goff)
+    if (warp == 0) {
+        int run = 0;
+        for (int v0 = 0; v0 < K; v0 += 32) {
+            const int v = v0 + lane;
+            const int len = v < K ? rlen[v] : 0;
+            int inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(GJ_FULL_MASK, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (v < K) V.goff[v] = run + inc - len;
+            run += __shfl_sync(GJ_FULL_MASK, inc, 31);
+        }
+    }
+    __syncthreads();
+    for (int v = warp; v < K; v += kGindexWarps) {
+        const int len = rlen[v], p = V.goff[v];
+        for (int i = lane; i < len; i += 32) { V.gstop[p + i] = rs[(size_t)v * n + i]; V.gdst[p + i] = v * n + i; }
+    }
+    if (warp == 0) {
+        const int32_t* cnt = V.cnt + (size_t)I * V.cnt_stride;
+        int distinct = 0;
+        for (int i = lane; i < V.cnt_stride; i += 32) distinct += cnt[i] > 0 ? 1 : 0;
+        distinct = gj_warp_sum(distinct);
+        distinct = __shfl_sync(GJ_FULL_MASK, distinct, 0);
+        if (lane == 0) {
+            unsigned long long* tot = V.tot + (size_t)I * 4;
+            tot[0] = (unsigned long long)(n - distinct);
+            tot[1] = sh_pen[0];
+            tot[2] = sh_pen[1];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *V.gidx_ver = ver;
 }
 
 // Between launches (cold path): update_global_top adopt half (agent_base.rs:465-489), route index of
@@ -235,12 +310,13 @@ k_vrp_chain_gindex(GjProblemDev P, int I, const int32_t* gbest, const int* gver,
 // nothing pending leave after three loads.
 __global__ void __launch_bounds__(kVrpChainWarps * 32)
 k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
-    __shared__ GjVrpcScratch sh_q[kVrpChainWarps];
+    __shared__ GjVrpcScratchLite sh_q[kVrpChainWarps];
+    __shared__ int sh_rlen[kVrpChainWarps][GJ_VRPC_KSM];
     constexpr int LV = 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int island = blockIdx.x * kVrpChainWarps + warp;
     if (island >= A.I) return;
-    GjVrpcScratch& q = sh_q[warp];
+    GjVrpcScratchLite& q = sh_q[warp];
     const int n = P.n_entities, K = P.n_vehicles;
     int32_t* row = A.cur + (size_t)island * A.stride;
     int32_t* best_row = A.best + (size_t)island * A.stride;
@@ -289,7 +365,7 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
         if (lane < 3) V.tot[(size_t)island * 4 + lane] = V.tot[gI * 4 + lane];
         if (lane == 0) V.stale[island] = 0;
     } else if (stale || adopted) {
-        gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, lane);
+        gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, sh_rlen[warp], lane);
     }
     // the replaced solution against the agent's top (update_top_individual)
     if (gj_score_le(cur, top, LV)) {

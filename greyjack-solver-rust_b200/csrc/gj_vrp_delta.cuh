@@ -39,7 +39,7 @@ struct GjVrpChainState {
     // slot I of every array above = the route index of the published global top, built once per
     // published version (k_vrp_chain_gindex); adopting chains copy it instead of re-walking K routes
     int32_t* gstop; int32_t* gdst;   // [n] its stop lists flattened: rs[gdst[p]] = gstop[p]
-    int* gidx_ver;
+    int* gidx_ver; int32_t* goff;    // [K] offsets of the routes in the flattened lists
     int32_t* diff; int* ndiff;       // [I][GJ_VRPC_DIFF], [I]: stops where the chain differs from its top row
 };
 
