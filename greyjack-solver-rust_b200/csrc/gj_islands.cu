@@ -1664,8 +1664,11 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     if (g->vrp_chain) {
         k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
         GJ_LAUNCH_CHECK();
-        k_vrp_chains<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(
-            P, g->groups, A, g->vcs);
+        const unsigned vgrid = (unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps);
+        if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE)
+            k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, kVrpChainWarps * 32, 0, st>>>(P, g->groups, A, g->vcs);
+        else
+            k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, kVrpChainWarps * 32, 0, st>>>(P, g->groups, A, g->vcs);
     } else if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_la_chains<GJ_NQUEENS>, smem))) return rc;
         k_la_chains<GJ_NQUEENS><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);

@@ -383,6 +383,7 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
 #ifndef GJ_VRPC_MINBLOCKS
 #define GJ_VRPC_MINBLOCKS 8
 #endif
+template <int AGENT>            // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING: one rule per instantiation
 __global__ void __launch_bounds__(kVrpChainWarps * 32, GJ_VRPC_MINBLOCKS)
 k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     __shared__ GjVrpcScratch sh_q[kVrpChainWarps];
@@ -406,7 +407,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     int32_t* diff = V.diff + (size_t)island * GJ_VRPC_DIFF;
     uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
     double* late_g = A.late ? A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS : nullptr;
-    const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
+    constexpr bool is_la = AGENT == GJ_AGENT_LATE_ACCEPTANCE;
     int late_head = is_la ? A.late_head[island] : 0, late_len = is_la ? A.late_len[island] : 0;
     double temp[GJ_MAX_LEVELS] = {1.0, 1.0, 1.0};
     if (!is_la)
@@ -540,7 +541,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
         gj_score_round(sc, P);                          // agent_base.rs:311-314
         // ---- acceptance ---------------------------------------------------------------------------------
         bool accept;
-        if (is_la) {
+        if constexpr (is_la) {
             GjScore late_native = cur;                  // late_acceptance_base.rs:196-213
             if (late_len > 0) late_native = gj_load_score(late_g + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
             accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
