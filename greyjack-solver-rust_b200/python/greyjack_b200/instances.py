@@ -244,3 +244,66 @@ def vrp_greedy(spec: ProblemSpec) -> np.ndarray:
     out[0::2] = veh
     out[1::2] = cus
     return out
+
+
+# ---- TSPLIB files (host side only) -------------------------------------
+def read_tsplib(text: str):
+    """DomainBuilder::read_tsp_file (examples/tsp/src/persistence/domain_builder.rs:90-192): header
+    lines up to NODE_COORD_SECTION (NAME, EDGE_WEIGHT_TYPE kept: last space-separated token), then
+    `id x y [name]` lines up to EOF; for a type other than EUC_2D a distance matrix follows (one row
+    per line, up to the next EOF).  Returns (metadata, coords f64 [L, 2], matrix or None)."""
+    lines = iter(text.splitlines())
+    meta = {}
+    for line in lines:
+        if "NODE_COORD_SECTION" in line:
+            break
+        if "NAME" in line:
+            meta["dataset_name"] = line.split(" ")[-1].strip()
+        if "EDGE_WEIGHT_TYPE" in line:
+            meta["distance_type"] = line.split(" ")[-1].strip()
+    else:
+        raise ValueError("no NODE_COORD_SECTION")
+    if "distance_type" not in meta:
+        raise ValueError("no EDGE_WEIGHT_TYPE")
+    xy = []
+    for line in lines:
+        if "EOF" in line:
+            break
+        parts = line.split()
+        if len(parts) < 3:
+            raise ValueError(f"bad location line {line!r}")
+        xy.append((float(parts[1]), float(parts[2])))
+    coords = np.array(xy, dtype=np.float64).reshape(-1, 2)
+    matrix = None
+    if "EUC_2D" not in meta["distance_type"]:
+        rows = []
+        for line in lines:
+            if "EOF" in line:
+                break
+            parts = line.split(" ")[:-1]          # the reference drops the last token of every row
+            rows.append([float(x) for x in parts if x != ""])
+        if rows:
+            matrix = np.array(rows, dtype=np.float64)
+    return meta, coords, matrix
+
+
+def tsp_from_tsplib(text: str, greedy: bool = True) -> ProblemSpec:
+    """The TSP model of examples/tsp over a TSPLIB instance: depot = first location, one stop
+    variable per remaining location (cotwin_builder.rs:49-77), distances by the example's formula
+    (location.rs:38-50: Euclid truncated to 3 decimals) unless the file carries a matrix."""
+    meta, xy, matrix = read_tsplib(text)
+    L = xy.shape[0]
+    if L < 2:
+        raise ValueError("need at least two locations")
+    D = matrix if matrix is not None else distance_matrix(xy)
+    if D.shape != (L, L):
+        raise ValueError(f"distance matrix is {D.shape}, expected {(L, L)}")
+    n = L - 1
+    spec = ProblemSpec(
+        kind=TSP, n_vars=n, lower_bounds=np.ones(n), upper_bounds=np.full(n, float(L - 1)),
+        initial=np.arange(1, L, dtype=np.float64), groups={"common": np.arange(n, dtype=np.int32)},
+        n_locations=L, distance_matrix=D, coords=xy, n_depots=1, score_precision=[3, 3],
+        name=meta.get("dataset_name", "tsplib"))
+    if greedy:
+        spec.initial = tsp_greedy(D)
+    return spec
