@@ -1664,11 +1664,15 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     if (g->vrp_chain) {
         k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
         GJ_LAUNCH_CHECK();
-        const unsigned vgrid = (unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps);
-        if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE)
-            k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, kVrpChainWarps * 32, 0, st>>>(P, g->groups, A, g->vcs);
-        else
-            k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, kVrpChainWarps * 32, 0, st>>>(P, g->groups, A, g->vcs);
+        const unsigned vgrid = (unsigned)((g->I + kVrpStepWarps - 1) / kVrpStepWarps);
+        const size_t vsmem = sizeof(GjVrpcScratch) * kVrpStepWarps;
+        if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE) {
+            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE>, vsmem))) return rc;
+            k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, kVrpStepWarps * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
+        } else {
+            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING>, vsmem))) return rc;
+            k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, kVrpStepWarps * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
+        }
     } else if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_la_chains<GJ_NQUEENS>, smem))) return rc;
         k_la_chains<GJ_NQUEENS><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);

@@ -19,7 +19,11 @@
 #pragma once
 
 
-static constexpr int kVrpChainWarps = 4;
+static constexpr int kVrpChainWarps = 4;        // prepare kernel
+#ifndef GJ_VRPC_STEP_WARPS
+#define GJ_VRPC_STEP_WARPS 32
+#endif
+static constexpr int kVrpStepWarps = GJ_VRPC_STEP_WARPS;   // step kernel: warps of a CTA re-align every step
 #define GJ_VRPC_Q 48             // 32 stops of the old route + <= 16 arrivals
 #define GJ_VRPC_DIFF 512          // stops the agent's top may trail the chain by before a whole-row copy
 
@@ -384,13 +388,14 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
 #define GJ_VRPC_MINBLOCKS 8
 #endif
 template <int AGENT>            // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING: one rule per instantiation
-__global__ void __launch_bounds__(kVrpChainWarps * 32, GJ_VRPC_MINBLOCKS)
+__global__ void __launch_bounds__(kVrpStepWarps * 32, 32 / kVrpStepWarps)
 k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
-    __shared__ GjVrpcScratch sh_q[kVrpChainWarps];
+    extern __shared__ __align__(16) unsigned char vrpc_smem[];
+    GjVrpcScratch* sh_q = reinterpret_cast<GjVrpcScratch*>(vrpc_smem);
     constexpr int LV = 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int island = blockIdx.x * kVrpChainWarps + warp;
-    if (island >= A.I) return;                       // whole warps only; no CTA-wide barrier below
+    const int island = blockIdx.x * kVrpStepWarps + warp;
+    if (island >= A.I) return;                       // whole warps only: the barrier below counts live warps
     GjVrpcScratch& q = sh_q[warp];
     const int n = P.n_entities, K = P.n_vehicles;
     const int tw_mode = gj_vrp_tw_mode(P);
@@ -436,6 +441,9 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     bool top_pending = false;
 
     for (int it = 0; it < A.n_steps; ++it) {
+        // the warps of a CTA run the same code on different chains; re-aligning them every step keeps
+        // them in the same instruction-cache lines (instruction fetch was the top stall without it)
+        __syncthreads();
         const uint64_t step = A.step0 + (uint64_t)it;
         // ---- generate (every lane computes the same move) -----------------------------------------------
         GjMoverParams M = A.M;
@@ -523,6 +531,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             off += r.len;
             __syncwarp();
         }
+        __syncthreads();                                // re-align (see the top of the loop)
         // ---- totals -----------------------------------------------------------------------------------
         unsigned long long cap_pen = tot[1], late_pen = tot[2];
         for (int a = 0; a < nav; ++a) {
