@@ -1664,14 +1664,20 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     if (g->vrp_chain) {
         k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
         GJ_LAUNCH_CHECK();
-        const unsigned vgrid = (unsigned)((g->I + kVrpStepWarps - 1) / kVrpStepWarps);
-        const size_t vsmem = sizeof(GjVrpcScratch) * kVrpStepWarps;
+        // warps (chains) per CTA: as many as share an SM anyway, so that every SM gets chains and the
+        // warps of a CTA -- which re-align every step -- are the ones that share its instruction cache
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->p->device);
+        int vw = 4;
+        while (vw < kVrpStepWarps && (int64_t)vw * sms < g->I) vw *= 2;
+        const unsigned vgrid = (unsigned)((g->I + vw - 1) / vw);
+        const size_t vsmem = sizeof(GjVrpcScratch) * vw;
         if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE) {
-            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE>, vsmem))) return rc;
-            k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, kVrpStepWarps * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
+            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE>, sizeof(GjVrpcScratch) * kVrpStepWarps))) return rc;
+            k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, vw * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
         } else {
-            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING>, vsmem))) return rc;
-            k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, kVrpStepWarps * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
+            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING>, sizeof(GjVrpcScratch) * kVrpStepWarps))) return rc;
+            k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, vw * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
         }
     } else if (P.kind == GJ_NQUEENS) {
         if ((rc = opt_in_smem(k_la_chains<GJ_NQUEENS>, smem))) return rc;

@@ -183,22 +183,32 @@ __device__ __forceinline__ void gj_vrpc_bucket(const GjProblemDev& P, const int3
     for (int i = lane; i < V.cnt_stride; i += 32) cnt[i] = 0;
     for (int v = lane; v < K; v += 32) rlen[v] = 0;
     __syncwarp();
-    int2 nxt = lane < n ? *reinterpret_cast<const int2*>(row + 2 * lane) : make_int2(0, 0);
-    for (int s0 = 0; s0 < n; s0 += 32) {
-        const int s = s0 + lane;
-        const bool on = s < n;
-        const int2 vc = nxt;
-        if (s + 32 < n) nxt = *reinterpret_cast<const int2*>(row + 2 * (s + 32));     // next chunk in flight
-        const int v = on ? vc.x : -1 - lane;
-        const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
-        if (on) {
-            const int rank = __popc(grp & ((1u << lane) - 1u));
-            rs[(size_t)v * n + rlen[v] + rank] = s;
-            atomicAdd(&cnt[vc.y - P.val_lo], 1);
+    // four 32-stop chunks in flight: the (vehicle, customer) loads are issued together, the ordered
+    // placement then runs out of registers
+    for (int s0 = 0; s0 < n; s0 += 128) {
+        int2 vc4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + 32 * u + lane;
+            vc4[u] = s < n ? *reinterpret_cast<const int2*>(row + 2 * s) : make_int2(0, 0);
         }
-        __syncwarp();
-        if (on && lane == 31 - __clz(grp)) rlen[v] += __popc(grp);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int s = s0 + 32 * u + lane;
+            if (s0 + 32 * u >= n) break;                      // uniform
+            const bool on = s < n;
+            const int2 vc = vc4[u];
+            const int v = on ? vc.x : -1 - lane;
+            const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
+            if (on) {
+                const int rank = __popc(grp & ((1u << lane) - 1u));
+                rs[(size_t)v * n + rlen[v] + rank] = s;
+                atomicAdd(&cnt[vc.y - P.val_lo], 1);
+            }
+            __syncwarp();
+            if (on && lane == 31 - __clz(grp)) rlen[v] += __popc(grp);
+            __syncwarp();
+        }
     }
     if (sh_rlen) for (int v = lane; v < K; v += 32) rlen_g[v] = sh_rlen[v];
     __syncwarp();
@@ -388,13 +398,13 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
 #define GJ_VRPC_MINBLOCKS 8
 #endif
 template <int AGENT>            // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING: one rule per instantiation
-__global__ void __launch_bounds__(kVrpStepWarps * 32, 32 / kVrpStepWarps)
+__global__ void __launch_bounds__(kVrpStepWarps * 32, 1)
 k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     extern __shared__ __align__(16) unsigned char vrpc_smem[];
     GjVrpcScratch* sh_q = reinterpret_cast<GjVrpcScratch*>(vrpc_smem);
     constexpr int LV = 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int island = blockIdx.x * kVrpStepWarps + warp;
+    const int island = blockIdx.x * (blockDim.x >> 5) + warp;    // 4..kVrpStepWarps warps per CTA (host picks)
     if (island >= A.I) return;                       // whole warps only: the barrier below counts live warps
     GjVrpcScratch& q = sh_q[warp];
     const int n = P.n_entities, K = P.n_vehicles;
