@@ -13,13 +13,36 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libgj_oracle.so")
 
 
+def _host_signature() -> str:
+    """CPU model + ISA flags of THIS host: the oracle is built with -march=native, so
+    a library that travelled from another machine (the build container -> the GPU box) is rebuilt."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        keep = [ln for ln in txt.splitlines() if ln.startswith(("model name", "flags"))][:2]
+        return hashlib.sha1("\n".join(keep).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "gj_oracle.c")
     hdr = os.path.join(_HERE, "gj_oracle.h")
+    stamp = _SO + ".host"
+    sig = _host_signature()
     stale = (not os.path.exists(_SO)) or any(
         os.path.getmtime(f) > os.path.getmtime(_SO) for f in (src, hdr))
+    if not stale:
+        try:
+            with open(stamp) as f:
+                stale = f.read().strip() != sig
+        except OSError:
+            stale = True
     if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-s", "libgj_oracle.so"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libgj_oracle.so"])
+        with open(stamp, "w") as f:
+            f.write(sig)
     return _SO
 
 
