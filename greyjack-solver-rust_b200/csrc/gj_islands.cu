@@ -18,8 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "gj_eval.cuh"
-#include "gj_islands.hpp"
+#include "gj_islands_dev.cuh"
 
 static constexpr int kWarps = 4;
 
@@ -201,10 +200,6 @@ k_score_fallback_warp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C,
 }
 
 // ---- VRP delta scoring (gj_vrp_delta.cuh) -------------------------------------------------------
-__device__ __forceinline__ int gj_vrp_tw_mode(const GjProblemDev& P) {
-    return P.kind == GJ_VRP_SERVICE ? GJ_TW_ISC_SERVICE : GJ_TW_ISC_FILE;      // islands score with the ISC
-}
-
 // one thread per neighbour: generate the move, re-walk the routes it touches
 __global__ void __launch_bounds__(128)
 k_score_delta_vrp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C, const int32_t* __restrict__ cur,
@@ -277,11 +272,6 @@ k_score_fallback_vrp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C, c
         }
     }
 }
-
-__device__ __forceinline__ GjScore gj_load_score(const double* p, int levels);
-__device__ __forceinline__ void gj_update_top(int island, int levels, int stride, int n_vars,
-                                              const int32_t* cur, const double* cur_score,
-                                              int32_t* best, double* best_score, int* dirty);
 
 // Rebuilds the cached state of every island whose current solution changed: value counts, and the
 // FULL evaluation (reference summation order) of the solution -> raw terms; after an accepted
@@ -419,144 +409,6 @@ k_vrp_state(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double*
 }
 
 // ---- selection ----------------------------------------------------------------------------------
-struct GjSelectArgs {
-    int agent;                  // GJ_AGENT_TABU_SEARCH / GJ_AGENT_LATE_ACCEPTANCE
-    int K, stride, levels, n_vars;
-    int late_size;
-    int noop;
-    int n_groups;
-    const GjMove* moves;        // stored moves, or nullptr: regenerate from the counter RNG
-    GjMoverParams M; uint64_t seed; uint64_t step; int island_base;
-    const double* cand_scores;
-    int32_t* cur; double* cur_score;
-    int32_t* best; double* best_score;
-    int* dirty;
-    double* late; int* late_head; int* late_len;      // LA: circular deque per island
-    unsigned long long* counters;                     // [0] candidates [1] steps [2] accepted
-    // tabu state: rank-indexed deques (slot 0 = newest), read from _old, written to _new
-    uint32_t* tabu_bits; int tabu_words_per_island; const int32_t* tabu_word_off;
-    const int32_t* tabu_ring_old; int32_t* tabu_ring_new; int tabu_ring_per_island; const int32_t* tabu_ring_off;
-    const int32_t* tabu_size; int* tabu_fill;
-    // delta scoring: the island's cached state goes stale when cur changes; update_top_individual
-    // is deferred to k_refresh (after the exact re-score of the accepted neighbour)
-    int* stale; int defer_top; int* work_count;
-    // SimulatedAnnealing: temperatures per island [I][GJ_MAX_LEVELS], schedule
-    double* sa_temp; GjSaParams sa;
-    // fused islands adopt the published global top at the START of their next step (P0)
-    int compare_to_global;
-    int32_t* gbest; double* gbest_score; int* gver; int* gseen;
-    // trace
-    long long* selected_out; int* accepted_out; double* aux_out;
-};
-
-// uniform [0, 1) of the acceptance rule of (island, step): its own RNG stream
-__device__ __forceinline__ double gj_accept_uniform(uint64_t seed, uint32_t island_global, uint64_t step) {
-    GjPhilox rng;
-    gj_rng_init(rng, seed, island_global, (uint32_t)step, (uint32_t)(step >> 32), 0xFFFFFFF0u);
-    return gj_rng_f64(rng);
-}
-
-// SimulatedAnnealing acceptance of one island's single neighbour (thread 0 of its CTA / lane 0)
-__device__ __forceinline__ bool gj_sa_step_accept(const GjSelectArgs& A, int island, const GjScore& b,
-                                                  const GjScore& cur) {
-    double* temp = A.sa_temp + (size_t)island * GJ_MAX_LEVELS;
-    double t[GJ_MAX_LEVELS] = {temp[0], temp[1], temp[2]};
-    const double u = gj_accept_uniform(A.seed, (uint32_t)(A.island_base + island), A.step);
-    double proba;
-    const bool accept = gj_sa_accept(b, cur, A.levels, t, A.sa, u, &proba);
-    for (int l = 0; l < GJ_MAX_LEVELS; ++l) temp[l] = t[l];
-    if (A.aux_out) {
-        double* o = A.aux_out + (size_t)island * 5;
-        o[0] = u; o[1] = proba; o[2] = t[0]; o[3] = t[1]; o[4] = t[2];
-    }
-    return accept;
-}
-
-__device__ __forceinline__ GjScore gj_load_score(const double* p, int levels) {
-    GjScore s;
-    for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.v[l] = (l < levels) ? p[l] : 0.0;
-    return s;
-}
-
-// positions a move selected (what select_non_tabu_ids pushed into the tabu deque)
-__device__ __forceinline__ int gj_move_selected(const GjMove& m, int* out) {
-    if (m.kind == GJ_MOVE_NULL) return 0;
-    if (m.kind == 3) { out[0] = m.a[0]; return 1; }
-    const int k = (m.kind >= 4) ? 2 : m.k;
-#pragma unroll
-    for (int i = 0; i < GJ_MOVE_MAXK; ++i) out[i] = m.a[i];
-    return k;
-}
-
-// update_top_individual (agent_base.rs:220-224): population[0] <= agent_top -> replace.
-// Cooperative over the CTA; `dirty` marks islands whose population[0] changed.
-__device__ __forceinline__ void gj_update_top(int island, int levels, int stride, int n_vars,
-                                              const int32_t* cur, const double* cur_score,
-                                              int32_t* best, double* best_score, int* dirty) {
-    if (dirty[island]) {
-        GjScore c = gj_load_score(cur_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        GjScore top = gj_load_score(best_score + (size_t)island * GJ_MAX_LEVELS, levels);
-        if (gj_score_le(c, top, levels)) {
-            const int32_t* cur_row = cur + (size_t)island * stride;
-            int32_t* best_row = best + (size_t)island * stride;
-            for (int i = threadIdx.x; i < n_vars; i += blockDim.x) best_row[i] = cur_row[i];
-            if (threadIdx.x == 0)
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) best_score[(size_t)island * GJ_MAX_LEVELS + l] = c.v[l];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) dirty[island] = 0;
-    }
-}
-
-// Rebuilds one group's tabu table (membership bits, then the exclusive prefix count of free
-// positions per word; layout in gj_moves.cuh) from its deque.  Cooperative over the CTA;
-// `scan` holds blockDim ints of shared memory.
-__device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen, const int32_t* ring,
-                                                      int fill, int* scan) {
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int W = (glen + 31) >> 5;
-    int32_t* prefix = (int32_t*)(table + W + 1);
-    __syncthreads();
-    for (int w = tid; w <= W; w += nthr) table[w] = 0u;
-    __syncthreads();
-    for (int i = tid; i < fill; i += nthr) {
-        const int pos = ring[i];
-        atomicOr(&table[pos >> 5], 1u << (pos & 31));
-    }
-    __syncthreads();
-    int carry = 0;
-    for (int base = 0; base < W; base += nthr) {
-        const int w = base + tid;
-        int f = 0;
-        if (w < W) {
-            const int rem = glen - 32 * w;
-            const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-            f = __popc(~table[w] & valid);
-        }
-        scan[tid] = f;
-        __syncthreads();
-        for (int o = 1; o < nthr; o <<= 1) {
-            const int x = (tid >= o) ? scan[tid - o] : 0;
-            __syncthreads();
-            scan[tid] += x;
-            __syncthreads();
-        }
-        if (w < W) prefix[w] = carry + scan[tid] - f;
-        carry += scan[nthr - 1];
-        __syncthreads();
-    }
-    if (tid == 0) prefix[W] = carry;
-    __syncthreads();
-    // compact the free positions, ascending: position p lands at prefix[word] + (free bits below it)
-    int32_t* free_list = (int32_t*)(table + 2 * (W + 1));
-    for (int pos = tid; pos < glen; pos += nthr) {
-        const int w = pos >> 5, b = pos & 31;
-        const uint32_t fm = ~table[w];
-        if ((fm >> b) & 1u) free_list[prefix[w] + __popc(fm & ((1u << b) - 1u))] = pos;
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(1024)
 k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     extern __shared__ int32_t smem_row[];          // [n_vars] copy of the base for in-place apply
@@ -708,31 +560,6 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     }
 }
 
-// update_global_top, adopt half (agent_base.rs:465-489), for fused islands: once per published
-// version of the global top, an island whose own top is strictly worse takes it over (TabuSearch:
-// only with compare_to_global).  Decision and bookkeeping (score, late list, flags) by ONE thread;
-// returns whether the island's solution is to be replaced by the gbest row.
-__device__ __forceinline__ bool gj_adopt_decide(const GjSelectArgs& A, int island) {
-    const int ver = *A.gver;
-    if (ver == A.gseen[island]) return false;
-    A.gseen[island] = ver;
-    const GjScore g = gj_load_score(A.gbest_score, A.levels);
-    const GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, A.levels);
-    const bool take = !gj_score_le(top, g, A.levels) && A.compare_to_global;     // global < agent_top
-    if (!take) return false;
-    if (A.agent == GJ_AGENT_LATE_ACCEPTANCE) {
-        double* lt = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
-        const int head = (A.late_head[island] + A.late_size - 1) % A.late_size;
-        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
-            lt[(size_t)head * GJ_MAX_LEVELS + l] = A.cur_score[(size_t)island * GJ_MAX_LEVELS + l];
-        A.late_head[island] = head; A.late_len[island] = min(A.late_len[island] + 1, A.late_size);
-    }
-    for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = g.v[l];
-    A.dirty[island] = 1;
-    if (A.stale) A.stale[island] = 1;
-    return true;
-}
-
 // Applies pending adoptions outside a step (before the host reads / exports current solutions).
 __global__ void __launch_bounds__(128)
 k_apply_adoption(GjSelectArgs A) {
@@ -744,14 +571,10 @@ k_apply_adoption(GjSelectArgs A) {
         for (int i = threadIdx.x; i < A.n_vars; i += blockDim.x) A.cur[(size_t)island * A.stride + i] = A.gbest[i];
 }
 
-#include "gj_islands_fused.cuh"
-#include "gj_islands_chain.cuh"
-#include "gj_islands_vrp_chain.cuh"
 
 // ---- migration (ring i -> i+1, solver.rs:85-92) ------------------------------------------------------
 // mailbox slot s: [stride int32][GJ_MAX_LEVELS f64]; slot[i+1] = island i's outgoing migrant,
 // slot[0] = what island 0 receives (the wrap-around or another GPU's last island).
-__device__ __forceinline__ size_t gj_slot_bytes(int stride) { return (size_t)stride * 4 + GJ_MAX_LEVELS * 8; }
 
 __global__ void k_migrate_pack(const int32_t* __restrict__ cur, const double* __restrict__ cur_score,
                                int stride, int n_vars, unsigned char* mailbox) {
@@ -1261,6 +1084,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
             if ((rc = dev_alloc(g.get(), K, &V.goff))) return rc;
             if ((rc = dev_alloc(g.get(), (size_t)I * GJ_VRPC_DIFF, &V.diff))) return rc;
             if ((rc = dev_alloc(g.get(), (size_t)I, &V.ndiff))) return rc;
+            if ((rc = dev_alloc(g.get(), (size_t)I, &V.pend))) return rc;
             if ((rc = dev_alloc(g.get(), I1, &g->ds.stale))) return rc;
             V.stale = g->ds.stale;
             std::vector<int> ones((size_t)I, 1);
@@ -1403,7 +1227,7 @@ static gj_status launch_score_moves(gj_islands* g, cudaStream_t st) {
     return GJ_OK;
 }
 
-static GjSelectArgs make_select_args(gj_islands* g, bool trace, bool stored_moves) {
+GjSelectArgs gj_make_select_args(gj_islands* g, bool trace, bool stored_moves) {
     GjSelectArgs A{};
     A.agent = g->prm.agent; A.K = g->K; A.stride = g->stride; A.levels = g->levels; A.n_vars = g->n_vars;
     A.late_size = g->late_size; A.noop = g->noop; A.n_groups = g->groups.n_groups;
@@ -1422,6 +1246,7 @@ static GjSelectArgs make_select_args(gj_islands* g, bool trace, bool stored_move
     A.sa_temp = g->sa_temp; A.sa = g->sa;
     A.compare_to_global = g->prm.agent == GJ_AGENT_TABU_SEARCH ? g->prm.compare_to_global : 1;
     A.gbest = g->gbest; A.gbest_score = g->gbest_score; A.gver = g->gver; A.gseen = g->gseen;
+    A.chain_mode = g->chain ? 1 : 0;
     A.selected_out = trace ? g->selected : nullptr; A.accepted_out = trace ? g->accepted : nullptr;
     A.aux_out = trace ? g->trace_aux : nullptr;
     return A;
@@ -1439,14 +1264,6 @@ static size_t warp_eval_smem(const GjProblemDev& P, int warps, bool with_clone) 
     return (size_t)warps * (size_t)(P.bm_words + P.desc_words + P.asc_words + (with_clone ? P.n_vars : 0)) * 4;
 }
 
-template <class Kern>
-static gj_status opt_in_smem(Kern kernel, size_t bytes) {
-    // static + dynamic shared memory beyond 48 KB needs the opt-in; kernels here carry up to
-    // ~19 KB of static shared memory
-    if (bytes > 24 * 1024)
-        GJ_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return GJ_OK;
-}
 
 // k_refresh for every island (early exit for islands whose state is current)
 static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top) {
@@ -1524,43 +1341,6 @@ static gj_status launch_score_delta(gj_islands* g, cudaStream_t st, bool trace) 
     return GJ_OK;
 }
 
-static gj_status launch_fused_step(gj_islands* g, cudaStream_t st, bool trace) {
-    const GjProblemDev& P = g->p->dev;
-    GjFusedArgs F{};
-    F.A = make_select_args(g, trace, false);
-    F.S = g->ds;
-    F.symmetric = g->p->symmetric_D ? 1 : 0;
-    F.n_clone = g->fused_clones;
-    F.lean = g->fused_lean ? 1 : 0;
-    F.scores_out = trace ? g->cand_scores : nullptr;
-    F.moves_out = trace ? g->moves : nullptr;
-    F.worklist = g->worklist;
-    F.phase_clocks = g->phase_clocks;
-    gj_status rc;
-    // registers per thread are capped by the CTA size (64 K registers per SM): 1024 threads -> 64,
-    // 512 -> 128.  The kernel keeps a neighbour's move, its score keys and the RNG in registers.
-#define GJ_LAUNCH_FUSED(KIND, NT)                                                                   \
-    do {                                                                                            \
-        if ((rc = opt_in_smem(k_ls_step_fused<KIND, NT>, g->fused_smem))) return rc;               \
-        k_ls_step_fused<KIND, NT><<<g->I, g->fused_threads, g->fused_smem, st>>>(P, g->groups, F);  \
-    } while (0)
-    const int nt = g->fused_threads;
-    if (P.kind == GJ_NQUEENS) {
-        if (nt > 512) GJ_LAUNCH_FUSED(GJ_NQUEENS, 1024);
-        else if (nt > 256) GJ_LAUNCH_FUSED(GJ_NQUEENS, 512);
-        else if (nt > 128) GJ_LAUNCH_FUSED(GJ_NQUEENS, 256);
-        else GJ_LAUNCH_FUSED(GJ_NQUEENS, 128);
-    } else {
-        if (nt > 512) GJ_LAUNCH_FUSED(GJ_TSP, 1024);
-        else if (nt > 256) GJ_LAUNCH_FUSED(GJ_TSP, 512);
-        else if (nt > 128) GJ_LAUNCH_FUSED(GJ_TSP, 256);
-        else GJ_LAUNCH_FUSED(GJ_TSP, 128);
-    }
-#undef GJ_LAUNCH_FUSED
-    GJ_LAUNCH_CHECK();
-    return GJ_OK;
-}
-
 static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     const GjProblemDev& P = g->p->dev;
     const int64_t total = (int64_t)g->I * g->K;
@@ -1569,7 +1349,7 @@ static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     if (g->fused) {
         // generation, delta scoring, selection, apply, exact re-score and tabu update in one kernel
         if ((rc = gj_prof_begin(g, st))) return rc;
-        if ((rc = launch_fused_step(g, st, trace))) return rc;
+        if ((rc = gj_launch_fused_step(g, st, trace))) return rc;
         if ((rc = gj_prof_end(g, st))) return rc;
         g->step += 1;
         return GJ_OK;
@@ -1590,7 +1370,7 @@ static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     size_t smem = (size_t)g->n_vars * 4;
     if ((rc = opt_in_smem(k_select, smem))) return rc;
     // row copies dominate for long solutions: a wider CTA then
-    k_select<<<g->I, g->n_vars > 4096 ? 1024 : 256, smem, st>>>(P, g->groups, make_select_args(g, trace, !delta));
+    k_select<<<g->I, g->n_vars > 4096 ? 1024 : 256, smem, st>>>(P, g->groups, gj_make_select_args(g, trace, !delta));
     GJ_LAUNCH_CHECK();
     // delta mode: exact re-score of accepted neighbours + state rebuild, then update_top_individual
     if (delta && (rc = launch_refresh(g, st, true))) return rc;
@@ -1623,12 +1403,12 @@ gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
         g->I, g->levels, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score, g->gver);
     GJ_LAUNCH_CHECK();
     if (!g->fused && !g->chain) {
-        k_apply_adoption<<<g->I, 128, 0, st>>>(make_select_args(g, false, false));
+        k_apply_adoption<<<g->I, 128, 0, st>>>(gj_make_select_args(g, false, false));
         GJ_LAUNCH_CHECK();
     }
     if (g->vrp_chain) {
-        k_vrp_chain_gindex<<<1, kGindexWarps * 32, 0, st>>>(g->p->dev, g->I, g->gbest, g->gver, g->vcs);
-        GJ_LAUNCH_CHECK();
+        gj_status rc = gj_launch_vrp_gindex(g, st);
+        if (rc) return rc;
     }
     return GJ_OK;
 }
@@ -1636,7 +1416,7 @@ gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
 // fused islands: pending adoptions must land before anyone looks at (or exports) current solutions
 static gj_status apply_pending_adoption(gj_islands* g, cudaStream_t st) {
     if (!g->fused && !g->chain) return GJ_OK;          // the other paths adopt right after publishing
-    k_apply_adoption<<<g->I, 128, 0, st>>>(make_select_args(g, false, false));
+    k_apply_adoption<<<g->I, 128, 0, st>>>(gj_make_select_args(g, false, false));
     GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
@@ -1658,35 +1438,8 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     if (trace) A.trace_aux = g->trace_aux;
     // trace (n == 1): the step's move / score / decision land where the per-step path puts them
     if (trace) { A.trace_moves = g->moves; A.trace_scores = g->cand_scores; A.trace_accept = g->accepted; }
-    const size_t smem = g->chain_bytes * kChainWarps;
-    const unsigned grid = (unsigned)((g->I + kChainWarps - 1) / kChainWarps);
-    gj_status rc;
-    if (g->vrp_chain) {
-        k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
-        GJ_LAUNCH_CHECK();
-        // warps (chains) per CTA: as many as share an SM anyway, so that every SM gets chains and the
-        // warps of a CTA -- which re-align every step -- are the ones that share its instruction cache
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->p->device);
-        int vw = 4;
-        while (vw < kVrpStepWarps && (int64_t)vw * sms < g->I) vw *= 2;
-        const unsigned vgrid = (unsigned)((g->I + vw - 1) / vw);
-        const size_t vsmem = sizeof(GjVrpcScratch) * vw;
-        if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE) {
-            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE>, sizeof(GjVrpcScratch) * kVrpStepWarps))) return rc;
-            k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, vw * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
-        } else {
-            if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING>, sizeof(GjVrpcScratch) * kVrpStepWarps))) return rc;
-            k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, vw * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
-        }
-    } else if (P.kind == GJ_NQUEENS) {
-        if ((rc = opt_in_smem(k_la_chains<GJ_NQUEENS>, smem))) return rc;
-        k_la_chains<GJ_NQUEENS><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);
-    } else {
-        if ((rc = opt_in_smem(k_la_chains<GJ_TSP>, smem))) return rc;
-        k_la_chains<GJ_TSP><<<grid, kChainWarps * 32, smem, st>>>(P, g->groups, A, g->chain_bytes);
-    }
-    GJ_LAUNCH_CHECK();
+    gj_status rc = g->vrp_chain ? gj_launch_vrp_chains(g, A, st) : gj_launch_la_chains(g, A, st);
+    if (rc) return rc;
     g->step += (uint64_t)n;
     return GJ_OK;
 }

@@ -22,26 +22,6 @@
 // is the declared relaxation).
 #pragma once
 
-struct GjChainArgs {
-    int agent;                  // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING
-    double* sa_temp; GjSaParams sa; double* trace_aux;
-    int I, stride, n_vars, late_size, noop, n_groups, symmetric, island_base;
-    GjMoverParams M;
-    uint64_t seed, step0;
-    int n_steps;
-    int32_t* cur; double* cur_score;
-    int32_t* best; double* best_score;
-    int* dirty;
-    double* late; int* late_head; int* late_len;
-    unsigned long long* counters;
-    // chain tabu state, per island and group (global, persistent):
-    //   bits [W + 1] words | ring [T] ints | head, fill
-    uint32_t* ctabu; int ctabu_words_per_island; const int32_t* ctabu_off; const int32_t* tabu_size;
-    // published global top (one-CTA k_global_top); adopted here, at the start of a launch
-    const int32_t* gbest; const double* gbest_score; const int* gver; int* gseen;
-    // trace (tests): [n_steps][I]
-    GjMove* trace_moves; double* trace_scores; int* trace_accept;
-};
 
 struct GjChainSmem {
     int32_t* t;         // [n_pad + 8], solution at +4 (sentinels around it)
@@ -53,17 +33,6 @@ struct GjChainSmem {
     double* late;       // [late_size][GJ_MAX_LEVELS]
 };
 
-__host__ __device__ inline size_t gj_chain_smem_bytes(int n_vars, int words, int ctabu_words, int late_size,
-                                                      bool tsp) {
-    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
-    const size_t scratch = n_pad < 32 ? 32 : n_pad;      // also holds <= 17 ints of a small move's columns
-    size_t b = (n_pad + 8) * 4 + (size_t)32 * words * 4 + scratch * 4 + (size_t)words * 4;
-    b += (((size_t)ctabu_words + 3) & ~(size_t)3) * 4;
-    b = (b + 15) & ~(size_t)15;
-    if (tsp) b += (((size_t)n_vars + 2) & ~(size_t)1) * 8;
-    b += (size_t)late_size * GJ_MAX_LEVELS * 8;
-    return (b + 15) & ~(size_t)15;
-}
 
 __device__ __forceinline__ GjChainSmem gj_chain_carve(unsigned char* smem, int n_vars, int words,
                                                       int ctabu_words, int late_size, bool tsp) {
@@ -135,7 +104,6 @@ __device__ __forceinline__ void gj_chain_combine(const GjProblemDev& P, double r
     else gj_combine_tsp(P, true, r0, r1, s.v);
 }
 
-static constexpr int kChainWarps = 4;
 
 template <int KIND>
 __global__ void __launch_bounds__(kChainWarps * 32)
@@ -154,19 +122,27 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     int32_t* best_row = A.best + (size_t)island * A.stride;
 
     // ---- stage ---------------------------------------------------------------------------------
-    // update_global_top, adopt half (agent_base.rs:465-489): a newly published global top that beats
-    // this chain's own top replaces its solution (once per published version)
-    int adopted = 0;
+    // update_global_top, adopt half (agent_base.rs:465-489).  The reference tests
+    // `global.score < agent_top.score` at the end of EVERY iteration and, while it holds, resets
+    // population[0] to the global top (LateAcceptance pushes the score it leaves behind each time).
+    // A chain sees the global top published before its launch (`G`); the test of the launch's first
+    // iteration is made here, the later ones inside the step loop ("holding" below).
+    // gseen[island] == version  <=>  the chain's stored solution IS that version's gbest row.
+    int adopted = 0, have_g = 0, cur_is_g = 0, g_ver = 0;
     if (lane == 0 && A.gver) {
-        const int ver = *A.gver;
-        if (ver != A.gseen[island]) {
-            A.gseen[island] = ver;
+        g_ver = *A.gver;
+        have_g = g_ver != 0;
+        cur_is_g = (have_g && A.gseen[island] == g_ver && A.dirty[island] != 1) ? 1 : 0;
+        if (have_g && !cur_is_g) {
             const GjScore g = gj_load_score(A.gbest_score, LV);
             const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
             adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
         }
     }
     adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
+    have_g = __shfl_sync(GJ_FULL_MASK, have_g, 0);
+    g_ver = __shfl_sync(GJ_FULL_MASK, g_ver, 0);
+    cur_is_g = __shfl_sync(GJ_FULL_MASK, cur_is_g, 0) | adopted;
     const int32_t* src_row = adopted ? A.gbest : cur_row;
     for (int i = lane; i < n; i += 32) s.t[i] = src_row[i];
     if (lane == 0) { s.t[-1] = 0; s.t[n] = 0; }
@@ -187,6 +163,8 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     raw0 = __shfl_sync(GJ_FULL_MASK, raw0, 0);
     GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
     GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
+    GjScore gsc = cur;
+    if (have_g) gsc = gj_load_score(A.gbest_score, LV);
     if (adopted) {
         if (is_la) {          // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
             late_head = (late_head + A.late_size - 1) % A.late_size;
@@ -195,15 +173,12 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
             late_len = min(late_len + 1, A.late_size);
             __syncwarp();
         }
-        cur = gj_load_score(A.gbest_score, LV);
+        cur = gsc;
     }
-    // a migrant / the global best may have replaced the solution since the last launch
-    if (A.dirty[island] || adopted) {
-        if (gj_score_le(cur, top, LV)) {
-            for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
-            top = cur;
-        }
-    }
+    // update_top_individual (agent_base.rs:220-224) runs once per iteration, AFTER the step: a
+    // solution that arrived between steps (migrant, global top) is compared with the agent's top
+    // only after the next step had its chance to replace it.
+    bool top_check_pending = A.dirty[island] || adopted || (cur_is_g && have_g && !gj_score_le(top, gsc, LV));
     int accepted_total = 0;
     bool cur_from_step = false;                      // cur was produced by an accepted step of this launch
     bool top_from_step = false;                      // ... and so was the agent's top individual
@@ -262,7 +237,43 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                 A.trace_accept[(size_t)it * A.I + island] = accept ? 1 : 0;
             }
         }
-        if (accept) {
+        // standing on the global top while it still beats the agent's own top (update_global_top)
+        const bool holding = cur_is_g && have_g && !gj_score_le(top, gsc, LV);
+        const bool bounced = accept && holding && !gj_score_le(sc, cur, LV);
+        if (bounced) {
+            // A WORSE neighbour accepted on the global top.  The reference moves to it
+            // (late_acceptance_base.rs:207-211), update_top_individual may record it as agent_top, and
+            // update_global_top of the same iteration puts population[0] back on the global top, pushing
+            // the neighbour's score once more (agent_base.rs:465-471).  Net effect, reproduced without
+            // moving: the solution stays, the late list grows by two, agent_top may take the neighbour.
+            accepted_total += 1;
+            if (is_la) {
+                for (int rep = 0; rep < 2; ++rep) {
+                    late_head = (late_head + A.late_size - 1) % A.late_size;
+                    if (lane == 0)
+                        for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+                    late_len = min(late_len + 1, A.late_size);
+                }
+            }
+            if (gj_score_le(sc, top, LV)) {
+                top = sc;
+                top_from_step = true;
+                if (!ok) {
+                    for (int i = lane; i < n; i += 32) best_row[i] = s.scratch[i];
+                } else {
+                    for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
+                    __syncwarp();
+                    if (lane == 0) sh_mv[warp] = m;
+                    __syncwarp();
+                    const GjMove ms = sh_mv[warp];
+                    gj_apply_move(P, ms, G, true, A.noop != 0, lane, 32,
+                                  [&](int id) { return s.t[id]; }, [&](int id, int v) { best_row[id] = v; });
+                }
+            }
+            __syncwarp();
+        } else if (accept) {
+            cur_is_g = 0;
+            top_check_pending = true;
             // ---- apply in shared memory ------------------------------------------------------------
             if (!ok) {
                 for (int i = lane; i < n; i += 32) s.t[i] = s.scratch[i];
@@ -335,10 +346,14 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                     for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
                 late_len = min(late_len + 1, A.late_size);
             }
-            // update_top_individual (agent_base.rs:220-224)
+            __syncwarp();
+        }
+        // update_top_individual (agent_base.rs:220-224): population[0] <= agent_top -> replace
+        if (top_check_pending && !bounced) {
+            top_check_pending = false;
             if (gj_score_le(cur, top, LV)) {
                 top = cur;
-                top_from_step = true;
+                top_from_step = cur_from_step;
                 for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
             }
             __syncwarp();
@@ -403,6 +418,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         if (is_la) { A.late_head[island] = late_head; A.late_len[island] = late_len; }
         else for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.sa_temp[(size_t)island * GJ_MAX_LEVELS + l] = temp[l];
         A.dirty[island] = 0;
+        if (A.gseen) A.gseen[island] = cur_is_g ? g_ver : 0;
         atomicAdd(&A.counters[0], (unsigned long long)A.n_steps);
         if (island == 0) atomicAdd(&A.counters[1], (unsigned long long)A.n_steps);
         if (accepted_total) atomicAdd(&A.counters[2], (unsigned long long)accepted_total);

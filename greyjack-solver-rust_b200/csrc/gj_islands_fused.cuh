@@ -41,20 +41,6 @@ struct GjFusedSmem {
     double* edge;               // [n + 1] TSP: edge[i] = D[t[i-1]][t[i]], depot at both ends
 };
 
-__host__ __device__ inline size_t gj_fused_smem_bytes_lean(int n_vars, int words) {
-    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
-    return (((n_pad + 8) * 4 + (size_t)words * 4) + 15) & ~(size_t)15;
-}
-
-__host__ __device__ inline size_t gj_fused_smem_bytes(int n_vars, int cnt_stride, int tabu_words,
-                                                      int words, int n_clone) {
-    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
-    size_t b = (n_pad + 8) * 4 + (size_t)cnt_stride * 4 + (((size_t)tabu_words + 3) & ~(size_t)3) * 4;
-    b += (size_t)n_clone * (size_t)words * 4 + (size_t)n_clone * n_pad * 4;
-    b = (b + 15) & ~(size_t)15;
-    b += ((size_t)n_vars + 1) * 8;
-    return b;
-}
 
 __device__ __forceinline__ GjFusedSmem gj_fused_carve(unsigned char* smem, int n_vars, int cnt_stride,
                                                       int tabu_words, int words, int n_clone, bool lean) {

@@ -1,0 +1,34 @@
+// gj_islands_vrp_chain.cu -- translation unit of the VRP LateAcceptance / SimulatedAnnealing chains
+// (kernels: gj_islands_vrp_chain.cuh).
+#include "gj_islands_dev.cuh"
+#include "gj_islands_vrp_chain.cuh"
+
+gj_status gj_launch_vrp_gindex(gj_islands* g, cudaStream_t st) {
+    k_vrp_chain_gindex<<<1, kGindexWarps * 32, 0, st>>>(g->p->dev, g->I, g->gbest, g->gver, g->vcs);
+    GJ_LAUNCH_CHECK();
+    return GJ_OK;
+}
+
+gj_status gj_launch_vrp_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t st) {
+    const GjProblemDev& P = g->p->dev;
+    gj_status rc;
+    k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
+    GJ_LAUNCH_CHECK();
+    // warps (chains) per CTA: as many as share an SM anyway, so that every SM gets chains and the
+    // warps of a CTA -- which re-align every step -- are the ones that share its instruction cache
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->p->device);
+    int vw = 4;
+    while (vw < kVrpStepWarps && (int64_t)vw * sms < g->I) vw *= 2;
+    const unsigned vgrid = (unsigned)((g->I + vw - 1) / vw);
+    const size_t vsmem = sizeof(GjVrpcScratch) * vw;
+    if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE) {
+        if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE>, sizeof(GjVrpcScratch) * kVrpStepWarps))) return rc;
+        k_vrp_chains<GJ_AGENT_LATE_ACCEPTANCE><<<vgrid, vw * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
+    } else {
+        if ((rc = opt_in_smem(k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING>, sizeof(GjVrpcScratch) * kVrpStepWarps))) return rc;
+        k_vrp_chains<GJ_AGENT_SIMULATED_ANNEALING><<<vgrid, vw * 32, vsmem, st>>>(P, g->groups, A, g->vcs);
+    }
+    GJ_LAUNCH_CHECK();
+    return GJ_OK;
+}

@@ -25,7 +25,6 @@ static constexpr int kVrpChainWarps = 4;        // prepare kernel
 #endif
 static constexpr int kVrpStepWarps = GJ_VRPC_STEP_WARPS;   // step kernel: warps of a CTA re-align every step
 #define GJ_VRPC_Q 48             // 32 stops of the old route + <= 16 arrivals
-#define GJ_VRPC_DIFF 512          // stops the agent's top may trail the chain by before a whole-row copy
 
 struct GjVrpcScratch {
     int32_t qc[GJ_VRPC_Q];       // customers
@@ -335,22 +334,26 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
     int32_t* row = A.cur + (size_t)island * A.stride;
     int32_t* best_row = A.best + (size_t)island * A.stride;
     const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
+    // update_global_top, adopt half: the test the reference makes at the end of every iteration
+    // (agent_base.rs:465-489) -- here for the last iteration of the previous launch; the step kernel
+    // makes the later ones itself ("holding").  gseen[island] == version <=> the stored solution IS
+    // that version's gbest row; dirty == 1: a migrant replaced it since.
     int adopted = 0;
+    const int stale = V.stale[island], dirty = A.dirty[island];
     if (lane == 0 && A.gver) {
         const int ver = *A.gver;
-        if (ver != A.gseen[island]) {
-            A.gseen[island] = ver;
+        const bool cur_is_g = ver != 0 && A.gseen[island] == ver && dirty != 1;
+        if (ver != 0 && !cur_is_g) {
             const GjScore g = gj_load_score(A.gbest_score, LV);
             const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
             adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
             if (adopted && *V.gidx_ver == ver) adopted = 2;              // ... and its route index is ready
+            A.gseen[island] = adopted ? ver : 0;
         }
     }
     adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
-    const int stale = V.stale[island], dirty = A.dirty[island];
     if (!adopted && !stale && !dirty) return;
     GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
-    GjScore top = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
     if (adopted) {
         for (int i = lane; i < A.n_vars; i += 32) row[i] = A.gbest[i];
         if (is_la && lane == 0) {   // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
@@ -381,17 +384,14 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
     } else if (stale || adopted) {
         gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, sh_rlen[warp], lane);
     }
-    // the replaced solution against the agent's top (update_top_individual)
-    if (gj_score_le(cur, top, LV)) {
-        for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
-        if (lane == 0) {
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
-            V.ndiff[island] = 0;
-        }
-    } else if (lane == 0) {
-        V.ndiff[island] = -1;                       // row and best_row are unrelated vectors now
+    // A solution that arrived between steps meets the agent's top only after the next step
+    // (update_top_individual runs once per iteration, agent_base.rs:149-152): the step kernel owes
+    // that comparison.  row and best_row are unrelated vectors from here on.
+    if ((adopted || dirty) && lane == 0) {
+        V.pend[island] = 1;
+        V.ndiff[island] = -1;
+        A.dirty[island] = 0;
     }
-    if (lane == 0) A.dirty[island] = 0;
 }
 
 #ifndef GJ_VRPC_MINBLOCKS
@@ -449,6 +449,15 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     // update_top_individual copies are lazy: while the top IS the current solution, best_row is only
     // written when the chain is about to leave it (or at the end of the launch)
     bool top_pending = false;
+    // update_global_top inside a launch (see k_vrp_chain_prepare): G = the global top published before
+    // the launch; while the chain stands on it and it still beats the chain's own top, a worse
+    // neighbour that gets accepted "bounces" (the reference moves and is reset within the same iteration)
+    const int g_ver = A.gver ? *A.gver : 0;
+    const bool have_g = g_ver != 0;
+    bool cur_is_g = have_g && A.gseen[island] == g_ver;
+    GjScore gsc = cur;
+    if (have_g) gsc = gj_load_score(A.gbest_score, LV);
+    bool check_pending = V.pend[island] != 0 || (cur_is_g && !gj_score_le(top, gsc, LV));
 
     for (int it = 0; it < A.n_steps; ++it) {
         // the warps of a CTA run the same code on different chains; re-aligning them every step keeps
@@ -578,7 +587,36 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             for (int l = 0; l < LV; ++l) A.trace_scores[((size_t)it * A.I + island) * LV + l] = sc.v[l];
             A.trace_accept[(size_t)it * A.I + island] = accept ? 1 : 0;
         }
-        if (accept) {
+        const bool holding = cur_is_g && !gj_score_le(top, gsc, LV);
+        const bool bounced = accept && holding && !gj_score_le(sc, cur, LV);
+        if (bounced) {
+            // late_acceptance_base.rs:207-211 pushes the accepted score, agent_base.rs:465-471 pushes
+            // population[0].score (the same neighbour) once more and restores the global top
+            accepted_total += 1;
+            if (is_la) {
+                for (int rep = 0; rep < 2; ++rep) {
+                    late_head = (late_head + A.late_size - 1) % A.late_size;
+                    if (lane == 0)
+                        for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+                    late_len = min(late_len + 1, A.late_size);
+                }
+            }
+            if (gj_score_le(sc, top, LV)) {
+                // agent_top = the neighbour: best_row := row with the move's stops re-labelled
+                materialize_top();
+                if (lane < ncs) {
+                    const int st = q.cs_stop[lane];
+                    best_row[2 * st] = q.cs_v[lane];
+                    best_row[2 * st + 1] = q.cs_c[lane];
+                    diff[lane] = st;
+                }
+                ndiff = ncs;
+                top = sc;
+                top_pending = false;
+            }
+            __syncwarp();
+        } else if (accept) {
+            cur_is_g = false;
             if (top_pending && !gj_score_le(sc, top, LV)) {
                 materialize_top();
                 top_pending = false;
@@ -622,6 +660,11 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             __syncwarp();
             // update_top_individual (agent_base.rs:220-224)
             if (gj_score_le(cur, top, LV)) { top = cur; top_pending = true; }
+            check_pending = false;
+        } else if (check_pending) {
+            // nothing moved: the solution that arrived between steps meets the agent's top now
+            check_pending = false;
+            if (gj_score_le(cur, top, LV)) { top = cur; top_pending = true; }
         }
         // ---- tabu deque (mover.rs:75-96): every id the move selected enters, the oldest leave ------
         if (tabu_g && m.kind != GJ_MOVE_NULL && lane == 0) {
@@ -659,6 +702,8 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     if (top_pending) materialize_top();
     if (lane == 0) {
         V.ndiff[island] = ndiff;
+        V.pend[island] = check_pending ? 1 : 0;
+        if (A.gseen) A.gseen[island] = cur_is_g ? g_ver : 0;
         for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
             A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
             A.best_score[(size_t)island * GJ_MAX_LEVELS + l] = top.v[l];

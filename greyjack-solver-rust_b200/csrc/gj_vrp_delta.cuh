@@ -41,6 +41,8 @@ struct GjVrpChainState {
     int32_t* gstop; int32_t* gdst;   // [n] its stop lists flattened: rs[gdst[p]] = gstop[p]
     int* gidx_ver; int32_t* goff;    // [K] offsets of the routes in the flattened lists
     int32_t* diff; int* ndiff;       // [I][GJ_VRPC_DIFF], [I]: stops where the chain differs from its top row
+    int* pend;                       // [I] update_top_individual still owes a comparison for a solution that
+                                     // arrived between steps (migrant / adopted global top)
 };
 
 #define GJ_VRP_MAXCS 16              // changed stops of a small move
