@@ -504,60 +504,12 @@ k_select(GjProblemDev P, GjGroups G, GjSelectArgs A) {
     if (!A.defer_top)
         gj_update_top(island, levels, A.stride, A.n_vars, A.cur, A.cur_score, A.best, A.best_score, A.dirty);
 
-    // tabu deque update (Mover::select_non_tabu_ids :75-96): every id selected this step is pushed
-    // to the front in candidate order; ids beyond the deque's size fall off the back.  The deque is
-    // stored by recency rank (slot 0 = newest), so only the newest `size` ids of the step are
-    // needed: walk the candidates backwards and stop once the deque is full.
-    if (A.tabu_bits) {
-        uint32_t* bits_rw = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
-        const int32_t* ring_old_island = A.tabu_ring_old + (size_t)island * A.tabu_ring_per_island;
-        int32_t* ring_new_island = A.tabu_ring_new + (size_t)island * A.tabu_ring_per_island;
-        const int n_chunks = (K + blockDim.x - 1) / blockDim.x;
-        for (int g = 0; g < A.n_groups; ++g) {
-            const int T = A.tabu_size[g];
-            const int32_t* ring_old = ring_old_island + A.tabu_ring_off[g];
-            int32_t* ring_new = ring_new_island + A.tabu_ring_off[g];
-            const int glen = G.offsets[g + 1] - G.offsets[g];
-            const int fill_old = A.tabu_fill[island * A.n_groups + g];
-            int collected = 0;
-            for (int chunk = n_chunks - 1; chunk >= 0 && collected < T; --chunk) {
-                const int j = chunk * blockDim.x + tid;
-                int sel[GJ_MOVE_MAXK]; int cnt = 0;
-                if (j < K) {
-                    const GjMove m = load_move(j);
-                    if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
-                }
-                // ids pushed by later candidates of this chunk (exclusive suffix sum)
-                sh_scan[tid] = cnt;
-                __syncthreads();
-                for (int o = 1; o < blockDim.x; o <<= 1) {
-                    const int x = (tid + o < blockDim.x) ? sh_scan[tid + o] : 0;
-                    __syncthreads();
-                    sh_scan[tid] += x;
-                    __syncthreads();
-                }
-                const int total = sh_scan[0];
-                const int after = sh_scan[tid] - cnt;
-#pragma unroll
-                for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
-                    if (i < cnt) {
-                        const int rank = collected + after + (cnt - 1 - i);
-                        if (rank < T) ring_new[rank] = sel[i];
-                    }
-                }
-                __syncthreads();
-                collected += total;
-            }
-            // older ids keep their order behind the new ones
-            for (int r = collected + tid; r < T; r += blockDim.x) {
-                const int rho = r - collected;
-                if (rho < fill_old) ring_new[r] = ring_old[rho];
-            }
-            const int fill = min(T, fill_old + collected);
-            if (tid == 0) A.tabu_fill[island * A.n_groups + g] = fill;
-            gj_tabu_table_rebuild(bits_rw + A.tabu_word_off[g], glen, ring_new, fill, sh_scan);
-        }
-    }
+    if (A.tabu_bits)
+        gj_tabu_deque_advance(A.tabu_bits + (size_t)island * A.tabu_words_per_island,
+                              A.tabu_ring_old + (size_t)island * A.tabu_ring_per_island,
+                              A.tabu_ring_new + (size_t)island * A.tabu_ring_per_island, A.tabu_ring_off,
+                              A.tabu_size, A.tabu_word_off, A.tabu_fill + (size_t)island * A.n_groups,
+                              A.n_groups, G, K, load_move, sh_scan);
 }
 
 // Applies pending adoptions outside a step (before the host reads / exports current solutions).
@@ -810,6 +762,16 @@ static uint64_t splitmix64(uint64_t& s) {
     return z ^ (z >> 31);
 }
 
+// Tabu deque size of a semantic group: max(ceil(rate * group_len), 1) (tabu_search_base.rs:115-121).
+// The reference draws ids until it finds k that are not tabu (mover.rs:75-96) and would spin
+// forever on a group with fewer than k free positions; here the deque is capped so that
+// GJ_MOVE_MAXK positions always stay free (only bites when rate * group_len > group_len - 8).
+int gj_tabu_deque_size(double rate, int group_len) {
+    int T = std::max((int)std::ceil(rate * (double)group_len), 1);
+    if (T > group_len - GJ_MOVE_MAXK) T = std::max(1, group_len - GJ_MOVE_MAXK);
+    return T;
+}
+
 // Mover::new thresholds (mover.rs:36-62)
 static gj_status build_thresholds(const gj_agent_params& prm, double* thr) {
     double probas[6];
@@ -844,6 +806,17 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
     if ((rc = build_thresholds(*prm, g->mover.thresholds))) return rc;
     g->mover.tabu_entity_rate = prm->tabu_entity_rate;
     g->mover.mutation_rate_multiplier = prm->has_mutation_rate_multiplier ? prm->mutation_rate_multiplier : 0.0;
+    // change count of a change / swap / swap_edges move ~ Binomial(n_vars, multiplier / group_len)
+    // (mover.rs:138-140); a move descriptor holds at most GJ_MOVE_MAXK positions, so the draw is
+    // truncated at 8.  With a mean <= 4 that truncation touches < 2.2 % of the moves (declared in
+    // DESIGN.md); larger means are refused instead of silently distorted.
+    for (auto& grp : p->groups) {
+        if (grp.empty()) continue;
+        const double mean = g->mover.mutation_rate_multiplier * (double)p->dev.n_vars / (double)grp.size();
+        if (mean > 4.0 + 1e-9)
+            return gj_fail(GJ_ERR_UNSUPPORTED, "mutation_rate_multiplier * n_vars / group_len > 4: a move would change more "
+                                                "than the 8 positions a device move descriptor holds");
+    }
 
     // semantic groups
     std::vector<int32_t> offs(1, 0), ids;
@@ -885,9 +858,7 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
         int words = 0, ring = 0;
         for (auto& grp : p->groups) {
             word_off.push_back(words); ring_off.push_back(ring);
-            int T = std::max((int)std::ceil(prm->tabu_entity_rate * (double)grp.size()), 1);
-            T = std::min(T, std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK));   // keep free ids to draw from
-            T = std::max(T, 1);
+            const int T = gj_tabu_deque_size(prm->tabu_entity_rate, (int)grp.size());
             tsize.push_back(T);
             words += gj_tabu_region_words((int)grp.size());       // bits + free-prefix + free list (gj_moves.cuh)
             ring += T;
@@ -1094,8 +1065,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
                 int cw = 0;
                 for (auto& grp : p->groups) {
                     coff.push_back(cw);
-                    const int T = std::max(1, std::min((int)std::ceil(prm->tabu_entity_rate * (double)grp.size()),
-                                                       std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK)));
+                    const int T = gj_tabu_deque_size(prm->tabu_entity_rate, (int)grp.size());
                     cw += ((int)grp.size() + 31) / 32 + 1 + T + 2;      // bits | ring | head, fill
                 }
                 g->ctabu_words = cw;
@@ -1172,8 +1142,7 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
             int cw = 0;
             for (auto& grp : p->groups) {
                 coff.push_back(cw);
-                const int T = std::max(1, std::min((int)std::ceil(prm->tabu_entity_rate * (double)grp.size()),
-                                                   std::max(1, (int)grp.size() - 2 * GJ_MOVE_MAXK)));
+                const int T = gj_tabu_deque_size(prm->tabu_entity_rate, (int)grp.size());
                 cw += ((int)grp.size() + 31) / 32 + 1 + T + 2;      // bits | ring | head, fill
             }
             const size_t per_chain = gj_chain_smem_bytes(P.n_vars, words, cw, g->late_size, P.kind == GJ_TSP);
@@ -1530,6 +1499,46 @@ extern "C" gj_status gj_islands_trace_aux(gj_islands* g, int32_t island, double*
     GJ_CUDA_TRY(cudaSetDevice(g->p->device));
     GJ_CUDA_TRY(cudaDeviceSynchronize());
     GJ_CUDA_TRY(cudaMemcpy(out, g->trace_aux + (size_t)island * 5, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_trace_tabu(gj_islands* g, int32_t island, int32_t group, int32_t* ids,
+                                           int32_t capacity, int32_t* fill, int32_t* size) {
+    if (!g || island < 0 || island >= g->I || group < 0 || group >= g->groups.n_groups)
+        return gj_fail(GJ_ERR_INVALID, "bad island / group");
+    if (fill) *fill = 0;
+    if (size) *size = 0;
+    if (g->prm.tabu_entity_rate == 0.0 || !g->tabu_size) return GJ_OK;
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    GJ_CUDA_TRY(cudaDeviceSynchronize());
+    const int glen = (int)g->p->groups[group].size();
+    const int T = gj_tabu_deque_size(g->prm.tabu_entity_rate, glen);
+    if (size) *size = T;
+    std::vector<int32_t> ring(T), out;
+    int n_fill = 0;
+    if (g->chain) {
+        // chain layout per group: bits [W + 1] | ring [T] (circular) | head, fill
+        if (!g->ctabu) return GJ_OK;
+        std::vector<int32_t> off(g->groups.n_groups);
+        GJ_CUDA_TRY(cudaMemcpy(off.data(), g->ctabu_off, off.size() * 4, cudaMemcpyDeviceToHost));
+        const int W = (glen + 31) / 32;
+        const uint32_t* base = g->ctabu + (size_t)island * g->ctabu_words + off[group] + W + 1;
+        std::vector<int32_t> raw(T + 2);
+        GJ_CUDA_TRY(cudaMemcpy(raw.data(), base, raw.size() * 4, cudaMemcpyDeviceToHost));
+        const int head = raw[T];
+        n_fill = raw[T + 1];
+        for (int r = 0; r < n_fill; ++r) out.push_back(raw[((head - 1 - r) % T + T) % T]);
+    } else {
+        // TabuSearch / GeneticAlgorithm layout: rank-indexed (slot 0 = newest), double-buffered by step parity
+        std::vector<int32_t> off(g->groups.n_groups);
+        GJ_CUDA_TRY(cudaMemcpy(off.data(), g->tabu_ring_off, off.size() * 4, cudaMemcpyDeviceToHost));
+        GJ_CUDA_TRY(cudaMemcpy(&n_fill, g->tabu_fill + (size_t)island * g->groups.n_groups + group, 4, cudaMemcpyDeviceToHost));
+        GJ_CUDA_TRY(cudaMemcpy(ring.data(), g->tabu_ring[g->step & 1] + (size_t)island * g->tabu_ring_len + off[group],
+                               (size_t)T * 4, cudaMemcpyDeviceToHost));
+        out.assign(ring.begin(), ring.begin() + n_fill);
+    }
+    if (fill) *fill = n_fill;
+    if (ids) for (int i = 0; i < n_fill && i < capacity; ++i) ids[i] = out[i];
     return GJ_OK;
 }
 

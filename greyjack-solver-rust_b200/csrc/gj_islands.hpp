@@ -84,10 +84,13 @@ struct gj_islands {
     int* order = nullptr;          // [I][pop] rank -> row index after the sort
     int* ga_src = nullptr;         // [I][pop] replacement source (trace)
     int* ga_rank = nullptr;        // [I][pop] rank scratch of the counting sort (kept zeroed)
+    double* ga_trace_sel = nullptr;  // [I][half][8] trace of the parent draws (gj_islands_ga_trace_generation)
+    double* ga_trace_rep = nullptr;  // [I][pop][3] trace of the p-worst draws
 
     ~gj_islands();
 };
 
+int gj_tabu_deque_size(double rate, int group_len);
 gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_params* prm);
 void gj_islands_start_vector(const gj_problem* p, const double* given, uint64_t& rng, std::vector<int32_t>& row);
 

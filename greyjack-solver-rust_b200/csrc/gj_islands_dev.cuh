@@ -150,6 +150,66 @@ __device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen,
     __syncthreads();
 }
 
+// Tabu deque update of one island after a step (Mover::select_non_tabu_ids, mover.rs:75-96): every id
+// selected by the step's K moves is pushed to the front in candidate order; ids beyond the deque's
+// size fall off the back.  The deque is stored by recency rank (slot 0 = newest), so only the newest
+// `size` ids of the step are needed: walk the candidates backwards and stop once the deque is full.
+// Cooperative over the CTA; `scan` holds blockDim ints of shared memory; load_move(j) yields move j.
+template <class LoadMove>
+__device__ __forceinline__ void gj_tabu_deque_advance(uint32_t* bits_rw, const int32_t* ring_old_island,
+                                                      int32_t* ring_new_island, const int32_t* ring_off,
+                                                      const int32_t* tabu_size, const int32_t* word_off,
+                                                      int* fill_island, int n_groups, const GjGroups& G, int K,
+                                                      LoadMove load_move, int* scan) {
+    const int tid = threadIdx.x;
+    const int n_chunks = (K + blockDim.x - 1) / blockDim.x;
+    for (int g = 0; g < n_groups; ++g) {
+        const int T = tabu_size[g];
+        const int32_t* ring_old = ring_old_island + ring_off[g];
+        int32_t* ring_new = ring_new_island + ring_off[g];
+        const int glen = G.offsets[g + 1] - G.offsets[g];
+        const int fill_old = fill_island[g];
+        int collected = 0;
+        for (int chunk = n_chunks - 1; chunk >= 0 && collected < T; --chunk) {
+            const int j = chunk * blockDim.x + tid;
+            int sel[GJ_MOVE_MAXK]; int cnt = 0;
+            if (j < K) {
+                const GjMove m = load_move(j);
+                if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
+            }
+            // ids pushed by later candidates of this chunk (exclusive suffix sum)
+            scan[tid] = cnt;
+            __syncthreads();
+            for (int o = 1; o < blockDim.x; o <<= 1) {
+                const int x = (tid + o < blockDim.x) ? scan[tid + o] : 0;
+                __syncthreads();
+                scan[tid] += x;
+                __syncthreads();
+            }
+            const int total = scan[0];
+            const int after = scan[tid] - cnt;
+#pragma unroll
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                if (i < cnt) {
+                    const int rank = collected + after + (cnt - 1 - i);
+                    if (rank < T) ring_new[rank] = sel[i];
+                }
+            }
+            __syncthreads();
+            collected += total;
+        }
+        // older ids keep their order behind the new ones
+        for (int r = collected + tid; r < T; r += blockDim.x) {
+            const int rho = r - collected;
+            if (rho < fill_old) ring_new[r] = ring_old[rho];
+        }
+        const int fill = min(T, fill_old + collected);
+        __syncthreads();
+        if (tid == 0) fill_island[g] = fill;
+        gj_tabu_table_rebuild(bits_rw + word_off[g], glen, ring_new, fill, scan);
+    }
+}
+
 // update_global_top, adopt half (agent_base.rs:465-489).  The reference re-evaluates
 // `global.score < agent_top.score` after EVERY step and re-assigns population[0] = global each time
 // it holds (LateAcceptance also pushes the score it leaves behind on late_scores, every time).

@@ -12,8 +12,7 @@
 #include <cmath>
 #include <memory>
 
-#include "gj_eval.cuh"
-#include "gj_islands.hpp"
+#include "gj_islands_dev.cuh"
 
 struct GjGaArgs {
     int I, pop, half, n_cand, stride, n_vars, levels, noop;
@@ -22,13 +21,15 @@ struct GjGaArgs {
     int island_base;
 };
 
-__device__ __forceinline__ int gj_ga_p_rank(GjPhilox& rng, double p_best_rate, int pop, bool worst) {
+__device__ __forceinline__ int gj_ga_p_rank(GjPhilox& rng, double p_best_rate, int pop, bool worst,
+                                            double* trace /* nullable: {p, last_top, id} */) {
     // select_p_best / select_p_worst (genetic_algorithm_base.rs:83-103):
     // p ~ U(1e-6, p_best_rate); last_top = ceil(p * pop); id ~ U[0, last_top) | U[pop-last_top, pop)
     const double p = 0.000001 + gj_rng_f64(rng) * (p_best_rate - 0.000001);
     int last_top = (int)ceil(p * (double)pop);
     last_top = max(1, min(last_top, pop));
     const int id = (int)gj_rng_below(rng, (uint32_t)last_top);
+    if (trace) { trace[0] = p; trace[1] = (double)last_top; trace[2] = (double)id; }
     return worst ? (pop - last_top + id) : id;
 }
 
@@ -36,7 +37,9 @@ __device__ __forceinline__ int gj_ga_p_rank(GjPhilox& rng, double p_best_rate, i
 __global__ void __launch_bounds__(128)
 k_ga_offspring(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A,
                const int32_t* __restrict__ pop_rows, const int* __restrict__ order,
-               int32_t* __restrict__ cand_rows, GjMove* __restrict__ moves) {
+               int32_t* __restrict__ cand_rows, GjMove* __restrict__ moves,
+               const uint32_t* __restrict__ tabu_bits, int tabu_words_per_island,
+               const int32_t* __restrict__ tabu_word_off, double* __restrict__ trace_sel) {
     __shared__ int sh_parent;
     __shared__ GjMove sh_move;
     const int island = blockIdx.x / A.n_cand;
@@ -46,18 +49,29 @@ k_ga_offspring(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A,
         GjPhilox rng;
         gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
                     (uint32_t)(A.step >> 32), 0x40000000u + (uint32_t)q);
-        int r1 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false);
-        int r2 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false);
+        // trace record of pair q (written by its first child): {p1, last_top1, id1, p2, last_top2, id2,
+        // u_cross, w_raw (-1 = no crossover)}
+        double* tr = (trace_sel && child == 0) ? trace_sel + ((size_t)island * A.half + q) * 8 : nullptr;
+        int r1 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false, tr);
+        int r2 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false, tr ? tr + 3 : nullptr);
         // cross (:105-134): ONE weight for every gene (vec![sample(); n] evaluates the RNG once);
         // integer variables get rint(w) in {0, 1}, so the children are the parents, possibly
         // swapped.  w ~ U[0,1]; rint ties (0.5) go to ceil.
-        if (gj_rng_f64(rng) <= A.crossover_probability) {
-            const double w = gj_rint(gj_rng_f64(rng));
+        const double u_cross = gj_rng_f64(rng);
+        double w_raw = -1.0;
+        if (u_cross <= A.crossover_probability) {
+            w_raw = gj_rng_f64(rng);
+            const double w = gj_rint(w_raw);
             if (w == 0.0) { int t = r1; r1 = r2; r2 = t; }
         }
+        if (tr) { tr[6] = u_cross; tr[7] = w_raw; }
         sh_parent = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
+        // Mover::do_move with the agent's tabu deque (genetic_algorithm_base.rs:148-155, mover.rs:75-96):
+        // every offspring of the generation sees the deque as the generation found it; it advances once
+        // per generation (k_ga_tabu_update), like a TabuSearch step's neighbourhood
+        const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
         sh_move = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step,
-                                   (uint32_t)c, nullptr, nullptr);
+                                   (uint32_t)c, bits, tabu_word_off);
         moves[(size_t)island * A.n_cand + c] = sh_move;
     }
     __syncthreads();
@@ -69,6 +83,21 @@ k_ga_offspring(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A,
     const GjMove m = sh_move;
     gj_apply_move(P, m, G, false, A.noop != 0, threadIdx.x, blockDim.x,
                   [&](int id) { return parent[id]; }, [&](int id, int v) { out[id] = v; });
+}
+
+// The GA mover's tabu deque after a generation: the ids its n_cand moves selected, in candidate order.
+__global__ void __launch_bounds__(256)
+k_ga_tabu_update(GjGroups G, int n_cand, int n_groups, const GjMove* __restrict__ moves, uint32_t* tabu_bits,
+                 int tabu_words_per_island, const int32_t* tabu_word_off, const int32_t* ring_old,
+                 int32_t* ring_new, int ring_per_island, const int32_t* ring_off, const int32_t* tabu_size,
+                 int* tabu_fill) {
+    __shared__ int sh_scan[256];
+    const int island = blockIdx.x;
+    const GjMove* mv = moves + (size_t)island * n_cand;
+    gj_tabu_deque_advance(tabu_bits + (size_t)island * tabu_words_per_island,
+                          ring_old + (size_t)island * ring_per_island, ring_new + (size_t)island * ring_per_island,
+                          ring_off, tabu_size, tabu_word_off, tabu_fill + (size_t)island * n_groups, n_groups, G,
+                          n_cand, [&](int j) { return mv[j]; }, sh_scan);
 }
 
 __global__ void k_round_scores(GjProblemDev P, double* scores, int64_t n) {
@@ -85,14 +114,15 @@ __global__ void __launch_bounds__(128)
 k_ga_replace(GjGaArgs A, const int32_t* __restrict__ pop_rows, const double* __restrict__ pop_scores,
              const int* __restrict__ order, const int32_t* __restrict__ cand_rows,
              const double* __restrict__ cand_scores, int32_t* __restrict__ pop_next,
-             double* __restrict__ pop_scores_next, int* __restrict__ ga_src) {
+             double* __restrict__ pop_scores_next, int* __restrict__ ga_src, double* __restrict__ trace_rep) {
     __shared__ int sh_from_cand, sh_native;
     const int island = blockIdx.x / A.pop, i = blockIdx.x % A.pop;
     if (threadIdx.x == 0) {
         GjPhilox rng;
         gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
                     (uint32_t)(A.step >> 32), 0x80000000u + (uint32_t)i);
-        const int rank = gj_ga_p_rank(rng, A.p_best_rate, A.pop, true);
+        const int rank = gj_ga_p_rank(rng, A.p_best_rate, A.pop, true,
+                                      trace_rep ? trace_rep + ((size_t)island * A.pop + i) * 3 : nullptr);
         const int native = order[(size_t)island * A.pop + rank];
         GjScore c, w;
         for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
@@ -371,8 +401,15 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
     gj_status rc;
     for (int64_t s = 0; s < n_steps; ++s) {
         GjGaArgs A = ga_args(g);
-        k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves);
+        k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves,
+                                                         g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
         GJ_LAUNCH_CHECK();
+        if (g->tabu_bits) {
+            k_ga_tabu_update<<<g->I, 256, 0, st>>>(g->groups, g->n_cand, g->groups.n_groups, g->moves, g->tabu_bits, g->tabu_words,
+                                                   g->tabu_word_off, g->tabu_ring[g->step & 1], g->tabu_ring[(g->step + 1) & 1],
+                                                   g->tabu_ring_len, g->tabu_ring_off, g->tabu_size, g->tabu_fill);
+            GJ_LAUNCH_CHECK();
+        }
         const int64_t S = (int64_t)g->I * g->n_cand;
         if ((rc = gj_prof_begin(g, st))) return rc;
         if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
@@ -380,7 +417,7 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
         GJ_LAUNCH_CHECK();
         k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,
-                                                   g->pop_next, g->pop_scores_next, g->ga_src);
+                                                   g->pop_next, g->pop_scores_next, g->ga_src, g->ga_trace_rep);
         GJ_LAUNCH_CHECK();
         std::swap(g->pop_rows, g->pop_next);
         std::swap(g->pop_scores, g->pop_scores_next);
@@ -457,4 +494,72 @@ gj_status gj_ga_import(gj_islands* g, const void* d_buffer, cudaStream_t st) {
     const size_t slot = (size_t)g->migrants * ((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
     GJ_CUDA_TRY(cudaMemcpyAsync(g->mailbox, d_buffer, slot, cudaMemcpyDeviceToDevice, st));
     return ga_migrate_recv(g, st);
+}
+
+// ---- test / inspection hooks ---------------------------------------------------------------------------
+extern "C" gj_status gj_islands_ga_population(gj_islands* g, int32_t island, double* rows, double* scores,
+                                              int32_t* order) {
+    if (!g || g->prm.agent != GJ_AGENT_GENETIC_ALGORITHM || island < 0 || island >= g->I)
+        return gj_fail(GJ_ERR_INVALID, "bad GA island");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    GJ_CUDA_TRY(cudaDeviceSynchronize());
+    const int pop = g->pop, n = g->n_vars;
+    if (rows) {
+        std::vector<int32_t> h((size_t)pop * g->stride);
+        GJ_CUDA_TRY(cudaMemcpy(h.data(), g->pop_rows + (size_t)island * pop * g->stride, h.size() * 4, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < pop; ++k)
+            for (int i = 0; i < n; ++i) rows[(size_t)k * n + i] = (double)h[(size_t)k * g->stride + i];
+    }
+    if (scores) {
+        std::vector<double> h((size_t)pop * GJ_MAX_LEVELS);
+        GJ_CUDA_TRY(cudaMemcpy(h.data(), g->pop_scores + (size_t)island * pop * GJ_MAX_LEVELS, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < pop; ++k)
+            for (int l = 0; l < g->levels; ++l) scores[(size_t)k * g->levels + l] = h[(size_t)k * GJ_MAX_LEVELS + l];
+    }
+    if (order) GJ_CUDA_TRY(cudaMemcpy(order, g->order + (size_t)island * pop, (size_t)pop * 4, cudaMemcpyDeviceToHost));
+    return GJ_OK;
+}
+
+extern "C" gj_status gj_islands_ga_trace_generation(gj_islands* g, int32_t island, gj_ga_trace* out) {
+    if (!g || !out || g->prm.agent != GJ_AGENT_GENETIC_ALGORITHM || island < 0 || island >= g->I)
+        return gj_fail(GJ_ERR_INVALID, "bad GA island");
+    GJ_CUDA_TRY(cudaSetDevice(g->p->device));
+    gj_status rc;
+    if (!g->ga_trace_sel) {
+        if ((rc = ga_alloc(g, (size_t)g->I * g->half * 8, &g->ga_trace_sel))) return rc;
+        if ((rc = ga_alloc(g, (size_t)g->I * g->pop * 3, &g->ga_trace_rep))) return rc;
+    }
+    GJ_CUDA_TRY(cudaDeviceSynchronize());
+    const int pop = g->pop, n = g->n_vars, nc = g->n_cand;
+    if (out->order_before)
+        GJ_CUDA_TRY(cudaMemcpy(out->order_before, g->order + (size_t)island * pop, (size_t)pop * 4, cudaMemcpyDeviceToHost));
+    cudaStream_t st = g->p->stream;
+    if ((rc = gj_ga_step(g, 1, st))) return rc;
+    GJ_CUDA_TRY(cudaStreamSynchronize(st));
+    if (out->pairs)
+        GJ_CUDA_TRY(cudaMemcpy(out->pairs, g->ga_trace_sel + (size_t)island * g->half * 8, (size_t)g->half * 8 * 8, cudaMemcpyDeviceToHost));
+    if (out->replace)
+        GJ_CUDA_TRY(cudaMemcpy(out->replace, g->ga_trace_rep + (size_t)island * pop * 3, (size_t)pop * 3 * 8, cudaMemcpyDeviceToHost));
+    if (out->src)
+        GJ_CUDA_TRY(cudaMemcpy(out->src, g->ga_src + (size_t)island * pop, (size_t)pop * 4, cudaMemcpyDeviceToHost));
+    if (out->move_desc) {
+        std::vector<GjMove> mv(nc);
+        GJ_CUDA_TRY(cudaMemcpy(mv.data(), g->moves + (size_t)island * nc, (size_t)nc * sizeof(GjMove), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < nc; ++j) {
+            int32_t* d = out->move_desc + (size_t)j * 20;
+            d[0] = mv[j].kind; d[1] = mv[j].group; d[2] = mv[j].k; d[3] = 0;
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) { d[4 + i] = mv[j].a[i]; d[12 + i] = mv[j].v[i]; }
+        }
+    }
+    if (out->cand_rows) {
+        std::vector<int32_t> h((size_t)nc * g->stride);
+        GJ_CUDA_TRY(cudaMemcpy(h.data(), g->cand_rows + (size_t)island * nc * g->stride, h.size() * 4, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < nc; ++k)
+            for (int i = 0; i < n; ++i) out->cand_rows[(size_t)k * n + i] = (double)h[(size_t)k * g->stride + i];
+    }
+    if (out->cand_scores)
+        GJ_CUDA_TRY(cudaMemcpy(out->cand_scores, g->cand_scores + (size_t)island * nc * g->levels,
+                               (size_t)nc * g->levels * 8, cudaMemcpyDeviceToHost));
+    // switch the trace writes off again (the buffers stay allocated)
+    return GJ_OK;
 }

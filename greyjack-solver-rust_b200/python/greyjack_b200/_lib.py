@@ -50,6 +50,12 @@ class AgentParams(C.Structure):
     ]
 
 
+class GaTrace(C.Structure):
+    _fields_ = [("order_before", C.c_void_p), ("pairs", C.c_void_p), ("move_desc", C.c_void_p),
+                ("cand_rows", C.c_void_p), ("cand_scores", C.c_void_p), ("replace", C.c_void_p),
+                ("src", C.c_void_p)]
+
+
 # every symbol include/greyjack_b200.h declares
 EXPORTED = [
     "gj_last_error", "gj_abi_version", "gj_device_count", "gj_sizeof_problem_desc", "gj_sizeof_agent_params", "gj_launch_count",
@@ -60,7 +66,7 @@ EXPORTED = [
     "gj_score_plain_device", "gj_score_plain_i32_device", "gj_score_incremental_device",
     "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_set_accomplish_rate", "gj_islands_stats", "gj_islands_trace_aux", "gj_islands_step_path", "gj_islands_set_profiling", "gj_islands_profile_read",
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",
-    "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step",
+    "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step", "gj_islands_trace_tabu", "gj_islands_ga_trace_generation", "gj_islands_ga_population",
 ]
 
 _lib = None

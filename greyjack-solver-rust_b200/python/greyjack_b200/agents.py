@@ -303,6 +303,38 @@ class Islands:
     def import_migrants(self, d_buffer: int, stream=0):
         _lib.check(self._L.gj_islands_import_migrants(self.handle, C.c_void_p(d_buffer), C.c_void_p(stream)))
 
+    def ga_population(self, island=0):
+        """(rows [pop][n_vars], scores [pop][levels], order [pop]) of a GeneticAlgorithm island."""
+        pop, n, lv = int(self.builder.population_size), self.problem.n_vars, self.problem.levels
+        rows = np.zeros((pop, n)); scores = np.zeros((pop, lv)); order = np.zeros(pop, dtype=np.int32)
+        _lib.check(self._L.gj_islands_ga_population(self.handle, C.c_int32(island), _ptr(rows), _ptr(scores), _ptr(order)))
+        return rows, scores, order
+
+    def ga_trace_generation(self, island=0):
+        """One GA generation of every island, the decisions of `island` exposed (gj_ga_trace)."""
+        pop, n, lv = int(self.builder.population_size), self.problem.n_vars, self.problem.levels
+        half = (pop + 1) // 2
+        nc = 2 * half
+        out = {"order_before": np.zeros(pop, dtype=np.int32), "pairs": np.zeros((half, 8)),
+               "desc": np.zeros((nc, 20), dtype=np.int32), "cand_rows": np.zeros((nc, n)),
+               "cand_scores": np.zeros((nc, lv)), "replace": np.zeros((pop, 3)), "src": np.zeros(pop, dtype=np.int32)}
+        t = _lib.GaTrace()
+        t.order_before = out["order_before"].ctypes.data; t.pairs = out["pairs"].ctypes.data
+        t.move_desc = out["desc"].ctypes.data; t.cand_rows = out["cand_rows"].ctypes.data
+        t.cand_scores = out["cand_scores"].ctypes.data; t.replace = out["replace"].ctypes.data
+        t.src = out["src"].ctypes.data
+        _lib.check(self._L.gj_islands_ga_trace_generation(self.handle, C.c_int32(island), C.byref(t)))
+        return out
+
+    def trace_tabu(self, island=0, group=0):
+        """The tabu deque of one island / semantic group, newest id first -> (ids, size)."""
+        cap = max(1, self.problem.n_vars)
+        ids = np.zeros(cap, dtype=np.int32)
+        fill, size = C.c_int32(0), C.c_int32(0)
+        _lib.check(self._L.gj_islands_trace_tabu(self.handle, C.c_int32(island), C.c_int32(group), _ptr(ids),
+                                                 C.c_int32(cap), C.byref(fill), C.byref(size)))
+        return ids[:fill.value].copy(), size.value
+
     def trace_step(self, island=0):
         """One TS/LA step with everything exposed (see gj_islands_trace_step)."""
         K, n, lv = self.K, self.problem.n_vars, self.problem.levels

@@ -324,6 +324,35 @@ GJ_API gj_status gj_islands_trace_step(gj_islands* g, int32_t island,
    out[2..4] = temperatures per level after the step's update.                              */
 GJ_API gj_status gj_islands_trace_aux(gj_islands* g, int32_t island, double* out /*[5]*/);
 
+/* Test / inspection hooks for GeneticAlgorithm islands: one generation of every island with the
+   decisions of ONE island exposed, so that select_p_best / cross / Mover::do_move(plain) /
+   build_updated_population (genetic_algorithm_base.rs:83-134, 141-213) can be replayed decision by
+   decision through the reference's rules.  Every buffer is the caller's; any may be NULL.          */
+typedef struct gj_ga_trace {
+    int32_t* order_before;  /* [pop] rank -> individual index: population.sort() before sampling      */
+    double*  pairs;         /* [ceil(pop/2)][8]: select_p_best draws of the pair {p1, last_top1, id1,
+                               p2, last_top2, id2}, the crossover coin u, the crossover weight w
+                               before rint (-1: no crossover)                                        */
+    int32_t* move_desc;     /* [n_cand][20] as gj_islands_trace_step                                  */
+    double*  cand_rows;     /* [n_cand][n_vars] offspring after cross + move + fix_variables          */
+    double*  cand_scores;   /* [n_cand][levels] their PSC scores, rounded (agent_base.rs:284-287)     */
+    double*  replace;       /* [pop][3] select_p_worst draws of slot i: {p, last_top, id}             */
+    int32_t* src;           /* [pop] slot i of the new population: i = candidate i, -(rank+1) = the
+                               p-worst native of that rank                                          */
+} gj_ga_trace;
+GJ_API gj_status gj_islands_ga_trace_generation(gj_islands* g, int32_t island, gj_ga_trace* out);
+/* population of one GA island as stored (unsorted) + its rank table; rows [pop][n_vars],
+   scores [pop][levels], order [pop].                                                              */
+GJ_API gj_status gj_islands_ga_population(gj_islands* g, int32_t island, double* rows, double* scores,
+                                          int32_t* order);
+
+/* Test / inspection hook: the tabu deque of one island and semantic group
+   (Mover::tabu_ids_vecdeque_map, mover.rs:75-96), newest id first.  ids: caller buffer of `capacity`
+   ints (group positions); *fill = ids currently held, *size = the deque's capacity
+   max(ceil(tabu_entity_rate * group_len), 1) (0 when tabu_entity_rate == 0).                      */
+GJ_API gj_status gj_islands_trace_tabu(gj_islands* g, int32_t island, int32_t group, int32_t* ids,
+                                       int32_t capacity, int32_t* fill, int32_t* size);
+
 /* Name of the kernel path a step of this group takes, chosen at creation: "fused", "fused_lean",
    "chain", "vrp_chain", "delta", "vrp_delta", "full" or "ga" (static string).                     */
 GJ_API const char* gj_islands_step_path(const gj_islands* g);

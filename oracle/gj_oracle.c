@@ -770,6 +770,30 @@ void gjo_ga_replace(const double* cand_scores, const double* pop_scores, const i
     }
 }
 
+/* genetic_algorithm_base.rs:83-103: select_p_best / select_p_worst with the two random draws made
+   explicit.  p_best_proba ~ U(1e-6, p_best_rate); last_top_id = ceil(p * pop); chosen_id =
+   U[0, last_top_id) (best) | U[pop - last_top_id, pop) (worst) -- `id_draw` is the offset inside that
+   range.  Returns the chosen index into the SORTED population, or -1 when the draw is out of range. */
+int64_t gjo_ga_select(double p_best_proba, int64_t id_draw, int64_t pop, int worst, int64_t* last_top_out) {
+    int64_t last_top_id = (int64_t)ceil(p_best_proba * (double)pop);
+    if (last_top_out) *last_top_out = last_top_id;
+    if (id_draw < 0 || id_draw >= last_top_id || last_top_id > pop) return -1;
+    return worst ? (pop - last_top_id + id_draw) : id_draw;
+}
+
+/* genetic_algorithm_base.rs:105-134: cross with ONE weight for every gene (`vec![sample(); n]` draws
+   once), rint-ed on discrete columns; children are convex sums of the parents.  discrete: [n] 0/1
+   or NULL (= all discrete, every GJInteger problem). */
+void gjo_ga_cross(const double* c1, const double* c2, int n, double weight, const uint8_t* discrete,
+                  double* out1, double* out2) {
+    for (int i = 0; i < n; ++i) {
+        double w = weight;
+        if (!discrete || discrete[i]) w = gjo_rint(w);
+        out1[i] = c1[i] * w + c2[i] * (1.0 - w);
+        out2[i] = c2[i] * w + c1[i] * (1.0 - w);
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* CPU baseline drivers                                                      */
 /* ------------------------------------------------------------------------- */
@@ -967,4 +991,293 @@ int64_t gjo_bench_plain(const gjo_problem* p, const double* samples, int64_t S, 
     *seconds = now_s() - t0;
     free(th); free(jobs);
     return S * repeats;
+}
+
+/* ------------------------------------------------------------------------- */
+/* LateAcceptance and GeneticAlgorithm baseline drivers (BASELINE configs 1, 3, 4) */
+/* ------------------------------------------------------------------------- */
+
+typedef struct {
+    const gjo_problem* p;
+    const double* base;
+    const int64_t* group_offsets; const int32_t* group_ids; int n_groups;
+    int late_size, n_steps, tid;
+    uint64_t seed;
+    const double* move_probas;
+    const int64_t* precision;
+    int64_t scored;
+    double best[3];
+} la_job;
+
+/* One LateAcceptance agent: Agent::step_incremental (agent_base.rs:300-320) with
+   LateAcceptanceBase (late_acceptance_base.rs:116-241): ONE neighbour per step -- a move of minimal
+   size on a random semantic group -- scored by the pseudo-incremental ISC (full re-evaluation of
+   base + deltas), accepted against the late list.  tabu_entity_rate = 0 and no Polars
+   marshalling: faster than the real reference (CPU-favouring).  Only change / swap / insertion /
+   inverse are drawn (what the examples' LateAcceptance configurations use).                      */
+static void* la_worker(void* arg) {
+    la_job* job = (la_job*)arg;
+    const gjo_problem* p = job->p;
+    const int n = p->n_vars, levels = gjo_levels(p->kind);
+    scratch_t s;
+    scratch_init(&s, p);
+    uint64_t rng = job->seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(job->tid + 1));
+    double* cur = (double*)malloc(sizeof(double) * (size_t)n);
+    memcpy(cur, job->base, sizeof(double) * (size_t)n);
+    int64_t* base_dec = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    int64_t* work = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    int32_t* cols32 = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n + 8));
+    double* dv = (double*)malloc(sizeof(double) * (size_t)(n + 8));
+    uint64_t* ids = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(n + 8));
+    double* late = (double*)calloc((size_t)(job->late_size + 2) * 3, sizeof(double));
+    int late_len = 0;
+    double cur_score[3] = {0, 0, 0}, top[3], sc[3];
+    int64_t prec[3] = {-1, -1, -1};
+    if (job->precision) for (int l = 0; l < levels; ++l) prec[l] = job->precision[l];
+    for (int i = 0; i < n; ++i) base_dec[i] = decode_var(p, i, cur[i]);
+    score_one_incremental(p, &s, base_dec, work, NULL, NULL, 0, cur_score);
+    memcpy(top, cur_score, sizeof(top));
+    double thr[6], acc = 0.0;
+    for (int m = 0; m < 6; ++m) { acc += job->move_probas[m]; thr[m] = acc; }
+    for (int step = 0; step < job->n_steps; ++step) {
+        const int gi = rnd_below(&rng, job->n_groups);
+        const int32_t* group = job->group_ids + job->group_offsets[gi];
+        const int glen = (int)(job->group_offsets[gi + 1] - job->group_offsets[gi]);
+        const double u = rnd01(&rng);
+        int mv = 5;
+        for (int m = 0; m < 6; ++m) if (u <= thr[m]) { mv = m; break; }
+        int a = rnd_below(&rng, glen), b = rnd_below(&rng, glen - 1);
+        if (b >= a) ++b;
+        int32_t chosen[2] = {a, b};
+        int k;
+        if (mv == GJO_MOVE_CHANGE) {
+            double nv = p->lower_bounds[group[a]] + rnd01(&rng) * (p->upper_bounds[group[a]] - p->lower_bounds[group[a]]);
+            k = gjo_move_change(cur, n, group, glen, chosen, 1, &nv, 1, cols32, dv, NULL);
+        } else if (mv == GJO_MOVE_INSERTION) {
+            k = gjo_move_insertion(cur, n, group, glen, a, b, 1, cols32, dv, NULL);
+        } else if (mv == GJO_MOVE_INVERSE) {
+            k = gjo_move_inverse(cur, n, group, glen, a, b, 1, cols32, dv, NULL);
+        } else {
+            k = gjo_move_swap(cur, n, group, glen, chosen, 2, 1, cols32, dv, NULL);
+        }
+        if (k < 0) k = 0;
+        gjo_fix_deltas(p, cols32, dv, k);
+        for (int d = 0; d < k; ++d) ids[d] = (uint64_t)cols32[d];
+        score_one_incremental(p, &s, base_dec, work, ids, dv, k, sc);
+        gjo_score_round(sc, prec, levels);                       /* agent_base.rs:311-314 */
+        if (gjo_la_accept(sc, cur_score, late, &late_len, job->late_size, levels)) {
+            for (int d = 0; d < k; ++d) { cur[cols32[d]] = dv[d]; base_dec[cols32[d]] = decode_var(p, cols32[d], dv[d]); }
+            memcpy(cur_score, sc, sizeof(double) * (size_t)levels);
+            if (gjo_score_le(cur_score, top, levels)) memcpy(top, cur_score, sizeof(top));   /* agent_base.rs:220-224 */
+        }
+    }
+    job->scored = job->n_steps;
+    memcpy(job->best, top, sizeof(top));
+    free(cur); free(base_dec); free(work); free(cols32); free(dv); free(ids); free(late);
+    scratch_free(&s);
+    return NULL;
+}
+
+int64_t gjo_bench_la(const gjo_problem* p, const double* base, const int64_t* group_offsets,
+                     const int32_t* group_ids, int n_groups, int late_size, int n_steps, int n_threads,
+                     uint64_t seed, const double* move_probas, const int64_t* precision,
+                     double* seconds, double* best_out) {
+    if (n_threads < 1) n_threads = 1;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    la_job* jobs = (la_job*)calloc((size_t)n_threads, sizeof(la_job));
+    double t0 = now_s();
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t].p = p; jobs[t].base = base; jobs[t].group_offsets = group_offsets; jobs[t].group_ids = group_ids;
+        jobs[t].n_groups = n_groups; jobs[t].late_size = late_size; jobs[t].n_steps = n_steps; jobs[t].tid = t;
+        jobs[t].seed = seed; jobs[t].move_probas = move_probas; jobs[t].precision = precision;
+        pthread_create(&th[t], NULL, la_worker, &jobs[t]);
+    }
+    int64_t total = 0;
+    const int levels = gjo_levels(p->kind);
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(th[t], NULL);
+        total += jobs[t].scored;
+        if (best_out && (t == 0 || gjo_score_cmp(jobs[t].best, best_out, levels) < 0))
+            memcpy(best_out, jobs[t].best, sizeof(double) * (size_t)levels);
+    }
+    *seconds = now_s() - t0;
+    free(th); free(jobs);
+    return total;
+}
+
+typedef struct {
+    const gjo_problem* p;
+    const int64_t* group_offsets; const int32_t* group_ids; int n_groups;
+    int pop, n_generations, tid;
+    double crossover_probability, p_best_rate;
+    uint64_t seed;
+    const double* move_probas;
+    const int64_t* precision;
+    int64_t scored;
+    double best[3];
+} ga_job;
+
+static int g_ga_levels;         /* qsort comparator context (one value for every worker of a run) */
+static const double* g_ga_dummy;
+typedef struct { double sc[3]; int idx; } ga_key;
+static int ga_key_cmp(const void* a, const void* b) {
+    const ga_key* x = (const ga_key*)a; const ga_key* y = (const ga_key*)b;
+    int c = gjo_score_cmp(x->sc, y->sc, g_ga_levels);
+    if (c) return c;
+    return (x->idx > y->idx) - (x->idx < y->idx);      /* Vec::sort is stable */
+}
+
+/* One GeneticAlgorithm agent: Agent::step_plain (agent_base.rs:273-298) with GeneticAlgorithmBase
+   (genetic_algorithm_base.rs:141-213): population.sort(); per pair two p-best parents, crossover
+   (one rint-ed weight: the parents swap or stay), one plain-form move each, fix_variables;
+   request_score_plain on the offspring (PSC), round; slot i = candidate i if <= a random p-worst
+   native.  Initial population = uniform samples (GJInteger::sample, initial None).               */
+static void* ga_worker(void* arg) {
+    ga_job* job = (ga_job*)arg;
+    const gjo_problem* p = job->p;
+    const int n = p->n_vars, levels = gjo_levels(p->kind), pop = job->pop;
+    const int half = (pop + 1) / 2, nc = 2 * half;
+    uint64_t rng = job->seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(job->tid + 1));
+    double* rows = (double*)malloc(sizeof(double) * (size_t)pop * (size_t)n);
+    double* next = (double*)malloc(sizeof(double) * (size_t)pop * (size_t)n);
+    double* cand = (double*)malloc(sizeof(double) * (size_t)nc * (size_t)n);
+    double* sc = (double*)malloc(sizeof(double) * (size_t)pop * 3);
+    double* sc_next = (double*)malloc(sizeof(double) * (size_t)pop * 3);
+    double* csc = (double*)malloc(sizeof(double) * (size_t)nc * 3);
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)n);
+    ga_key* keys = (ga_key*)malloc(sizeof(ga_key) * (size_t)pop);
+    int32_t* cols32 = (int32_t*)malloc(sizeof(int32_t) * (size_t)(2 * n + 16));
+    double* dv = (double*)malloc(sizeof(double) * (size_t)(2 * n + 16));
+    int64_t prec[3] = {-1, -1, -1};
+    if (job->precision) for (int l = 0; l < levels; ++l) prec[l] = job->precision[l];
+    for (int k = 0; k < pop; ++k)
+        for (int i = 0; i < n; ++i) {
+            const int64_t lo = (int64_t)p->lower_bounds[i], hi = (int64_t)p->upper_bounds[i];
+            rows[(size_t)k * n + i] = (double)(lo + (int64_t)(splitmix64(&rng) % (uint64_t)(hi - lo + 1)));
+        }
+    {
+        double* flat = (double*)malloc(sizeof(double) * (size_t)pop * (size_t)levels);
+        gjo_score_plain(p, rows, pop, flat);
+        for (int k = 0; k < pop; ++k) for (int l = 0; l < levels; ++l) sc[(size_t)k * 3 + l] = flat[(size_t)k * levels + l];
+        free(flat);
+    }
+    double top[3] = {1.7976931348623157e308, 0, 0};
+    double thr[6], acc = 0.0;
+    for (int m = 0; m < 6; ++m) { acc += job->move_probas[m]; thr[m] = acc; }
+    double* flat = (double*)malloc(sizeof(double) * (size_t)nc * (size_t)levels);
+    int64_t scored = 0;
+    for (int gen = 0; gen < job->n_generations; ++gen) {
+        for (int k = 0; k < pop; ++k) { memcpy(keys[k].sc, sc + (size_t)k * 3, sizeof(double) * 3); keys[k].idx = k; }
+        qsort(keys, (size_t)pop, sizeof(ga_key), ga_key_cmp);              /* population.sort() */
+        if (gjo_score_le(keys[0].sc, top, levels)) memcpy(top, keys[0].sc, sizeof(top));
+        for (int q = 0; q < half; ++q) {
+            int64_t r[2];
+            for (int h = 0; h < 2; ++h) {
+                const double pb = 0.000001 + rnd01(&rng) * (job->p_best_rate - 0.000001);
+                int64_t last_top = (int64_t)ceil(pb * (double)pop);
+                if (last_top < 1) last_top = 1;
+                r[h] = gjo_ga_select(pb, rnd_below(&rng, (int)last_top), pop, 0, NULL);
+            }
+            const double* p1 = rows + (size_t)keys[r[0]].idx * n;
+            const double* p2 = rows + (size_t)keys[r[1]].idx * n;
+            double* c1 = cand + (size_t)(2 * q) * n;
+            double* c2 = cand + (size_t)(2 * q + 1) * n;
+            if (rnd01(&rng) <= job->crossover_probability) gjo_ga_cross(p1, p2, n, rnd01(&rng), NULL, c1, c2);
+            else { memcpy(c1, p1, sizeof(double) * (size_t)n); memcpy(c2, p2, sizeof(double) * (size_t)n); }
+            for (int h = 0; h < 2; ++h) {
+                double* c = h ? c2 : c1;
+                const int gi = rnd_below(&rng, job->n_groups);
+                const int32_t* group = job->group_ids + job->group_offsets[gi];
+                const int glen = (int)(job->group_offsets[gi + 1] - job->group_offsets[gi]);
+                const double u = rnd01(&rng);
+                int mv = 5;
+                for (int m = 0; m < 6; ++m) if (u <= thr[m]) { mv = m; break; }
+                int a = rnd_below(&rng, glen), b = rnd_below(&rng, glen - 1);
+                if (b >= a) ++b;
+                int32_t chosen[2] = {a, b};
+                int k = -1;
+                switch (mv) {
+                    case GJO_MOVE_CHANGE: {
+                        double nv = p->lower_bounds[group[a]] + rnd01(&rng) * (p->upper_bounds[group[a]] - p->lower_bounds[group[a]]);
+                        k = gjo_move_change(c, n, group, glen, chosen, 1, &nv, 0, cols32, dv, tmp);
+                    } break;
+                    case GJO_MOVE_SWAP: k = gjo_move_swap(c, n, group, glen, chosen, 2, 0, cols32, dv, tmp); break;
+                    case GJO_MOVE_SWAP_EDGES: {
+                        int32_t ce[2] = {rnd_below(&rng, glen - 1), 0};
+                        ce[1] = rnd_below(&rng, glen - 2); if (ce[1] >= ce[0]) ++ce[1];
+                        k = gjo_move_swap_edges(c, n, group, glen, ce, 2, 0, cols32, dv, tmp);
+                    } break;
+                    case GJO_MOVE_SCRAMBLE: {
+                        int count = 3 + rnd_below(&rng, 4);
+                        int32_t perm[6] = {0, 1, 2, 3, 4, 5};
+                        for (int i = count - 1; i > 0; --i) { int rr = rnd_below(&rng, i + 1); int32_t t = perm[i]; perm[i] = perm[rr]; perm[rr] = t; }
+                        k = gjo_move_scramble(c, n, group, glen, rnd_below(&rng, glen - count), count, perm, 0, cols32, dv, tmp);
+                    } break;
+                    case GJO_MOVE_INSERTION: k = gjo_move_insertion(c, n, group, glen, a, b, 0, cols32, dv, tmp); break;
+                    default: k = gjo_move_inverse(c, n, group, glen, a, b, 0, cols32, dv, tmp); break;
+                }
+                if (k >= 0) {
+                    memcpy(c, tmp, sizeof(double) * (size_t)n);
+                    gjo_fix_variables(p, c, cols32, k);
+                }
+            }
+        }
+        gjo_score_plain(p, cand, nc, flat);                                     /* request_score_plain */
+        for (int k = 0; k < nc; ++k) {
+            gjo_score_round(flat + (size_t)k * levels, prec, levels);           /* agent_base.rs:284-287 */
+            for (int l = 0; l < 3; ++l) csc[(size_t)k * 3 + l] = l < levels ? flat[(size_t)k * levels + l] : 0.0;
+        }
+        scored += nc;
+        for (int i = 0; i < pop; ++i) {                                         /* :198-213 */
+            const double pb = 0.000001 + rnd01(&rng) * (job->p_best_rate - 0.000001);
+            int64_t last_top = (int64_t)ceil(pb * (double)pop);
+            if (last_top < 1) last_top = 1;
+            const int64_t rk = gjo_ga_select(pb, rnd_below(&rng, (int)last_top), pop, 1, NULL);
+            const int native = keys[rk].idx;
+            if (gjo_score_le(csc + (size_t)i * 3, sc + (size_t)native * 3, levels)) {
+                memcpy(next + (size_t)i * n, cand + (size_t)i * n, sizeof(double) * (size_t)n);
+                memcpy(sc_next + (size_t)i * 3, csc + (size_t)i * 3, sizeof(double) * 3);
+            } else {
+                memcpy(next + (size_t)i * n, rows + (size_t)native * n, sizeof(double) * (size_t)n);
+                memcpy(sc_next + (size_t)i * 3, sc + (size_t)native * 3, sizeof(double) * 3);
+            }
+        }
+        { double* t = rows; rows = next; next = t; t = sc; sc = sc_next; sc_next = t; }
+    }
+    for (int k = 0; k < pop; ++k) if (gjo_score_le(sc + (size_t)k * 3, top, levels)) memcpy(top, sc + (size_t)k * 3, sizeof(top));
+    job->scored = scored;
+    memcpy(job->best, top, sizeof(top));
+    free(rows); free(next); free(cand); free(sc); free(sc_next); free(csc); free(tmp); free(keys);
+    free(cols32); free(dv); free(flat);
+    return NULL;
+}
+
+int64_t gjo_bench_ga(const gjo_problem* p, const int64_t* group_offsets, const int32_t* group_ids,
+                     int n_groups, int pop, double crossover_probability, double p_best_rate,
+                     int n_generations, int n_threads, uint64_t seed, const double* move_probas,
+                     const int64_t* precision, double* seconds, double* best_out) {
+    if (n_threads < 1) n_threads = 1;
+    g_ga_levels = gjo_levels(p->kind);
+    (void)g_ga_dummy;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    ga_job* jobs = (ga_job*)calloc((size_t)n_threads, sizeof(ga_job));
+    double t0 = now_s();
+    for (int t = 0; t < n_threads; ++t) {
+        jobs[t].p = p; jobs[t].group_offsets = group_offsets; jobs[t].group_ids = group_ids; jobs[t].n_groups = n_groups;
+        jobs[t].pop = pop; jobs[t].n_generations = n_generations; jobs[t].tid = t;
+        jobs[t].crossover_probability = crossover_probability; jobs[t].p_best_rate = p_best_rate;
+        jobs[t].seed = seed; jobs[t].move_probas = move_probas; jobs[t].precision = precision;
+        pthread_create(&th[t], NULL, ga_worker, &jobs[t]);
+    }
+    int64_t total = 0;
+    const int levels = gjo_levels(p->kind);
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(th[t], NULL);
+        total += jobs[t].scored;
+        if (best_out && (t == 0 || gjo_score_cmp(jobs[t].best, best_out, levels) < 0))
+            memcpy(best_out, jobs[t].best, sizeof(double) * (size_t)levels);
+    }
+    *seconds = now_s() - t0;
+    free(th); free(jobs);
+    return total;
 }

@@ -170,6 +170,22 @@ int64_t gjo_bench_ts(const gjo_problem* p, const double* base, int n_moves, int 
 int64_t gjo_bench_plain(const gjo_problem* p, const double* samples, int64_t S,
                         int n_threads, int repeats, double* seconds, double* out);
 
+/* GeneticAlgorithm decisions with explicit draws (genetic_algorithm_base.rs:83-134) */
+int64_t gjo_ga_select(double p_best_proba, int64_t id_draw, int64_t pop, int worst, int64_t* last_top_out);
+void gjo_ga_cross(const double* c1, const double* c2, int n, double weight, const uint8_t* discrete,
+                  double* out1, double* out2);
+
+/* CPU baselines for BASELINE configs 1 / 4 (LateAcceptance) and 3 (GeneticAlgorithm): one agent per
+   host thread like the reference (solver.rs:94); returns candidates scored. */
+int64_t gjo_bench_la(const gjo_problem* p, const double* base, const int64_t* group_offsets,
+                     const int32_t* group_ids, int n_groups, int late_size, int n_steps, int n_threads,
+                     uint64_t seed, const double* move_probas, const int64_t* precision,
+                     double* seconds, double* best_out);
+int64_t gjo_bench_ga(const gjo_problem* p, const int64_t* group_offsets, const int32_t* group_ids,
+                     int n_groups, int pop, double crossover_probability, double p_best_rate,
+                     int n_generations, int n_threads, uint64_t seed, const double* move_probas,
+                     const int64_t* precision, double* seconds, double* best_out);
+
 #ifdef __cplusplus
 }
 #endif

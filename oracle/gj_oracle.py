@@ -83,6 +83,10 @@ def lib():
         L.gjo_ts_select.restype = C.c_int64
         L.gjo_bench_ts.restype = C.c_int64
         L.gjo_bench_plain.restype = C.c_int64
+        L.gjo_bench_la.restype = C.c_int64
+        L.gjo_bench_ga.restype = C.c_int64
+        L.gjo_ga_select.restype = C.c_int64
+        L.gjo_ga_select.argtypes = [C.c_double, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -212,6 +216,38 @@ class OracleProblem:
                                C.byref(secs), _ptr(best))
         return int(n), secs.value, best[: self.levels].copy()
 
+    def _groups_csr(self):
+        offs, ids = [0], []
+        for g in self.spec.groups.values():
+            ids.extend(int(x) for x in g)
+            offs.append(len(ids))
+        return np.asarray(offs, dtype=np.int64), np.asarray(ids, dtype=np.int32)
+
+    def bench_la(self, base, late_size, n_steps, n_threads, seed, move_probas, precision):
+        """One LateAcceptance agent per thread (late_acceptance_base.rs:116-241) -> (candidates, seconds, best)."""
+        b = np.ascontiguousarray(base, dtype=np.float64)
+        mp = np.ascontiguousarray(move_probas, dtype=np.float64)
+        pr = None if precision is None else np.ascontiguousarray(precision, dtype=np.int64)
+        offs, ids = self._groups_csr()
+        secs = C.c_double(0.0)
+        best = np.zeros(3, dtype=np.float64)
+        n = lib().gjo_bench_la(C.byref(self.c), _ptr(b), _ptr(offs), _ptr(ids), C.c_int(len(offs) - 1),
+                               C.c_int(late_size), C.c_int(n_steps), C.c_int(n_threads), C.c_uint64(seed),
+                               _ptr(mp), _ptr(pr), C.byref(secs), _ptr(best))
+        return int(n), secs.value, best[: self.levels].copy()
+
+    def bench_ga(self, pop, crossover_probability, p_best_rate, n_generations, n_threads, seed, move_probas, precision):
+        """One GeneticAlgorithm agent per thread (genetic_algorithm_base.rs:141-213) -> (candidates, seconds, best)."""
+        mp = np.ascontiguousarray(move_probas, dtype=np.float64)
+        pr = None if precision is None else np.ascontiguousarray(precision, dtype=np.int64)
+        offs, ids = self._groups_csr()
+        secs = C.c_double(0.0)
+        best = np.zeros(3, dtype=np.float64)
+        n = lib().gjo_bench_ga(C.byref(self.c), _ptr(offs), _ptr(ids), C.c_int(len(offs) - 1), C.c_int(pop),
+                               C.c_double(crossover_probability), C.c_double(p_best_rate), C.c_int(n_generations),
+                               C.c_int(n_threads), C.c_uint64(seed), _ptr(mp), _ptr(pr), C.byref(secs), _ptr(best))
+        return int(n), secs.value, best[: self.levels].copy()
+
     def bench_plain(self, samples, n_threads, repeats=1):
         x = np.ascontiguousarray(samples, dtype=np.float64).reshape(-1, self.spec.n_vars)
         out = np.empty((x.shape[0], self.levels), dtype=np.float64)
@@ -321,6 +357,22 @@ def ga_replace(cand_scores, pop_scores, worst_ids):
     out = np.zeros(len(w), dtype=np.int64)
     lib().gjo_ga_replace(_ptr(cs), _ptr(ps), _ptr(w), C.c_int64(len(w)), C.c_int(cs.shape[1]), _ptr(out))
     return out
+
+
+def ga_select(p_best_proba, id_draw, pop, worst=False):
+    """select_p_best / select_p_worst with explicit draws -> (index into the sorted population or -1, last_top_id)."""
+    lt = C.c_int64(0)
+    r = lib().gjo_ga_select(C.c_double(p_best_proba), C.c_int64(int(id_draw)), C.c_int64(pop), C.c_int(int(worst)),
+                            C.cast(C.byref(lt), C.c_void_p))
+    return int(r), int(lt.value)
+
+
+def ga_cross(c1, c2, weight):
+    """GeneticAlgorithmBase::cross for all-discrete problems -> (child1, child2)."""
+    a = np.ascontiguousarray(c1, dtype=np.float64); b = np.ascontiguousarray(c2, dtype=np.float64)
+    o1 = np.empty_like(a); o2 = np.empty_like(a)
+    lib().gjo_ga_cross(_ptr(a), _ptr(b), C.c_int(len(a)), C.c_double(weight), None, _ptr(o1), _ptr(o2))
+    return o1, o2
 
 
 def distance_matrix(xy):

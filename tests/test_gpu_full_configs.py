@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from greyjack_b200 import (GeneticAlgorithm, LateAcceptance, Problem, TabuSearch, instances as inst)
-from test_gpu_islands import _same_score
+from test_gpu_islands import _final_state, _oracle_move, _same_score
+from test_gpu_delta import QUANTUM, _check_delta_scores
 
 pytestmark = pytest.mark.gpu
 
@@ -34,6 +35,97 @@ def test_c1_nqueens256_late_acceptance_single_agent(oracle):
         assert prev[0] < 0.6 * s0[0]                                 # 10 000 LA steps make real progress
         assert isl.stats() == {"candidates": 10000, "steps": 10000, "accepted": isl.stats()["accepted"]}
         isl.close(); gp.close()
+
+
+def _selected_ids(d):
+    """positions a move pushed into the tabu deque (Mover::select_non_tabu_ids, mover.rs:75-96)"""
+    kind, k = int(d[0]), int(d[2])
+    if kind == 255:
+        return []
+    if kind == 3:
+        return [int(d[4])]
+    return [int(x) for x in d[4:4 + (2 if kind >= 4 else k)]]
+
+
+def _replay_ts_step(isl, island, spec, op, oracle, exact):
+    """One traced TabuSearch step of `island`, everything replayed through the oracle: the K moves
+    (mover.rs:145-421), their scores (ISC scorer + ScoreTrait::round), the selection
+    (tabu_search_base.rs:157-188), the stored individual and the tabu deque (mover.rs:75-96)."""
+    K = isl.K
+    base, cur_score = isl.current(island)
+    full = oracle.score_round(op.score_incremental(base, [[]])[0], spec.score_precision)
+    unr = op.score_incremental(base, [[]])[0]
+    assert cur_score[0] in (full[0], unr[0]) and min(abs(cur_score[1] - full[1]), abs(cur_score[1] - unr[1])) <= (0.0 if exact else QUANTUM)
+    tabu_before, T = isl.trace_tabu(island, 0)
+    assert T == int(np.ceil(0.5 * spec.n_vars))
+    tr = isl.trace_step(island)
+    banned = set(tabu_before.tolist())
+    pushed = []
+    for j in range(K):
+        d = tr["desc"][j]
+        want = _oracle_move(op, spec, base, d)
+        assert _final_state(spec.n_vars, tr["deltas"][j]) == _final_state(spec.n_vars, want), (island, j, d)
+        sel = _selected_ids(d)
+        assert not (set(sel) & banned), (island, j, sel)       # every neighbour sees the step-start deque
+        pushed += sel
+    _check_delta_scores(tr["scores"], op.score_incremental(base, tr["deltas"]), spec, oracle)
+    sel, acc = oracle.ts_select(tr["scores"], cur_score)
+    assert (tr["selected"], tr["accepted"]) == (sel, acc)
+    new, new_score = isl.current(island)
+    want_vec = base.copy()
+    if acc:
+        for c, v in tr["deltas"][sel]:
+            want_vec[c] = v
+        want_score = oracle.score_round(op.score_incremental(new, [[]])[0], spec.score_precision)
+        assert new_score[0] == want_score[0]
+        if exact:
+            assert np.array_equal(new_score, want_score)        # stored score = full evaluation, reference order
+        else:
+            assert abs(new_score[1] - want_score[1]) <= QUANTUM
+    else:
+        assert np.array_equal(new_score, cur_score)
+    assert np.array_equal(new, want_vec)
+    # the deque advanced once, by the step's ids in candidate order (newest first), older ids behind
+    tabu_after, _ = isl.trace_tabu(island, 0)
+    assert tabu_after.tolist() == (pushed[::-1] + tabu_before.tolist())[:T]
+    return acc
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact-sums", "tree-sums"])
+def test_c2_tsp1000_tabu_fused_bench_shape(exact, oracle):
+    """C2 exactly as bench.py runs it: TSP-1000 seed 1, TabuSearch(4096 neighbours, tabu 0.5,
+    compare_to_global, swap + 2-opt, migration every 10), 592 islands, the fused delta-scoring step
+    with 16 neighbours per thread and a multi-chunk tabu update -- traced on the first, a middle and
+    the last island, before and after a migration / global-top adoption."""
+    spec = inst.tsp(1000, seed=1)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    gp.set_exact_sums(exact)
+    isl = TabuSearch(4096, 0.5, True, None, [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 10, scoring="delta").build_agent(
+        gp, n_islands=592, seed=1000)
+    assert isl.step_path.startswith("fused")
+    islands = (0, 295, 591)
+    accepted = 0
+    for i in islands:                                   # fresh islands, empty deques
+        accepted += _replay_ts_step(isl, i, spec, op, oracle, exact)
+    isl.step(10)                                        # one ring migration + ten global-top publications
+    g_vec, g_score = isl.best(-1)
+    adopted = 0
+    for i in islands:                                   # the published global top is adopted at the step's start
+        adopted += int(np.array_equal(isl.current(i)[0], g_vec))
+        accepted += _replay_ts_step(isl, i, spec, op, oracle, exact)
+    isl.step(7)
+    for i in islands:                                   # full deques (500 ids), mid-run
+        assert len(isl.trace_tabu(i, 0)[0]) == 500
+        accepted += _replay_ts_step(isl, i, spec, op, oracle, exact)
+    assert adopted >= 2 and accepted >= 6
+    st = isl.stats()
+    assert st["steps"] == 26 and st["candidates"] == 26 * 4096 * 592
+    v, s = isl.best(-1)
+    assert sorted(v.tolist()) == list(range(1, 1000))
+    want = oracle.score_round(op.score_incremental(v, [[]])[0], spec.score_precision)
+    assert s[0] == want[0] and abs(s[1] - want[1]) <= (0.0 if exact else QUANTUM)
+    isl.close(); gp.close()
 
 
 def test_c3_cvrp2000_genetic_algorithm_pop8192(oracle):
@@ -104,6 +196,21 @@ def test_c5_tsp20000_ga_and_tabu_islands(oracle):
     # 80 KB shared-memory clone per warp: the kernels drop to two warps per CTA)
     got = gp.request_score_incremental(base, tr["deltas"][:48])
     assert np.array_equal(got, op.score_incremental(base, tr["deltas"][:48]))
+    # bench.py runs C5 with tree sums: the same trace in that mode (lean layout: edge lengths in HBM)
+    gp.set_exact_sums(False)
+    tt = TabuSearch(4096, 0.2, True, None, [0, 0.5, 0, 0, 0, 0.5], 10, scoring="delta").build_agent(gp, n_islands=4, seed=9)
+    assert tt.step_path == "fused_lean"
+    for _ in range(2):
+        tbase, tcur = tt.current(1)
+        ttr = tt.trace_step(1)
+        pick = list(range(0, 4096, 64))
+        twant = oracle.score_round(op.score_incremental(tbase, [ttr["deltas"][j] for j in pick]), spec.score_precision)
+        assert np.array_equal(ttr["scores"][pick, 0], twant[:, 0])
+        assert np.max(np.abs(ttr["scores"][pick, 1] - twant[:, 1])) <= 1.001e-3
+        tsel, tacc = oracle.ts_select(ttr["scores"], tcur)
+        assert (ttr["selected"], ttr["accepted"]) == (tsel, tacc)
+    tt.close()
+    gp.set_exact_sums(True)
     tf = TabuSearch(64, 0.2, True, None, [0, 0.5, 0, 0, 0, 0.5], 10, scoring="full").build_agent(gp, n_islands=2, seed=4)
     trf = tf.trace_step(1)
     assert np.array_equal(trf["scores"], oracle.score_round(op.score_incremental(base, trf["deltas"]), spec.score_precision))

@@ -249,3 +249,35 @@ def test_simulated_annealing_rule(oracle):
     assert list(t) == [0.25, 0.25] and p > 1.0 and acc                       # improving moves always pass
     _, t, _ = oracle.sa_accept([1.0], [1.0], [1.5e-6], 0.5, 1.0, 0.0)
     assert list(t) == [1e-7]                                                 # < 1e-6 -> 1e-7 floor
+
+
+# ---- GeneticAlgorithm decisions (genetic_algorithm_base.rs:83-134) with explicit draws ----------------
+def test_ga_select_and_cross_restatement(oracle):
+    # last_top_id = ceil(p * pop); best: U[0, last_top) ; worst: U[pop - last_top, pop)
+    assert oracle.ga_select(0.1, 3, 256) == (3, 26)
+    assert oracle.ga_select(0.1, 3, 256, worst=True) == (256 - 26 + 3, 26)
+    assert oracle.ga_select(0.000001, 0, 256) == (0, 1)              # the smallest p still reaches rank 0
+    assert oracle.ga_select(0.1, 26, 256)[0] == -1                   # outside Uniform::new(0, last_top_id)
+    # one weight for every gene, rint-ed on discrete columns (ties -> ceil): parents swap or stay
+    a, b = [1.0, 2.0, 3.0], [4.0, 5.0, 6.0]
+    c1, c2 = oracle.ga_cross(a, b, 0.4)
+    assert c1.tolist() == b and c2.tolist() == a
+    c1, c2 = oracle.ga_cross(a, b, 0.5)
+    assert c1.tolist() == a and c2.tolist() == b
+    c1, c2 = oracle.ga_cross(a, b, 1.0)
+    assert c1.tolist() == a and c2.tolist() == b
+
+
+def test_la_and_ga_baseline_drivers_make_progress(oracle):
+    from greyjack_b200 import instances as inst
+    spec = inst.nqueens(64)
+    op = oracle.OracleProblem(spec)
+    s0 = op.score_incremental(spec.initial, [[]])[0]
+    n, secs, best = op.bench_la(spec.initial, 16, 4000, 2, 1, [0, 1.0, 0, 0, 0, 0], None)
+    assert n == 8000 and secs > 0 and best[0] < s0[0]
+    spec = inst.cvrp(40, 4, seed=2, greedy=False)
+    op = oracle.OracleProblem(spec)
+    n, secs, best = op.bench_ga(64, 0.5, 0.2, 40, 2, 3, [1 / 6.0] * 6, [0, 0, 3])
+    assert n == 2 * 40 * 64
+    n2, _, best2 = op.bench_ga(64, 0.5, 0.2, 2, 2, 3, [1 / 6.0] * 6, [0, 0, 3])
+    assert oracle.score_cmp(best, best2) <= 0                        # more generations never end worse (same seed)
