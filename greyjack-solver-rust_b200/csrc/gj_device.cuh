@@ -37,6 +37,8 @@ struct GjProblemDev {
     // utility objects
     int n_locations;
     const double* D;             // [L][L] row-major distance matrix
+    const int32_t* D32;          // [L][L] the same in milli-units (rint(D * 1000)) when every entry is a
+                                 // whole number of them (the examples truncate to 3 decimals); else nullptr
     int n_vehicles;
     const int32_t* veh_depot;    // [K]
     const unsigned long long* veh_capacity;

@@ -50,6 +50,7 @@ struct gj_problem {
     std::vector<std::vector<int32_t>> groups;   // semantic groups, frozen ids dropped
     int64_t precision[3] = {-1, -1, -1};
     bool symmetric_D = false;
+    int d32_state = 0;                     // milli-unit matrix (dev.D32): 0 not built, 1 valid, -1 unavailable
     int n_warps_vrp = 4;
 
     // scratch for host-buffer calls
@@ -57,6 +58,8 @@ struct gj_problem {
 
     ~gj_problem();
 };
+
+gj_status gj_problem_ensure_d32(gj_problem* p);
 
 // launchers shared by the ABI entry points and the island code (gj_score.cu)
 gj_status gj_launch_score_plain_f64(gj_problem* p, const double* d_samples, int64_t S,

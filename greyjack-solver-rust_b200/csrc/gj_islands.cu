@@ -937,7 +937,12 @@ __global__ void k_init_scores(int I, const double* __restrict__ scored, int leve
 
 static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top);
 
-static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const double* initial, gj_islands** out) {
+static gj_status ls_create(gj_problem* p, const gj_agent_params* prm_in, const double* initial, gj_islands** out) {
+    // GJ_SCORING_DELTA_F64 = DELTA minus the fixed-point TSP step
+    gj_agent_params prm_delta = *prm_in;
+    const bool no_fixed_point = prm_in->scoring_mode == GJ_SCORING_DELTA_F64;
+    if (no_fixed_point) prm_delta.scoring_mode = GJ_SCORING_DELTA;
+    const gj_agent_params* prm = &prm_delta;
     std::unique_ptr<gj_islands> g(new gj_islands());
     gj_status rc;
     if ((rc = gj_islands_common_init(g.get(), p, prm))) return rc;
@@ -1135,6 +1140,28 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm, const doub
                 }
             }
         }
+        // TSP + TabuSearch on a milli-unit matrix: the fused step in fixed point (gj_islands_tsfast.cuh)
+        if (g->fused && !g->fused_lean && P.kind == GJ_TSP && ts && p->groups.size() == 1 && affine &&
+            p->groups[0].size() >= 16 && p->symmetric_D && g->mover.mutation_rate_multiplier == 0.0 &&
+            P.w[0] == 1.0 && p->precision[1] == 3 && !no_fixed_point && !getenv("GJ_NO_TSFAST")) {
+            if ((rc = gj_problem_ensure_d32(p))) return rc;
+            if (p->d32_state == 1) {
+                g->ts_edge_stride = (P.n_vars + 2) & ~1;
+                if ((rc = dev_alloc(g.get(), (size_t)I * g->ts_edge_stride, &g->ts_edge))) return rc;
+                g->ts_fast = true;
+                g->fused_smem = gj_tsfast_smem(g.get());
+                // CTA shape from the islands per SM: 256 threads x 4 resident CTAs (<= 64 registers) up to
+                // 4 islands per SM, x 6 (<= 40 registers) beyond; wider CTAs when islands are few
+                int sms = 148;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+                int threads = I >= 3 * sms ? 256 : (I >= 2 * sms ? 512 : 1024);
+                int mb = threads == 256 ? (I > 4 * sms ? 6 : 4) : (threads == 512 ? 2 : 1);
+                if (const char* e = getenv("GJ_FUSED_THREADS")) threads = std::max(256, std::min(1024, atoi(e)));
+                if (const char* e = getenv("GJ_FUSED_MB")) mb = atoi(e);
+                g->fused_mb = mb;
+                g->fused_threads = threads;
+            }
+        }
         // LateAcceptance (one neighbour per step): chains that run many steps per launch
         if (prm->scoring_mode == GJ_SCORING_DELTA && (la || sa)) {
             const int words = P.bm_words + P.desc_words + P.asc_words;
@@ -1318,7 +1345,7 @@ static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     if (g->fused) {
         // generation, delta scoring, selection, apply, exact re-score and tabu update in one kernel
         if ((rc = gj_prof_begin(g, st))) return rc;
-        if ((rc = gj_launch_fused_step(g, st, trace))) return rc;
+        if ((rc = g->ts_fast ? gj_launch_tsfast_step(g, st, trace) : gj_launch_fused_step(g, st, trace))) return rc;
         if ((rc = gj_prof_end(g, st))) return rc;
         g->step += 1;
         return GJ_OK;
@@ -1549,7 +1576,7 @@ extern "C" const char* gj_islands_step_path(const gj_islands* g) {
     if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return "ga";
     if (g->vrp_chain) return "vrp_chain";
     if (g->chain) return "chain";
-    if (g->fused) return g->fused_lean ? "fused_lean" : "fused";
+    if (g->fused) return g->ts_fast ? "fused_fixed" : (g->fused_lean ? "fused_lean" : "fused");
     if (g->scoring_mode == GJ_SCORING_DELTA) return g->p->dev.kind >= GJ_VRP ? "vrp_delta" : "delta";
     return "full";
 }

@@ -54,9 +54,13 @@ struct gj_islands {
     // fused single-kernel step (gj_islands_fused.cuh)
     bool fused = false;
     bool fused_lean = false;             // long solutions: only the solution is staged in shared memory
-    int fused_threads = 0, fused_clones = 0;
+    int fused_threads = 0, fused_clones = 0, fused_mb = 0;
     size_t fused_smem = 0;
     long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid
+    // fixed-point TabuSearch step for TSP (gj_islands_tsfast.cuh): the fused step with integer arithmetic
+    bool ts_fast = false;
+    double* ts_edge = nullptr;           // [I][ts_edge_stride] persistent f64 edge lengths
+    int ts_edge_stride = 0;
     // LateAcceptance chains: many steps per launch, one warp per island (gj_islands_chain.cuh)
     bool chain = false;
     bool vrp_chain = false;              // ... on a VRP model: route index in HBM (gj_islands_vrp_chain.cuh)

@@ -326,6 +326,8 @@ static gj_status opt_in_smem(Kern kernel, size_t bytes) {
 // host-side builders / launchers that cross translation units
 GjSelectArgs gj_make_select_args(gj_islands* g, bool trace, bool stored_moves);
 gj_status gj_launch_fused_step(gj_islands* g, cudaStream_t st, bool trace);                  // gj_islands_fused.cu
+gj_status gj_launch_tsfast_step(gj_islands* g, cudaStream_t st, bool trace);                 // gj_islands_tsfast.cu
+size_t gj_tsfast_smem(const gj_islands* g);
 gj_status gj_launch_la_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t st);          // gj_islands_chain.cu
 gj_status gj_launch_vrp_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t st);         // gj_islands_vrp_chain.cu
 gj_status gj_launch_vrp_gindex(gj_islands* g, cudaStream_t st);

@@ -1,0 +1,439 @@
+// gj_islands_tsfast.cuh -- the TabuSearch island step for TSP in FIXED POINT (included by
+// gj_islands_tsfast.cu).  Same phases and the same observable behaviour as k_ls_step_fused
+// (gj_islands_fused.cuh); what changes is the arithmetic of the hot loop:
+//
+//   * The examples' distance matrix is truncated to 3 decimals (location.rs:42-47), i.e. it is a table
+//     of milli-units.  gj_problem keeps an int32 copy D32 = rint(D * 1000) (validated entry by entry),
+//     and a neighbour's tour-length change is an exact integer: (sum of <= 4 added edges) - (sum of
+//     <= 4 removed edges).  ScoreTrait::round at precision 3 (agent_base.rs:311-314 ->
+//     math_utils.rs:10-13) maps a score to its milli-unit index, so ordering neighbours by
+//     (duplicate-stop change, tour-length change) IS ordering them by their rounded scores -- with no
+//     f64 instruction, no rounding key and half the L2 sectors per gathered edge.  The reference's own
+//     f64 fold lands within one quantum of that index (the exact tour length sits ON a truncation
+//     boundary; which side it falls is decided by its summation order), the declared float tolerance.
+//   * A swap of two stops, a 2-opt reversal and an insertion need: ONE Philox4x32-10 block (move
+//     kind, group draw, two ranks), two loads from the island's free-position list, six tour loads
+//     and <= 4 removed-edge loads from shared memory, <= 4 added-edge gathers from D32 in L2.
+//     Nothing is indexed dynamically: no GjMove descriptor, no local memory.  Every other move
+//     (change / swap_edges / scramble) goes to a work list and through the generic generator +
+//     delta evaluator of gj_moves.cuh / gj_delta.cuh in an out-of-line slow path.
+//   * The island's n + 1 edge lengths persist in HBM (f64, the values the matrix holds) and arrive
+//     with the tour and the tabu table as TMA bulk copies; an accepted move patches only the edges it
+//     touched.  The stored score of an accepted neighbour is still the FULL evaluation in the
+//     reference's summation order (exact sums), or the exact integer sum of the edges (tree mode).
+//
+// Eligibility (checked by the host, gj_islands.cu): TSP, TabuSearch, one semantic group of consecutive
+// columns with uniform bounds, symmetric matrix with a valid D32, weight 1, score_precision[1] == 3,
+// mutation_rate_multiplier None.  Everything else keeps k_ls_step_fused.
+#pragma once
+
+struct GjTsFastArgs {
+    GjSelectArgs A;
+    double* edge;               // [I][edge_stride] f64 edge lengths (n + 1 live) of every island's current tour
+    int edge_stride;            // n + 1 rounded up to an even count: 16-byte rows for the TMA copies
+    int* stale;                 // [I] 1: the tour was replaced (migrant / global top) -> rebuild the edges
+    uint32_t kind_thr[5];       // move-kind thresholds on the raw 32-bit draw (see gj_kind_thresholds_u32)
+    int first;                  // first column of the group (columns first .. first + glen - 1)
+    int glen;
+    int cnt_stride;             // 32 * bm_words: value counts of the slow path
+    double* scores_out;         // trace only: [I][K][2]
+    GjMove* moves_out;          // trace only
+    int* worklist;              // [I][K]
+    long long* phase_clocks;
+};
+
+__host__ __device__ inline size_t gj_tsfast_smem_bytes(int n_vars, int tabu_words, int cnt_stride) {
+    const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;
+    size_t b = (n_pad + 8) * 4;                                  // tour with sentinels
+    b += (((size_t)n_vars + 1 + 3) & ~(size_t)3) * 4;           // e32
+    b += (((size_t)tabu_words + 3) & ~(size_t)3) * 4;           // tabu table
+    b += (size_t)cnt_stride * 4;                                 // value counts (slow path)
+    b = (b + 15) & ~(size_t)15;
+    b += (((size_t)n_vars + 2) & ~(size_t)1) * 8;               // e64
+    return b;
+}
+
+// neighbour ordering key: (-d_uniq) * 2^40 + delta_milli; lower is better
+#define GJ_TSF_HSHIFT 40
+__device__ __forceinline__ long long gj_tsf_key(int d_uniq, long long delta_milli) {
+    return ((long long)(-d_uniq) << GJ_TSF_HSHIFT) + delta_milli;
+}
+__device__ __forceinline__ void gj_tsf_unkey(long long key, int& d_uniq, long long& delta_milli) {
+    const long long h = (key + (1ll << (GJ_TSF_HSHIFT - 1))) >> GJ_TSF_HSHIFT;
+    d_uniq = (int)(-h);
+    delta_milli = key - (h << GJ_TSF_HSHIFT);
+}
+
+// milli-unit index of a stored score level: floor(v) * 1000 + floor(frac * 1000), the integer pair
+// ScoreTrait::round (math_utils.rs:10-13) is built from
+__device__ __forceinline__ long long gj_tsf_milli_index(double v) {
+    const double fl = floor(v);
+    return (long long)fl * 1000ll + (long long)floor((v - fl) * 1000.0);
+}
+// ... and the score value the reference's rounding produces for that index
+__device__ __forceinline__ double gj_tsf_from_index(long long k) {
+    long long q = k / 1000, r = k % 1000;
+    if (r < 0) { r += 1000; q -= 1; }
+    return (double)q + (double)r / 1000.0;
+}
+
+// ---- out-of-line slow path: generic generator / evaluator (rare) ------------------------------------
+static __device__ __noinline__ void gj_tsf_generate(const GjProblemDev& P, const GjGroups& G, const GjSelectArgs& A,
+                                                    const uint32_t* table, int island, int c, GjMove* out) {
+    *out = gj_generate_move(P, G, A.M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, table,
+                            A.tabu_word_off);
+}
+
+static __device__ __noinline__ long long gj_tsf_slow_key(const GjProblemDev& P, const GjGroups& G, const GjSelectArgs& A,
+                                                         const uint32_t* table, const int32_t* t, const int32_t* cnt,
+                                                         int island, int c, GjMove* trace_out) {
+    GjMove m;
+    gj_tsf_generate(P, G, A, table, island, c, &m);
+    if (trace_out) *trace_out = m;
+    GjTspBase B{t, P.n_vars, P.D, (size_t)P.n_locations, nullptr, true};
+    int d_uniq = 0; double d_dist = 0.0;
+    gj_tsp_move_delta(P, G, m, A.noop != 0, true, B, cnt, d_uniq, d_dist);
+    return gj_tsf_key(d_uniq, llrint(d_dist * 1000.0));
+}
+
+// TRACE: the instantiation gj_islands_trace_step uses (writes every neighbour's move and score)
+// MB: resident CTAs per SM the register allocation is sized for (launch bounds)
+template <int NT, int MB, bool TRACE>
+__global__ void __launch_bounds__(NT, MB)
+k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ GjGroups G,
+               const __grid_constant__ GjTsFastArgs F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long sh_wkey[32];
+    __shared__ int sh_widx[32];
+    __shared__ int sh_sel0[NT], sh_sel1[NT], sh_selinfo[NT];   // ids the last chunk's moves selected
+    __shared__ int sh_scan[NT];
+    __shared__ long long sh_isum[32];
+    __shared__ __align__(8) uint64_t sh_mbar;
+    __shared__ long long sh_curkey;
+    __shared__ long long sh_bestkey;
+    __shared__ int sh_accept, sh_best, sh_nwork, sh_adopt;
+    __shared__ GjMove sh_mv;
+
+    const GjSelectArgs& A = F.A;
+    const int island = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const int K = A.K, n = P.n_vars;
+    const size_t n_pad = ((size_t)n + 3) & ~(size_t)3;
+    // carve
+    size_t o = 0;
+    int32_t* t = (int32_t*)(smem_raw + o) + 4; o += (n_pad + 8) * 4;
+    int32_t* e32 = (int32_t*)(smem_raw + o); o += (((size_t)n + 1 + 3) & ~(size_t)3) * 4;
+    uint32_t* table = (uint32_t*)(smem_raw + o); o += (((size_t)A.tabu_words_per_island + 3) & ~(size_t)3) * 4;
+    int32_t* cnt = (int32_t*)(smem_raw + o); o += (size_t)F.cnt_stride * 4;
+    o = (o + 15) & ~(size_t)15;
+    double* e64 = (double*)(smem_raw + o);
+
+    int32_t* cur_row = A.cur + (size_t)island * A.stride;
+    double* edge_g = F.edge + (size_t)island * (size_t)F.edge_stride;
+    const size_t L = (size_t)P.n_locations;
+    auto stamp = [&](int k) {
+        if (F.phase_clocks && tid == 0) F.phase_clocks[(size_t)island * 8 + k] = clock64();
+    };
+    stamp(0);
+
+    // ---- P0: stage ---------------------------------------------------------------------------------
+    if (tid == 0) {
+        gj_mbar_init(&sh_mbar, 1);
+        sh_nwork = 0;
+        sh_adopt = gj_adopt_decide(A, island) ? 1 : 0;     // update_global_top, adopt half
+    }
+    __syncthreads();
+    const bool adopted = sh_adopt != 0;
+    const int state_stale = F.stale[island];
+    if (tid == 0) {
+        const uint32_t row_bytes = (uint32_t)(n_pad * 4);
+        const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
+        const uint32_t edge_bytes = state_stale ? 0u : (uint32_t)((size_t)F.edge_stride * 8);
+        gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes + edge_bytes);
+        gj_tma_load_1d(t, adopted ? A.gbest : cur_row, row_bytes, &sh_mbar);
+        if (tabu_bytes) gj_tma_load_1d(table, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
+        if (edge_bytes) gj_tma_load_1d(e64, edge_g, edge_bytes, &sh_mbar);
+    }
+    gj_mbar_wait(&sh_mbar, 0);
+    if (tid == 0) { t[-1] = 0; t[n] = 0; }               // depot before the first and after the last stop
+    if (adopted)
+        for (int i = tid; i < n; i += NT) cur_row[i] = t[i];
+    __syncthreads();
+    if (state_stale) {
+        // the tour was replaced since the last step: all n + 1 edge lengths from the matrix
+        for (int i = tid; i <= n; i += NT) {
+            const double d = __ldg(&P.D[(size_t)t[i - 1] * L + (size_t)t[i]]);
+            e64[i] = d;
+            edge_g[i] = d;
+        }
+        if (tid == 0) F.stale[island] = 0;
+        __syncthreads();
+    }
+    for (int i = tid; i <= n; i += NT) e32[i] = (int32_t)__double2int_rn(e64[i] * 1000.0);
+    if (tid == 0) sh_curkey = gj_tsf_milli_index(A.cur_score[(size_t)island * GJ_MAX_LEVELS + 1]);
+    sh_selinfo[tid] = 0;
+    __syncthreads();
+
+    const uint32_t* table_ro = A.tabu_bits ? table : nullptr;
+    const int W = (F.glen + 31) >> 5;
+    const int32_t* free_list = table_ro ? (const int32_t*)(table + 2 * (W + 1)) : nullptr;
+    const int n_free = table_ro ? ((const int32_t*)table)[2 * W + 1] : 0;
+    // Mover::select_non_tabu_ids: a fully tabu group falls back to plain choice (gj_pick_positions)
+    const bool use_tabu = free_list != nullptr && n_free >= 2;
+    const uint32_t Fd = use_tabu ? (uint32_t)n_free : (uint32_t)F.glen;
+    const uint32_t gisl = (uint32_t)(A.island_base + island);
+    const uint32_t key0 = (uint32_t)A.seed ^ (gisl * 0x9E3779B1u), key1 = (uint32_t)(A.seed >> 32) + gisl;
+    const uint32_t step_lo = (uint32_t)A.step, step_hi = (uint32_t)(A.step >> 32);
+    const int32_t* __restrict__ D32 = P.D32;
+    const int Li = P.n_locations;
+    const double cur_h = A.cur_score[(size_t)island * GJ_MAX_LEVELS + 0];
+    const int n_chunks = (K + NT - 1) / NT;
+    int* worklist = F.worklist + (size_t)island * K;
+
+    stamp(1);
+    // ---- P1: generate + score ------------------------------------------------------------------------
+    // the hot loop's neighbours never change the duplicate count: their key is the 32-bit length change
+    int best32 = 0x7fffffff;
+    int best_idx = -1;
+#pragma unroll 2
+    for (int c = tid; c < K; c += NT) {
+        uint32_t ctr[4] = {step_lo, (uint32_t)c, step_hi, 0u}, key[2] = {key0, key1}, x[4];
+        gj_philox_block(ctr, key, x);
+        // draws in the order gj_generate_move consumes them: x[3] kind, x[2] group (one group: unused),
+        // x[1] and x[0] the two position ranks
+        const uint32_t xk = x[3];
+        int kind = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) kind += (xk > F.kind_thr[i]) ? 1 : 0;
+        const bool last_chunk = c >= (n_chunks - 1) * NT;
+        if (!((0x32u >> kind) & 1u)) {                      // not swap / insertion / inverse
+            worklist[atomicAdd(&sh_nwork, 1)] = c;
+            if (last_chunk) sh_selinfo[tid] = 0xff;         // P4 regenerates it
+            continue;
+        }
+        const int r0 = (int)__umulhi(x[1], Fd);
+        int r1 = (int)__umulhi(x[0], Fd - 1u);
+        r1 += (r1 >= r0) ? 1 : 0;
+        const int a0 = use_tabu ? free_list[r0] : r0;
+        const int a1 = use_tabu ? free_list[r1] : r1;
+        if (last_chunk) { sh_sel0[tid] = a0; sh_sel1[tid] = a1; sh_selinfo[tid] = 3; }   // two ids, group 0
+        const int p = F.first + min(a0, a1), q = F.first + max(a0, a1);
+        const int pm = t[p - 1], tp = t[p], pn = t[p + 1];
+        const int qm = t[q - 1], tq = t[q], qp = t[q + 1];
+        const bool adj = (q == p + 1);
+        const bool inv = (kind == 5);
+        const bool ins_l = (kind == 4) && (a0 < a1);        // t[p] travels to the end
+        const bool ins_r = (kind == 4) && !ins_l;           // t[q] travels to the front
+        const bool swp_far = (kind == 1) && !adj;
+        const int x0 = ins_l ? pn : tq;
+        const int y1 = ins_r ? qm : tp;
+        const int a2b = swp_far ? pn : tp;
+        // removed edges: the island's own edge cache; added edges: D32 in L2 (see gj_tsp_move_delta)
+        int removed = e32[p] + e32[q + 1];
+        int added = __ldg(&D32[pm * Li + x0]) + __ldg(&D32[y1 * Li + qp]);
+        if (!inv) { removed += e32[ins_r ? q : p + 1]; added += __ldg(&D32[tq * Li + a2b]); }
+        if (swp_far) { removed += e32[q]; added += __ldg(&D32[qm * Li + tp]); }
+        const int k32 = added - removed;
+        const long long k64 = (long long)k32;
+        if (TRACE && F.moves_out) {
+            GjMove m;
+            m.kind = (uint8_t)kind; m.group = 0; m.k = 2; m.pad = 0;
+#pragma unroll
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) { m.a[i] = 0; m.v[i] = 0; }
+            m.a[0] = a0; m.a[1] = a1;
+            F.moves_out[(size_t)island * K + c] = m;
+        }
+        if (TRACE && F.scores_out) {
+            double* so = F.scores_out + ((size_t)island * K + c) * 2;
+            so[0] = cur_h; so[1] = gj_tsf_from_index(sh_curkey + k64);
+        }
+        if (k32 < best32) { best32 = k32; best_idx = c; }      // increasing c: the first minimum stays
+    }
+    long long best_key = best_idx >= 0 ? (long long)best32 : 0x7fffffffffffffffll;
+    __syncthreads();
+
+    // ---- P1b: the queued neighbours (generic generator + delta evaluator, out of line) -----------------
+    const int n_work = sh_nwork;
+    if (n_work > 0) {
+        for (int i = tid; i < F.cnt_stride; i += NT) cnt[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) atomicAdd(&cnt[t[i] - P.val_lo], 1);
+        __syncthreads();
+        for (int w = tid; w < n_work; w += NT) {
+            const int c = worklist[w];
+            const long long k64 = gj_tsf_slow_key(P, G, A, table_ro, t, cnt, island, c,
+                                                  (TRACE && F.moves_out) ? F.moves_out + (size_t)island * K + c : nullptr);
+            if (TRACE && F.scores_out) {
+                int du; long long dm;
+                gj_tsf_unkey(k64, du, dm);
+                double* so = F.scores_out + ((size_t)island * K + c) * 2;
+                so[0] = cur_h - (double)du; so[1] = gj_tsf_from_index(sh_curkey + dm);
+            }
+            if (k64 < best_key || (k64 == best_key && c < best_idx)) { best_key = k64; best_idx = c; }
+        }
+    }
+
+    stamp(2);
+    // ---- P2: first minimum (tabu_search_base.rs:166-171) + acceptance (:174) ---------------------------
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const long long ok = __shfl_xor_sync(GJ_FULL_MASK, best_key, off);
+        const int oi = __shfl_xor_sync(GJ_FULL_MASK, best_idx, off);
+        if (oi >= 0 && (best_idx < 0 || ok < best_key || (ok == best_key && oi < best_idx))) { best_key = ok; best_idx = oi; }
+    }
+    if (lane == 0) { sh_wkey[warp] = best_key; sh_widx[warp] = best_idx; }
+    __syncthreads();
+    if (tid == 0) {
+        long long bk = sh_wkey[0]; int bi = sh_widx[0];
+        for (int w = 1; w < nwarps; ++w) {
+            const long long ok = sh_wkey[w]; const int oi = sh_widx[w];
+            if (oi >= 0 && (bi < 0 || ok < bk || (ok == bk && oi < bi))) { bk = ok; bi = oi; }
+        }
+        // candidate <= current (tabu_search_base.rs:174): hard level first, then the milli-unit index
+        const bool accept = bi >= 0 && bk <= 0;
+        sh_accept = accept ? 1 : 0;
+        sh_best = bi;
+        sh_bestkey = bk;
+        if (accept) gj_tsf_generate(P, G, A, table_ro, island, bi, &sh_mv);
+        if (A.selected_out) { A.selected_out[island] = bi; A.accepted_out[island] = accept ? 1 : 0; }
+        atomicAdd(&A.counters[0], (unsigned long long)K);
+        if (island == 0) atomicAdd(&A.counters[1], 1ull);
+        if (accept) atomicAdd(&A.counters[2], 1ull);
+    }
+    __syncthreads();
+
+    stamp(3);
+    // ---- P3: apply, write back, patch the edges, exact re-score, update_top_individual ----------------
+    if (sh_accept) {
+        const GjMove m = sh_mv;
+        gj_apply_move(P, m, G, true, A.noop != 0, tid, NT,
+                      [&](int id) { return cur_row[id]; }, [&](int id, int v) { t[id] = v; });
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) cur_row[i] = t[i];
+        const bool identity = m.kind == GJ_MOVE_NULL || (A.noop && (m.kind == 3 || (m.kind == 2 && m.k == 2)));
+        if (!identity) {
+            const int c0 = F.first + m.a[0], c1 = F.first + m.a[1];
+            const int p = min(c0, c1), q = max(c0, c1);
+            auto regather = [&](int i) {
+                if (i >= 0 && i <= n) {
+                    const double d = __ldg(&P.D[(size_t)t[i - 1] * L + (size_t)t[i]]);
+                    e64[i] = d; edge_g[i] = d;
+                }
+            };
+            if (m.kind == 1 && m.k == 2) {
+                if (tid == 0) regather(p);
+                if (tid == 1) regather(p + 1);
+                if (tid == 2) regather(q);
+                if (tid == 3) regather(q + 1);
+            } else if (m.kind == 5) {
+                // symmetric matrix: the interior edges p+1 .. q keep their lengths in reverse order
+                const int len = q - p;
+                for (int j = tid; j < len / 2; j += NT) {
+                    const double xa = e64[p + 1 + j], ya = e64[q - j];
+                    e64[p + 1 + j] = ya; e64[q - j] = xa;
+                    edge_g[p + 1 + j] = ya; edge_g[q - j] = xa;
+                }
+                if (tid == 0) regather(p);
+                if (tid == 1) regather(q + 1);
+            } else if (m.kind == 4) {
+                for (int i = p + tid; i <= q + 1; i += NT) regather(i);
+            } else {
+                for (int i = tid; i <= n; i += NT) regather(i);       // generic small move
+            }
+        }
+        __syncthreads();
+        // the accepted neighbour's stored score = FULL evaluation of the stored vector: hard from the
+        // exact duplicate count, soft as the reference's own fold (tsp ISC :76-80) or the integer sum
+        int du; long long dm;
+        gj_tsf_unkey(sh_bestkey, du, dm);
+        const double hard = cur_h - (double)du;
+        if (P.exact_sums) {
+            if (tid == 0) {
+                double fold = 0.0;
+#pragma unroll 8
+                for (int i = 1; i < n; ++i) fold = fold + e64[i];
+                double sample_distance = 0.0;
+                sample_distance += e64[0];                 // D[0][s0]
+                sample_distance += e64[n];                 // D[s_last][0]
+                sample_distance += fold;
+                GjScore sc;
+                sc.v[0] = hard; sc.v[1] = sample_distance; sc.v[2] = 0.0;
+                // ISC: both levels carry weights[0] == 1 (checked by the host): 0.0 + 1.0 * x == x
+                gj_score_round(sc, P);
+                A.cur_score[(size_t)island * GJ_MAX_LEVELS + 0] = sc.v[0];
+                A.cur_score[(size_t)island * GJ_MAX_LEVELS + 1] = sc.v[1];
+                A.cur_score[(size_t)island * GJ_MAX_LEVELS + 2] = 0.0;
+                A.dirty[island] = 1;
+            }
+        } else {
+            long long acc = 0;
+            for (int i = tid; i <= n; i += NT) acc += (long long)__double2int_rn(e64[i] * 1000.0);
+            acc = gj_warp_sum(acc);
+            if (lane == 0) sh_isum[warp] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                long long tot = 0;
+                for (int w = 0; w < nwarps; ++w) tot += sh_isum[w];
+                A.cur_score[(size_t)island * GJ_MAX_LEVELS + 0] = hard;
+                A.cur_score[(size_t)island * GJ_MAX_LEVELS + 1] = gj_tsf_from_index(tot);
+                A.cur_score[(size_t)island * GJ_MAX_LEVELS + 2] = 0.0;
+                A.dirty[island] = 1;
+            }
+        }
+        __syncthreads();
+    }
+    gj_update_top(island, A.levels, A.stride, n, A.cur, A.cur_score, A.best, A.best_score, A.dirty);
+
+    stamp(4);
+    // ---- P4: tabu deque update (mover.rs:75-96; see gj_tabu_deque_advance) -------------------------------
+    if (A.tabu_bits) {
+        uint32_t* bits_rw = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
+        const int32_t* ring_old = A.tabu_ring_old + (size_t)island * A.tabu_ring_per_island + A.tabu_ring_off[0];
+        int32_t* ring_new = A.tabu_ring_new + (size_t)island * A.tabu_ring_per_island + A.tabu_ring_off[0];
+        const int T = A.tabu_size[0];
+        const int fill_old = A.tabu_fill[island * A.n_groups];
+        int collected = 0;
+        for (int chunk = n_chunks - 1; chunk >= 0 && collected < T; --chunk) {
+            const int j = chunk * NT + tid;
+            int sel[GJ_MOVE_MAXK]; int cntsel = 0;
+            if (j < K) {
+                const int info = sh_selinfo[tid];
+                if (chunk == n_chunks - 1 && info != 0xff) {
+                    if (info == 3) { cntsel = 2; sel[0] = sh_sel0[tid]; sel[1] = sh_sel1[tid]; }
+                } else {
+                    GjMove m;
+                    gj_tsf_generate(P, G, A, table_ro, island, j, &m);
+                    if (m.kind != GJ_MOVE_NULL) cntsel = gj_move_selected(m, sel);
+                }
+            }
+            sh_scan[tid] = cntsel;
+            __syncthreads();
+            for (int off = 1; off < NT; off <<= 1) {
+                const int xv = (tid + off < NT) ? sh_scan[tid + off] : 0;
+                __syncthreads();
+                sh_scan[tid] += xv;
+                __syncthreads();
+            }
+            const int total = sh_scan[0];
+            const int after = sh_scan[tid] - cntsel;
+#pragma unroll
+            for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
+                if (i < cntsel) {
+                    const int rank = collected + after + (cntsel - 1 - i);
+                    if (rank < T) ring_new[rank] = sel[i];
+                }
+            }
+            __syncthreads();
+            collected += total;
+        }
+        for (int r = collected + tid; r < T; r += NT) {
+            const int rho = r - collected;
+            if (rho < fill_old) ring_new[r] = ring_old[rho];
+        }
+        const int fill = min(T, fill_old + collected);
+        __syncthreads();
+        if (tid == 0) A.tabu_fill[island * A.n_groups] = fill;
+        gj_tabu_table_rebuild(bits_rw + A.tabu_word_off[0], F.glen, ring_new, fill, sh_scan);
+    }
+    stamp(5);
+}

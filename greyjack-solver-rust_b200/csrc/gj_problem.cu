@@ -97,6 +97,43 @@ __global__ void gj_check_symmetric_kernel(const double* __restrict__ D, int n, i
     }
 }
 
+// Fixed-point copy of the matrix: D32[i][j] = rint(D[i][j] * 1000).  The examples truncate every
+// distance to 3 decimals (location.rs:42-47), so the matrix is a table of milli-units; `flag` drops
+// to 0 if an entry is not within 1e-6 of a whole milli-unit or too large for sums of four in int32.
+__global__ void gj_build_d32_kernel(const double* __restrict__ D, size_t total, int32_t* __restrict__ D32, int* flag) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const double x = D[idx] * 1000.0;
+        const double r = rint(x);
+        if (!(fabs(x - r) <= 1e-6) || !(r >= 0.0) || r > 268435456.0) atomicExch(flag, 0);
+        D32[idx] = (int32_t)fmin(fmax(r, 0.0), 268435456.0);
+    }
+}
+
+// Builds (once) the milli-unit matrix; p->d32_state: 0 = not tried, 1 = valid, -1 = the matrix is not
+// a table of milli-units (delta scoring then stays in f64).
+gj_status gj_problem_ensure_d32(gj_problem* p) {
+    if (p->d32_state != 0) return GJ_OK;
+    p->d32_state = -1;
+    if (!p->dev.D || p->dev.n_locations <= 0) return GJ_OK;
+    GJ_CUDA_TRY(cudaSetDevice(p->device));
+    const size_t total = (size_t)p->dev.n_locations * (size_t)p->dev.n_locations;
+    int32_t* d32 = nullptr;
+    int* flag = nullptr;
+    if (cudaMalloc(&d32, total * 4) != cudaSuccess) { cudaGetLastError(); return GJ_OK; }   // no room: stay in f64
+    p->allocs.push_back(d32);
+    GJ_CUDA_TRY(cudaMalloc(&flag, 4));
+    int one = 1;
+    GJ_CUDA_TRY(cudaMemcpy(flag, &one, 4, cudaMemcpyHostToDevice));
+    gj_build_d32_kernel<<<148 * 8, 256, 0, p->stream>>>(p->dev.D, total, d32, flag);
+    GJ_LAUNCH_CHECK();
+    GJ_CUDA_TRY(cudaStreamSynchronize(p->stream));
+    GJ_CUDA_TRY(cudaMemcpy(&one, flag, 4, cudaMemcpyDeviceToHost));
+    cudaFree(flag);
+    if (one) { p->dev.D32 = d32; p->d32_state = 1; }
+    return GJ_OK;
+}
+
 static bool fits_i32(double x) { return x >= -2147483647.0 && x <= 2147483647.0 && x == x; }
 
 // host restatement of GJInteger::fix on a bound (only used to pre-round the bounds)

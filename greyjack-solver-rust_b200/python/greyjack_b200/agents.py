@@ -19,7 +19,7 @@ from . import _lib
 from .problem import Problem, _ptr
 
 TS, LA, GA, SA = 0, 1, 2, 3
-SCORING_FULL, SCORING_DELTA, SCORING_DELTA_UNFUSED = 0, 1, 2     # GJ_SCORING_* (include/greyjack_b200.h)
+SCORING_FULL, SCORING_DELTA, SCORING_DELTA_UNFUSED, SCORING_DELTA_F64 = 0, 1, 2, 3     # GJ_SCORING_* (include/greyjack_b200.h)
 
 
 # ---- termination strategies (TerminationStrategiesVariants::{StL, TSL, SNI, ScL}) ------------
@@ -113,7 +113,8 @@ class _Builder:
         p.migration_frequency = int(self.migration_frequency)
         p.reference_noop_moves = int(getattr(self, "reference_noop_moves", True))
         mode = getattr(self, "scoring", "full")
-        p.scoring_mode = {"full": SCORING_FULL, "delta": SCORING_DELTA, "delta_unfused": SCORING_DELTA_UNFUSED}[mode]
+        p.scoring_mode = {"full": SCORING_FULL, "delta": SCORING_DELTA, "delta_unfused": SCORING_DELTA_UNFUSED,
+                          "delta_f64": SCORING_DELTA_F64}[mode]
         p.chain_steps_per_launch = int(getattr(self, "chain_steps_per_launch", 0))
         return p
 

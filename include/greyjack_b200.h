@@ -76,9 +76,13 @@ enum {
           does not cover (listed in DESIGN.md) are re-scored by the FULL kernel inside the
           same step.                                                                        */
 enum { GJ_SCORING_FULL = 0, GJ_SCORING_DELTA = 1,
-       GJ_SCORING_DELTA_UNFUSED = 2   /* DELTA as separate kernels (generate+score | select |
+       GJ_SCORING_DELTA_UNFUSED = 2,  /* DELTA as separate kernels (generate+score | select |
                                          refresh); what DELTA falls back to when an island does
-                                         not fit in shared memory.  Exposed for tests / ablation. */ };
+                                         not fit in shared memory.  Exposed for tests / ablation. */
+       GJ_SCORING_DELTA_F64 = 3       /* DELTA without the fixed-point TabuSearch step DELTA picks for
+                                         TSP on a milli-unit matrix (neighbours ordered by integer
+                                         tour-length changes): the same fused kernel in f64.  Exposed
+                                         for tests / ablation.                                      */ };
 
 /* Agents = AgentBuildersVariants (agents/agent_builders_variants.rs:9-18). */
 enum { GJ_AGENT_TABU_SEARCH = 0, GJ_AGENT_LATE_ACCEPTANCE = 1, GJ_AGENT_GENETIC_ALGORITHM = 2,
@@ -353,7 +357,7 @@ GJ_API gj_status gj_islands_ga_population(gj_islands* g, int32_t island, double*
 GJ_API gj_status gj_islands_trace_tabu(gj_islands* g, int32_t island, int32_t group, int32_t* ids,
                                        int32_t capacity, int32_t* fill, int32_t* size);
 
-/* Name of the kernel path a step of this group takes, chosen at creation: "fused", "fused_lean",
+/* Name of the kernel path a step of this group takes, chosen at creation: "fused", "fused_fixed", "fused_lean",
    "chain", "vrp_chain", "delta", "vrp_delta", "full" or "ga" (static string).                     */
 GJ_API const char* gj_islands_step_path(const gj_islands* g);
 

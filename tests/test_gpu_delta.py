@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 QUANTUM = 1.0e-3 * (1 + 1e-9)
 # "delta": the fused single-kernel step (gj_islands_fused.cuh); "delta_unfused": the same
 # arithmetic as separate kernels (what DELTA uses when an island does not fit in shared memory)
-SCORINGS = ["delta", "delta_unfused"]
+# "delta_f64": the fused step in f64 where "delta" would pick the fixed-point TSP step (gj_islands_tsfast.cuh)
+SCORINGS = ["delta", "delta_f64", "delta_unfused"]
 
 
 def _check_delta_scores(got, want_unrounded, spec, oracle):

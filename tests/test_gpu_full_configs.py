@@ -91,8 +91,9 @@ def _replay_ts_step(isl, island, spec, op, oracle, exact):
     return acc
 
 
+@pytest.mark.parametrize("scoring", ["delta", "delta_f64"], ids=["fixed-point", "f64"])
 @pytest.mark.parametrize("exact", [True, False], ids=["exact-sums", "tree-sums"])
-def test_c2_tsp1000_tabu_fused_bench_shape(exact, oracle):
+def test_c2_tsp1000_tabu_fused_bench_shape(exact, scoring, oracle):
     """C2 exactly as bench.py runs it: TSP-1000 seed 1, TabuSearch(4096 neighbours, tabu 0.5,
     compare_to_global, swap + 2-opt, migration every 10), 592 islands, the fused delta-scoring step
     with 16 neighbours per thread and a multi-chunk tabu update -- traced on the first, a middle and
@@ -101,9 +102,9 @@ def test_c2_tsp1000_tabu_fused_bench_shape(exact, oracle):
     op = oracle.OracleProblem(spec)
     gp = Problem(spec)
     gp.set_exact_sums(exact)
-    isl = TabuSearch(4096, 0.5, True, None, [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 10, scoring="delta").build_agent(
+    isl = TabuSearch(4096, 0.5, True, None, [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 10, scoring=scoring).build_agent(
         gp, n_islands=592, seed=1000)
-    assert isl.step_path.startswith("fused")
+    assert isl.step_path == ("fused_fixed" if scoring == "delta" else "fused")
     islands = (0, 295, 591)
     accepted = 0
     for i in islands:                                   # fresh islands, empty deques
