@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--e2e-agents", type=int, default=4)
     ap.add_argument("--scoring", default="delta", choices=["delta", "full"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -315,6 +316,12 @@ def main():
                      "candidates_per_launch": per_launch_cands},
     }
 
+    if args.no_e2e:
+        line["clocks"] = sampler.summary()
+        line["step_path"] = isl.step_path
+        if rank == 0:
+            print(json.dumps(line))
+        return
     if rank != 0:
         sampler.summary()
     if rank == 0:

@@ -190,6 +190,34 @@ __device__ __forceinline__ double gj_block_sum(double x, double* scratch) {
     return tot;
 }
 
+// CTA-wide inclusive prefix sum (every thread gets the sum of x over threads 0..tid; *total = the CTA's
+// sum).  `warp_tot` holds 33 ints of shared memory.  Two barriers, whatever the CTA size.
+__device__ __forceinline__ int gj_block_scan_incl(int x, int* warp_tot, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(GJ_FULL_MASK, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();                       // warp_tot may still be read from a previous call
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? warp_tot[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(GJ_FULL_MASK, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_tot[lane] = w;                // inclusive over warps
+        if (lane == 31) warp_tot[32] = w;
+    }
+    __syncthreads();
+    if (warp > 0) x += warp_tot[warp - 1];
+    if (total) *total = warp_tot[32];
+    return x;
+}
+
 // ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) + mbarrier ------------------------------
 // Stages a contiguous table (a solution row, a tabu table, a fact table) from global to shared
 // memory with one instruction issued by one thread; consumers wait on the mbarrier's phase.

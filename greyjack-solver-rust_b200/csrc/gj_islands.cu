@@ -675,7 +675,7 @@ __global__ void k_i32_to_f64(const int32_t* __restrict__ in, double* __restrict_
 // ===================================================================================================
 
 gj_islands::~gj_islands() {
-    cudaSetDevice(p->device);
+    cudaSetDevice(device);
     if (phase_clocks) {
         // development aid: phase durations (cycles) of the LAST fused step, island 0 and the mean
         std::vector<long long> h((size_t)I * 8);
@@ -796,6 +796,7 @@ static gj_status build_thresholds(const gj_agent_params& prm, double* thr) {
 
 gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_params* prm) {
     g->p = p;
+    g->device = p->device;
     g->prm = *prm;
     g->I = prm->n_islands;
     g->levels = p->dev.levels;
@@ -807,15 +808,17 @@ gj_status gj_islands_common_init(gj_islands* g, gj_problem* p, const gj_agent_pa
     g->mover.tabu_entity_rate = prm->tabu_entity_rate;
     g->mover.mutation_rate_multiplier = prm->has_mutation_rate_multiplier ? prm->mutation_rate_multiplier : 0.0;
     // change count of a change / swap / swap_edges move ~ Binomial(n_vars, multiplier / group_len)
-    // (mover.rs:138-140); a move descriptor holds at most GJ_MOVE_MAXK positions, so the draw is
-    // truncated at 8.  With a mean <= 4 that truncation touches < 2.2 % of the moves (declared in
-    // DESIGN.md); larger means are refused instead of silently distorted.
+    // (mover.rs:138-140, unbounded); a device move descriptor holds GJ_MOVE_MAXK = 8 positions, so the
+    // draw is truncated at 8 (declared in DESIGN.md section 2).  The reference's examples run at a mean of
+    // <= 2 (multiplier <= 1, groups of n_vars / 2), where the truncation touches < 0.03 % of the moves;
+    // 2.1 % at a mean of 4, 41 % at 8.  Beyond that the move-size distribution would mostly be the cap:
+    // refused instead of silently distorted.
     for (auto& grp : p->groups) {
         if (grp.empty()) continue;
         const double mean = g->mover.mutation_rate_multiplier * (double)p->dev.n_vars / (double)grp.size();
-        if (mean > 4.0 + 1e-9)
-            return gj_fail(GJ_ERR_UNSUPPORTED, "mutation_rate_multiplier * n_vars / group_len > 4: a move would change more "
-                                                "than the 8 positions a device move descriptor holds");
+        if (mean > 8.0 + 1e-9)
+            return gj_fail(GJ_ERR_UNSUPPORTED, "mutation_rate_multiplier * n_vars / group_len > 8: most moves would change "
+                                                "more than the 8 positions a device move descriptor holds");
     }
 
     // semantic groups

@@ -10,6 +10,7 @@
 
 struct gj_islands {
     gj_problem* p = nullptr;
+    int device = 0;              // p->device (kept here: the handle may outlive a destroyed problem in a failing caller)
     gj_agent_params prm{};
     int I = 0;                   // islands in the group
     int K = 1;                   // candidates per island per step (TS: neighbours; LA: 1)

@@ -103,7 +103,7 @@ __device__ __forceinline__ void gj_update_top(int island, int levels, int stride
 
 // Rebuilds one group's tabu table (membership bits, then the exclusive prefix count of free
 // positions per word; layout in gj_moves.cuh) from its deque.  Cooperative over the CTA;
-// `scan` holds blockDim ints of shared memory.
+// `scan` holds max(blockDim, 33) ints of shared memory.
 __device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen, const int32_t* ring,
                                                       int fill, int* scan) {
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -126,16 +126,10 @@ __device__ __forceinline__ void gj_tabu_table_rebuild(uint32_t* table, int glen,
             const uint32_t valid = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
             f = __popc(~table[w] & valid);
         }
-        scan[tid] = f;
-        __syncthreads();
-        for (int o = 1; o < nthr; o <<= 1) {
-            const int x = (tid >= o) ? scan[tid - o] : 0;
-            __syncthreads();
-            scan[tid] += x;
-            __syncthreads();
-        }
-        if (w < W) prefix[w] = carry + scan[tid] - f;
-        carry += scan[nthr - 1];
+        int chunk_total;
+        const int incl = gj_block_scan_incl(f, scan, &chunk_total);
+        if (w < W) prefix[w] = carry + incl - f;
+        carry += chunk_total;
         __syncthreads();
     }
     if (tid == 0) prefix[W] = carry;
@@ -178,16 +172,9 @@ __device__ __forceinline__ void gj_tabu_deque_advance(uint32_t* bits_rw, const i
                 if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
             }
             // ids pushed by later candidates of this chunk (exclusive suffix sum)
-            scan[tid] = cnt;
-            __syncthreads();
-            for (int o = 1; o < blockDim.x; o <<= 1) {
-                const int x = (tid + o < blockDim.x) ? scan[tid + o] : 0;
-                __syncthreads();
-                scan[tid] += x;
-                __syncthreads();
-            }
-            const int total = scan[0];
-            const int after = scan[tid] - cnt;
+            int total;
+            const int incl = gj_block_scan_incl(cnt, scan, &total);
+            const int after = total - incl;
 #pragma unroll
             for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
                 if (i < cnt) {

@@ -524,16 +524,9 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
                         if (m.kind != GJ_MOVE_NULL && m.group == g) cnt = gj_move_selected(m, sel);
                     }
                 }
-                sh_scan[tid] = cnt;
-                __syncthreads();
-                for (int o = 1; o < blockDim.x; o <<= 1) {
-                    const int x = (tid + o < blockDim.x) ? sh_scan[tid + o] : 0;
-                    __syncthreads();
-                    sh_scan[tid] += x;
-                    __syncthreads();
-                }
-                const int total = sh_scan[0];
-                const int after = sh_scan[tid] - cnt;
+                int total;
+                const int incl = gj_block_scan_incl(cnt, sh_scan, &total);
+                const int after = total - incl;
 #pragma unroll
                 for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
                     if (i < cnt) {

@@ -64,11 +64,12 @@ __device__ __forceinline__ void gj_tsf_unkey(long long key, int& d_uniq, long lo
     delta_milli = key - (h << GJ_TSF_HSHIFT);
 }
 
-// milli-unit index of a stored score level: floor(v) * 1000 + floor(frac * 1000), the integer pair
-// ScoreTrait::round (math_utils.rs:10-13) is built from
+// milli-unit index of a stored score level (the integer ScoreTrait::round, math_utils.rs:10-13,
+// is built from)
 __device__ __forceinline__ long long gj_tsf_milli_index(double v) {
-    const double fl = floor(v);
-    return (long long)fl * 1000ll + (long long)floor((v - fl) * 1000.0);
+    // nearest, not floor: a stored score is either already rounded (fl + j / 1000, whose fraction
+    // times 1000 may land a hair under j) or an unrounded initial fold within 1e-9 of a whole index
+    return llrint(v * 1000.0);
 }
 // ... and the score value the reference's rounding produces for that index
 __device__ __forceinline__ double gj_tsf_from_index(long long k) {
@@ -137,23 +138,43 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     stamp(0);
 
     // ---- P0: stage ---------------------------------------------------------------------------------
+    // Everything the step's serial prologue touches is cold after another island group / kernel used
+    // the L2: the lanes of warp 1 pull those lines in while thread 0 starts the bulk copies, so the
+    // adoption test below runs on L2 hits instead of a chain of HBM round trips.
+    const uint32_t row_bytes = (uint32_t)(n_pad * 4);
+    const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
+    const uint32_t edge_bytes = (uint32_t)((size_t)F.edge_stride * 8);
+    if (warp == 1) {
+        const void* pf = nullptr;
+        switch (lane) {
+            case 0: pf = A.gver; break;
+            case 1: pf = A.gseen + island; break;
+            case 2: pf = A.gbest_score; break;
+            case 3: pf = A.best_score + (size_t)island * GJ_MAX_LEVELS; break;
+            case 4: pf = A.cur_score + (size_t)island * GJ_MAX_LEVELS; break;
+            case 5: pf = F.stale + island; break;
+            case 6: pf = A.dirty + island; break;
+            case 7: pf = A.tabu_fill ? A.tabu_fill + (size_t)island * A.n_groups : nullptr; break;
+            case 8: pf = A.tabu_size; break;
+            case 9: pf = A.tabu_ring_off; break;
+            case 10: pf = A.tabu_word_off; break;
+            default: break;
+        }
+        if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
     if (tid == 0) {
         gj_mbar_init(&sh_mbar, 1);
         sh_nwork = 0;
-        sh_adopt = gj_adopt_decide(A, island) ? 1 : 0;     // update_global_top, adopt half
+        gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes + edge_bytes);
+        if (tabu_bytes) gj_tma_load_1d(table, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
+        gj_tma_load_1d(e64, edge_g, edge_bytes, &sh_mbar);       // overwritten below when the tour was replaced
+        const bool adopt = gj_adopt_decide(A, island);            // update_global_top, adopt half
+        sh_adopt = adopt ? 1 : 0;
+        gj_tma_load_1d(t, adopt ? A.gbest : cur_row, row_bytes, &sh_mbar);
     }
     __syncthreads();
     const bool adopted = sh_adopt != 0;
     const int state_stale = F.stale[island];
-    if (tid == 0) {
-        const uint32_t row_bytes = (uint32_t)(n_pad * 4);
-        const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
-        const uint32_t edge_bytes = state_stale ? 0u : (uint32_t)((size_t)F.edge_stride * 8);
-        gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes + edge_bytes);
-        gj_tma_load_1d(t, adopted ? A.gbest : cur_row, row_bytes, &sh_mbar);
-        if (tabu_bytes) gj_tma_load_1d(table, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
-        if (edge_bytes) gj_tma_load_1d(e64, edge_g, edge_bytes, &sh_mbar);
-    }
     gj_mbar_wait(&sh_mbar, 0);
     if (tid == 0) { t[-1] = 0; t[n] = 0; }               // depot before the first and after the last stop
     if (adopted)
@@ -406,16 +427,9 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
                     if (m.kind != GJ_MOVE_NULL) cntsel = gj_move_selected(m, sel);
                 }
             }
-            sh_scan[tid] = cntsel;
-            __syncthreads();
-            for (int off = 1; off < NT; off <<= 1) {
-                const int xv = (tid + off < NT) ? sh_scan[tid + off] : 0;
-                __syncthreads();
-                sh_scan[tid] += xv;
-                __syncthreads();
-            }
-            const int total = sh_scan[0];
-            const int after = sh_scan[tid] - cntsel;
+            int total;
+            const int incl = gj_block_scan_incl(cntsel, sh_scan, &total);
+            const int after = total - incl;
 #pragma unroll
             for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
                 if (i < cntsel) {

@@ -15,7 +15,7 @@ from test_gpu_islands import ALL, MIX, _final_state, _oracle_move, _same_score
 
 pytestmark = pytest.mark.gpu
 
-QUANTUM = 1.0e-3 * (1 + 1e-9)
+QUANTUM = 1.0e-3 + 1e-8      # one ScoreTrait::round quantum (+ f64 noise of subtracting two ~1e4 scores)
 # "delta": the fused single-kernel step (gj_islands_fused.cuh); "delta_unfused": the same
 # arithmetic as separate kernels (what DELTA uses when an island does not fit in shared memory)
 # "delta_f64": the fused step in f64 where "delta" would pick the fixed-point TSP step (gj_islands_tsfast.cuh)
