@@ -239,6 +239,12 @@ __device__ __forceinline__ void gj_tma_load_1d(void* smem_dst, const void* gmem_
                  ::"r"(gj_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(gj_smem_u32(mbar))
                  : "memory");
 }
+// Pulls a contiguous global range into L2 without a destination (cp.async.bulk.prefetch.L2): turns the
+// first touches of a gather table that another kernel evicted into one streamed read.  16-byte
+// aligned address, bytes a multiple of 16.
+__device__ __forceinline__ void gj_l2_prefetch_bulk(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void gj_mbar_wait(uint64_t* mbar, uint32_t phase) {
     uint32_t done = 0;
     while (!done) {

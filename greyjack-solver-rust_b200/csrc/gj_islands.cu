@@ -587,55 +587,13 @@ __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, in
         for (int i = threadIdx.x; i < n_vars; i += blockDim.x) cur[(size_t)island * stride + i] = row[i];
 }
 
-// update_global_top, publish half (agent_base.rs:451-461), ONE CTA.  Agent tops only ever improve
-// and the global top is refreshed from them after every step, so the new global top is simply the
-// best agent top (first index on ties); it replaces the published one when strictly better (:451)
-// and bumps the version that gj_adopt_decide (the adopt half) watches.
 __global__ void __launch_bounds__(1024)
 k_global_top(int I, int levels, int stride, int n_vars, const int32_t* __restrict__ best,
              const double* __restrict__ best_score, int32_t* gbest, double* gbest_score, int* gver) {
     __shared__ GjScore sh_s[32];
     __shared__ int sh_i[32];
     __shared__ int sh_publish;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    GjScore mine; int mine_idx = -1;
-    mine.v[0] = mine.v[1] = mine.v[2] = 0.0;
-    for (int i = tid; i < I; i += blockDim.x) {
-        GjScore s = gj_load_score(best_score + (size_t)i * GJ_MAX_LEVELS, levels);
-        if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        GjScore other; const int oidx = __shfl_xor_sync(GJ_FULL_MASK, mine_idx, o);
-        for (int l = 0; l < GJ_MAX_LEVELS; ++l) other.v[l] = __shfl_xor_sync(GJ_FULL_MASK, mine.v[l], o);
-        if (oidx >= 0) {
-            const int c = (mine_idx < 0) ? 1 : gj_score_cmp(mine, other, levels);
-            if (c > 0 || (c == 0 && oidx < mine_idx)) { mine = other; mine_idx = oidx; }
-        }
-    }
-    if (lane == 0) { sh_s[warp] = mine; sh_i[warp] = mine_idx; }
-    __syncthreads();
-    if (tid == 0) {
-        GjScore b = sh_s[0]; int bi = sh_i[0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
-            if (sh_i[w] < 0) continue;
-            const int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_s[w], levels);
-            if (c > 0 || (c == 0 && sh_i[w] < bi)) { b = sh_s[w]; bi = sh_i[w]; }
-        }
-        sh_i[0] = bi;
-        sh_publish = 0;
-        const GjScore g = gj_load_score(gbest_score, levels);
-        if (bi >= 0 && !gj_score_le(g, b, levels)) {            // strict: agent_top < global (:451)
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
-            sh_publish = 1;
-            *gver += 1;
-        }
-    }
-    __syncthreads();
-    if (sh_publish) {
-        const int32_t* win_row = best + (size_t)sh_i[0] * stride;
-        for (int i = tid; i < n_vars; i += blockDim.x) gbest[i] = win_row[i];
-    }
+    gj_global_top_cta(I, levels, stride, n_vars, best, best_score, gbest, gbest_score, gver, sh_s, sh_i, &sh_publish);
 }
 
 // Expands move descriptors into the (column, value) lists of the reference's incremental form.
@@ -686,6 +644,11 @@ gj_islands::~gj_islands() {
             double mean = 0;
             for (int i = 0; i < I; ++i) mean += (double)(h[(size_t)i * 8 + k + 1] - h[(size_t)i * 8 + k]);
             fprintf(stderr, "[gj phase] %-10s island0 %8lld cycles, mean %10.0f\n", names[k], h[k + 1] - h[k], mean / I);
+        }
+        if (h[6]) {
+            double mean = 0;
+            for (int i = 0; i < I; ++i) mean += (double)(h[(size_t)i * 8 + 6] - h[(size_t)i * 8]);
+            fprintf(stderr, "[gj phase] P0 until the bulk copies landed: island0 %8lld cycles, mean %10.0f\n", h[6] - h[0], mean / I);
         }
     }
     for (void* a : allocs) cudaFree(a);
@@ -1151,6 +1114,12 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm_in, const d
             if (p->d32_state == 1) {
                 g->ts_edge_stride = (P.n_vars + 2) & ~1;
                 if ((rc = dev_alloc(g.get(), (size_t)I * g->ts_edge_stride, &g->ts_edge))) return rc;
+                if ((rc = dev_alloc(g.get(), 1, &g->done_counter))) return rc;
+                if ((rc = dev_alloc(g.get(), 4, &g->ts_pub, false))) return rc;
+                {
+                    const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+                    GJ_CUDA_TRY(cudaMemcpy(g->ts_pub, init, sizeof(init), cudaMemcpyHostToDevice));
+                }
                 g->ts_fast = true;
                 g->fused_smem = gj_tsfast_smem(g.get());
                 // CTA shape from the islands per SM: 256 threads x 4 resident CTAs (<= 64 registers) up to
@@ -1158,8 +1127,10 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm_in, const d
                 int sms = 148;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
                 int threads = I >= 3 * sms ? 256 : (I >= 2 * sms ? 512 : 1024);
-                int mb = threads == 256 ? (I > 4 * sms ? 6 : 4) : (threads == 512 ? 2 : 1);
-                if (const char* e = getenv("GJ_FUSED_THREADS")) threads = std::max(256, std::min(1024, atoi(e)));
+                // (measured on C2: six resident CTAs at <= 40 registers spill in the scoring loop and lose to
+                // four at 64 even when there are islands to fill them: 30 vs 38 G candidates/s at 1184 islands)
+                int mb = threads == 256 ? 4 : (threads == 512 ? 2 : 1);
+                if (const char* e = getenv("GJ_FUSED_THREADS")) threads = std::max(128, std::min(1024, atoi(e)));
                 if (const char* e = getenv("GJ_FUSED_MB")) mb = atoi(e);
                 g->fused_mb = mb;
                 g->fused_threads = threads;
@@ -1483,7 +1454,8 @@ static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
             }
             g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
         }
-        if ((rc = gj_ls_global_top(g, st))) return rc;      // agent_base.rs:185
+        // agent_base.rs:185 (the fixed-point step publishes from its last island, inside the launch)
+        if (!g->ts_fast && (rc = gj_ls_global_top(g, st))) return rc;
         // delta mode: islands that received a migrant / adopted the global best rebuild their state
         if (g->scoring_mode == GJ_SCORING_DELTA && !g->fused && (rc = launch_refresh(g, st, false))) return rc;
     }

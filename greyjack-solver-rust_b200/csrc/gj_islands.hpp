@@ -62,6 +62,8 @@ struct gj_islands {
     bool ts_fast = false;
     double* ts_edge = nullptr;           // [I][ts_edge_stride] persistent f64 edge lengths
     int ts_edge_stride = 0;
+    unsigned long long* ts_pub = nullptr;   // {best key offered, key of the published global top, lock}
+    unsigned int* done_counter = nullptr;   // islands finished in the current launch (the last one publishes the global top)
     // LateAcceptance chains: many steps per launch, one warp per island (gj_islands_chain.cuh)
     bool chain = false;
     bool vrp_chain = false;              // ... on a VRP model: route index in HBM (gj_islands_vrp_chain.cuh)

@@ -270,6 +270,59 @@ struct GjChainArgs {
     GjMove* trace_moves; double* trace_scores; int* trace_accept;
 };
 
+// update_global_top, publish half (agent_base.rs:451-461), ONE CTA.  Agent tops only ever improve
+// and the global top is refreshed from them after every step, so the new global top is simply the
+// best agent top (first index on ties); it replaces the published one when strictly better (:451)
+// and bumps the version that gj_adopt_decide (the adopt half) watches.
+// Cooperative over ONE CTA (k_global_top, or the last CTA of a fused step to finish -- see
+// gj_islands_tsfast.cuh); sh_s / sh_i: 32 entries of shared memory each.
+__device__ __forceinline__ void gj_global_top_cta(int I, int levels, int stride, int n_vars,
+                                                  const int32_t* __restrict__ best, const double* __restrict__ best_score,
+                                                  int32_t* gbest, double* gbest_score, int* gver,
+                                                  GjScore* sh_s, int* sh_i, int* sh_publish_p) {
+    int& sh_publish = *sh_publish_p;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GjScore mine; int mine_idx = -1;
+    mine.v[0] = mine.v[1] = mine.v[2] = 0.0;
+    for (int i = tid; i < I; i += blockDim.x) {
+        GjScore s;                              // L2 loads: another SM may have written the score this launch
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.v[l] = (l < levels) ? __ldcg(best_score + (size_t)i * GJ_MAX_LEVELS + l) : 0.0;
+        if (mine_idx < 0 || gj_score_cmp(s, mine, levels) < 0) { mine = s; mine_idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        GjScore other; const int oidx = __shfl_xor_sync(GJ_FULL_MASK, mine_idx, o);
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) other.v[l] = __shfl_xor_sync(GJ_FULL_MASK, mine.v[l], o);
+        if (oidx >= 0) {
+            const int c = (mine_idx < 0) ? 1 : gj_score_cmp(mine, other, levels);
+            if (c > 0 || (c == 0 && oidx < mine_idx)) { mine = other; mine_idx = oidx; }
+        }
+    }
+    if (lane == 0) { sh_s[warp] = mine; sh_i[warp] = mine_idx; }
+    __syncthreads();
+    if (tid == 0) {
+        GjScore b = sh_s[0]; int bi = sh_i[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+            if (sh_i[w] < 0) continue;
+            const int c = (bi < 0) ? 1 : gj_score_cmp(b, sh_s[w], levels);
+            if (c > 0 || (c == 0 && sh_i[w] < bi)) { b = sh_s[w]; bi = sh_i[w]; }
+        }
+        sh_i[0] = bi;
+        sh_publish = 0;
+        const GjScore g = gj_load_score(gbest_score, levels);
+        if (bi >= 0 && !gj_score_le(g, b, levels)) {            // strict: agent_top < global (:451)
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = b.v[l];
+            sh_publish = 1;
+            *gver += 1;
+        }
+    }
+    __syncthreads();
+    if (sh_publish) {
+        const int32_t* win_row = best + (size_t)sh_i[0] * stride;
+        for (int i = tid; i < n_vars; i += blockDim.x) gbest[i] = __ldcg(&win_row[i]);
+    }
+}
+
 // ---- shared-memory plans / launch constants the host side needs when it picks a step path ----------
 __host__ __device__ inline size_t gj_fused_smem_bytes_lean(int n_vars, int words) {
     const size_t n_pad = ((size_t)n_vars + 3) & ~(size_t)3;

@@ -300,8 +300,11 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
         if (tabu_bytes)
             gj_tma_load_1d(s.bits, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
     }
-    gj_mbar_wait(&sh_mbar, 0);
-    if (tid == 0) { s.t[-1] = 0; s.t[n] = 0; }     // depot before the first and after the last stop
+    if (tid == 0) {                                 // one poller (spinning warps burn issue slots); the rest sleep
+        gj_mbar_wait(&sh_mbar, 0);
+        s.t[-1] = 0; s.t[n] = 0;                    // depot before the first and after the last stop
+    }
+    __syncthreads();
     if (adopted)
         for (int i = tid; i < n; i += blockDim.x) cur_row[i] = s.t[i];
     gj_fused_counts<KIND>(P, s, cnt_stride);

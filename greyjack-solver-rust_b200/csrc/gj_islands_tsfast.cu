@@ -33,6 +33,8 @@ gj_status gj_launch_tsfast_step(gj_islands* g, cudaStream_t st, bool trace) {
     F.moves_out = trace ? g->moves : nullptr;
     F.worklist = g->worklist;
     F.phase_clocks = g->phase_clocks;
+    F.done_counter = trace ? nullptr : g->done_counter;   // a trace bypasses the global-top bookkeeping
+    F.pub = (trace || g->I > 4096) ? nullptr : g->ts_pub;
     gj_status rc;
 #define GJ_LAUNCH_TSFAST(NT, MB, TR)                                                         \
     do {                                                                                     \
@@ -46,7 +48,8 @@ gj_status gj_launch_tsfast_step(gj_islands* g, cudaStream_t st, bool trace) {
     if (trace) GJ_LAUNCH_TSFAST(256, 4, true);
     else if (nt > 512) GJ_LAUNCH_TSFAST(1024, 1, false);
     else if (nt > 256) { if (mb >= 3) GJ_LAUNCH_TSFAST(512, 3, false); else GJ_LAUNCH_TSFAST(512, 2, false); }
-    else { if (mb >= 6) GJ_LAUNCH_TSFAST(256, 6, false); else GJ_LAUNCH_TSFAST(256, 4, false); }
+    else if (nt > 128) { if (mb >= 6) GJ_LAUNCH_TSFAST(256, 6, false); else GJ_LAUNCH_TSFAST(256, 4, false); }
+    else GJ_LAUNCH_TSFAST(128, 8, false);
 #undef GJ_LAUNCH_TSFAST
     GJ_LAUNCH_CHECK();
     return GJ_OK;

@@ -40,6 +40,11 @@ struct GjTsFastArgs {
     GjMove* moves_out;          // trace only
     int* worklist;              // [I][K]
     long long* phase_clocks;
+    unsigned int* done_counter; // not null: the last island to finish publishes the global top (k_global_top's work)
+    // not null: update_global_top's publish half by key tournament (see the end of the kernel):
+    // pub[0] = best key offered so far, pub[1] = key of the published global top, pub[2] = lock word,
+    // pub[3] = step that published it (+1)
+    unsigned long long* pub;
 };
 
 __host__ __device__ inline size_t gj_tsfast_smem_bytes(int n_vars, int tabu_words, int cnt_stride) {
@@ -99,6 +104,28 @@ static __device__ __noinline__ long long gj_tsf_slow_key(const GjProblemDev& P, 
 
 // TRACE: the instantiation gj_islands_trace_step uses (writes every neighbour's move and score)
 // MB: resident CTAs per SM the register allocation is sized for (launch bounds)
+// The draws of neighbour c in the order gj_generate_move consumes them (one Philox4x32-10 block):
+// x[3] move kind, x[2] semantic group (one group: unused), x[1] and x[0] the two position ranks among
+// the F free (non-tabu) positions.  Returns the kind; a0 / a1 are only meaningful for swap (1),
+// insertion (4) and inverse (5), the kinds the fixed-point path scores itself.
+__device__ __forceinline__ int gj_tsf_draw(uint32_t key0, uint32_t key1, uint32_t step_lo, uint32_t step_hi, int c,
+                                           const uint32_t (&kind_thr)[5], uint32_t F, const int32_t* free_list,
+                                           int& a0, int& a1) {
+    const uint32_t ctr[4] = {step_lo, (uint32_t)c, step_hi, 0u}, key[2] = {key0, key1};
+    uint32_t x[4];
+    gj_philox_block(ctr, key, x);
+    int kind = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) kind += (x[3] > kind_thr[i]) ? 1 : 0;
+    const int r0 = (int)__umulhi(x[1], F);
+    int r1 = (int)__umulhi(x[0], F - 1u);
+    r1 += (r1 >= r0) ? 1 : 0;
+    a0 = free_list ? free_list[r0] : r0;
+    a1 = free_list ? free_list[r1] : r1;
+    return kind;
+}
+#define GJ_TSF_FAST_KINDS 0x32u        // bit k set: kind k is scored by the fixed-point path (1, 4, 5)
+
 template <int NT, int MB, bool TRACE>
 __global__ void __launch_bounds__(NT, MB)
 k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ GjGroups G,
@@ -114,6 +141,9 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     __shared__ long long sh_bestkey;
     __shared__ int sh_accept, sh_best, sh_nwork, sh_adopt;
     __shared__ GjMove sh_mv;
+    __shared__ GjScore sh_gs[32];
+    __shared__ int sh_gi[32];
+    __shared__ int sh_gpub, sh_last;
 
     const GjSelectArgs& A = F.A;
     const int island = blockIdx.x;
@@ -144,6 +174,23 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     const uint32_t row_bytes = (uint32_t)(n_pad * 4);
     const uint32_t tabu_bytes = A.tabu_bits ? (uint32_t)(A.tabu_words_per_island * 4) : 0u;
     const uint32_t edge_bytes = (uint32_t)((size_t)F.edge_stride * 8);
+    if (tid == 64) {
+        // this CTA's slice of the milli-unit matrix (the whole grid covers it once): the gathers of P1
+        // then hit L2 even when another kernel evicted the table since the last step
+        const size_t total = (size_t)P.n_locations * (size_t)P.n_locations * 4;
+        size_t per = (total + gridDim.x - 1) / gridDim.x;
+        per = (per + 127) & ~(size_t)127;
+        const size_t off = (size_t)blockIdx.x * per;
+        if (off < total) {
+            const size_t len = min(per, total - off) & ~(size_t)15;
+            if (len) gj_l2_prefetch_bulk((const char*)P.D32 + off, (uint32_t)len);
+        }
+        if (A.tabu_bits) {
+            const int T = A.tabu_ring_per_island;
+            const uint32_t bytes = (uint32_t)(((size_t)T * 4) & ~(size_t)15);     // rounded down: stays inside
+            if (bytes) gj_l2_prefetch_bulk(A.tabu_ring_old + (size_t)island * T - (((size_t)island * T) & 3), bytes);
+        }
+    }
     if (warp == 1) {
         const void* pf = nullptr;
         switch (lane) {
@@ -165,17 +212,27 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     if (tid == 0) {
         gj_mbar_init(&sh_mbar, 1);
         sh_nwork = 0;
+        // all three bulk copies leave at once; the island's own row is loaded speculatively -- an adoption
+        // (rare after the first steps) reloads the row from the global top in a second phase
         gj_mbar_expect_tx(&sh_mbar, row_bytes + tabu_bytes + edge_bytes);
+        gj_tma_load_1d(t, cur_row, row_bytes, &sh_mbar);
         if (tabu_bytes) gj_tma_load_1d(table, A.tabu_bits + (size_t)island * A.tabu_words_per_island, tabu_bytes, &sh_mbar);
         gj_tma_load_1d(e64, edge_g, edge_bytes, &sh_mbar);       // overwritten below when the tour was replaced
         const bool adopt = gj_adopt_decide(A, island);            // update_global_top, adopt half
         sh_adopt = adopt ? 1 : 0;
-        gj_tma_load_1d(t, adopt ? A.gbest : cur_row, row_bytes, &sh_mbar);
+        // the issuing thread polls the mbarrier (a spinning try_wait burns issue slots: with all eight
+        // warps on it the poll loop was ~45 % of the kernel's executed instructions); the rest sleep
+        gj_mbar_wait(&sh_mbar, 0);
+        if (adopt) {
+            gj_mbar_expect_tx(&sh_mbar, row_bytes);
+            gj_tma_load_1d(t, A.gbest, row_bytes, &sh_mbar);
+            gj_mbar_wait(&sh_mbar, 1);
+        }
     }
     __syncthreads();
+    stamp(6);
     const bool adopted = sh_adopt != 0;
     const int state_stale = F.stale[island];
-    gj_mbar_wait(&sh_mbar, 0);
     if (tid == 0) { t[-1] = 0; t[n] = 0; }               // depot before the first and after the last stop
     if (adopted)
         for (int i = tid; i < n; i += NT) cur_row[i] = t[i];
@@ -218,25 +275,14 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     int best_idx = -1;
 #pragma unroll 2
     for (int c = tid; c < K; c += NT) {
-        uint32_t ctr[4] = {step_lo, (uint32_t)c, step_hi, 0u}, key[2] = {key0, key1}, x[4];
-        gj_philox_block(ctr, key, x);
-        // draws in the order gj_generate_move consumes them: x[3] kind, x[2] group (one group: unused),
-        // x[1] and x[0] the two position ranks
-        const uint32_t xk = x[3];
-        int kind = 0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) kind += (xk > F.kind_thr[i]) ? 1 : 0;
+        int a0, a1;
+        const int kind = gj_tsf_draw(key0, key1, step_lo, step_hi, c, F.kind_thr, Fd, use_tabu ? free_list : nullptr, a0, a1);
         const bool last_chunk = c >= (n_chunks - 1) * NT;
-        if (!((0x32u >> kind) & 1u)) {                      // not swap / insertion / inverse
+        if (!((GJ_TSF_FAST_KINDS >> kind) & 1u)) {           // not swap / insertion / inverse
             worklist[atomicAdd(&sh_nwork, 1)] = c;
             if (last_chunk) sh_selinfo[tid] = 0xff;         // P4 regenerates it
             continue;
         }
-        const int r0 = (int)__umulhi(x[1], Fd);
-        int r1 = (int)__umulhi(x[0], Fd - 1u);
-        r1 += (r1 >= r0) ? 1 : 0;
-        const int a0 = use_tabu ? free_list[r0] : r0;
-        const int a1 = use_tabu ? free_list[r1] : r1;
         if (last_chunk) { sh_sel0[tid] = a0; sh_sel1[tid] = a1; sh_selinfo[tid] = 3; }   // two ids, group 0
         const int p = F.first + min(a0, a1), q = F.first + max(a0, a1);
         const int pm = t[p - 1], tp = t[p], pn = t[p + 1];
@@ -315,7 +361,19 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
         sh_accept = accept ? 1 : 0;
         sh_best = bi;
         sh_bestkey = bk;
-        if (accept) gj_tsf_generate(P, G, A, table_ro, island, bi, &sh_mv);
+        if (accept) {
+            // the winning move again (a pure function of its index): inline for the common kinds
+            int a0, a1;
+            const int kind = gj_tsf_draw(key0, key1, step_lo, step_hi, bi, F.kind_thr, Fd, use_tabu ? free_list : nullptr, a0, a1);
+            if ((GJ_TSF_FAST_KINDS >> kind) & 1u) {
+                sh_mv.kind = (uint8_t)kind; sh_mv.group = 0; sh_mv.k = 2; sh_mv.pad = 0;
+#pragma unroll
+                for (int i = 0; i < GJ_MOVE_MAXK; ++i) { sh_mv.a[i] = 0; sh_mv.v[i] = 0; }
+                sh_mv.a[0] = a0; sh_mv.a[1] = a1;
+            } else {
+                gj_tsf_generate(P, G, A, table_ro, island, bi, &sh_mv);
+            }
+        }
         if (A.selected_out) { A.selected_out[island] = bi; A.accepted_out[island] = accept ? 1 : 0; }
         atomicAdd(&A.counters[0], (unsigned long long)K);
         if (island == 0) atomicAdd(&A.counters[1], 1ull);
@@ -327,10 +385,32 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     // ---- P3: apply, write back, patch the edges, exact re-score, update_top_individual ----------------
     if (sh_accept) {
         const GjMove m = sh_mv;
-        gj_apply_move(P, m, G, true, A.noop != 0, tid, NT,
-                      [&](int id) { return cur_row[id]; }, [&](int id, int v) { t[id] = v; });
-        __syncthreads();
-        for (int i = tid; i < n; i += NT) cur_row[i] = t[i];
+        const bool fast_kind = ((GJ_TSF_FAST_KINDS >> m.kind) & 1u) && m.k == 2 && m.kind != GJ_MOVE_NULL;
+        if (fast_kind) {
+            // swap / 2-opt / insertion on the staged tour itself (the group's columns are consecutive
+            // and share their bounds: no clamp, no group table); only the touched range goes back to HBM
+            const int c0 = F.first + m.a[0], c1 = F.first + m.a[1];
+            const int p = min(c0, c1), q = max(c0, c1);
+            const int len = q - p + 1;
+            if (m.kind == 1) {
+                if (tid == 0) { const int x = t[p]; t[p] = t[q]; t[q] = x; }
+            } else if (m.kind == 5) {
+                for (int j = tid; j < len / 2; j += NT) { const int x = t[p + j]; t[p + j] = t[q - j]; t[q - j] = x; }
+            } else {
+                int32_t* scratch = e32;                      // dead since the end of P1
+                for (int i = tid; i < len; i += NT) scratch[i] = t[p + i];
+                __syncthreads();
+                for (int i = tid; i < len; i += NT) t[p + i] = scratch[gj_segment_src_slot(m, true, i, len)];
+            }
+            __syncthreads();
+            if (m.kind == 1) { if (tid < 2) cur_row[tid ? q : p] = t[tid ? q : p]; }
+            else for (int i = p + tid; i <= q; i += NT) cur_row[i] = t[i];
+        } else {
+            gj_apply_move(P, m, G, true, A.noop != 0, tid, NT,
+                          [&](int id) { return cur_row[id]; }, [&](int id, int v) { t[id] = v; });
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) cur_row[i] = t[i];
+        }
         const bool identity = m.kind == GJ_MOVE_NULL || (A.noop && (m.kind == 3 || (m.kind == 2 && m.k == 2)));
         if (!identity) {
             const int c0 = F.first + m.a[0], c1 = F.first + m.a[1];
@@ -408,9 +488,12 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     stamp(4);
     // ---- P4: tabu deque update (mover.rs:75-96; see gj_tabu_deque_advance) -------------------------------
     if (A.tabu_bits) {
+        // the new deque and the new table are built in shared memory (e32 and the staged table are dead
+        // by now) and leave as coalesced copies: no global round trip between the phases of the rebuild
         uint32_t* bits_rw = A.tabu_bits + (size_t)island * A.tabu_words_per_island;
         const int32_t* ring_old = A.tabu_ring_old + (size_t)island * A.tabu_ring_per_island + A.tabu_ring_off[0];
         int32_t* ring_new = A.tabu_ring_new + (size_t)island * A.tabu_ring_per_island + A.tabu_ring_off[0];
+        int32_t* ring_s = e32;                               // T <= glen <= n ints
         const int T = A.tabu_size[0];
         const int fill_old = A.tabu_fill[island * A.n_groups];
         int collected = 0;
@@ -422,9 +505,15 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
                 if (chunk == n_chunks - 1 && info != 0xff) {
                     if (info == 3) { cntsel = 2; sel[0] = sh_sel0[tid]; sel[1] = sh_sel1[tid]; }
                 } else {
-                    GjMove m;
-                    gj_tsf_generate(P, G, A, table_ro, island, j, &m);
-                    if (m.kind != GJ_MOVE_NULL) cntsel = gj_move_selected(m, sel);
+                    int a0, a1;
+                    const int kind = gj_tsf_draw(key0, key1, step_lo, step_hi, j, F.kind_thr, Fd, use_tabu ? free_list : nullptr, a0, a1);
+                    if ((GJ_TSF_FAST_KINDS >> kind) & 1u) {
+                        cntsel = 2; sel[0] = a0; sel[1] = a1;
+                    } else {
+                        GjMove m;
+                        gj_tsf_generate(P, G, A, table_ro, island, j, &m);
+                        if (m.kind != GJ_MOVE_NULL) cntsel = gj_move_selected(m, sel);
+                    }
                 }
             }
             int total;
@@ -434,7 +523,7 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
             for (int i = 0; i < GJ_MOVE_MAXK; ++i) {
                 if (i < cntsel) {
                     const int rank = collected + after + (cntsel - 1 - i);
-                    if (rank < T) ring_new[rank] = sel[i];
+                    if (rank < T) ring_s[rank] = sel[i];
                 }
             }
             __syncthreads();
@@ -442,12 +531,80 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
         }
         for (int r = collected + tid; r < T; r += NT) {
             const int rho = r - collected;
-            if (rho < fill_old) ring_new[r] = ring_old[rho];
+            if (rho < fill_old) ring_s[r] = ring_old[rho];
         }
         const int fill = min(T, fill_old + collected);
         __syncthreads();
         if (tid == 0) A.tabu_fill[island * A.n_groups] = fill;
-        gj_tabu_table_rebuild(bits_rw + A.tabu_word_off[0], F.glen, ring_new, fill, sh_scan);
+        for (int r = tid; r < fill; r += NT) ring_new[r] = ring_s[r];
+        gj_tabu_table_rebuild(table + A.tabu_word_off[0], F.glen, ring_s, fill, sh_scan);
+        for (int w = tid; w < A.tabu_words_per_island; w += NT) bits_rw[w] = table[w];
     }
     stamp(5);
+    // ---- update_global_top, publish half (agent_base.rs:451-461) ------------------------------------------
+    // The global top is the best agent top, lowest island on ties, replaced only by a strictly better
+    // one (k_global_top).  In fixed point an agent top packs into 64 bits -- hard level | milli-unit
+    // index | island -- whose unsigned order IS that rule, so the reduction over all islands is one
+    // atomicMin per island, and the island that holds the minimum when it finishes copies its row under
+    // a lock (a later, better island simply overwrites it; a worse one never does).  No extra launch,
+    // no serial tail; the outcome does not depend on the order in which islands finish.
+    if (F.pub) {
+        unsigned long long* pub = F.pub;
+        if (tid == 0) {
+            const double th = A.best_score[(size_t)island * GJ_MAX_LEVELS + 0];
+            const double ts = A.best_score[(size_t)island * GJ_MAX_LEVELS + 1];
+            const unsigned long long key = ((unsigned long long)llrint(th) << 48) |
+                                           ((unsigned long long)gj_tsf_milli_index(ts) << 12) | (unsigned long long)island;
+            atomicMin(&pub[0], key);
+            __threadfence();
+            // against a top published by an EARLIER launch only a strictly better score counts
+            // (agent_base.rs:451); against one published earlier in THIS launch the full key decides,
+            // i.e. the lowest island among equal scores -- k_global_top's "first index on ties"
+            const unsigned long long now = (unsigned long long)A.step + 1ull;
+            auto beats = [&](unsigned long long pk, unsigned long long pstep) {
+                return pstep == now ? (key < pk) : ((key >> 12) < (pk >> 12));
+            };
+            int take = 0;
+            if (__ldcg(&pub[0]) == key && beats(__ldcg(&pub[1]), __ldcg(&pub[3]))) {
+                while (atomicCAS(&pub[2], 0ull, 1ull) != 0ull) __nanosleep(64);
+                __threadfence();
+                take = beats(__ldcg(&pub[1]), __ldcg(&pub[3])) ? 1 : 0;
+                if (!take) { __threadfence(); atomicExch(&pub[2], 0ull); }
+            }
+            sh_last = take;
+        }
+        __syncthreads();
+        if (sh_last) {
+            const int32_t* my_best = A.best + (size_t)island * A.stride;
+            for (int i = tid; i < n; i += NT) A.gbest[i] = __ldcg(&my_best[i]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.gbest_score[l] = A.best_score[(size_t)island * GJ_MAX_LEVELS + l];
+                *A.gver += 1;
+                const double th = A.best_score[(size_t)island * GJ_MAX_LEVELS + 0];
+                const double ts = A.best_score[(size_t)island * GJ_MAX_LEVELS + 1];
+                pub[1] = ((unsigned long long)llrint(th) << 48) | ((unsigned long long)gj_tsf_milli_index(ts) << 12) |
+                         (unsigned long long)island;
+                pub[3] = (unsigned long long)A.step + 1ull;
+                __threadfence();
+                atomicExch(&pub[2], 0ull);
+            }
+        }
+    } else if (F.done_counter) {
+        // fallback (more than 4096 islands): the LAST island to finish runs k_global_top's reduction
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(F.done_counter, 1u);
+            sh_last = (prev == gridDim.x - 1) ? 1 : 0;
+            if (sh_last) *F.done_counter = 0u;
+        }
+        __syncthreads();
+        if (sh_last) {
+            __threadfence();
+            gj_global_top_cta((int)gridDim.x, A.levels, A.stride, n, A.best, A.best_score, A.gbest, A.gbest_score, A.gver,
+                              sh_gs, sh_gi, &sh_gpub);
+        }
+    }
 }
