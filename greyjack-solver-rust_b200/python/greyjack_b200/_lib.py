@@ -66,7 +66,9 @@ EXPORTED = [
     "gj_score_plain_device", "gj_score_plain_i32_device", "gj_score_incremental_device",
     "gj_islands_create", "gj_islands_destroy", "gj_islands_step", "gj_islands_set_accomplish_rate", "gj_islands_stats", "gj_islands_trace_aux", "gj_islands_step_path", "gj_islands_set_profiling", "gj_islands_profile_read",
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",
-    "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants", "gj_islands_trace_step", "gj_islands_trace_tabu", "gj_islands_ga_trace_generation", "gj_islands_ga_population",
+    "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants",
+    "gj_islands_global_top_bytes", "gj_islands_export_global_top", "gj_islands_import_global_top",
+    "gj_ring_create", "gj_ring_destroy", "gj_ring_handle", "gj_ring_connect", "gj_ring_exchange", "gj_ring_stats", "gj_islands_trace_step", "gj_islands_trace_tabu", "gj_islands_ga_trace_generation", "gj_islands_ga_population",
 ]
 
 _lib = None
@@ -95,6 +97,9 @@ def load():
             getattr(L, name).restype = None
     if hasattr(L, "gj_islands_migrant_bytes"):
         L.gj_islands_migrant_bytes.restype = C.c_int64
+    if hasattr(L, "gj_islands_global_top_bytes"):
+        L.gj_islands_global_top_bytes.restype = C.c_int64
+        L.gj_ring_destroy.restype = None
     _lib = L
     return L
 

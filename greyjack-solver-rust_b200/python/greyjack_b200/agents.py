@@ -327,6 +327,15 @@ class Islands:
         _lib.check(self._L.gj_islands_ga_trace_generation(self.handle, C.c_int32(island), C.byref(t)))
         return out
 
+    def global_top_bytes(self) -> int:
+        return int(self._L.gj_islands_global_top_bytes(self.handle))
+
+    def export_global_top(self, d_buffer: int, stream=0):
+        _lib.check(self._L.gj_islands_export_global_top(self.handle, C.c_void_p(d_buffer), C.c_void_p(stream)))
+
+    def import_global_top(self, d_records: int, count: int, stream=0):
+        _lib.check(self._L.gj_islands_import_global_top(self.handle, C.c_void_p(d_records), C.c_int32(count), C.c_void_p(stream)))
+
     def trace_tabu(self, island=0, group=0):
         """The tabu deque of one island / semantic group, newest id first -> (ids, size)."""
         cap = max(1, self.problem.n_vars)

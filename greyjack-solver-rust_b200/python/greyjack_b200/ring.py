@@ -27,13 +27,22 @@ def global_island_base(rank: int, islands_per_rank: int) -> int:
 
 
 class RingMigrator:
-    def __init__(self, islands, rank: int, world: int, islands_per_rank: int, device="cuda", group=None):
+    """Ring (and, for local-search agents, the shared global top) with the transport in
+    torch.distributed: NCCL on GPUs, gloo in the CPU tests."""
+
+    def __init__(self, islands, rank: int, world: int, islands_per_rank: int, device="cuda", group=None,
+                 share_global_top: bool = False):
         self.islands, self.rank, self.world, self.group = islands, rank, world, group
         self.dst, self.src = ring_neighbours(rank, world)
         islands.set_external_ring(world > 1, global_island_base(rank, islands_per_rank))
         n = int(islands.migrant_bytes())
         self.out = torch.empty(n, dtype=torch.uint8, device=device)
         self.inp = torch.empty(n, dtype=torch.uint8, device=device)
+        self.share_global_top = share_global_top and world > 1
+        if self.share_global_top:
+            gb = int(islands.global_top_bytes())
+            self.g_out = torch.zeros(gb, dtype=torch.uint8, device=device)
+            self.g_all = torch.zeros(gb * world, dtype=torch.uint8, device=device)
         self.exchanges = 0
 
     def exchange(self, stream: int = 0):
@@ -48,7 +57,58 @@ class RingMigrator:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
         self.islands.import_migrants(self.inp.data_ptr(), stream)
+        if self.share_global_top:
+            # update_global_top across ranks (agent_base.rs:446-490): every rank's record to every rank,
+            # the best one adopted on the device when strictly better -- no host decision
+            self.islands.export_global_top(self.g_out.data_ptr(), stream)
+            dist.all_gather_into_tensor(self.g_all, self.g_out, group=self.group)
+            self.islands.import_global_top(self.g_all.data_ptr(), self.world, stream)
         self.exchanges += 1
+
+
+class PeerRing:
+    """Ring + shared global top over CUDA peer memory (csrc/gj_ring.cu): migrants and global-top
+    records are stored straight into the neighbours' inboxes over NVLink, nothing waits on the host
+    and no collective runs on the data path.  torch.distributed is only used ONCE, to hand the IPC
+    handles of the inboxes around."""
+
+    def __init__(self, islands, rank: int, world: int, islands_per_rank: int, group=None):
+        import ctypes as C
+        from . import _lib
+        self.islands, self.rank, self.world = islands, rank, world
+        self._L = _lib.load()
+        islands.set_external_ring(world > 1, global_island_base(rank, islands_per_rank))
+        self.handle = C.c_void_p()
+        _lib.check(self._L.gj_ring_create(islands.handle, C.c_int32(rank), C.c_int32(world), C.byref(self.handle)))
+        mine = (C.c_ubyte * 64)()
+        _lib.check(self._L.gj_ring_handle(self.handle, mine))
+        table = [None] * world
+        if world > 1:
+            dist.all_gather_object(table, bytes(mine), group=group)
+            flat = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(table))
+            _lib.check(self._L.gj_ring_connect(self.handle, flat))
+            dist.barrier(group=group)
+        self.exchanges = 0
+
+    def exchange(self, stream: int = 0):
+        from . import _lib
+        import ctypes as C
+        if self.world == 1:
+            return
+        _lib.check(self._L.gj_ring_exchange(self.handle, C.c_void_p(stream)))
+        self.exchanges += 1
+
+    def stats(self):
+        from . import _lib
+        import ctypes as C
+        e, m = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.gj_ring_stats(self.handle, C.byref(e), C.byref(m)))
+        return {"exchanges": e.value, "missed": m.value}
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._L.gj_ring_destroy(self.handle)
+            self.handle = None
 
 
 def run_steps(islands, migrator: RingMigrator, n_steps: int, migration_frequency: int, stream: int = 0,

@@ -307,6 +307,35 @@ GJ_API gj_status gj_islands_set_external_ring(gj_islands* g, int32_t on, int32_t
 GJ_API gj_status gj_islands_export_migrants(gj_islands* g, void* d_buffer, void* stream);
 GJ_API gj_status gj_islands_import_migrants(gj_islands* g, const void* d_buffer, void* stream);
 
+/* The group's global_top_individual as a device record [n_vars int32 (row stride) | levels f64], for a
+   caller-owned transport between ranks (NCCL all-gather, gloo in tests): export packs it,
+   import takes `count` records (gj_islands_global_top_bytes apart) and adopts the best one when it is
+   STRICTLY better than the group's own (agent_base.rs:451); islands then adopt it by their usual rule
+   (agent_base.rs:465-489).  Replaces the Arc<Mutex<global_top_individual>> across processes.        */
+GJ_API int64_t   gj_islands_global_top_bytes(const gj_islands* g);
+GJ_API gj_status gj_islands_export_global_top(gj_islands* g, void* d_buffer, void* stream);
+GJ_API gj_status gj_islands_import_global_top(gj_islands* g, const void* d_records, int32_t count, void* stream);
+
+/*
+ * The ring and the shared global top across GPUs over CUDA peer memory (NVLink), one process per GPU,
+ * no collective library on the data path (csrc/gj_ring.cu).  Set-up: every rank creates its ring,
+ * publishes gj_ring_handle (an IPC handle of its inbox) to the others by any host channel, and
+ * connects with the table of all handles.  gj_ring_exchange, called by every rank every
+ * migration_frequency steps on its stream: migrants of the rank's last island -> first island of
+ * rank + 1 (solver.rs:85-92, acceptance rule agent_base.rs:414-440), every rank's global top -> every
+ * rank (agent_base.rs:446-490).  Asynchronous: nothing waits on the host.  Requires
+ * gj_islands_set_external_ring(g, 1, rank * islands_per_rank).
+ */
+typedef struct gj_ring gj_ring;
+typedef struct gj_peer_handle { unsigned char bytes[64]; } gj_peer_handle;
+GJ_API gj_status gj_ring_create(gj_islands* g, int32_t rank, int32_t world, gj_ring** out);
+GJ_API void      gj_ring_destroy(gj_ring* r);
+GJ_API gj_status gj_ring_handle(gj_ring* r, gj_peer_handle* out);
+GJ_API gj_status gj_ring_connect(gj_ring* r, const gj_peer_handle* handles /*[world]*/);
+GJ_API gj_status gj_ring_exchange(gj_ring* r, void* stream);
+/* exchanges done; flags that did not arrive within the time-out (a missed exchange, never a hang) */
+GJ_API gj_status gj_ring_stats(gj_ring* r, int64_t* exchanges, int64_t* missed);
+
 /*
  * Test / inspection hook: runs ONE TabuSearch/LateAcceptance step of one island and
  * returns what happened -- the generated moves as delta lists (CSR, capacities given

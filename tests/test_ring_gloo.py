@@ -43,6 +43,27 @@ class FakeIslands:
         ctypes.memmove(ptr, buf, len(buf))
         self.log.append("export")
 
+    # the group's global top as a device record (row int32 | score f64), gj_islands_*_global_top
+    def global_top_bytes(self):
+        return (self.n_vars * 4 + self.levels * 8 + 15) // 16 * 16
+
+    def export_global_top(self, ptr, stream=0):
+        gv, gs = getattr(self, "gtop", (self.vec, self.score))
+        buf = gv.tobytes() + gs.tobytes()
+        ctypes.memmove(ptr, buf, len(buf))
+        self.log.append("export_gtop")
+
+    def import_global_top(self, ptr, count, stream=0):
+        gv, gs = getattr(self, "gtop", (self.vec, self.score))
+        for r in range(count):
+            raw = ctypes.string_at(ptr + r * self.global_top_bytes(), self.n_vars * 4 + self.levels * 8)
+            vec = np.frombuffer(raw[: self.n_vars * 4], dtype=np.int32)
+            score = np.frombuffer(raw[self.n_vars * 4:], dtype=np.float64)
+            if self.o.score_cmp(score, gs) < 0:          # strictly better (agent_base.rs:451)
+                gv, gs = vec.copy(), score.copy()
+        self.gtop = (gv, gs)
+        self.log.append("import_gtop")
+
     def import_migrants(self, ptr, stream=0):
         raw = ctypes.string_at(ptr, self.migrant_bytes())
         vec = np.frombuffer(raw[: self.n_vars * 4], dtype=np.int32)
@@ -111,6 +132,37 @@ def test_ring_exchange_and_global_best(world, oracle):
     # the best individual has spread around the ring, so several ranks tie; the lowest rank wins
     assert len({r["owner"] for r in res}) == 1
     assert res[0]["after3_vec0"] == last and res[0]["owner"] == 0
+
+
+def _gtop_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    isl = FakeIslands(rank)
+    mig = ring.RingMigrator(isl, rank, world, islands_per_rank=5, device="cpu", share_global_top=True)
+    ring.run_steps(isl, mig, n_steps=2, migration_frequency=2)
+    out.put({"rank": rank, "gtop_vec0": int(isl.gtop[0][0]), "gtop_score": isl.gtop[1].tolist(), "log": list(isl.log)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_top_is_shared_across_ranks_in_one_exchange(oracle):
+    """update_global_top across ranks (agent_base.rs:446-490): after ONE exchange every rank holds the
+    best rank's individual as its global top (not one ring hop per exchange like the migrants)."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gtop_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((out.get(timeout=120) for _ in range(world)), key=lambda r: r["rank"])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in res:
+        assert r["gtop_vec0"] == world - 1 and r["gtop_score"] == [0.0, 100.0 - 10.0 * (world - 1)]
+        assert r["log"] == ["step", "step", "export", "import", "export_gtop", "import_gtop"]
 
 
 def test_single_rank_is_a_no_op():
