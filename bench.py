@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- candidate moves scored per second on BASELINE.json's headline configuration.
+"""bench.py -- candidate moves scored per second on BASELINE.json's configurations.
 
-Workload (config C2): TSP, 1 000 synthetic cities, TabuSearch, swap / 2-opt neighbourhood of
-4 096 moves per step per island.  A "step" is one TabuSearch step of every island resident on
-the GPU (move generation -> scoring -> selection, all on the device).
+Headline (config C2): TSP, 1 000 synthetic cities, TabuSearch, swap / 2-opt neighbourhood of 4 096
+moves per step per island.  A "step" is one TabuSearch step of every island resident on the GPU
+(move generation -> scoring -> selection -> apply -> tabu update -> global top, all on the device).
 
-  value  : candidates scored / s, whole job, islands resident in HBM (device-timed, CUDA events)
+  value  : candidates scored / s, whole job, islands resident in HBM (device-timed, CUDA events,
+           L2 flushed between timed steps)
   e2e    : the same metric through the reference-facing call gj_score_incremental
-           (OOPScoreRequester::request_score_incremental) with HOST buffers: every step copies
-           the base + the delta lists host->device and the scores device->host.
+           (OOPScoreRequester::request_score_incremental) with HOST buffers, on EVERY rank: each step
+           copies the base + the delta lists host->device and the scores device->host.
   cpu_baseline / --impl reference : the oracle's restatement of the reference's own CPU path
-           (one island per host thread, pseudo-incremental scoring), timed on this box.
+           (one agent per host thread, pseudo-incremental scoring), timed on this box.
+  other_configs : C1 / C3 / C4 / C5 of BASELINE.json on the same N GPUs, each with its own roofline
+           and (at N = 1) its own CPU baseline; C5 also as GA + TabuSearch hybrid islands over a fixed
+           wall time.
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 """
@@ -33,19 +37,24 @@ NEIGHBOURS = 4096
 MOVE_PROBAS = [0.0, 0.5, 0.0, 0.0, 0.0, 0.5]       # swap + inverse (2-opt)
 TABU_RATE = 0.5                                     # examples/tsp/src/main.rs:47
 MIGRATION_FREQUENCY = 10
+ISLANDS_PER_GPU = 2368                              # 16 per SM: four waves of four resident CTAs
 METRIC = "candidate moves scored/sec (whole box)"
 UNIT = "candidates/s"
+WORKLOAD = "C2: TSP 1000 cities, TabuSearch, swap/2-opt, 4096 moves per step"
 # algorithmic bytes per candidate
 A_FULL = 4 * (N_CITIES - 1) + 8 * N_CITIES + 16     # 12 012 B: full (pseudo-incremental) evaluation
 A_DELTA = 0.5 * 96 + 0.5 * 56                       # swap 96 B / 2-opt 56 B, 50:50 mix
 SCORING_DESC = {
     "full": "full re-evaluation of base+move per candidate (the reference's pseudo-incremental ISC semantics)",
-    "delta": "fused island step: move generated in registers, delta-scored against the island's state staged in "
-             "shared memory (tour, edge lengths, value counts, tabu table), added edges gathered from the "
-             "L2-resident matrix; selection, apply, full re-score of the accepted neighbour and tabu update in "
-             "the same kernel",
+    "delta": "fused island step in fixed point: one Philox block per neighbour, the move kept in registers, the "
+             "tour-length change as an exact integer of milli-units against the island's state staged in shared "
+             "memory (tour, edge lengths, free-position list), added edges gathered from the L2-resident int32 "
+             "matrix; selection, apply, full re-score of the accepted neighbour, tabu update and the global-top "
+             "publication in the same kernel",
+    "delta_f64": "the same fused step in f64 (k_ls_step_fused)",
 }
-SCORING_KERNEL = {"full": "k_score_moves_warp<GJ_TSP>", "delta": "k_ls_step_fused<GJ_TSP,256>"}
+SCORING_KERNEL = {"full": "k_score_moves_warp<GJ_TSP>", "delta": "k_ts_step_fast<256,4>",
+                  "delta_f64": "k_ls_step_fused<GJ_TSP,256>"}
 
 
 def peaks():
@@ -54,6 +63,15 @@ def peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def limiter_note():
+    """What actually limits the headline kernel (from the committed ncu capture, profiles/)."""
+    path = os.path.join(ROOT, "profiles", "roofline_limiter.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -138,66 +156,292 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C2: TSP 1000 cities, TabuSearch, swap/2-opt, 4096 moves per step",
-                   "islands": cores, "moves_per_island_step": NEIGHBOURS},
+        "config": {"workload": WORKLOAD, "islands": cores, "moves_per_island_step": NEIGHBOURS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} TabuSearch steps x {cores} islands x {NEIGHBOURS} moves; "
-                                   "oracle port of the reference ISC path WITHOUT its Polars marshalling "
-                                   "(CPU-favouring)"},
+                                   "oracle port (-O3 -march=native) of the reference ISC path: moves generated "
+                                   "and scored inside the timed region, WITHOUT the reference's Polars "
+                                   "marshalling (CPU-favouring)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def other_configs(gj, inst, torch):
-    """BASELINE.json's other configurations (parity-test cases, not bench lines): device-timed
-    candidates/s of the agent each one names, islands resident in HBM, no L2 flush.  Reported for
-    context next to the headline; a failure here never touches the headline numbers."""
+# ---------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed helpers that degrade to the single-process case"""
+
+    def __init__(self, torch, dist, world):
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+
+    def reduce(self, x, op):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM,
+                                    "min": self.dist.ReduceOp.MIN}[op])
+        return float(t.item())
+
+    def best_score(self, score):
+        """lexicographic minimum of a score vector over the ranks"""
+        if self.world == 1:
+            return [float(x) for x in score]
+        t = self.torch.tensor([float(x) for x in score], device="cuda", dtype=self.torch.float64)
+        allv = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(allv, t)
+        return list(min(tuple(v.tolist()) for v in allv))
+
+
+def make_ring(ring, isl, rank, world, islands_per_rank):
+    """cross-GPU ring + shared global top: peer memory (csrc/gj_ring.cu), NCCL as the fallback"""
+    if world == 1:
+        return None, "single rank"
+    if os.environ.get("GJ_BENCH_RING", "p2p") == "p2p":
+        try:
+            return ring.PeerRing(isl, rank, world, islands_per_rank), "peer memory over NVLink (gj_ring_exchange)"
+        except Exception as e:                  # noqa: BLE001
+            sys.stderr.write(f"[bench] peer ring unavailable ({e}); NCCL\n")
+    return ring.RingMigrator(isl, rank, world, islands_per_rank, device="cuda", share_global_top=True), \
+        "NCCL send/recv + all-gather (torch.distributed)"
+
+
+def timed_island_steps(torch, D, isl, migrator, steps, warmup, stream, migration_frequency, flush=None,
+                       steps_per_call=1):
+    """W warm-up + K timed calls of isl.step(steps_per_call) with the ring exchange every
+    migration_frequency agent steps; per-call CUDA events on the launching stream; max over ranks."""
+    state = {"done": 0, "sent": 0}
+
+    def one():
+        isl.step(steps_per_call, stream)
+        state["done"] += steps_per_call
+        if migrator is not None and state["done"] - state["sent"] >= migration_frequency:
+            migrator.exchange(stream)            # AgentToAgentUpdate ring i -> i+1 across GPUs (agent_base.rs:161-183)
+            state["sent"] = state["done"]
+
+    for _ in range(warmup):
+        one()
+    if migrator is not None:
+        migrator.exchange(stream)                # untimed: first touch of every peer mapping / connection
+    D.barrier()
+    isl.set_profiling(True)
+    c0 = isl.stats()["candidates"]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for i in range(steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)                # L2 flush between timed iterations (untimed)
+        evs[i][0].record()
+        one()
+        evs[i][1].record()
+    D.barrier()
+    total_ms = D.reduce(sum(a.elapsed_time(b) for a, b in evs), "max")
+    cands = D.reduce(isl.stats()["candidates"] - c0, "sum")
+    k_ms, k_n = isl.profile_read()
+    isl.set_profiling(False)
+    return total_ms, cands, k_ms / max(1, k_n), k_n
+
+
+def roofline(kernel, per_launch_units, a_bytes, kernel_ms, a_name, peak, peak_src, extra=None):
+    achieved = per_launch_units * a_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "traffic": None, "peak_source": peak_src, "kernel": kernel, "kernel_ms": kernel_ms,
+         "algorithmic_bytes_per_candidate": a_bytes, "algorithmic_bytes": a_name,
+         "candidates_per_launch": per_launch_units}
+    if extra:
+        r.update(extra)
+    return r
+
+
+class _NoClose:
+    """lets run() 'close' a problem that later runs still use"""
+
+    def __init__(self, p):
+        self._p = p
+
+    def __getattr__(self, k):
+        return getattr(self._p, k)
+
+    def close(self):
+        pass
+
+
+def other_configs(gj, inst, ring, torch, D, rank, world, local_rank, args):
+    """BASELINE.json's configurations 1, 3, 4, 5 on the same N GPUs (islands sharded over the ranks,
+    ring + global top across them), device-timed like the headline, each with its own roofline and,
+    at N = 1, a CPU baseline from the oracle's drivers.  A failure here never touches the headline."""
     out = {}
     stream = torch.cuda.current_stream().cuda_stream
+    peak, peak_src = peaks()
+    cores = os.cpu_count() or 1
+    want_cpu = world == 1 and rank == 0 and not args.no_cpu_baseline
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    def timed(name, make, steps):
+    def cpu_note(kind):
+        return (f"oracle port (-O3 -march=native) of the reference {kind} path, one agent per host thread, no Polars "
+                "marshalling (CPU-favouring)")
+
+    def run(name, make, steps, warmup, mig_freq, steps_per_call, kernel, a_bytes, a_name, cpu=None, use_flush=False,
+            note=None):
         try:
-            prob, isl = make()
-            isl.step(max(1, steps // 10), stream)
-            torch.cuda.synchronize()
-            c0 = isl.stats()["candidates"]
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); isl.step(steps, stream); b.record()
-            torch.cuda.synchronize()
-            ms = a.elapsed_time(b)
-            out[name] = {"candidates_per_s": (isl.stats()["candidates"] - c0) / (ms * 1e-3),
-                         "us_per_step": 1e3 * ms / steps, "best": [float(x) for x in isl.best(-1)[1]]}
+            prob, isl, per_launch = make()
+            migrator, transport = make_ring(ring, isl, rank, world, isl.n_islands)
+            total_ms, cands, kernel_ms, _ = timed_island_steps(torch, D, isl, migrator, steps, warmup, stream,
+                                                               mig_freq, flush if use_flush else None, steps_per_call)
+            entry = {"value": cands / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                     "us_per_agent_step": 1e3 * total_ms / (steps * steps_per_call),
+                     "islands_per_gpu": isl.n_islands, "step_path": isl.step_path, "transport": transport,
+                     "best": D.best_score(isl.best(-1)[1]),
+                     "roofline": roofline(kernel, per_launch, a_bytes, kernel_ms, a_name, peak, peak_src)}
+            if note:
+                entry["note"] = note
+            if want_cpu and cpu is not None:
+                entry["cpu_baseline"] = cpu(prob)
+            out[name] = entry
+            if hasattr(migrator, "close"):
+                migrator.close()
             isl.close(); prob.close()
         except Exception as e:                      # noqa: BLE001
-            out[name] = {"error": str(e)[:200]}
+            out[name] = {"error": str(e)[:300]}
+        torch.cuda.synchronize()
+
+    # ---- C1: N-Queens 256, LateAcceptance ------------------------------------------------------------
+    spec1 = inst.nqueens(256, seed=45)
 
     def c1():
-        p = gj.Problem(inst.nqueens(256, seed=45))
-        return p, gj.LateAcceptance(32, 0.2, None, [0, 1.0, 0, 0, 0, 0], 100, scoring="delta").build_agent(p, n_islands=4096, seed=1)
+        p = gj.Problem(spec1, device=local_rank)
+        isl = gj.LateAcceptance(32, 0.2, None, [0, 1.0, 0, 0, 0, 0], 100, scoring="delta",
+                                chain_steps_per_launch=50).build_agent(p, n_islands=4096, seed=1 + rank)
+        return p, isl, 4096 * 50
+
+    def c1_cpu(prob):
+        from oracle import gj_oracle
+        op = gj_oracle.OracleProblem(spec1)
+        n, s, _ = op.bench_la(spec1.initial, 32, 20000, cores, 3, [0, 1.0, 0, 0, 0, 0], None)
+        steps = int(max(20000, min(4e6, 5.0 * 20000 / max(s, 1e-3))))
+        n, s, best = op.bench_la(spec1.initial, 32, steps, cores, 4, [0, 1.0, 0, 0, 0, 0], None)
+        return {"value": n / s, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{steps} LateAcceptance steps x {cores} agents ({s:.1f} s); " + cpu_note("ISC")}
+
+    run("C1 nqueens-256 LateAcceptance(32), 4096 chains per GPU", c1, 20, 3, 100, 50, "k_la_chains<GJ_NQUEENS>",
+        48.0, "A_delta: N-Queens swap 48 B", c1_cpu, use_flush=True,
+        note="BASELINE config 1 is a single agent on the CPU scorer; the GPU runs 4096 independent chains of it")
+
+    # ---- C3: CVRP 2000 x 50, GeneticAlgorithm, population 8192 --------------------------------------------
+    spec3 = inst.cvrp(2000, 50, seed=2, greedy=False)
+    spec3.initial = np.full(spec3.n_vars, np.nan)
 
     def c3():
-        spec = inst.cvrp(2000, 50, seed=2, greedy=False)
-        spec.initial = np.full(spec.n_vars, np.nan)
-        p = gj.Problem(spec)
-        return p, gj.GeneticAlgorithm(8192, 0.5, 0.2, 0.05, 1.0, None, 0.00001, 10).build_agent(p, n_islands=1, seed=2)
+        p = gj.Problem(spec3, device=local_rank)
+        isl = gj.GeneticAlgorithm(8192, 0.5, 0.2, 0.05, 1.0, None, 0.00001, 10).build_agent(p, n_islands=1, seed=2 + rank)
+        return p, isl, 8192
+
+    def c3_cpu(prob):
+        from oracle import gj_oracle
+        op = gj_oracle.OracleProblem(spec3)
+        thr = min(cores, 8)                          # 3 x 262 MB of f64 populations per agent
+        n, s, _ = op.bench_ga(8192, 0.5, 0.2, 2, thr, 5, [1 / 6.0] * 6, [0, 0, 3])
+        return {"value": n / s, "unit": UNIT, "cores": thr, "kind": "port",
+                "sample": f"2 generations x {thr} agents x 8192 offspring ({s:.1f} s); " + cpu_note("PSC")}
+
+    run("C3 cvrp-2000x50 GeneticAlgorithm pop 8192, one island per GPU", c3, 10, 3, 10, 1, "k_plain_vrp",
+        40424.0, "A_full: 4*4000 + 8*2050 + 4*2000 + 24 B", c3_cpu,
+        note="population 8192 x 4000 int32 = 131 MB per generation: larger than L2, no flush needed")
+
+    # ---- C4: vrp_service VRPTW 5000 stops, LateAcceptance islands --------------------------------------------
+    spec4 = inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False)
 
     def c4():
-        p = gj.Problem(inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False))
-        return p, gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 50, scoring="delta",
-                                    chain_steps_per_launch=64).build_agent(p, n_islands=4096, seed=3)
+        p = gj.Problem(spec4, device=local_rank)
+        isl = gj.LateAcceptance(32, 0.2, None, [0.5, 0.5, 0, 0, 0, 0], 64, scoring="delta",
+                                chain_steps_per_launch=64).build_agent(p, n_islands=4096, seed=3 + rank)
+        return p, isl, 4096 * 64
 
-    def c5():
-        p = gj.Problem(inst.tsp(20000, seed=4, with_matrix=False), use_coords=True)
-        p.set_exact_sums(False)
-        return p, gj.TabuSearch(4096, 0.2, True, None, MOVE_PROBAS, 10, scoring="delta").build_agent(p, n_islands=148, seed=4)
+    def c4_cpu(prob):
+        from oracle import gj_oracle
+        op = gj_oracle.OracleProblem(spec4)
+        n, s, _ = op.bench_la(spec4.initial, 32, 2000, cores, 3, [0.5, 0.5, 0, 0, 0, 0], [0, 0, 3])
+        steps = int(max(2000, min(1e6, 5.0 * 2000 / max(s, 1e-3))))
+        n, s, _ = op.bench_la(spec4.initial, 32, steps, cores, 4, [0.5, 0.5, 0, 0, 0, 0], [0, 0, 3])
+        return {"value": n / s, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{steps} LateAcceptance steps x {cores} agents ({s:.1f} s); " + cpu_note("ISC")}
 
-    timed("C1 nqueens-256 LateAcceptance x4096 chains (k_la_chains)", c1, 1000)
-    timed("C3 cvrp-2000x50 GeneticAlgorithm pop 8192 x1 island", c3, 10)
-    timed("C4 vrptw-5000 (vrp_service) LateAcceptance x4096 chains (k_vrp_chains, route-level delta)", c4, 640)
-    timed("C5 tsp-20000 TabuSearch 4096 moves x148 islands (fused step, lean layout)", c5, 20)
+    run("C4 vrptw-5000 (vrp_service) LateAcceptance(32), 4096 chains per GPU", c4, 10, 3, 64, 64, "k_vrp_chains",
+        144.0, "A_delta: VRP swap with time windows 144 B (SURVEY 8d); the route re-walk itself reads ~3.4 KB",
+        c4_cpu, note="chain state 4096 x ~130 KB = 532 MB per GPU: larger than L2, no flush needed")
+
+    # ---- C5: TSP 20000, TabuSearch islands (device-timed) + GA/Tabu hybrid ring over a fixed wall time ---------
+    spec5 = inst.tsp(20000, seed=4, with_matrix=False)
+    c5_wall = float(os.environ.get("GJ_BENCH_C5_WALL_S", "60"))
+    try:
+        p5 = gj.Problem(spec5, use_coords=True, device=local_rank)
+
+        def c5():
+            isl = gj.TabuSearch(4096, 0.2, True, None, MOVE_PROBAS, 10, scoring="delta").build_agent(
+                p5, n_islands=148, seed=4 + rank)
+            return _NoClose(p5), isl, 148 * 4096
+
+        def c5_cpu(prob):
+            from oracle import gj_oracle
+            s5 = inst.tsp(20000, seed=4, with_matrix=False)
+            s5.distance_matrix = p5.distance_matrix()          # the device-built 3.2 GB matrix
+            s5.initial = np.arange(1, 20000, dtype=np.float64)
+            op = gj_oracle.OracleProblem(s5)
+            n, s, _ = op.bench_ts(s5.initial, 4096, 1, cores, 3, MOVE_PROBAS, [3, 3])
+            return {"value": n / s, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"1 TabuSearch step x {cores} islands x 4096 moves ({s:.1f} s); " + cpu_note("ISC")}
+
+        run("C5 tsp-20000 TabuSearch 4096 moves, 148 islands per GPU", c5, 10, 3, 10, 1, "k_ls_step_fused<GJ_TSP> (lean)",
+            A_DELTA, "A_delta: swap 96 B / 2-opt 56 B", c5_cpu,
+            note="3.2 GB matrix in HBM: larger than L2, no flush needed")
+        if c5_wall > 0:
+            try:
+                out["C5 hybrid GA + TabuSearch islands, fixed wall time"] = c5_hybrid(gj, ring, torch, D, p5, rank,
+                                                                                      world, c5_wall, stream)
+            except Exception as e:                  # noqa: BLE001
+                out["C5 hybrid GA + TabuSearch islands, fixed wall time"] = {"error": str(e)[:300]}
+        p5.close()
+    except Exception as e:                          # noqa: BLE001
+        out["C5 tsp-20000"] = {"error": str(e)[:300]}
     return out
+
+
+def c5_hybrid(gj, ring, torch, D, prob, rank, world, wall, stream):
+    """BASELINE config 5: GA + TabuSearch hybrid islands with elite migration, fixed wall time.  Per GPU a
+    TabuSearch group and a GeneticAlgorithm group share one ring (ring.HybridRing): ... -> TS islands -> GA
+    islands -> next GPU's TS islands -> ...; the exchange moves elites with the receiving agent's own
+    acceptance rule (agent_base.rs:405-440)."""
+    ts = gj.TabuSearch(4096, 0.2, True, None, MOVE_PROBAS, 10, scoring="delta").build_agent(prob, n_islands=144, seed=40 + rank)
+    ga = gj.GeneticAlgorithm(1024, 0.5, 0.2, 0.0, 1.0, MOVE_PROBAS, 0.0005, 10).build_agent(
+        prob, n_islands=4, seed=50 + rank, initial=np.tile(ts.best(0)[0], (4, 1)))
+    hyb = ring.HybridRing([ts, ga], rank, world)
+    start = D.best_score(ts.best(-1)[1])
+    D.barrier()
+    t0 = time.perf_counter()
+    rounds = 0
+    c0 = ts.stats()["candidates"] + ga.stats()["candidates"]
+    while True:
+        ts.step(10, stream)
+        ga.step(10, stream)
+        hyb.exchange(stream)
+        rounds += 1
+        torch.cuda.synchronize()
+        if D.reduce(1.0 if time.perf_counter() - t0 >= wall else 0.0, "max") > 0:
+            break
+    secs = time.perf_counter() - t0
+    cands = D.reduce(ts.stats()["candidates"] + ga.stats()["candidates"] - c0, "sum")
+    best_ts, best_ga = D.best_score(ts.best(-1)[1]), D.best_score(ga.best(-1)[1])
+    res = {"wall_s": secs, "n_gpus": world, "steps_per_group": rounds * 10, "candidates_per_s": cands / secs,
+           "start": start, "best_tabu_group": best_ts, "best_ga_group": best_ga, "best": min(best_ts, best_ga),
+           "islands_per_gpu": {"TabuSearch(4096 neighbours)": 144, "GeneticAlgorithm(pop 1024)": 4},
+           "ring": hyb.describe()}
+    hyb.close(); ga.close(); ts.close()
+    return res
 
 
 def main():
@@ -206,9 +450,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--islands", type=int, default=int(os.environ.get("GJ_BENCH_ISLANDS", "592")))
+    ap.add_argument("--islands", type=int, default=int(os.environ.get("GJ_BENCH_ISLANDS", str(ISLANDS_PER_GPU))))
     ap.add_argument("--e2e-agents", type=int, default=4)
-    ap.add_argument("--scoring", default="delta", choices=["delta", "full"])
+    ap.add_argument("--scoring", default="delta", choices=["delta", "delta_f64", "full"])
+    ap.add_argument("--tree-sums", action="store_true", help="gj_problem_set_exact_sums(0) for the headline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="development: device-timed value only")
     args = ap.parse_args()
@@ -225,6 +470,7 @@ def main():
     import torch.distributed as dist
     import greyjack_b200 as gj
     from greyjack_b200 import instances as inst
+    from greyjack_b200 import ring
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -232,210 +478,207 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D = Dist(torch, dist, world)
 
     spec = inst.tsp(N_CITIES, seed=1)
     prob = gj.Problem(spec, device=local_rank)
-    prob.set_exact_sums(False)
+    prob.set_exact_sums(not args.tree_sums)
     SCORING = args.scoring
     builder = gj.TabuSearch(NEIGHBOURS, TABU_RATE, True, None, MOVE_PROBAS, MIGRATION_FREQUENCY, scoring=SCORING)
     isl = builder.build_agent(prob, n_islands=args.islands, seed=1000 + rank)
-    from greyjack_b200 import ring
-    migrator = ring.RingMigrator(isl, rank, world, args.islands, device="cuda")
+    migrator, transport = make_ring(ring, isl, rank, world, args.islands)
     stream = torch.cuda.current_stream().cuda_stream
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flush = None if os.environ.get("GJ_BENCH_NO_FLUSH") else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    def one_step(i):
-        isl.step(1, stream)
-        if (i + 1) % MIGRATION_FREQUENCY == 0:
-            # AgentToAgentUpdate ring i -> i+1 across GPUs (agent_base.rs:161-183) over NCCL
-            migrator.exchange(stream)
-
-    for i in range(args.warmup):
-        one_step(i)
-    migrator.exchange(stream)      # untimed: sets up the NCCL point-to-point connections (no-op at N=1)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    isl.set_profiling(True)
-    c0 = isl.stats()["candidates"]
     launches0 = gj.load().gj_launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    for i in range(args.steps):
-        if not os.environ.get("GJ_BENCH_NO_FLUSH"):      # development only: the reported protocol flushes
-            flush.fill_(i & 0xFF)                # L2 flush between timed iterations (untimed)
-        evs[i][0].record()
-        one_step(args.warmup + i)
-        evs[i][1].record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
-    cands = isl.stats()["candidates"] - c0
+    total_ms, cands, kernel_ms, _ = timed_island_steps(torch, D, isl, migrator, args.steps, args.warmup, stream,
+                                                       MIGRATION_FREQUENCY, flush)
     gpu_launches = int(gj.load().gj_launch_count() - launches0)     # counted by the library itself
-    if world > 1:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        c = torch.tensor([cands], device="cuda", dtype=torch.float64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        cands = float(c.item())
     value = cands / (total_ms * 1e-3)
+    step_path = isl.step_path
 
-    # dominant kernel (the scorer): CUDA events on its launch stream, inside the timed region
-    k_total_ms, k_launches = isl.profile_read()
-    isl.set_profiling(False)
-    kernel_ms = k_total_ms / max(1, k_launches)
     per_launch_cands = args.islands * NEIGHBOURS
     a_bytes = A_FULL if SCORING == "full" else A_DELTA
     peak, peak_src = peaks()
-    achieved = per_launch_cands * a_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
+    roof = roofline(SCORING_KERNEL[SCORING], per_launch_cands, a_bytes, kernel_ms,
+                    "A_full 12 012 B" if SCORING == "full" else "A_delta: swap 96 B / 2-opt 56 B, 50:50 mix", peak, peak_src,
+                    {"traffic": traffic,
+                     "kernel_share_of_step": kernel_ms / (total_ms / args.steps) if world == 1 else None,
+                     "bound_note": "reported against the HBM roofline as SURVEY 8(d) prescribes; the kernel keeps its "
+                                   "working set in shared memory / L2 (DRAM traffic is a few % of peak) and is limited "
+                                   "by the L1TEX/LSU wavefronts of its random gathers and by issue slots -- see limiter",
+                     "limiter": limiter_note()})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: TSP 1000 cities, TabuSearch, swap/2-opt, 4096 moves per step",
-                   "islands_per_gpu": args.islands, "moves_per_island_step": NEIGHBOURS,
+        "config": {"workload": WORKLOAD, "islands_per_gpu": args.islands, "moves_per_island_step": NEIGHBOURS,
                    "move_probas": MOVE_PROBAS, "tabu_entity_rate": TABU_RATE,
                    "migration_frequency": MIGRATION_FREQUENCY, "score_precision": [3, 3],
-                   "scoring": SCORING_DESC[SCORING], "float_sums": "tree (gj_problem_set_exact_sums(0))", "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": f"islands x{world}"},
-        "clocks": None, "gpu_launches": gpu_launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": SCORING_KERNEL[SCORING], "kernel_ms": kernel_ms,
-                     "kernel_share_of_step": kernel_ms / (total_ms / args.steps) if world == 1 else None,
-                     "algorithmic_bytes_per_candidate": a_bytes,
-                     "candidates_per_launch": per_launch_cands},
+                   "scoring": SCORING_DESC[SCORING], "step_path": step_path,
+                   "float_sums": "tree (gj_problem_set_exact_sums(0))" if args.tree_sums else
+                                 "exact: stored scores are the reference-order f64 fold (library default)",
+                   "arithmetic": "candidates ordered by exact integer milli-unit deltas (the matrix is truncated to "
+                                 "3 decimals), stored scores in the reference's f64",
+                   "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "NOT flushed (development)",
+                   "ring": transport, "parallelism": f"islands x{world}"},
+        "clocks": None, "gpu_launches": gpu_launches, "roofline": roof,
     }
-
     if args.no_e2e:
         line["clocks"] = sampler.summary()
-        line["step_path"] = isl.step_path
+        line["step_path"] = step_path
         if rank == 0:
             print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
-    if rank != 0:
-        sampler.summary()
-    if rank == 0:
-        # ---- e2e: reference-facing call, host buffers, H2D + D2H inside the timed region ------
-        A = args.e2e_agents
-        rng = np.random.default_rng(5)
-        base = spec.initial.copy()
-        probs = [prob] + [gj.Problem(spec, device=local_rank) for _ in range(A - 1)]
+
+    # ---- e2e: reference-facing call, host buffers, H2D + D2H inside the timed region, on EVERY rank ------
+    A = args.e2e_agents
+    rng = np.random.default_rng(5 + rank)
+    base = spec.initial.copy()
+    probs = [prob] + [gj.Problem(spec, device=local_rank) for _ in range(A - 1)]
+    keep = []
+
+    def pin(a):
         # inputs and outputs live in page-locked host memory (gj_host_alloc): the copies inside
         # gj_score_incremental are then asynchronous DMA at PCIe speed
-        keep = []
+        holder, view = gj.pinned_copy(a)
+        keep.append(holder)
+        return view
 
-        def pin(a):
-            holder, view = gj.pinned_copy(a)
-            keep.append(holder)
-            return view
+    base = pin(base)
+    sets = [tuple(pin(x) for x in host_moves(base, NEIGHBOURS, rng)) for _ in range(A)]
+    outs = [pin(np.empty((NEIGHBOURS, 2))) for _ in range(A)]
+    h2d = sum(base.nbytes + o.nbytes + i.nbytes + v.nbytes for o, i, v in sets)
+    d2h = sum(o.nbytes for o in outs)
 
-        base = pin(base)
-        sets = [tuple(pin(x) for x in host_moves(base, NEIGHBOURS, rng)) for _ in range(A)]
-        outs = [pin(np.empty((NEIGHBOURS, 2))) for _ in range(A)]
-        h2d = sum(base.nbytes + o.nbytes + i.nbytes + v.nbytes for o, i, v in sets)
-        d2h = sum(o.nbytes for o in outs)
+    def run_agents(fn, n):
+        th = [threading.Thread(target=fn, args=(a, n)) for a in range(A)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
 
-        def agent(a, n):
-            o, i, v = sets[a]
-            for _ in range(n):
-                probs[a].request_score_incremental_csr(base, o, i, v, out=outs[a])
+    def agent(a, n):
+        o, i, v = sets[a]
+        for _ in range(n):
+            probs[a].request_score_incremental_csr(base, o, i, v, out=outs[a])
 
-        def run_agents(n):
-            th = [threading.Thread(target=agent, args=(a, n)) for a in range(A)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
+    run_agents(agent, args.warmup)
+    D.barrier()
+    l0 = gj.load().gj_launch_count()
+    t0 = time.perf_counter()
+    run_agents(agent, args.steps)
+    torch.cuda.synchronize()
+    e2e_s = D.reduce(time.perf_counter() - t0, "max")
+    e2e_launches = int(gj.load().gj_launch_count() - l0)
+    line["clocks"] = sampler.summary()           # the sampler covered both timed regions
+    line["e2e"] = {"value": world * A * NEIGHBOURS * args.steps / e2e_s, "unit": UNIT,
+                   "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+                   "agents_per_gpu": A, "n_gpus": world, "host_memory": "pinned (gj_host_alloc)",
+                   "call": "gj_score_incremental (request_score_incremental), host CSR deltas in the reference's "
+                           "(usize, f64) layout, one call per agent per step, agents on separate host threads / "
+                           "CUDA streams, every rank measured (sum of candidates / max of wall times)",
+                   "excluded": "the delta lists are built before the timed region (the reference builds them in "
+                               "Mover::do_move on the host; the CPU arm generates its moves inside its timed region)"}
+    line["gpu_launches"] = gpu_launches + e2e_launches      # both timed regions, counted by the library
 
-        run_agents(args.warmup)
-        l0 = gj.load().gj_launch_count()
+    # additional figure: the same call with the packed wire format (u32 ids, i32 values)
+    psets = [(o, pin(i.astype(np.uint32)), pin(np.rint(v).astype(np.int32))) for o, i, v in sets]
+    ph2d = sum(base.nbytes + o.nbytes + i.nbytes + v.nbytes for o, i, v in psets)
+
+    def agent_packed(a, n):
+        o, i, v = psets[a]
+        for _ in range(n):
+            probs[a].request_score_incremental_packed(base, o, i, v, out=outs[a])
+
+    run_agents(agent_packed, args.warmup)
+    D.barrier()
+    t0 = time.perf_counter()
+    run_agents(agent_packed, args.steps)
+    torch.cuda.synchronize()
+    p_s = D.reduce(time.perf_counter() - t0, "max")
+    line["e2e"]["packed"] = {"value": world * A * NEIGHBOURS * args.steps / p_s, "unit": UNIT,
+                             "h2d_bytes_per_step": int(ph2d) * world,
+                             "call": "gj_score_incremental_packed: 8 B per delta instead of the reference "
+                                     "layout's 16 B (not the headline)"}
+    for p in probs[1:]:
+        p.close()
+
+    # ---- cpu_baseline + quality (metric ii: best score at fixed wall time) ---------------------------------
+    wall = float(os.environ.get("GJ_BENCH_QUALITY_WALL_S", "10.0"))
+    cores = os.cpu_count() or 1
+    cpu_q = {}
+    op = None
+    cpu_steps = 1
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import gj_oracle
+        op = gj_oracle.OracleProblem(spec)
+        n1, s1, _ = op.bench_ts(base, NEIGHBOURS, 1, cores, 3, MOVE_PROBAS, [3, 3])
+        steps = max(2, min(800, int(12.0 / max(s1, 1e-3))))
+        n, secs, _ = op.bench_ts(base, NEIGHBOURS, steps, cores, 4, MOVE_PROBAS, [3, 3])
+        line["cpu_baseline"] = {
+            "value": n / secs, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} TabuSearch steps x {cores} islands x {NEIGHBOURS} moves ({secs:.1f} s); oracle port "
+                      "(-O3 -march=native) of the reference ISC path without its Polars marshalling (CPU-favouring)"}
+        cpu_steps = max(1, int(wall * (n / secs) / (cores * NEIGHBOURS)))
+    if wall > 0:
+        q_isl = builder.build_agent(prob, n_islands=args.islands, seed=4242 + rank)
+        q_ring, _ = make_ring(ring, q_isl, rank, world, args.islands)
+        if q_ring is not None:
+            q_ring.exchange(stream)
+        D.barrier()
+
+        def cpu_arm():
+            # the CPU arm runs at the same time as the GPU arm (one host thread drives the GPU)
+            thr = max(1, cores - 1)
+            _, cw, cb = op.bench_ts(base, NEIGHBOURS, cpu_steps, thr, 5, MOVE_PROBAS, [3, 3])
+            cpu_q.update({"wall_s": cw, "best": [float(x) for x in cb], "steps": cpu_steps, "islands": thr,
+                          "note": "oracle port, one TabuSearch island per host thread, concurrent with the GPU arm"})
+
+        th = threading.Thread(target=cpu_arm) if op is not None else None
+        if th:
+            th.start()
         t0 = time.perf_counter()
-        run_agents(args.steps)
-        e2e_s = time.perf_counter() - t0
-        e2e_launches = int(gj.load().gj_launch_count() - l0)
-        # the sampler has been running since before the device-timed region: both timed regions
-        line["clocks"] = sampler.summary()
-        line["e2e"] = {"value": A * NEIGHBOURS * args.steps / e2e_s, "unit": UNIT,
-                       "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "agents": A, "host_memory": "pinned (gj_host_alloc)",
-                       "call": "gj_score_incremental (request_score_incremental), host CSR deltas, "
-                               "one call per agent per step, agents on separate host threads / CUDA streams"}
-        line["gpu_launches"] = gpu_launches + e2e_launches      # both timed regions, counted by the library
-
-        # ---- additional figure: the same call with the packed wire format (u32 ids, i32 values) ----
-        psets = []
-        for o, i, v in sets:
-            psets.append((o, pin(i.astype(np.uint32)), pin(np.rint(v).astype(np.int32))))
-        ph2d = sum(base.nbytes + o.nbytes + i.nbytes + v.nbytes for o, i, v in psets)
-
-        def agent_packed(a, n):
-            o, i, v = psets[a]
-            for _ in range(n):
-                probs[a].request_score_incremental_packed(base, o, i, v, out=outs[a])
-
-        def run_packed(n):
-            th = [threading.Thread(target=agent_packed, args=(a, n)) for a in range(A)]
-            for t in th:
-                t.start()
-            for t in th:
-                t.join()
-
-        run_packed(args.warmup)
-        t0 = time.perf_counter()
-        run_packed(args.steps)
-        p_s = time.perf_counter() - t0
-        line["e2e"]["packed"] = {"value": A * NEIGHBOURS * args.steps / p_s, "unit": UNIT,
-                                 "h2d_bytes_per_step": int(ph2d),
-                                 "call": "gj_score_incremental_packed: 8 B per delta instead of the "
-                                         "reference layout's 16 B (not the headline)"}
-
-        # ---- cpu_baseline: oracle port on the host cores, bounded sample ------------------------
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import gj_oracle
-            op = gj_oracle.OracleProblem(spec)
-            cores = os.cpu_count() or 1
-            n1, s1, _ = op.bench_ts(base, NEIGHBOURS, 1, cores, 3, MOVE_PROBAS, [3, 3])
-            steps = max(2, min(800, int(12.0 / max(s1, 1e-3))))
-            n, secs, _ = op.bench_ts(base, NEIGHBOURS, steps, cores, 4, MOVE_PROBAS, [3, 3])
-            line["cpu_baseline"] = {
-                "value": n / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{steps} TabuSearch steps x {cores} islands x {NEIGHBOURS} moves ({secs:.1f} s); "
-                          "oracle port of the reference ISC path without its Polars marshalling (CPU-favouring)"}
-            # ---- metric (ii): best score at fixed wall time, same instance, same move mix ---------
-            wall = float(os.environ.get("GJ_BENCH_QUALITY_WALL_S", "2.0"))
-            q_isl = builder.build_agent(prob, n_islands=args.islands, seed=4242)
+        q_steps = 0
+        while True:
+            q_isl.step(MIGRATION_FREQUENCY, stream)
+            if q_ring is not None:
+                q_ring.exchange(stream)
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            q_steps = 0
-            while time.perf_counter() - t0 < wall:
-                q_isl.step(MIGRATION_FREQUENCY, stream)
-                torch.cuda.synchronize()
-                q_steps += MIGRATION_FREQUENCY
-            gpu_wall = time.perf_counter() - t0
-            _, gpu_best = q_isl.best(-1)
-            q_isl.close()
-            cpu_steps = max(1, int(wall * (n / secs) / (cores * NEIGHBOURS)))
-            _, cpu_wall, cpu_best = op.bench_ts(base, NEIGHBOURS, cpu_steps, cores, 5, MOVE_PROBAS, [3, 3])
-            line["quality"] = {
-                "metric": "best score (hard, soft) at fixed wall time; lower is better",
-                "start": [float(x) for x in op.score_incremental(base, [[]])[0]],
-                "gpu": {"wall_s": gpu_wall, "best": [float(x) for x in gpu_best], "steps": q_steps,
-                        "islands": args.islands},
-                "cpu": {"wall_s": cpu_wall, "best": [float(x) for x in cpu_best], "steps": cpu_steps,
-                        "islands": cores, "note": "oracle port, one TabuSearch island per host thread"}}
-        if world == 1 and os.environ.get("GJ_BENCH_EXTRAS", "1") != "0":
-            line["other_configs"] = other_configs(gj, inst, torch)
+            q_steps += MIGRATION_FREQUENCY
+            if D.reduce(1.0 if time.perf_counter() - t0 >= wall else 0.0, "max") > 0:
+                break
+        gpu_wall = time.perf_counter() - t0
+        gpu_best = D.best_score(q_isl.best(-1)[1])
+        if th:
+            th.join()
+        if hasattr(q_ring, "close"):
+            q_ring.close()
+        q_isl.close()
+        line["quality"] = {
+            "metric": "best score (hard, soft) at fixed wall time; lower is better",
+            "start": [float(x) for x in prob.request_score_plain(spec.initial[None, :])[0]],
+            "gpu": {"wall_s": gpu_wall, "best": gpu_best, "steps": q_steps, "islands": args.islands * world,
+                    "n_gpus": world}}
+        if cpu_q:
+            line["quality"]["cpu"] = cpu_q
+    if hasattr(migrator, "close"):
+        migrator.close()
+    isl.close()
+    if os.environ.get("GJ_BENCH_EXTRAS", "1") != "0":
+        line["other_configs"] = other_configs(gj, inst, ring, torch, D, rank, world, local_rank, args)
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -51,6 +51,10 @@ gj_status gj_launch_tsfast_step(gj_islands* g, cudaStream_t st, bool trace) {
     else if (nt > 128) { if (mb >= 6) GJ_LAUNCH_TSFAST(256, 6, false); else GJ_LAUNCH_TSFAST(256, 4, false); }
     else GJ_LAUNCH_TSFAST(128, 8, false);
 #undef GJ_LAUNCH_TSFAST
+    if (F.pub) {
+        GJ_LAUNCH_CHECK();
+        k_ts_publish<<<1, 256, 0, st>>>(g->ts_pub, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score, g->gver);
+    }
     GJ_LAUNCH_CHECK();
     return GJ_OK;
 }

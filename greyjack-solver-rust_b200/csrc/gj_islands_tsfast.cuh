@@ -42,8 +42,7 @@ struct GjTsFastArgs {
     long long* phase_clocks;
     unsigned int* done_counter; // not null: the last island to finish publishes the global top (k_global_top's work)
     // not null: update_global_top's publish half by key tournament (see the end of the kernel):
-    // pub[0] = best key offered so far, pub[1] = key of the published global top, pub[2] = lock word,
-    // pub[3] = step that published it (+1)
+    // pub[0] = best key offered so far, pub[1] = key of the published global top
     unsigned long long* pub;
 };
 
@@ -81,6 +80,28 @@ __device__ __forceinline__ double gj_tsf_from_index(long long k) {
     long long q = k / 1000, r = k % 1000;
     if (r < 0) { r += 1000; q -= 1; }
     return (double)q + (double)r / 1000.0;
+}
+
+// an agent top as a 64-bit key whose unsigned order is "better score first, lower island on ties"
+__device__ __forceinline__ unsigned long long gj_tsf_top_key(double hard, double soft, int island) {
+    return ((unsigned long long)llrint(hard) << 48) | ((unsigned long long)gj_tsf_milli_index(soft) << 12) |
+           (unsigned long long)island;
+}
+
+// update_global_top, publish half, after a fixed-point step: the launch's best key against the
+// published one (strictly better score only, agent_base.rs:451) -> row, score, version.  One CTA.
+__global__ void __launch_bounds__(256)
+k_ts_publish(unsigned long long* pub, int stride, int n_vars, const int32_t* __restrict__ best,
+             const double* __restrict__ best_score, int32_t* gbest, double* gbest_score, int* gver) {
+    const unsigned long long k = pub[0], pk = pub[1];
+    if ((k >> 12) >= (pk >> 12)) return;                       // uniform over the CTA
+    const int owner = (int)(k & 0xfffull);
+    for (int i = threadIdx.x; i < n_vars; i += blockDim.x) gbest[i] = best[(size_t)owner * stride + i];
+    if (threadIdx.x == 0) {
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = best_score[(size_t)owner * GJ_MAX_LEVELS + l];
+        *gver += 1;
+        pub[1] = k;
+    }
 }
 
 // ---- out-of-line slow path: generic generator / evaluator (rare) ------------------------------------
@@ -545,51 +566,14 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     // The global top is the best agent top, lowest island on ties, replaced only by a strictly better
     // one (k_global_top).  In fixed point an agent top packs into 64 bits -- hard level | milli-unit
     // index | island -- whose unsigned order IS that rule, so the reduction over all islands is one
-    // atomicMin per island, and the island that holds the minimum when it finishes copies its row under
-    // a lock (a later, better island simply overwrites it; a worse one never does).  No extra launch,
-    // no serial tail; the outcome does not depend on the order in which islands finish.
+    // atomicMin per island here; k_ts_publish (one small CTA after the step) compares the winner with
+    // the published top and copies its row.  (The row cannot be copied from inside this kernel: islands
+    // of a later wave may be reading the published row for their adoption at that very moment.)
     if (F.pub) {
-        unsigned long long* pub = F.pub;
         if (tid == 0) {
             const double th = A.best_score[(size_t)island * GJ_MAX_LEVELS + 0];
             const double ts = A.best_score[(size_t)island * GJ_MAX_LEVELS + 1];
-            const unsigned long long key = ((unsigned long long)llrint(th) << 48) |
-                                           ((unsigned long long)gj_tsf_milli_index(ts) << 12) | (unsigned long long)island;
-            atomicMin(&pub[0], key);
-            __threadfence();
-            // against a top published by an EARLIER launch only a strictly better score counts
-            // (agent_base.rs:451); against one published earlier in THIS launch the full key decides,
-            // i.e. the lowest island among equal scores -- k_global_top's "first index on ties"
-            const unsigned long long now = (unsigned long long)A.step + 1ull;
-            auto beats = [&](unsigned long long pk, unsigned long long pstep) {
-                return pstep == now ? (key < pk) : ((key >> 12) < (pk >> 12));
-            };
-            int take = 0;
-            if (__ldcg(&pub[0]) == key && beats(__ldcg(&pub[1]), __ldcg(&pub[3]))) {
-                while (atomicCAS(&pub[2], 0ull, 1ull) != 0ull) __nanosleep(64);
-                __threadfence();
-                take = beats(__ldcg(&pub[1]), __ldcg(&pub[3])) ? 1 : 0;
-                if (!take) { __threadfence(); atomicExch(&pub[2], 0ull); }
-            }
-            sh_last = take;
-        }
-        __syncthreads();
-        if (sh_last) {
-            const int32_t* my_best = A.best + (size_t)island * A.stride;
-            for (int i = tid; i < n; i += NT) A.gbest[i] = __ldcg(&my_best[i]);
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.gbest_score[l] = A.best_score[(size_t)island * GJ_MAX_LEVELS + l];
-                *A.gver += 1;
-                const double th = A.best_score[(size_t)island * GJ_MAX_LEVELS + 0];
-                const double ts = A.best_score[(size_t)island * GJ_MAX_LEVELS + 1];
-                pub[1] = ((unsigned long long)llrint(th) << 48) | ((unsigned long long)gj_tsf_milli_index(ts) << 12) |
-                         (unsigned long long)island;
-                pub[3] = (unsigned long long)A.step + 1ull;
-                __threadfence();
-                atomicExch(&pub[2], 0ull);
-            }
+            atomicMin(&F.pub[0], gj_tsf_top_key(th, ts, island));
         }
     } else if (F.done_counter) {
         // fallback (more than 4096 islands): the LAST island to finish runs k_global_top's reduction

@@ -109,7 +109,6 @@ k_ring_merge_gtop(const unsigned char* board, int world, int me, int parity, uns
                 // beyond every local one marks "owned by another rank"
                 ts_pub[1] = ((unsigned long long)llrint(best.v[0]) << 48) |
                             ((unsigned long long)llrint(best.v[1] * 1000.0) << 12) | 0xfffull;
-                ts_pub[3] = step;                       // published before the coming step: strict rule applies
             }
         }
     }
@@ -279,7 +278,6 @@ k_import_gtop(const unsigned char* recs, int count, size_t record_bytes, int str
             if (ts_pub) {
                 ts_pub[1] = ((unsigned long long)llrint(best.v[0]) << 48) |
                             ((unsigned long long)llrint(best.v[1] * 1000.0) << 12) | 0xfffull;
-                ts_pub[3] = step;
             }
         }
     }

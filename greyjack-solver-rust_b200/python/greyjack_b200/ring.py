@@ -111,6 +111,58 @@ class PeerRing:
             self.handle = None
 
 
+class HybridRing:
+    """ONE ring over island groups of different agent kinds (BASELINE config 5: GeneticAlgorithm +
+    TabuSearch hybrid islands).  On every rank the groups are chained g0 -> g1 -> ... -> g_last and
+    g_last feeds g0 of the next rank: the reference ring i -> (i + 1) mod n (solver.rs:85-92) over ALL
+    agents.  A link carries the sender group's migrants (its last island's individual; a GA island's
+    best `migrants` individuals) into the receiver group, which applies ITS OWN acceptance rule
+    (receive_updates, agent_base.rs:405-440: LocalSearch agents compare with population[0], Population
+    agents with their worst individuals).  Groups must agree on the bytes per exchange (give the GA a
+    migration_rate with ceil(rate * pop) == 1 next to local-search groups).  The cross-rank link uses
+    torch.distributed point-to-point (NCCL on GPUs)."""
+
+    def __init__(self, groups, rank: int, world: int, device="cuda", group=None):
+        self.groups, self.rank, self.world, self.group = list(groups), rank, world, group
+        per_rank = sum(g.n_islands for g in self.groups)
+        base = rank * per_rank
+        for g in self.groups:
+            g.set_external_ring(True, base)          # the ring is closed here, not inside gj_islands_step
+            base += g.n_islands
+        sizes = {int(g.migrant_bytes()) for g in self.groups}
+        if len(sizes) != 1:
+            raise ValueError(f"groups exchange different migrant sizes {sorted(sizes)}: set the GeneticAlgorithm's "
+                             "migration_rate so that ceil(rate * population) == 1")
+        n = sizes.pop()
+        self.out = [torch.empty(n, dtype=torch.uint8, device=device) for _ in self.groups]
+        self.inp = torch.empty(n, dtype=torch.uint8, device=device)
+        self.dst, self.src = ring_neighbours(rank, world)
+        self.exchanges = 0
+
+    def exchange(self, stream: int = 0):
+        # every agent sends the individual it held BEFORE receiving: export everything first
+        for g, buf in zip(self.groups, self.out):
+            g.export_migrants(buf.data_ptr(), stream)
+        for i in range(1, len(self.groups)):
+            self.groups[i].import_migrants(self.out[i - 1].data_ptr(), stream)
+        if self.world == 1:
+            self.groups[0].import_migrants(self.out[-1].data_ptr(), stream)
+        else:
+            ops = [dist.P2POp(dist.isend, self.out[-1], self.dst, group=self.group),
+                   dist.P2POp(dist.irecv, self.inp, self.src, group=self.group)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.groups[0].import_migrants(self.inp.data_ptr(), stream)
+        self.exchanges += 1
+
+    def describe(self) -> str:
+        kinds = " -> ".join(f"{type(g.builder).__name__} x{g.n_islands}" for g in self.groups)
+        return f"per GPU: {kinds} -> next GPU ({self.world} GPU{'s' if self.world > 1 else ''})"
+
+    def close(self):
+        pass
+
+
 def run_steps(islands, migrator: RingMigrator, n_steps: int, migration_frequency: int, stream: int = 0,
               first_step: int = 0):
     """Agent::solve's loop across ranks: step, and every migration_frequency steps exchange

@@ -590,3 +590,41 @@ def test_vrp_chain_migration_and_global_top_keep_the_index_in_sync(oracle):
             assert np.array_equal(cs, oracle.score_round(op.score_incremental(cv, [[]])[0], spec.score_precision))
     assert oracle.score_cmp(prev, s0) < 0
     isl.close(); gp.close()
+
+
+# ---- fixed-point TabuSearch step over many steps and several waves of CTAs ------------------------------
+@pytest.mark.parametrize("exact", [True, False], ids=["exact-sums", "tree-sums"])
+def test_fixed_point_long_run_keeps_every_island_consistent(exact, oracle):
+    """More islands than the GPU holds at once (several waves of CTAs), hundreds of steps with
+    migration and global-top adoption: every island's tour stays a permutation, its stored score is
+    the oracle's score of its stored tour, and the cached edge lengths never drift (the stored score
+    is folded from them)."""
+    spec = inst.tsp(300, seed=13)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    gp.set_exact_sums(exact)
+    I = 1500
+    isl = TabuSearch(256, 0.5, True, None, [0.0, 0.4, 0.0, 0.0, 0.2, 0.4], 5, scoring="delta").build_agent(
+        gp, n_islands=I, seed=77)
+    assert isl.step_path == "fused_fixed"
+    prev = None
+    for rnd in range(4):
+        isl.step(150)
+        gv, gs = isl.best(-1)
+        assert sorted(gv.tolist()) == list(range(1, 300))
+        want = oracle.score_round(op.score_incremental(gv, [[]])[0], spec.score_precision)
+        assert gs[0] == 0.0 and abs(gs[1] - want[1]) <= (0.0 if exact else QUANTUM)
+        if prev is not None:
+            assert oracle.score_cmp(gs, prev) <= 0
+        prev = gs
+        for i in list(range(0, I, 97)) + [I - 1]:
+            cv, cs = isl.current(i)
+            assert sorted(cv.tolist()) == list(range(1, 300)), (rnd, i)
+            want = oracle.score_round(op.score_incremental(cv, [[]])[0], spec.score_precision)
+            assert cs[0] == 0.0 and abs(cs[1] - want[1]) <= (0.0 if exact else QUANTUM), (rnd, i, cs, want)
+            bv, bs = isl.best(i)
+            want = oracle.score_round(op.score_incremental(bv, [[]])[0], spec.score_precision)
+            assert bs[0] == 0.0 and abs(bs[1] - want[1]) <= (0.0 if exact else QUANTUM)
+            assert oracle.score_cmp(gs, bs) <= 0
+    assert isl.stats()["steps"] == 600
+    isl.close(); gp.close()

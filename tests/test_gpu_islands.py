@@ -225,3 +225,43 @@ def test_genetic_algorithm_generations(mk, oracle):
         assert _same_score(cs, op.score_plain(cv)[0], spec, oracle)
     assert ga.stats()["candidates"] == 20 * 256 * 3
     ga.close(); gp.close()
+
+
+def test_hybrid_ring_moves_elites_between_tabu_and_ga_groups(oracle):
+    """BASELINE config 5's mixed ring: a TabuSearch group and a GeneticAlgorithm group on one problem,
+    chained by ring.HybridRing.  The GA group starts from random tours, the TabuSearch group from the
+    greedy tour: after one exchange the GA population holds the tabu group's individual (Population
+    rule: the migrant replaces the worst individual when it is <= it, agent_base.rs:405-412, 435-439);
+    the tabu group's first island keeps its own (LocalSearch rule: migrant <= population[0], :429-434)."""
+    torch = pytest.importorskip("torch")
+    from greyjack_b200 import ring
+    spec = inst.tsp(120, seed=6)
+    op = oracle.OracleProblem(spec)
+    gp = Problem(spec)
+    ts = TabuSearch(256, 0.2, True, None, [0, 0.5, 0, 0, 0, 0.5], 10, scoring="delta").build_agent(gp, n_islands=3, seed=1)
+    rnd = inst.tsp(120, seed=6, greedy=False)
+    rnd.initial = np.full(spec.n_vars, np.nan)
+    gp2 = Problem(rnd)
+    ga = GeneticAlgorithm(64, 0.5, 0.2, 0.0, 1.0, [0, 0.5, 0, 0, 0, 0.5], 0.01, 10).build_agent(gp2, n_islands=2, seed=2)
+    assert ts.migrant_bytes() == ga.migrant_bytes()          # ceil(0.01 * 64) == 1 individual per exchange
+    hyb = ring.HybridRing([ts, ga], 0, 1)
+    ts_cur = [ts.current(i) for i in range(3)]
+    ga_best_before = ga.best(0)[1]
+    assert oracle.score_cmp(ts_cur[2][1], ga_best_before) < 0
+    hyb.exchange(0)
+    torch.cuda.synchronize()
+    rows, scores, order = ga.ga_population(0)
+    # the last tabu island's individual now sits in GA island 0 (it beat that island's worst individual)
+    hit = [k for k in range(64) if np.array_equal(rows[k], ts_cur[2][0])]
+    assert len(hit) == 1 and np.array_equal(scores[hit[0]], ts_cur[2][1])
+    assert _same_score(scores[hit[0]], op.score_plain(rows[hit[0]])[0], spec, oracle)
+    # ... and is GA island 0's best individual after the re-sort
+    assert order[0] == hit[0]
+    # GA island 1 received GA island 0's best (in-group link), tabu island 0 was offered GA island 1's best
+    # (a random tour, far worse than the greedy one): rejected
+    assert np.array_equal(ts.current(0)[0], ts_cur[0][0])
+    assert "TabuSearch x3 -> GeneticAlgorithm x2" in hyb.describe()
+    ga.step(3); ts.step(3)
+    hyb.exchange(0)
+    assert oracle.score_cmp(ga.best(-1)[1], ga_best_before) < 0
+    ga.close(); ts.close(); gp.close(); gp2.close()
