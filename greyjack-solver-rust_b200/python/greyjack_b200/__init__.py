@@ -10,3 +10,4 @@ from .agents import (GeneticAlgorithm, Islands, LateAcceptance, ScoreLimit, Scor
                      SimulatedAnnealing, StepsLimit, TabuSearch, TimeSpentLimit)
 from .solver import Solver  # noqa: F401,E402
 from . import wire  # noqa: F401,E402
+from .program import ConstraintProgram, TermSpec, nqueens_program, tsp_program, vrp_program  # noqa: F401,E402

@@ -56,6 +56,17 @@ class GaTrace(C.Structure):
                 ("src", C.c_void_p)]
 
 
+class Term(C.Structure):
+    _fields_ = [("op", C.c_int32), ("value_offset", C.c_int32), ("value_stride", C.c_int32),
+                ("seg_offset", C.c_int32), ("seg_stride", C.c_int32),
+                ("key_value_coef", C.c_int32), ("key_index_coef", C.c_int32), ("variant", C.c_int32),
+                ("scale", C.c_double)]
+
+
+class Constraint(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("level", C.c_int32), ("n_terms", C.c_int32), ("terms", Term * 4)]
+
+
 # every symbol include/greyjack_b200.h declares
 EXPORTED = [
     "gj_last_error", "gj_abi_version", "gj_device_count", "gj_sizeof_problem_desc", "gj_sizeof_agent_params", "gj_launch_count",
@@ -68,6 +79,8 @@ EXPORTED = [
     "gj_islands_best", "gj_islands_current", "gj_islands_migrant_bytes",
     "gj_islands_set_external_ring", "gj_islands_export_migrants", "gj_islands_import_migrants",
     "gj_islands_global_top_bytes", "gj_islands_export_global_top", "gj_islands_import_global_top",
+    "gj_program_create", "gj_program_destroy", "gj_program_add_constraint", "gj_program_remove_constraint",
+    "gj_program_set_constraint_weights", "gj_program_n_constraints", "gj_program_get_score",
     "gj_ring_create", "gj_ring_destroy", "gj_ring_handle", "gj_ring_connect", "gj_ring_exchange", "gj_ring_stats", "gj_islands_trace_step", "gj_islands_trace_tabu", "gj_islands_ga_trace_generation", "gj_islands_ga_population",
 ]
 
@@ -100,6 +113,9 @@ def load():
     if hasattr(L, "gj_islands_global_top_bytes"):
         L.gj_islands_global_top_bytes.restype = C.c_int64
         L.gj_ring_destroy.restype = None
+    if hasattr(L, "gj_program_destroy"):
+        L.gj_program_destroy.restype = None
+        L.gj_program_n_constraints.restype = C.c_int32
     _lib = L
     return L
 

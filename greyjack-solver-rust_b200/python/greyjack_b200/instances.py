@@ -307,3 +307,213 @@ def tsp_from_tsplib(text: str, greedy: bool = True) -> ProblemSpec:
     if greedy:
         spec.initial = tsp_greedy(D)
     return spec
+
+
+# ---- VRP files, domain round trips, frozen replanning (host side only) --------
+def read_vrp(text: str):
+    """DomainBuilder::read_vrp_file (examples/vrp/src/persistence/domain_builder.rs:145-331): header up to
+    NODE_COORD_SECTION (vehicles count = the `-kNN` suffix of NAME, CAPACITY, EDGE_WEIGHT_TYPE, TYPE: last
+    space-separated token of the line), `id x y [name]` lines up to DEMAND_SECTION / EOF, an explicit
+    matrix (rows up to EOF) unless the type is EUC_2D, demand lines `id demand [tw_start tw_end service]`
+    up to DEPOT_SECTION / EOF, depot ids up to -1 / EOF.
+    Returns (metadata, coords [L, 2], ids, matrix or None, demand_info [[...]], depot_ids)."""
+    lines = iter(text.splitlines())
+    meta = {}
+    for line in lines:
+        if "NODE_COORD_SECTION" in line:
+            break
+        last = line.split(" ")[-1].strip()
+        if "NAME" in line:
+            meta["dataset_name"] = last
+            meta["vehicles_count"] = last.split("-")[-1].replace("k", "")
+        if "TYPE" in line:
+            meta["task_type"] = last
+        if "EDGE_WEIGHT_TYPE" in line:
+            meta["distance_type"] = last
+        if "CAPACITY" in line:
+            meta["vehicles_capacity"] = last
+    else:
+        raise ValueError("no NODE_COORD_SECTION")
+    for key in ("vehicles_count", "vehicles_capacity", "distance_type"):
+        if key not in meta:
+            raise ValueError(f"header lacks {key}")
+    xy, ids = [], []
+    for line in lines:
+        if "EOF" in line or "DEMAND_SECTION" in line:
+            break
+        parts = line.split()
+        if len(parts) < 3:
+            raise ValueError(f"bad customer line {line!r}")
+        ids.append(int(parts[0]))
+        xy.append((float(parts[1]), float(parts[2])))
+    matrix = None
+    if "EUC_2D" not in meta["distance_type"]:
+        rows = []
+        for line in lines:
+            if "EOF" in line:
+                break
+            parts = line.split(" ")[:-1]          # the reference drops the last token of every row
+            rows.append([float(x) for x in parts if x != ""])
+        if rows:
+            matrix = np.array(rows, dtype=np.float64)
+    demand_info = []
+    depot_ids = []
+    in_depots = False
+    for line in lines:
+        if "DEMAND_SECTION" in line:              # (the header line itself, when a matrix came first)
+            continue
+        if "DEPOT_SECTION" in line:
+            in_depots = True
+            continue
+        if "EOF" in line:
+            if in_depots:
+                break
+            continue
+        s = line.strip()
+        if not s:
+            continue
+        if in_depots:
+            if "-1" in s:
+                break
+            depot_ids.append(int(s))
+        else:
+            demand_info.append([int(x) for x in s.split(" ") if x != ""])
+    return meta, np.array(xy, dtype=np.float64).reshape(-1, 2), ids, matrix, demand_info, depot_ids
+
+
+def vrp_from_file(text: str, service_variant: bool = False, greedy: bool = True) -> ProblemSpec:
+    """DomainBuilder::build_domain_from_scratch (:18-91) + CotwinBuilder::build_cotwin of examples/vrp
+    (service_variant: examples/vrp_service): depots = the first len(DEPOT_SECTION) locations, vehicle i
+    starts at depot i % n_depots with the depot's window as its work day, every other location is one
+    planning stop (vehicle_id in [0, K-1], customer_id in [n_depots, L-1]); distances by the example's
+    formula unless the file carries a matrix (both truncated to 3 decimals)."""
+    meta, xy, ids, matrix, demand_info, depot_ids = read_vrp(text)
+    L = xy.shape[0]
+    if len(demand_info) != L:
+        raise ValueError("Customers or demands have been readed incorrect")
+    n_depots = len(depot_ids)
+    if n_depots < 1 or n_depots >= L:
+        raise ValueError("DEPOT_SECTION must name at least one depot and leave customers")
+    K = int(meta["vehicles_count"])
+    cap = int(meta["vehicles_capacity"])
+    demand = np.zeros(L, dtype=np.uint64)
+    tw_start = np.zeros(L, dtype=np.uint64); tw_end = np.zeros(L, dtype=np.uint64); service = np.zeros(L, dtype=np.uint64)
+    time_windowed = False
+    for i, row in enumerate(demand_info):
+        if row[0] != ids[i]:
+            raise ValueError("Invalid customer to demand mapping")
+        demand[i] = row[1]
+        if len(row) == 5:
+            time_windowed = True
+            tw_start[i], tw_end[i], service[i] = row[2], row[3], row[4]
+    if matrix is not None:
+        D = np.floor(matrix) + np.floor((matrix - np.floor(matrix)) * 1000.0) / 1000.0      # round(dm, 3), math_utils.rs:10-13
+    else:
+        D = distance_matrix(xy)
+    if D.shape != (L, L):
+        raise ValueError(f"distance matrix is {D.shape}, expected {(L, L)}")
+    kind = VRP_SERVICE if service_variant else VRP
+    n_stops = L - n_depots
+    n = 2 * n_stops
+    lb = np.empty(n); ub = np.empty(n)
+    lb[0::2] = 0.0; ub[0::2] = float(K - 1)
+    lb[1::2] = float(n_depots); ub[1::2] = float(L - 1)
+    groups = {"vehicle_assignment": np.arange(0, n, 2, dtype=np.int32), "customer_assignment": np.arange(1, n, 2, dtype=np.int32)}
+    if kind == VRP:
+        groups["common"] = np.arange(n, dtype=np.int32)
+    depot_of = (np.arange(K) % n_depots).astype(np.int64)
+    spec = ProblemSpec(
+        kind=kind, n_vars=n, lower_bounds=lb, upper_bounds=ub, groups=groups, n_locations=L, distance_matrix=D,
+        coords=xy, n_depots=n_depots, n_vehicles=K, vehicle_depot=depot_of,
+        vehicle_capacity=np.full(K, cap, dtype=np.uint64),
+        work_day_start=tw_start[depot_of].copy(), work_day_end=tw_end[depot_of].copy(),
+        demand=demand, tw_start=tw_start, tw_end=tw_end, service_time=service, time_windowed=time_windowed,
+        score_precision=[0, 0, 3], name=meta["dataset_name"])
+    spec.initial = vrp_greedy(spec) if greedy else np.full(n, np.nan)
+    return spec
+
+
+def vrp_routes_from_solution(spec: ProblemSpec, values) -> list:
+    """DomainBuilder::build_from_solution (examples/vrp .../domain_builder.rs:93-141): walk the planning
+    stops in entity order and append every stop's customer to its vehicle -> one customer list per
+    vehicle (visiting order = entity order, which is what the scorers assume)."""
+    v = np.asarray(values, dtype=np.float64)
+    routes = [[] for _ in range(spec.n_vehicles)]
+    for s in range(spec.n_vars // 2):
+        routes[int(v[2 * s])].append(int(v[2 * s + 1]))
+    return routes
+
+
+def tsp_path_from_solution(spec: ProblemSpec, values) -> list:
+    """examples/tsp DomainBuilder::build_from_solution (:58-77): the vehicle's trip path as location ids"""
+    return [int(x) for x in np.asarray(values, dtype=np.float64)]
+
+
+def vrp_replanning_spec(spec: ProblemSpec, routes, frozen_vehicles=(), drop_vehicles=()) -> ProblemSpec:
+    """The replanning scenario of examples/vrp/src/main.rs:120-141: an existing plan (routes per vehicle)
+    becomes the start of a new solve -- optionally with vehicles removed and the customers of some
+    vehicles pinned.  CotwinBuilder::build_planning_stops with is_already_initialized
+    (cotwin_builder.rs:108-119): planning stop i takes the i-th (vehicle, customer) pair of the plan in
+    vehicle-major route order as its initial value, frozen when the customer is pinned.  Customers of
+    dropped vehicles lose their assignment (initial None -> sampled)."""
+    import copy
+    out = copy.deepcopy(spec)
+    keep = [k for k in range(spec.n_vehicles) if k not in set(drop_vehicles)]
+    K = len(keep)
+    if K < 1:
+        raise ValueError("no vehicle left")
+    n_stops = spec.n_vars // 2
+    out.n_vehicles = K
+    out.vehicle_depot = np.asarray(spec.vehicle_depot)[keep].copy()
+    out.vehicle_capacity = np.asarray(spec.vehicle_capacity)[keep].copy()
+    out.work_day_start = np.asarray(spec.work_day_start)[keep].copy()
+    out.work_day_end = np.asarray(spec.work_day_end)[keep].copy()
+    out.upper_bounds = spec.upper_bounds.copy()
+    out.upper_bounds[0::2] = float(K - 1)
+    initial = np.full(spec.n_vars, np.nan)
+    frozen = np.zeros(spec.n_vars, dtype=np.uint8)
+    i = 0
+    for new_k, old_k in enumerate(keep):
+        for c in routes[old_k]:
+            initial[2 * i], initial[2 * i + 1] = float(new_k), float(c)
+            if old_k in set(frozen_vehicles):
+                frozen[2 * i] = frozen[2 * i + 1] = 1
+            i += 1
+    if i > n_stops:
+        raise ValueError("the plan holds more stops than the problem")
+    out.initial = initial
+    out.frozen = frozen
+    return out
+
+
+def write_vrp(spec: ProblemSpec, name: str = None) -> str:
+    """A ProblemSpec of the VRP family as a file read_vrp / the reference's DomainBuilder accepts (EUC_2D);
+    used for golden round trips and for handing synthetic instances to the reference-side dumper."""
+    name = name or f"synthetic-n{spec.n_locations}-k{spec.n_vehicles}"
+    if not name.split("-")[-1].startswith("k"):
+        name += f"-k{spec.n_vehicles}"
+    out = [f"NAME : {name}", "COMMENT : greyjack-b200 synthetic", "TYPE : CVRP", f"DIMENSION : {spec.n_locations}",
+           "EDGE_WEIGHT_TYPE : EUC_2D", f"CAPACITY : {int(spec.vehicle_capacity[0])}", "NODE_COORD_SECTION"]
+    for i in range(spec.n_locations):
+        out.append(f"{i + 1} {float(spec.coords[i, 0])!r} {float(spec.coords[i, 1])!r}")
+    out.append("DEMAND_SECTION")
+    for i in range(spec.n_locations):
+        if spec.time_windowed:
+            out.append(f"{i + 1} {int(spec.demand[i])} {int(spec.tw_start[i])} {int(spec.tw_end[i])} {int(spec.service_time[i])}")
+        else:
+            out.append(f"{i + 1} {int(spec.demand[i])}")
+    out.append("DEPOT_SECTION")
+    for d in range(spec.n_depots):
+        out.append(f"{d + 1}")
+    out += ["-1", "EOF", ""]
+    return "\n".join(out)
+
+
+def write_tsplib(spec: ProblemSpec, name: str = None) -> str:
+    """A TSP ProblemSpec as an EUC_2D TSPLIB file (read_tsplib / the reference's DomainBuilder)"""
+    out = [f"NAME : {name or spec.name}", "TYPE : TSP", f"DIMENSION : {spec.n_locations}", "EDGE_WEIGHT_TYPE : EUC_2D",
+           "NODE_COORD_SECTION"]
+    for i in range(spec.n_locations):
+        out.append(f"{i + 1} {float(spec.coords[i, 0])!r} {float(spec.coords[i, 1])!r}")
+    out += ["EOF", ""]
+    return "\n".join(out)

@@ -215,6 +215,51 @@ GJ_API gj_status gj_score_incremental_device(gj_problem* p, const double* d_base
                                              void* stream);
 
 /*
+ * Constraint programs: the constraint REGISTRY of the reference's score calculators
+ * (PlainScoreCalculator::{new, add_constraint, remove_constraint, set_constraint_weights, get_score},
+ * score_calculators/plain_score_calculator.rs:20-94) for constraints that are written as data instead
+ * of Polars closures.  A constraint = name + score level + up to four terms; a term = one relational
+ * primitive over a planning column (variables value_offset + row * value_stride):
+ *   GJ_OP_DISTINCT_DEFICIT   rows - n_unique(key_value_coef * value + key_index_coef * index(row))
+ *                            (index(row) = column_id of the variable when the problem has one, else row)
+ *   GJ_OP_GATHER_FOLD        fold of distance_matrix[prev][cur] along the column in row order, from and
+ *                            back to the depot (location 0; the segment's depot when segmented)
+ *   GJ_OP_SEGMENT_OVER_CAP   per segment: sum of demand[value] over the segment - capacity, if positive
+ *   GJ_OP_MAXPLUS_LATENESS   per segment: arrival = max(arrival, tw_start) + service along the route;
+ *                            lateness against tw_end by `variant` (0 file ISC, 1 service ISC, 2 PSC rule)
+ * Segmented terms (seg_stride != 0) need the VRP column layout of the problem: segment (vehicle) column
+ * seg_offset 0 / seg_stride 2, value (customer) column value_offset 1 / value_stride 2.
+ * get_score = request_score_plain through the program: for every sample and level
+ * sum over constraints of weight * (sum over terms of scale * term), constraints in insertion order.
+ */
+enum { GJ_OP_DISTINCT_DEFICIT = 0, GJ_OP_GATHER_FOLD = 1, GJ_OP_SEGMENT_OVER_CAP = 2, GJ_OP_MAXPLUS_LATENESS = 3 };
+#define GJ_PROGRAM_MAX_TERMS 4
+typedef struct gj_term {
+    int32_t op;
+    int32_t value_offset, value_stride;
+    int32_t seg_offset, seg_stride;            /* seg_stride == 0: one segment */
+    int32_t key_value_coef, key_index_coef;    /* GJ_OP_DISTINCT_DEFICIT */
+    int32_t variant;                           /* GJ_OP_MAXPLUS_LATENESS */
+    double  scale;                             /* constant factor of the term (1000 for the VRP duplicate penalty) */
+} gj_term;
+typedef struct gj_constraint {
+    char    name[48];
+    int32_t level;
+    int32_t n_terms;
+    gj_term terms[GJ_PROGRAM_MAX_TERMS];
+} gj_constraint;
+typedef struct gj_program gj_program;
+GJ_API gj_status gj_program_create(gj_problem* p, int32_t levels, gj_program** out);          /* ::new            */
+GJ_API void      gj_program_destroy(gj_program* g);
+GJ_API gj_status gj_program_add_constraint(gj_program* g, const gj_constraint* c);            /* add_constraint: a new name
+                                                                                                 gets weight 1.0   */
+GJ_API gj_status gj_program_remove_constraint(gj_program* g, const char* name);               /* remove_constraint */
+GJ_API gj_status gj_program_set_constraint_weights(gj_program* g, const char* const* names,
+                                                   const double* weights, int32_t n);          /* replaces the map  */
+GJ_API int32_t   gj_program_n_constraints(const gj_program* g);
+GJ_API gj_status gj_program_get_score(gj_program* g, const double* samples, int64_t S, double* scores);
+
+/*
  * Agent builders.  Field names and meaning mirror the Rust `::new` argument lists:
  *   TabuSearch::new(neighbours_count, tabu_entity_rate, compare_to_global,
  *                   mutation_rate_multiplier, move_probas, migration_frequency, termination)

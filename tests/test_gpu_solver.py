@@ -62,3 +62,31 @@ def test_warm_start_from_the_reference_solution_value(oracle):
     assert oracle.score_cmp(s2, s1) <= 0                     # the second stage starts where the first ended
     assert np.array_equal(oracle.score_round(op.score_incremental(v2, [[]])[0], spec.score_precision), s2)
     gp.close()
+
+
+def test_frozen_replanning_keeps_pinned_stops(oracle):
+    """examples/vrp/src/main.rs:120-141 on the device: a plan is rebuilt into a domain
+    (vrp_routes_from_solution = build_from_solution), a vehicle is dropped, the customers of another are
+    pinned, and the second solve starts from that plan -- the pinned stops never move and the scorer
+    ignores candidate values on frozen variables."""
+    import numpy as np
+    from greyjack_b200 import Problem, Solver, StepsLimit, TabuSearch, instances as inst
+    spec = inst.cvrp(40, 5, seed=9)
+    gp = Problem(spec)
+    v1, s1 = Solver.solve(gp, TabuSearch(128, 0.2, True, None, [0.5, 0.5, 0, 0, 0, 0], 10, scoring="delta"),
+                          n_jobs=8, termination_strategy=StepsLimit(60), seed=3)
+    gp.close()
+    routes = inst.vrp_routes_from_solution(spec, v1)
+    re = inst.vrp_replanning_spec(spec, routes, frozen_vehicles=[1], drop_vehicles=[0])
+    op = oracle.OracleProblem(re)
+    gp2 = Problem(re)
+    v2, s2 = Solver.solve(gp2, TabuSearch(128, 0.2, True, None, [0.5, 0.5, 0, 0, 0, 0], 10, scoring="delta"),
+                          n_jobs=8, termination_strategy=StepsLimit(60), seed=4)
+    frozen = re.frozen.astype(bool)
+    assert frozen.any() and np.array_equal(v2[frozen], re.initial[frozen])
+    want = op.score_incremental(v2, [[]])[0]
+    assert np.array_equal(s2, oracle.score_round(want, re.score_precision)) or np.array_equal(s2, want)
+    # the dropped vehicle's customers were re-assigned: every customer appears exactly once
+    assert sorted(v2[1::2].tolist()) == list(range(re.n_depots, re.n_locations))
+    assert s2[0] >= 0
+    gp2.close()
