@@ -517,3 +517,42 @@ def write_tsplib(spec: ProblemSpec, name: str = None) -> str:
         out.append(f"{i + 1} {float(spec.coords[i, 0])!r} {float(spec.coords[i, 1])!r}")
     out += ["EOF", ""]
     return "\n".join(out)
+
+
+def write_vrp_service_json(spec: ProblemSpec, name: str = None) -> dict:
+    """The JSON domain examples/vrp_service reads (persistence/domain_builder.rs:20-62): metadata strings,
+    customers_dict {n_customers, "0": {...}, ...}, depot_dict {n_depots, "0": id, ...}."""
+    cust = {"n_customers": int(spec.n_locations)}
+    for i in range(spec.n_locations):
+        cust[str(i)] = {"id": i + 1, "name": str(i + 1), "latitude": float(spec.coords[i, 0]),
+                        "longitude": float(spec.coords[i, 1]), "demand": float(spec.demand[i]),
+                        "time_window_start": int(spec.tw_start[i]), "time_window_end": int(spec.tw_end[i]),
+                        "service_time": int(spec.service_time[i])}
+    depots = {"n_depots": int(spec.n_depots)}
+    for d in range(spec.n_depots):
+        depots[str(d)] = d + 1
+    return {"metadata": {"dataset_name": name or spec.name, "distance_type": "EUC_2D", "task_type": "CVRPTW",
+                         "time_window_task_type": "true" if spec.time_windowed else "false",
+                         "vehicles_capacity": str(int(spec.vehicle_capacity[0])), "vehicles_count": str(int(spec.n_vehicles))},
+            "customers_dict": cust, "depot_dict": depots}
+
+
+def vrp_service_from_json(doc: dict, greedy: bool = True) -> ProblemSpec:
+    """examples/vrp_service DomainBuilder::build_domain_from_scratch (:20-110) + its CotwinBuilder: the
+    same model as vrp_from_file with the service lateness rule and two disjoint semantic groups."""
+    meta = doc["metadata"]
+    n = int(doc["customers_dict"]["n_customers"])
+    rows = [doc["customers_dict"][str(i)] for i in range(n)]
+    tw = str(meta["time_window_task_type"]).replace('"', "") == "true"
+    lines = [f"NAME : {meta['dataset_name']}-k{int(meta['vehicles_count'])}", "EDGE_WEIGHT_TYPE : EUC_2D",
+             f"CAPACITY : {int(meta['vehicles_capacity'])}", "NODE_COORD_SECTION"]
+    lines += [f"{r['id']} {float(r['latitude'])!r} {float(r['longitude'])!r}" for r in rows]
+    lines.append("DEMAND_SECTION")
+    for r in rows:
+        lines.append(f"{r['id']} {int(r['demand'])}" + (f" {int(r['time_window_start'])} {int(r['time_window_end'])} {int(r['service_time'])}" if tw else ""))
+    lines.append("DEPOT_SECTION")
+    lines += [str(int(doc["depot_dict"][str(d)])) for d in range(int(doc["depot_dict"]["n_depots"]))]
+    lines += ["-1", "EOF", ""]
+    spec = vrp_from_file("\n".join(lines), service_variant=True, greedy=greedy)
+    spec.name = str(meta["dataset_name"])
+    return spec
