@@ -161,6 +161,7 @@ struct GjVrpSmem {
     uint16_t* veh;           // [n_stops] decoded vehicle ids (relative to veh_lo)
     int32_t* cust;           // [n_stops] decoded customer ids
     int32_t* bucket;         // [n_stops] customers grouped by vehicle, stop order kept
+    double* wfold;           // [n_warps][32] leg lengths of the chunk a warp is folding
 };
 
 __host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_words, int n_warps) {
@@ -171,6 +172,8 @@ __host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_w
     b = (b + 7) & ~(size_t)7;
     b += (size_t)K * 8;
     b += 16;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)n_warps * 32 * 8;
     b += (size_t)n_stops * 4 * 2;
     b += ((size_t)n_stops * 2 + 7) & ~(size_t)7;
     return b;
@@ -186,6 +189,8 @@ __device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_sto
     o = (o + 7) & ~(size_t)7;
     s.vdist = (double*)(smem + o); o += (size_t)K * 8;
     s.acc = (unsigned long long*)(smem + o); o += 16;
+    o = (o + 15) & ~(size_t)15;
+    s.wfold = (double*)(smem + o); o += (size_t)n_warps * 32 * 8;
     s.cust = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
     s.bucket = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
     s.veh = (uint16_t*)(smem + o);
@@ -285,9 +290,14 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     }
     __syncthreads();
 
-    // route walks: one thread per vehicle, in the reference's own order.
+    // route walks: one WARP per vehicle.  The 32 stops of a chunk gather their customer facts and leg
+    // lengths in parallel (one L2 round trip per chunk instead of one per stop); demand and lateness are
+    // integer warp sums; the arrival-time recurrence arrival' = max(arrival, start) + service is a max-plus
+    // map a -> max(a + A, B), composed associatively by a warp scan; only the f64 distance fold stays
+    // sequential, in the reference's own order -- so every level is bit-identical to a one-thread-per-route
+    // walk (which this replaces: it paid one L2 round trip per stop).
     unsigned long long my_cap = 0ull, my_late = 0ull;
-    for (int v = tid; v < K; v += nthr) {
+    for (int v = warp; v < K; v += n_warps) {
         const int b = s.start[v], e = s.start[v + 1];
         const int len = e - b;
         double current_distance = 0.0;
@@ -295,41 +305,78 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         if (len != 0) {
             const int32_t* st = s.bucket + b;
             const size_t depot = (size_t)P.veh_depot[v];
-            current_distance += __ldg(&D[depot * L + (size_t)st[0]]);
-            current_distance += __ldg(&D[(size_t)st[len - 1] * L + depot]);
+            const int upto = (tw_mode == GJ_TW_PSC) ? len - 1 : len;      // the PSC walk skips the last stop (Q3)
+            unsigned long long arrival = P.day_start[v];
             double fold = 0.0;
-            unsigned long long load = (unsigned long long)P.cust[st[0]].x;
-#pragma unroll 4
-            for (int i = 1; i < len; ++i) {
-                fold = fold + __ldg(&D[(size_t)st[i - 1] * L + (size_t)st[i]]);
-                load += (unsigned long long)P.cust[st[i]].x;
-            }
-            current_distance += fold;
-            const unsigned long long capv = P.veh_capacity[v];
-            if (load > capv) my_cap += load - capv;
-            route_load = load;
-
-            if (P.time_windowed) {
-                unsigned long long arrival = P.day_start[v];
-                const unsigned long long day_end = P.day_end[v];
-                const int upto = (tw_mode == GJ_TW_PSC) ? len - 1 : len;
-                for (int i = 0; i < upto; ++i) {
-                    const uint4 c = P.cust[st[i]];
-                    const unsigned long long ws = c.y, we = c.z, sv = c.w;
-                    if (arrival < ws) arrival = ws;
-                    if (tw_mode == GJ_TW_ISC_FILE) {
-                        if (arrival + sv > we) route_late += (arrival + sv) - we;
-                    } else {
-                        if (arrival > we + sv) route_late += arrival - (we + sv);
-                    }
-                    arrival += sv;
+            for (int base = 0; base < len; base += 32) {
+                const int i = base + lane;
+                const bool on = i < len;
+                const int c = on ? st[i] : 0;
+                uint4 f = make_uint4(0u, 0u, 0u, 0u);
+                double d = 0.0;
+                if (on) {
+                    f = P.cust[c];
+                    if (i > 0) d = __ldg(&D[(size_t)st[i - 1] * L + (size_t)c]);
                 }
-                if (arrival > day_end) route_late += arrival - day_end;
-                my_late += route_late;
+                route_load += (unsigned long long)__reduce_add_sync(GJ_FULL_MASK, f.x & 0xffffu) +
+                              ((unsigned long long)__reduce_add_sync(GJ_FULL_MASK, f.x >> 16) << 16);
+                if (P.time_windowed) {
+                    const bool tw_on = i < upto;
+                    const unsigned long long ws = f.y, we = f.z, sv = tw_on ? (unsigned long long)f.w : 0ull;
+                    unsigned long long SA = sv, SB = tw_on ? ws + sv : 0ull;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned long long pa = __shfl_up_sync(GJ_FULL_MASK, SA, o);
+                        const unsigned long long pb = __shfl_up_sync(GJ_FULL_MASK, SB, o);
+                        if (lane >= o) { SB = max(pb + SA, SB); SA = pa + SA; }
+                    }
+                    const unsigned long long after = max(arrival + SA, SB);          // leaving stop i
+                    unsigned long long before = __shfl_up_sync(GJ_FULL_MASK, after, 1);
+                    if (lane == 0) before = arrival;
+                    const unsigned long long t = max(before, ws);                     // service start at stop i
+                    unsigned long long lt = 0ull;
+                    if (tw_on) {
+                        if (tw_mode == GJ_TW_ISC_FILE) { if (t + sv > we) lt = (t + sv) - we; }
+                        else { if (t > we + sv) lt = t - (we + sv); }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) lt += __shfl_xor_sync(GJ_FULL_MASK, lt, o);
+                    route_late += lt;
+                    arrival = __shfl_sync(GJ_FULL_MASK, after, 31);
+                }
+                // fold_{i >= 1} D[s_{i-1}][s_i], strictly in stop order.  The chunk's 32 leg lengths go through
+                // shared memory and are added by a chain of broadcast loads (two values per LDS.128, one DADD
+                // per stop) -- a shuffle per stop cost ~12 instructions and was 60 % of the kernel's
+                // instruction count.  Lane 0 of the first chunk and the lanes past the route's end hold 0.0:
+                // x + 0.0 == x, so the full 32-step chain yields the same bits as stopping at the last stop.
+                double* wf = s.wfold + warp * 32;
+                wf[lane] = d;
+                __syncwarp();
+                const double2* wf2 = reinterpret_cast<const double2*>(wf);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const double2 x = wf2[k];
+                    fold = fold + x.x;
+                    fold = fold + x.y;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                current_distance += __ldg(&D[depot * L + (size_t)st[0]]);
+                current_distance += __ldg(&D[(size_t)st[len - 1] * L + depot]);
+                current_distance += fold;
+                const unsigned long long capv = P.veh_capacity[v];
+                if (route_load > capv) my_cap += route_load - capv;
+                if (P.time_windowed) {
+                    if (arrival > P.day_end[v]) route_late += arrival - P.day_end[v];
+                    my_late += route_late;
+                }
             }
         }
-        s.vdist[v] = current_distance;
-        if (out) { out->rload[v] = route_load; out->rlate[v] = route_late; }
+        if (lane == 0) {
+            s.vdist[v] = current_distance;
+            if (out) { out->rload[v] = route_load; out->rlate[v] = route_late; }
+        }
     }
     if (my_cap) atomicAdd(&s.acc[0], my_cap);
     if (my_late) atomicAdd(&s.acc[1], my_late);

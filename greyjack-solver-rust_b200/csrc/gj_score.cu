@@ -65,7 +65,9 @@ k_plain_vrp(GjProblemDev P, const RowT* __restrict__ samples, int64_t stride, in
             v = gj_decode(P, 2 * i, pr.x);
             c = gj_decode(P, 2 * i + 1, pr.y);
         } else {
-            const int2 pr = *reinterpret_cast<const int2*>((const int32_t*)row + 2 * i);
+            // a candidate row is read exactly once: streaming (evict-first) loads keep the gather tables
+            // -- the distance matrix above all -- resident in L2 while 131 MB of offspring go by
+            const int2 pr = __ldcs(reinterpret_cast<const int2*>((const int32_t*)row + 2 * i));
             v = pr.x; c = pr.y;
         }
         s.veh[i] = (uint16_t)v;

@@ -95,17 +95,18 @@ def _replay_ts_step(isl, island, spec, op, oracle, exact):
 @pytest.mark.parametrize("exact", [True, False], ids=["exact-sums", "tree-sums"])
 def test_c2_tsp1000_tabu_fused_bench_shape(exact, scoring, oracle):
     """C2 exactly as bench.py runs it: TSP-1000 seed 1, TabuSearch(4096 neighbours, tabu 0.5,
-    compare_to_global, swap + 2-opt, migration every 10), 592 islands, the fused delta-scoring step
-    with 16 neighbours per thread and a multi-chunk tabu update -- traced on the first, a middle and
-    the last island, before and after a migration / global-top adoption."""
+    compare_to_global, swap + 2-opt, migration every 10), 2368 islands per GPU (bench.ISLANDS_PER_GPU:
+    four waves of CTAs), the fused step with 16 neighbours per thread -- in fixed point (what bench.py
+    times) and in f64 -- traced on the first, a middle and the last island, before and after a
+    migration / global-top adoption."""
     spec = inst.tsp(1000, seed=1)
     op = oracle.OracleProblem(spec)
     gp = Problem(spec)
     gp.set_exact_sums(exact)
     isl = TabuSearch(4096, 0.5, True, None, [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 10, scoring=scoring).build_agent(
-        gp, n_islands=592, seed=1000)
+        gp, n_islands=2368, seed=1000)
     assert isl.step_path == ("fused_fixed" if scoring == "delta" else "fused")
-    islands = (0, 295, 591)
+    islands = (0, 1183, 2367)
     accepted = 0
     for i in islands:                                   # fresh islands, empty deques
         accepted += _replay_ts_step(isl, i, spec, op, oracle, exact)
@@ -121,7 +122,7 @@ def test_c2_tsp1000_tabu_fused_bench_shape(exact, scoring, oracle):
         accepted += _replay_ts_step(isl, i, spec, op, oracle, exact)
     assert adopted >= 2 and accepted >= 6
     st = isl.stats()
-    assert st["steps"] == 26 and st["candidates"] == 26 * 4096 * 592
+    assert st["steps"] == 26 and st["candidates"] == 26 * 4096 * 2368
     v, s = isl.best(-1)
     assert sorted(v.tolist()) == list(range(1, 1000))
     want = oracle.score_round(op.score_incremental(v, [[]])[0], spec.score_precision)
