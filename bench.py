@@ -380,6 +380,10 @@ def other_configs(gj, inst, ring, torch, D, rank, world, local_rank, args):
     c5_wall = float(os.environ.get("GJ_BENCH_C5_WALL_S", "60"))
     try:
         p5 = gj.Problem(spec5, use_coords=True, device=local_rank)
+        # the stored score of an accepted neighbour is a 20 000-term SEQUENTIAL f64 fold in exact mode (one
+        # thread, ~85 us per accepted step); C5 is run with tree sums (1e-12 relative, one quantum after
+        # rounding) like round 1 and says so -- DESIGN.md quotes the exact-mode figure
+        p5.set_exact_sums(False)
 
         def c5():
             isl = gj.TabuSearch(4096, 0.2, True, None, MOVE_PROBAS, 10, scoring="delta").build_agent(
@@ -398,7 +402,7 @@ def other_configs(gj, inst, ring, torch, D, rank, world, local_rank, args):
 
         run("C5 tsp-20000 TabuSearch 4096 moves, 148 islands per GPU", c5, 10, 3, 10, 1, "k_ls_step_fused<GJ_TSP> (lean)",
             A_DELTA, "A_delta: swap 96 B / 2-opt 56 B", c5_cpu,
-            note="3.2 GB matrix in HBM: larger than L2, no flush needed")
+            note="3.2 GB matrix in HBM: larger than L2, no flush needed; float_sums: tree (gj_problem_set_exact_sums(0))")
         if c5_wall > 0:
             try:
                 out["C5 hybrid GA + TabuSearch islands, fixed wall time"] = c5_hybrid(gj, ring, torch, D, p5, rank,
