@@ -1621,6 +1621,19 @@ extern "C" int64_t gj_islands_migrant_bytes(const gj_islands* g) {
     return (int64_t)g->migrants * (int64_t)((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
 }
 
+// the group's outgoing migrants, packed in place: *d_slot = device address of what leaves the group
+// (gj_islands_migrant_bytes long).  Used by gj_islands_export_migrants and by the peer ring (gj_ring.cu),
+// which stores it straight into the next rank's inbox.
+gj_status gj_islands_pack_outgoing(gj_islands* g, cudaStream_t st, const unsigned char** d_slot) {
+    gj_status rc;
+    if (g->prm.agent == GJ_AGENT_GENETIC_ALGORITHM) return gj_ga_pack_outgoing(g, st, d_slot);
+    if ((rc = apply_pending_adoption(g, st))) return rc;
+    if ((rc = gj_ls_migrate_pack(g, st))) return rc;
+    const size_t sb = (size_t)g->stride * 4 + GJ_MAX_LEVELS * 8;
+    *d_slot = g->mailbox + (size_t)g->I * sb;
+    return GJ_OK;
+}
+
 extern "C" gj_status gj_islands_export_migrants(gj_islands* g, void* d_buffer, void* stream) {
     if (!g || !d_buffer) return gj_fail(GJ_ERR_INVALID, "bad argument");
     GJ_CUDA_TRY(cudaSetDevice(g->p->device));

@@ -106,6 +106,8 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st);
 gj_status gj_ga_global_top(gj_islands* g, cudaStream_t st);
 gj_status gj_ga_current(gj_islands* g, int32_t island, double* vars, double* score);
 gj_status gj_ga_export(gj_islands* g, void* d_buffer, cudaStream_t st);
+gj_status gj_ga_pack_outgoing(gj_islands* g, cudaStream_t st, const unsigned char** d_slot);
+gj_status gj_islands_pack_outgoing(gj_islands* g, cudaStream_t st, const unsigned char** d_slot);
 gj_status gj_ga_import(gj_islands* g, const void* d_buffer, cudaStream_t st);
 gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st);
 gj_status gj_prof_begin(gj_islands* g, cudaStream_t st);

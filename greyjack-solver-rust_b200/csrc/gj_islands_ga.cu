@@ -482,6 +482,15 @@ gj_status gj_ga_current(gj_islands* g, int32_t island, double* vars, double* sco
     return GJ_OK;
 }
 
+// packs the migrants of every island; *d_slot = the LAST island's outgoing slot (what leaves the group)
+gj_status gj_ga_pack_outgoing(gj_islands* g, cudaStream_t st, const unsigned char** d_slot) {
+    gj_status rc;
+    if ((rc = ga_migrate_pack(g, st))) return rc;
+    const size_t slot = (size_t)g->migrants * ((size_t)g->stride * 4 + GJ_MAX_LEVELS * 8);
+    *d_slot = g->mailbox + (size_t)g->I * slot;
+    return GJ_OK;
+}
+
 gj_status gj_ga_export(gj_islands* g, void* d_buffer, cudaStream_t st) {
     gj_status rc;
     if ((rc = ga_migrate_pack(g, st))) return rc;

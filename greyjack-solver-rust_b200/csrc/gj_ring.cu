@@ -44,11 +44,41 @@ struct gj_ring {
 // inbox layout: [2][flag 16 B | migrants]  then  [world][2][flag 16 B | row stride*4 | score 24 B]
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-__global__ void k_ring_set_flag(unsigned long long* flag, unsigned long long value) {
-    // the payload copies were issued earlier on this stream; make them visible system-wide first
+// The whole send side of an exchange as ONE launch: CTA `world` stores the outgoing migrants into the next
+// rank's inbox, CTA r (r != rank) stores this rank's global-top record into rank r's board -- plain
+// 16-byte stores on peer-mapped pointers -- each followed by a system-scope fence and the sequence flag.
+struct GjRingPeers { unsigned char* inbox[kRingMaxWorld]; };
+
+__global__ void __launch_bounds__(256)
+k_ring_send(GjRingPeers peers, int rank, int world, int parity, unsigned long long value, size_t slot_bytes,
+            size_t board_off, size_t record_bytes, const unsigned char* __restrict__ migrants, size_t migrant_bytes,
+            const int32_t* __restrict__ gbest, const double* __restrict__ gbest_score, int stride, int send_gtop) {
+    const int r = blockIdx.x;
+    unsigned char* dst;
+    if (r == world) {
+        dst = peers.inbox[(rank + 1) % world] + (size_t)parity * slot_bytes;
+        if (((reinterpret_cast<uintptr_t>(migrants) | migrant_bytes) & 15) == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(migrants);
+            uint4* out = reinterpret_cast<uint4*>(dst + 16);
+            for (size_t i = threadIdx.x; i < migrant_bytes / 16; i += blockDim.x) out[i] = src[i];
+        } else {                                                             // rows are int32, scores f64: 4-byte units
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(migrants);
+            uint32_t* out = reinterpret_cast<uint32_t*>(dst + 16);
+            for (size_t i = threadIdx.x; i < migrant_bytes / 4; i += blockDim.x) out[i] = src[i];
+        }
+    } else {
+        if (r == rank || !send_gtop) return;
+        dst = peers.inbox[r] + board_off + ((size_t)rank * 2 + parity) * record_bytes;
+        int32_t* row = reinterpret_cast<int32_t*>(dst + 16);
+        for (int i = threadIdx.x; i < stride; i += blockDim.x) row[i] = gbest[i];
+        if (threadIdx.x < GJ_MAX_LEVELS) reinterpret_cast<double*>(dst + 16 + (size_t)stride * 4)[threadIdx.x] = gbest_score[threadIdx.x];
+    }
     __threadfence_system();
-    *(volatile unsigned long long*)flag = value;
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *(volatile unsigned long long*)dst = value;
+        __threadfence_system();
+    }
 }
 
 __device__ __forceinline__ bool gj_ring_wait_flag(const unsigned long long* flag, unsigned long long value) {
@@ -192,25 +222,18 @@ extern "C" gj_status gj_ring_exchange(gj_ring* r, void* stream) {
     const unsigned long long value = r->seq + 1;
     const int parity = (int)(r->seq & 1ull);
     gj_status rc;
-    // ---- send: migrants -> next rank's inbox; global top -> every rank's board ---------------------------
-    const int next = (r->rank + 1) % r->world;
-    unsigned char* out_slot = r->peer[next] + (size_t)parity * r->slot_bytes;
-    if ((rc = gj_islands_export_migrants(g, out_slot + 16, st))) return rc;
-    k_ring_set_flag<<<1, 1, 0, st>>>((unsigned long long*)out_slot, value);
-    GJ_LAUNCH_CHECK();
+    // ---- send: migrants -> next rank's inbox; global top -> every rank's board (one launch) ------------------
+    const unsigned char* out_migrants = nullptr;
+    if ((rc = gj_islands_pack_outgoing(g, st, &out_migrants))) return rc;
     const bool local_search = g->prm.agent != GJ_AGENT_GENETIC_ALGORITHM;
-    if (local_search) {
-        if ((rc = gj_ls_global_top(g, st))) return rc;          // the record sent is current
-        k_ring_pack_gtop<<<1, 256, 0, st>>>(g->gbest, g->gbest_score, g->stride, r->staging + 16);
-        GJ_LAUNCH_CHECK();
-        for (int i = 0; i < r->world; ++i) {
-            if (i == r->rank) continue;
-            unsigned char* rec = r->peer[i] + r->board_off + ((size_t)r->rank * 2 + parity) * r->record_bytes;
-            GJ_CUDA_TRY(cudaMemcpyAsync(rec + 16, r->staging + 16, r->record_bytes - 16, cudaMemcpyDeviceToDevice, st));
-            k_ring_set_flag<<<1, 1, 0, st>>>((unsigned long long*)rec, value);
-            GJ_LAUNCH_CHECK();
-        }
-    }
+    // the record sent must be current (the fixed-point step publishes inside its own launches)
+    if (local_search && !g->ts_fast && (rc = gj_ls_global_top(g, st))) return rc;
+    GjRingPeers peers{};
+    for (int i = 0; i < r->world; ++i) peers.inbox[i] = r->peer[i];
+    k_ring_send<<<r->world + 1, 256, 0, st>>>(peers, r->rank, r->world, parity, value, r->slot_bytes, r->board_off,
+                                              r->record_bytes, out_migrants, r->migrant_bytes, g->gbest, g->gbest_score,
+                                              g->stride, local_search ? 1 : 0);
+    GJ_LAUNCH_CHECK();
     // ---- receive ------------------------------------------------------------------------------------------
     unsigned char* in_slot = r->inbox + (size_t)parity * r->slot_bytes;
     int* ok = (int*)(r->missed + 1);
