@@ -528,9 +528,12 @@ k_apply_adoption(GjSelectArgs A) {
 // mailbox slot s: [stride int32][GJ_MAX_LEVELS f64]; slot[i+1] = island i's outgoing migrant,
 // slot[0] = what island 0 receives (the wrap-around or another GPU's last island).
 
+// `parity` 0 / 1 restricts the launch to the even / odd islands (-1 = all): agent_base.rs:161-183
+// lets even agents send before they receive and odd agents receive before they send.
 __global__ void k_migrate_pack(const int32_t* __restrict__ cur, const double* __restrict__ cur_score,
-                               int stride, int n_vars, unsigned char* mailbox) {
+                               int stride, int n_vars, unsigned char* mailbox, int parity) {
     const int island = blockIdx.x;
+    if (parity >= 0 && (island & 1) != parity) return;
     unsigned char* slot = mailbox + (size_t)(island + 1) * gj_slot_bytes(stride);
     int32_t* row = (int32_t*)slot;
     double* sc = (double*)(slot + (size_t)stride * 4);
@@ -549,9 +552,10 @@ __global__ void k_migrate_wrap(int I, int stride, unsigned char* mailbox) {
 __global__ void k_migrate_recv(int agent, int levels, int stride, int n_vars, int late_size,
                                const unsigned char* __restrict__ mailbox, int32_t* cur,
                                double* cur_score, int* dirty, double* late, int* late_head,
-                               int* late_len, int* stale) {
+                               int* late_len, int* stale, int parity) {
     __shared__ int sh_take;
     const int island = blockIdx.x;
+    if (parity >= 0 && (island & 1) != parity) return;
     const unsigned char* slot = mailbox + (size_t)island * gj_slot_bytes(stride);
     const int32_t* row = (const int32_t*)slot;
     const double* sc = (const double*)(slot + (size_t)stride * 4);
@@ -1348,18 +1352,36 @@ static gj_status ls_one_step(gj_islands* g, cudaStream_t st, bool trace) {
     return GJ_OK;
 }
 
-gj_status gj_ls_migrate_pack(gj_islands* g, cudaStream_t st) {
-    k_migrate_pack<<<g->I, 128, 0, st>>>(g->cur, g->cur_score, g->stride, g->n_vars, g->mailbox);
+static gj_status ls_migrate_pack(gj_islands* g, cudaStream_t st, int parity) {
+    k_migrate_pack<<<g->I, 128, 0, st>>>(g->cur, g->cur_score, g->stride, g->n_vars, g->mailbox, parity);
     GJ_LAUNCH_CHECK();
     return GJ_OK;
 }
 
-gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
+static gj_status ls_migrate_recv(gj_islands* g, cudaStream_t st, int parity) {
     k_migrate_recv<<<g->I, 128, 0, st>>>(g->prm.agent, g->levels, g->stride, g->n_vars, g->late_size,
                                         g->mailbox, g->cur, g->cur_score, g->dirty, g->late,
-                                        g->late_head, g->late_len, g->ds.stale);
+                                        g->late_head, g->late_len, g->ds.stale, parity);
     GJ_LAUNCH_CHECK();
     return GJ_OK;
+}
+
+// The send half of one migration (agent_base.rs:161-183): even islands send what they hold, odd islands
+// take their migrant FIRST and send what they hold afterwards -- a migrant an odd island accepts travels
+// two hops in one migration.  Leaves the last island's migrant in slot I (what leaves the group).
+gj_status gj_ls_migrate_pack(gj_islands* g, cudaStream_t st) {
+    gj_status rc;
+    if ((rc = ls_migrate_pack(g, st, 0))) return rc;
+    if (g->I > 1) {
+        if ((rc = ls_migrate_recv(g, st, 1))) return rc;
+        if ((rc = ls_migrate_pack(g, st, 1))) return rc;
+    }
+    return GJ_OK;
+}
+
+// The receive half: the even islands (slot 0 = what entered the group) take their migrants.
+gj_status gj_ls_migrate_recv(gj_islands* g, cudaStream_t st) {
+    return ls_migrate_recv(g, st, 0);
 }
 
 static gj_status apply_pending_adoption(gj_islands* g, cudaStream_t st);

@@ -366,9 +366,10 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     const int n_chunks = (K + blockDim.x - 1) / blockDim.x;
     sh_selinfo[tid] = 0;
     // `in_order`: neighbours offered in increasing index order (the main loop).  ScoreTrait::round is
-    // monotone, so a neighbour whose UNROUNDED score is not below the thread's best cannot round to a
-    // smaller key, and on a tie the earlier index stays: the key arithmetic is only needed for the
-    // (rare) improving neighbours.
+    // monotone per level, so a neighbour that is >= the thread's best on EVERY level cannot round to a
+    // lexicographically smaller score, and on a tie the earlier index stays: the key arithmetic is only
+    // needed for the others.  (A lexicographic test on the unrounded values would not do: two different
+    // upper levels may round to the same value and leave the decision to a lower one.)
     auto offer = [&](const GjScore& sc, int c, bool in_order) {
         if (F.scores_out) {
             GjScore r = sc;
@@ -376,13 +377,10 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
             for (int l = 0; l < levels; ++l) F.scores_out[((size_t)island * K + c) * levels + l] = r.v[l];
         }
         if (in_order && mine.idx >= 0) {
-            bool below = false, decided = false;
+            bool not_below = true;
 #pragma unroll
-            for (int l = 0; l < LV; ++l) {
-                if (!decided && sc.v[l] < mine.val[l]) { below = true; decided = true; }
-                if (!decided && sc.v[l] > mine.val[l]) { decided = true; }
-            }
-            if (!below) return;
+            for (int l = 0; l < LV; ++l) not_below = not_below && (sc.v[l] >= mine.val[l]);
+            if (not_below) return;
         }
         GjBest<LV> o;
         o.idx = c;

@@ -343,7 +343,11 @@ GJ_API gj_status gj_islands_current(gj_islands* g, int32_t island, double* vars,
    the migrants of the LAST island of this group into a device buffer / accepts migrants
    into the FIRST island with the reference's acceptance rule (agent_base.rs:414-440).
    The transport between ranks (NCCL send/recv over NVLink) is the caller's.
-   Layout: n_migrants x (n_vars int32 + levels f64), see gj_islands_migrant_bytes.      */
+   Layout: n_migrants x (n_vars int32 + levels f64), see gj_islands_migrant_bytes.
+   The two calls are the two halves of ONE migration and keep the reference's order inside the
+   group (agent_base.rs:161-183, even agents send then receive, odd agents receive then send):
+   export = even islands send, odd islands receive and then send; import = even islands
+   receive (island 0 from d_buffer).  An import must follow the export of the same exchange.  */
 GJ_API int64_t   gj_islands_migrant_bytes(const gj_islands* g);
 /* on != 0: gj_islands_step stops doing the wrap-around (last island -> first island) and the
    caller moves the migrants between GPUs with export/import every migration_frequency steps;

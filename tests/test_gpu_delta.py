@@ -38,6 +38,15 @@ def _check_delta_scores(got, want_unrounded, spec, oracle):
     assert np.all(frac < 1e-6)
 
 
+def _tsp_fractional_hard_weight():
+    # a fractional weight on the hard level with precision 0 there: 1..3 duplicates all round to hard 0 and
+    # the decision falls to the soft level (the in-order shortcut of the fused step must not drop them)
+    spec = inst.tsp(120, seed=6)
+    spec.weights = np.array([0.3, 1.0, 1.0, 1.0])
+    spec.score_precision = [0, 3]
+    return spec
+
+
 CASES = [
     ("nq64-swap", lambda: inst.nqueens(64), [0.0, 1.0, 0.0, 0.0, 0.0, 0.0], 0.0, None),
     ("nq64-all", lambda: inst.nqueens(64), ALL, 0.2, 1.0),
@@ -46,6 +55,7 @@ CASES = [
     ("tsp200-all", lambda: inst.tsp(200, seed=3), ALL, 0.0, 1.0),
     ("tsp131-all-mult", lambda: inst.tsp(131, seed=8), ALL, 0.3, 3.0),
     ("tsp64-2opt", lambda: inst.tsp(64, seed=5), [0.0, 0.5, 0.0, 0.0, 0.0, 0.5], 0.5, None),
+    ("tsp120-fractional-hard", _tsp_fractional_hard_weight, [0.5, 0.25, 0.0, 0.0, 0.0, 0.25], 0.0, None),
 ]
 
 

@@ -187,7 +187,10 @@ def test_migration_and_global_best(oracle):
     isl.step(1)      # migration_frequency = 1: island 1 receives island 0's individual (<= rule)
     s1 = isl.current(1)[1]
     assert oracle.score_cmp(s1, scores0[1]) < 0
-    assert oracle.score_cmp(s1, isl.current(2)[1]) < 0      # the ring moves one hop per exchange
+    # agent_base.rs:161-183: odd agents receive BEFORE they send, so island 1 forwards what it just took to
+    # island 2; island 2 (even) had already sent its own individual to island 3
+    assert oracle.score_cmp(isl.current(2)[1], s1) == 0
+    assert oracle.score_cmp(s1, isl.current(3)[1]) < 0
     isl.step(3)
     gv, gs = isl.best(-1)
     for i in range(4):
