@@ -151,7 +151,9 @@ enum { GJ_TW_ISC_FILE = 0, GJ_TW_ISC_SERVICE = 1, GJ_TW_PSC = 2 };
 #endif
 static constexpr int kVrpWarps = GJ_VRP_WARPS;
 
-// Shared-memory plan of one VRP candidate (one CTA).
+// Shared-memory plan of one VRP candidate (one CTA).  `legs` (models without time windows): the decoded
+// columns are dead once the stops are bucketed, so their space -- padded to 8 bytes per stop -- is
+// reused for the leg lengths of the bucketed stops, and `rl` collects the per-route demand.
 struct GjVrpSmem {
     uint32_t* bm;            // customer-id bitmap, P.bm_words
     int* cnt;                // [n_warps][K] per-warp-block vehicle counts -> offsets
@@ -162,37 +164,43 @@ struct GjVrpSmem {
     int32_t* cust;           // [n_stops] decoded customer ids
     int32_t* bucket;         // [n_stops] customers grouped by vehicle, stop order kept
     double* wfold;           // [n_warps][32] leg lengths of the chunk a warp is folding
+    double* leg;             // legs: [n_stops] D[bucket[i-1]][bucket[i]], over cust / veh
+    uint32_t* rl;            // legs: [2][K] per-route demand, low and high 16-bit halves summed apart
 };
 
-__host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_words, int n_warps) {
+__host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_words, int n_warps, bool legs) {
     size_t b = 0;
     b += (size_t)bm_words * 4;
     b += (size_t)n_warps * (size_t)K * 4;
     b += (size_t)(K + 1) * 4;
+    if (legs) b += (size_t)K * 8;
     b = (b + 7) & ~(size_t)7;
     b += (size_t)K * 8;
     b += 16;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)n_warps * 32 * 8;
-    b += (size_t)n_stops * 4 * 2;
-    b += ((size_t)n_stops * 2 + 7) & ~(size_t)7;
+    b += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
+    b += legs ? (size_t)n_stops * 8 : (size_t)n_stops * 4 + (((size_t)n_stops * 2 + 7) & ~(size_t)7);
     return b;
 }
 
 __device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_stops, int K,
-                                                  int bm_words, int n_warps) {
+                                                  int bm_words, int n_warps, bool legs) {
     GjVrpSmem s;
     size_t o = 0;
     s.bm = (uint32_t*)(smem + o); o += (size_t)bm_words * 4;
     s.cnt = (int*)(smem + o); o += (size_t)n_warps * (size_t)K * 4;
     s.start = (int*)(smem + o); o += (size_t)(K + 1) * 4;
+    s.rl = (uint32_t*)(smem + o);
+    if (legs) o += (size_t)K * 8;
     o = (o + 7) & ~(size_t)7;
     s.vdist = (double*)(smem + o); o += (size_t)K * 8;
     s.acc = (unsigned long long*)(smem + o); o += 16;
     o = (o + 15) & ~(size_t)15;
     s.wfold = (double*)(smem + o); o += (size_t)n_warps * 32 * 8;
+    s.bucket = (int32_t*)(smem + o); o += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
+    s.leg = (double*)(smem + o);                     // [n_stops] f64 over cust (4 B / stop) + veh (2 B) + pad
     s.cust = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
-    s.bucket = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
     s.veh = (uint16_t*)(smem + o);
     return s;
 }
@@ -219,6 +227,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
 
     for (int w = tid; w < P.bm_words; w += nthr) s.bm[w] = 0u;
     for (int w = tid; w < n_warps * K; w += nthr) s.cnt[w] = 0;
+    if (!P.time_windowed) for (int w = tid; w < 2 * K; w += nthr) s.rl[w] = 0u;
     if (tid < 2) s.acc[tid] = 0ull;
     __syncthreads();
 
@@ -228,10 +237,32 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     const int lo = warp * blk;
     const int hi = min(n, lo + blk);
     int* mycnt = s.cnt + warp * K;
-    for (int i = lo + lane; i < hi; i += 32) {
-        unsigned b = (unsigned)(s.cust[i] - P.val_lo);
-        atomicOr(&s.bm[b >> 5], 1u << (b & 31));
-        atomicAdd(&mycnt[s.veh[i]], 1);
+    const bool legs = !P.time_windowed;
+    for (int i0 = lo + lane; i0 < hi; i0 += 4 * 32) {
+        int c[4], v[4];
+        unsigned dem[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 32;
+            c[u] = 0; v[u] = 0; dem[u] = 0u;
+            if (i < hi) {
+                c[u] = s.cust[i]; v[u] = s.veh[i];
+                // the demand a route carries does not depend on the stop order: summed here
+                if (legs) dem[u] = P.cust[c[u]].x;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * 32 >= hi) continue;
+            const unsigned b = (unsigned)(c[u] - P.val_lo);
+            atomicOr(&s.bm[b >> 5], 1u << (b & 31));
+            atomicAdd(&mycnt[v[u]], 1);
+            if (legs) {
+                // 16-bit halves apart, so that 32-bit shared atomics cannot overflow
+                atomicAdd(&s.rl[v[u]], dem[u] & 0xffffu);
+                if (dem[u] >> 16) atomicAdd(&s.rl[K + v[u]], dem[u] >> 16);
+            }
+        }
     }
     __syncthreads();
 
@@ -297,6 +328,58 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     // sequential, in the reference's own order -- so every level is bit-identical to a one-thread-per-route
     // walk (which this replaces: it paid one L2 round trip per stop).
     unsigned long long my_cap = 0ull, my_late = 0ull;
+    if (legs) {
+        // Without time windows a route is its demand (summed in pass 1) and its distance fold.  Every
+        // thread gathers the leg lengths of its share of the bucketed stops -- all 2 000 matrix gathers of
+        // a candidate in flight at once -- into the space the decoded columns no longer need; then ONE
+        // THREAD per route adds its legs strictly in stop order (a shared-memory load and a DADD per stop).
+        // The warp-per-route walk below spends 32 lanes on that serial chain: 3x the instructions.
+        // (a route's first stop gets a leg nobody reads.)  leg[] lies over cust / veh, last read before the
+        // barrier that closed pass 2.  Eight gathers per thread in flight before the first store.
+        {
+            constexpr int U = 8;
+            for (int i0 = tid; i0 < n; i0 += U * nthr) {
+                double d[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * nthr;
+                    d[u] = 0.0;
+                    if (i < n) d[u] = __ldg(&D[(size_t)s.bucket[i > 0 ? i - 1 : 0] * L + (size_t)s.bucket[i]]);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * nthr;
+                    if (i < n) s.leg[i] = d[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (int v = tid; v < K; v += nthr) {
+            const int b = s.start[v], e = s.start[v + 1];
+            double current_distance = 0.0;
+            const unsigned long long route_load = (unsigned long long)s.rl[v] + ((unsigned long long)s.rl[K + v] << 16);
+            if (e != b) {
+                const size_t depot = (size_t)P.veh_depot[v];
+                const double d_first = __ldg(&D[depot * L + (size_t)s.bucket[b]]);
+                const double d_last = __ldg(&D[(size_t)s.bucket[e - 1] * L + depot]);
+                // the loads run ahead of the dependent DADD chain, four legs at a time
+                double fold = 0.0;
+                int i = b + 1;
+                for (; i + 4 <= e; i += 4) {
+                    const double x0 = s.leg[i], x1 = s.leg[i + 1], x2 = s.leg[i + 2], x3 = s.leg[i + 3];
+                    fold = fold + x0; fold = fold + x1; fold = fold + x2; fold = fold + x3;
+                }
+                for (; i < e; ++i) fold = fold + s.leg[i];
+                current_distance += d_first;
+                current_distance += d_last;
+                current_distance += fold;
+                const unsigned long long capv = P.veh_capacity[v];
+                if (route_load > capv) my_cap += route_load - capv;
+            }
+            s.vdist[v] = current_distance;
+            if (out) { out->rload[v] = route_load; out->rlate[v] = 0ull; }
+        }
+    } else
     for (int v = warp; v < K; v += n_warps) {
         const int b = s.start[v], e = s.start[v + 1];
         const int len = e - b;
@@ -389,7 +472,12 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         if (lane == 0) {
             // vehicle_distances.iter().sum(): sequential, vehicle order (ISC :132)
             double sum_distance = 0.0;
-            for (int v = 0; v < K; ++v) sum_distance += s.vdist[v];
+            int v = 0;
+            for (; v + 4 <= K; v += 4) {
+                const double x0 = s.vdist[v], x1 = s.vdist[v + 1], x2 = s.vdist[v + 2], x3 = s.vdist[v + 3];
+                sum_distance += x0; sum_distance += x1; sum_distance += x2; sum_distance += x3;
+            }
+            for (; v < K; ++v) sum_distance += s.vdist[v];
             dist = sum_distance;
             dup1000 = 1000.0 * (double)(n - uniq);
             cap = (double)s.acc[0];

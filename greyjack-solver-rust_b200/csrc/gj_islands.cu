@@ -79,7 +79,7 @@ k_score_moves_vrp(GjProblemDev P, GjGroups G, const int32_t* __restrict__ cur, i
                   int noop, int isc, double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int64_t j = blockIdx.x;
     const int32_t* base = cur + (size_t)(j / K) * stride;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -239,7 +239,7 @@ k_score_fallback_vrp(GjProblemDev P, GjGroups G, GjMoverParams M, GjStepCtx C, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ GjMove sh_mv;
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int n_work = *work_count;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int j = worklist[w];
@@ -372,7 +372,7 @@ k_vrp_state(GjProblemDev P, int stride, const int32_t* __restrict__ cur, double*
     const int n = P.n_entities, K = P.n_vehicles;
     const int why = S.stale[island];
     if (why) {
-        GjVrpSmem s = gj_vrp_carve(smem_raw, n, K, P.bm_words, kVrpWarps);
+        GjVrpSmem s = gj_vrp_carve(smem_raw, n, K, P.bm_words, kVrpWarps, !P.time_windowed);
         const int32_t* row = cur + (size_t)island * stride;
         int32_t* cnt = S.cnt + (size_t)island * S.cnt_stride;
         for (int i = threadIdx.x; i < S.cnt_stride; i += blockDim.x) cnt[i] = 0;
@@ -1179,7 +1179,7 @@ static gj_status launch_score_moves(gj_islands* g, cudaStream_t st) {
     const GjProblemDev& P = g->p->dev;
     const int64_t total = (int64_t)g->I * g->K;
     if (P.kind >= GJ_VRP) {
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
         if (smem > 48 * 1024) GJ_CUDA_TRY(cudaFuncSetAttribute(k_score_moves_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_moves_vrp<<<(unsigned)total, kVrpWarps * 32, smem, st>>>(P, g->groups, g->cur, g->stride, g->moves, g->K, total, 1, g->noop, 1, g->cand_scores);
     } else {
@@ -1246,7 +1246,7 @@ static gj_status launch_refresh(gj_islands* g, cudaStream_t st, bool update_top)
     const size_t smem = 0;
     gj_status rc;
     if (P.kind >= GJ_VRP) {
-        const size_t vsmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+        const size_t vsmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
         if ((rc = opt_in_smem(k_vrp_state, vsmem))) return rc;
         k_vrp_state<<<g->I, kVrpWarps * 32, vsmem, st>>>(P, g->stride, g->cur, g->cur_score, g->ds, g->vs,
                                                          update_top ? 1 : 0, g->best, g->best_score, g->dirty);
@@ -1280,7 +1280,7 @@ static gj_status launch_score_delta(gj_islands* g, cudaStream_t st, bool trace) 
                                                                            g->cand_scores, g->worklist, g->work_count, moves_out);
         GJ_LAUNCH_CHECK();
         if (g->delta_may_fallback) {
-            const size_t vsmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+            const size_t vsmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
             if ((rc = opt_in_smem(k_score_fallback_vrp, vsmem))) return rc;
             const unsigned fgrid = (unsigned)std::min<int64_t>(total, 148 * 4);
             k_score_fallback_vrp<<<fgrid, kVrpWarps * 32, vsmem, st>>>(P, g->groups, g->mover, C, g->cur, g->worklist,

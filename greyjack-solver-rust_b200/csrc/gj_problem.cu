@@ -330,7 +330,7 @@ extern "C" gj_status gj_problem_create(const gj_problem_desc* desc, int32_t devi
         if ((st = upload(p.get(), ds.data(), K, &P.day_start))) return st;
         if ((st = upload(p.get(), de.data(), K, &P.day_end))) return st;
         if ((st = upload(p.get(), cust.data(), L, &P.cust))) return st;
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, K, P.bm_words, kVrpWarps);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, K, P.bm_words, kVrpWarps, !P.time_windowed);
         if (smem > 220 * 1024)
             return gj_fail(GJ_ERR_UNSUPPORTED, "VRP instance too large for the shared-memory route sort");
     }

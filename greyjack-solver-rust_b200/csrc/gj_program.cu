@@ -152,7 +152,7 @@ k_program_vrp(GjProblemDev P, const __grid_constant__ GjProgramDev G, const doub
               int tw_mode, double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int64_t j = blockIdx.x;
     const double* row = samples + j * (int64_t)P.n_vars;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -331,7 +331,7 @@ extern "C" gj_status gj_program_get_score(gj_program* g, const double* samples, 
     cudaStream_t st = p->stream;
     GJ_CUDA_TRY(cudaMemcpyAsync(p->d_samples.ptr, samples, in_bytes, cudaMemcpyHostToDevice, st));
     if (segmented) {
-        const size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+        const size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
         if (smem > 48 * 1024)
             GJ_CUDA_TRY(cudaFuncSetAttribute(k_program_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_program_vrp<<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, D, (const double*)p->d_samples.ptr, S, tw_mode,

@@ -55,23 +55,35 @@ k_plain_vrp(GjProblemDev P, const RowT* __restrict__ samples, int64_t stride, in
             int isc, double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int64_t j = blockIdx.x;
     const RowT* row = samples + j * stride;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int v, c;
-        if constexpr (sizeof(RowT) == 8) {
+    if constexpr (sizeof(RowT) == 8) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const double2 pr = *reinterpret_cast<const double2*>((const double*)row + 2 * i);
-            v = gj_decode(P, 2 * i, pr.x);
-            c = gj_decode(P, 2 * i + 1, pr.y);
-        } else {
-            // a candidate row is read exactly once: streaming (evict-first) loads keep the gather tables
-            // -- the distance matrix above all -- resident in L2 while 131 MB of offspring go by
-            const int2 pr = __ldcs(reinterpret_cast<const int2*>((const int32_t*)row + 2 * i));
-            v = pr.x; c = pr.y;
+            s.veh[i] = (uint16_t)gj_decode(P, 2 * i, pr.x);
+            s.cust[i] = gj_decode(P, 2 * i + 1, pr.y);
         }
-        s.veh[i] = (uint16_t)v;
-        s.cust[i] = c;
+    } else {
+        // a candidate row is read exactly once: streaming (evict-first) loads keep the gather tables
+        // -- the distance matrix above all -- resident in L2 while 131 MB of offspring go by.  Eight
+        // loads per thread are in flight before the first store: one DRAM round trip per 2 048 stops
+        // instead of one per loop iteration.
+        constexpr int U = 8;
+        for (int i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
+            int2 pr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                pr[u] = make_int2(0, 0);
+                if (i < n) pr[u] = __ldcs(reinterpret_cast<const int2*>((const int32_t*)row + 2 * i));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n) { s.veh[i] = (uint16_t)pr[u].x; s.cust[i] = pr[u].y; }
+            }
+        }
     }
     __syncthreads();
     const int tw_mode = isc ? (P.kind == GJ_VRP_SERVICE ? GJ_TW_ISC_SERVICE : GJ_TW_ISC_FILE)
@@ -160,7 +172,7 @@ k_incr_vrp(GjProblemDev P, const int32_t* __restrict__ base, const uint64_t* __r
            double* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n_entities;
-    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps);
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int64_t j = blockIdx.x;
     // clones of candidate_vehicle_ids / candidate_customer_ids (vrp ISC :63-64)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -204,7 +216,7 @@ static gj_status launch_plain(gj_problem* p, const RowT* d_samples, int64_t stri
     const GjProblemDev& P = p->dev;
     gj_status rc;
     if (P.kind >= GJ_VRP) {
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
         if ((rc = set_smem(k_plain_vrp<RowT>, smem))) return rc;
         k_plain_vrp<RowT><<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_samples, stride, S, isc, d_scores);
     } else {
@@ -246,7 +258,7 @@ static gj_status launch_incremental(gj_problem* p, const double* d_base, int32_t
         GJ_LAUNCH_CHECK();
     }
     if (P.kind >= GJ_VRP) {
-        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps);
+        size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
         if ((rc = set_smem(k_incr_vrp<IdT, ValT>, smem))) return rc;
         k_incr_vrp<IdT, ValT><<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, d_base_i32, d_offsets, d_ids, d_vals, S, d_scores);
     } else {
