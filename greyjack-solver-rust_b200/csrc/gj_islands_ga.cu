@@ -109,6 +109,139 @@ __global__ void k_round_scores(GjProblemDev P, double* scores, int64_t n) {
     }
 }
 
+// ---- VRP models: offspring are never materialised -----------------------------------------------------
+// cross() hands integer genes over whole (rint(w) in {0, 1}), so an offspring is ONE parent
+// plus one plain-form move.  k_ga_plan draws parents and moves (one thread per offspring), the scorer
+// below rebuilds the offspring in shared memory straight from the parent's row -- parents are the p-best
+// slice of the population, i.e. L2-resident -- and only the offspring that survive build_updated_population
+// are ever written (k_ga_replace_planned).  A generation moves 2 x 131 MB less through HBM than
+// copy -> score -> copy.
+__global__ void __launch_bounds__(128)
+k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int* __restrict__ order,
+          int* __restrict__ parent_slot, GjMove* __restrict__ moves, const uint32_t* __restrict__ tabu_bits,
+          int tabu_words_per_island, const int32_t* __restrict__ tabu_word_off, double* __restrict__ trace_sel) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)A.I * A.n_cand) return;
+    const int island = (int)(t / A.n_cand);
+    const int c = (int)(t % A.n_cand);
+    const int q = c >> 1, child = c & 1;
+    GjPhilox rng;
+    gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
+                (uint32_t)(A.step >> 32), 0x40000000u + (uint32_t)q);
+    double* tr = (trace_sel && child == 0) ? trace_sel + ((size_t)island * A.half + q) * 8 : nullptr;
+    int r1 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false, tr);
+    int r2 = gj_ga_p_rank(rng, A.p_best_rate, A.pop, false, tr ? tr + 3 : nullptr);
+    const double u_cross = gj_rng_f64(rng);                       // same draws as k_ga_offspring
+    double w_raw = -1.0;
+    if (u_cross <= A.crossover_probability) {
+        w_raw = gj_rng_f64(rng);
+        const double w = gj_rint(w_raw);
+        if (w == 0.0) { int tmp = r1; r1 = r2; r2 = tmp; }
+    }
+    if (tr) { tr[6] = u_cross; tr[7] = w_raw; }
+    parent_slot[t] = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
+    const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
+    moves[t] = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, bits,
+                                tabu_word_off);
+}
+
+// request_score_plain on an offspring = parent row + move, one CTA per offspring, PSC semantics,
+// rounded (agent_base.rs:284-287).  `cand_out` (trace only): the offspring row.
+__global__ void __launch_bounds__(kVrpWarps * 32)
+k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
+                       const int* __restrict__ parent_slot, const GjMove* __restrict__ moves,
+                       double* __restrict__ scores, int32_t* __restrict__ cand_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ GjMove sh_move;
+    const int n = P.n_entities;
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
+    const int64_t j = blockIdx.x;
+    const int island = (int)(j / A.n_cand);
+    const int32_t* parent = pop_rows + ((size_t)island * A.pop + parent_slot[j]) * A.stride;
+    if (threadIdx.x < (int)(sizeof(GjMove) / 4))
+        reinterpret_cast<int32_t*>(&sh_move)[threadIdx.x] = reinterpret_cast<const int32_t*>(moves + j)[threadIdx.x];
+    {
+        constexpr int U = 8;
+        for (int i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
+            int2 pr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                pr[u] = make_int2(0, 0);
+                if (i < n) pr[u] = __ldg(reinterpret_cast<const int2*>(parent + 2 * i));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n) { s.veh[i] = (uint16_t)pr[u].x; s.cust[i] = pr[u].y; }
+            }
+        }
+    }
+    __syncthreads();
+    // Mover::do_move(.., incremental = false) + fix_variables(changed columns), reads from the parent
+    gj_apply_move(P, sh_move, G, false, A.noop != 0, threadIdx.x, blockDim.x,
+                  [&](int id) { return __ldg(parent + id); },
+                  [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; });
+    __syncthreads();
+    if (cand_out) {
+        int32_t* out = cand_out + (size_t)j * A.stride;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { out[2 * i] = s.veh[i]; out[2 * i + 1] = s.cust[i]; }
+        __syncthreads();
+    }
+    double dup1000 = 0, cap = 0, dist = 0, late = 0;
+    gj_vrp_eval_cta(P, s, GJ_TW_PSC, dup1000, cap, dist, late);
+    if (threadIdx.x == 0) {
+        GjScore sc = {};
+        gj_combine_vrp(P, false, dup1000, cap, dist, late, sc.v);
+        gj_score_round(sc, P);
+        for (int l = 0; l < 3; ++l) scores[j * 3 + l] = sc.v[l];
+    }
+}
+
+// build_updated_population for planned offspring: slot i takes offspring i (= its parent's row with the
+// move applied) or a random p-worst native (:198-213).
+__global__ void __launch_bounds__(128)
+k_ga_replace_planned(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
+                     const double* __restrict__ pop_scores, const int* __restrict__ order,
+                     const int* __restrict__ parent_slot, const GjMove* __restrict__ moves,
+                     const double* __restrict__ cand_scores, int32_t* __restrict__ pop_next,
+                     double* __restrict__ pop_scores_next, int* __restrict__ ga_src, double* __restrict__ trace_rep) {
+    __shared__ int sh_from_cand, sh_src;
+    __shared__ GjMove sh_move;
+    const int island = blockIdx.x / A.pop, i = blockIdx.x % A.pop;
+    if (threadIdx.x == 0) {
+        GjPhilox rng;
+        gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
+                    (uint32_t)(A.step >> 32), 0x80000000u + (uint32_t)i);
+        const int rank = gj_ga_p_rank(rng, A.p_best_rate, A.pop, true,
+                                      trace_rep ? trace_rep + ((size_t)island * A.pop + i) * 3 : nullptr);
+        const int native = order[(size_t)island * A.pop + rank];
+        GjScore c, w;
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+            c.v[l] = (l < A.levels) ? cand_scores[((size_t)island * A.n_cand + i) * A.levels + l] : 0.0;
+            w.v[l] = pop_scores[((size_t)island * A.pop + native) * GJ_MAX_LEVELS + l];
+        }
+        const bool take = gj_score_le(c, w, A.levels);      // :207
+        sh_from_cand = take ? 1 : 0;
+        sh_src = take ? parent_slot[(size_t)island * A.n_cand + i] : native;
+        if (take) sh_move = moves[(size_t)island * A.n_cand + i];
+        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
+            pop_scores_next[((size_t)island * A.pop + i) * GJ_MAX_LEVELS + l] = take ? c.v[l] : w.v[l];
+        if (ga_src) ga_src[(size_t)island * A.pop + i] = take ? i : -(rank + 1);
+    }
+    __syncthreads();
+    const int32_t* src = pop_rows + ((size_t)island * A.pop + sh_src) * A.stride;
+    int32_t* dst = pop_next + ((size_t)island * A.pop + i) * A.stride;
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (int k = threadIdx.x; k < A.stride / 4; k += blockDim.x) d4[k] = s4[k];
+    if (sh_from_cand) {
+        __syncthreads();
+        gj_apply_move(P, sh_move, G, false, A.noop != 0, threadIdx.x, blockDim.x,
+                      [&](int id) { return __ldg(src + id); }, [&](int id, int v) { dst[id] = v; });
+    }
+}
+
 // One CTA per (island, slot).
 __global__ void __launch_bounds__(128)
 k_ga_replace(GjGaArgs A, const int32_t* __restrict__ pop_rows, const double* __restrict__ pop_scores,
@@ -340,6 +473,7 @@ gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* 
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->order))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_rank))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_src))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->ga_parent))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->best_score))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)stride, &g->gbest))) return rc;
@@ -399,26 +533,52 @@ static gj_status ga_migrate_recv(gj_islands* g, cudaStream_t st) {
 gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
     const GjProblemDev& P = g->p->dev;
     gj_status rc;
+    // VRP models (one CTA scores one candidate): offspring are planned, scored from their parent's row and
+    // written only when they survive; the other models copy, then score whole rows
+    const bool planned = P.kind >= GJ_VRP;
     for (int64_t s = 0; s < n_steps; ++s) {
         GjGaArgs A = ga_args(g);
-        k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves,
-                                                         g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
-        GJ_LAUNCH_CHECK();
+        const int64_t S = (int64_t)g->I * g->n_cand;
+        const bool trace = g->ga_trace_sel != nullptr;
+        if (planned) {
+            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->order, g->ga_parent, g->moves,
+                                                                  g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
+            GJ_LAUNCH_CHECK();
+        } else {
+            k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves,
+                                                             g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
+            GJ_LAUNCH_CHECK();
+        }
         if (g->tabu_bits) {
             k_ga_tabu_update<<<g->I, 256, 0, st>>>(g->groups, g->n_cand, g->groups.n_groups, g->moves, g->tabu_bits, g->tabu_words,
                                                    g->tabu_word_off, g->tabu_ring[g->step & 1], g->tabu_ring[(g->step + 1) & 1],
                                                    g->tabu_ring_len, g->tabu_ring_off, g->tabu_size, g->tabu_fill);
             GJ_LAUNCH_CHECK();
         }
-        const int64_t S = (int64_t)g->I * g->n_cand;
         if ((rc = gj_prof_begin(g, st))) return rc;
-        if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
+        if (planned) {
+            const size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
+            if (smem > 48 * 1024)
+                GJ_CUDA_TRY(cudaFuncSetAttribute(k_ga_score_planned_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_ga_score_planned_vrp<<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, g->groups, A, g->pop_rows, g->ga_parent, g->moves,
+                                                                             g->cand_scores, trace ? g->cand_rows : nullptr);
+            GJ_LAUNCH_CHECK();
+        } else {
+            if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
+        }
         if ((rc = gj_prof_end(g, st))) return rc;
-        k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
-        GJ_LAUNCH_CHECK();
-        k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,
-                                                   g->pop_next, g->pop_scores_next, g->ga_src, g->ga_trace_rep);
-        GJ_LAUNCH_CHECK();
+        if (planned) {
+            k_ga_replace_planned<<<g->I * g->pop, 128, 0, st>>>(P, g->groups, A, g->pop_rows, g->pop_scores, g->order, g->ga_parent,
+                                                               g->moves, g->cand_scores, g->pop_next, g->pop_scores_next,
+                                                               g->ga_src, g->ga_trace_rep);
+            GJ_LAUNCH_CHECK();
+        } else {
+            k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
+            GJ_LAUNCH_CHECK();
+            k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,
+                                                       g->pop_next, g->pop_scores_next, g->ga_src, g->ga_trace_rep);
+            GJ_LAUNCH_CHECK();
+        }
         std::swap(g->pop_rows, g->pop_next);
         std::swap(g->pop_scores, g->pop_scores_next);
         if ((rc = ga_sort_and_top(g, st, true))) return rc;
