@@ -150,6 +150,18 @@ enum { GJ_TW_ISC_FILE = 0, GJ_TW_ISC_SERVICE = 1, GJ_TW_PSC = 2 };
 #define GJ_VRP_WARPS 8
 #endif
 static constexpr int kVrpWarps = GJ_VRP_WARPS;
+// development aid (-DGJ_VRP_PHASE_CLOCKS): thread 0 of every CTA adds the cycles between phase marks
+#ifdef GJ_VRP_PHASE_CLOCKS
+static __device__ unsigned long long gj_vrp_phase_cycles[16];
+#define GJ_PHASE_DECL long long gj_ph_t0 = clock64(); (void)gj_ph_t0
+#define GJ_PHASE_MARK(k) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&gj_vrp_phase_cycles[k], (unsigned long long)(t_ - gj_ph_t0)); gj_ph_t0 = t_; } } while (0)
+#else
+#define GJ_PHASE_MARK(k) do { } while (0)
+#endif
+
+#ifndef GJ_VRP_SCAN_WARP0
+#define GJ_VRP_SCAN_WARP0 1
+#endif
 
 // Shared-memory plan of one VRP candidate (one CTA).  `legs` (models without time windows): the decoded
 // columns are dead once the stops are bucketed, so their space -- padded to 8 bytes per stop -- is
@@ -166,6 +178,7 @@ struct GjVrpSmem {
     double* wfold;           // [n_warps][32] leg lengths of the chunk a warp is folding
     double* leg;             // legs: [n_stops] D[bucket[i-1]][bucket[i]], over cust / veh
     uint32_t* rl;            // legs: [2][K] per-route demand, low and high 16-bit halves summed apart
+    double* dfl;             // legs: [2][K] depot -> first stop, last stop -> depot
 };
 
 __host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_words, int n_warps, bool legs) {
@@ -175,8 +188,9 @@ __host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_w
     b += (size_t)(K + 1) * 4;
     if (legs) b += (size_t)K * 8;
     b = (b + 7) & ~(size_t)7;
+    if (legs) b += (size_t)K * 16;
     b += (size_t)K * 8;
-    b += 16;
+    b += 32;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)n_warps * 32 * 8;
     b += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
@@ -194,8 +208,10 @@ __device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_sto
     s.rl = (uint32_t*)(smem + o);
     if (legs) o += (size_t)K * 8;
     o = (o + 7) & ~(size_t)7;
+    s.dfl = (double*)(smem + o);
+    if (legs) o += (size_t)K * 16;
     s.vdist = (double*)(smem + o); o += (size_t)K * 8;
-    s.acc = (unsigned long long*)(smem + o); o += 16;
+    s.acc = (unsigned long long*)(smem + o); o += 32;      // capacity, lateness, distinct customers, -
     o = (o + 15) & ~(size_t)15;
     s.wfold = (double*)(smem + o); o += (size_t)n_warps * 32 * 8;
     s.bucket = (int32_t*)(smem + o); o += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
@@ -212,24 +228,38 @@ struct GjVrpOut {
     unsigned long long* rlate;   // [K] lateness per vehicle
 };
 
+// Clears the counters of an evaluation.  A caller that has a barrier of its own between filling
+// s.veh / s.cust and the evaluation calls this before that barrier and passes zeroed = true.
+__device__ __forceinline__ void gj_vrp_eval_zero(const GjProblemDev& P, const GjVrpSmem& s) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int K = P.n_vehicles, n_warps = nthr >> 5;
+    for (int w = tid; w < P.bm_words; w += nthr) s.bm[w] = 0u;
+    for (int w = tid; w < n_warps * K; w += nthr) s.cnt[w] = 0;
+    if (!P.time_windowed) for (int w = tid; w < 2 * K; w += nthr) s.rl[w] = 0u;
+    if (tid < 3) s.acc[tid] = 0ull;
+}
+
 // Evaluates the candidate whose decoded (vehicle, customer) columns already sit in
 // s.veh / s.cust.  All threads of the CTA must call it.  Results valid in thread 0.
 __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjVrpSmem& s,
                                                 int tw_mode, double& dup1000, double& cap,
                                                 double& dist, double& late,
-                                                const GjVrpOut* out = nullptr) {
+                                                const GjVrpOut* out = nullptr, bool zeroed = false) {
     const int n = P.n_entities;
     const int K = P.n_vehicles;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, n_warps = nthr >> 5;
     const size_t L = (size_t)P.n_locations;
     const double* __restrict__ D = P.D;
+#ifdef GJ_VRP_PHASE_CLOCKS
+    GJ_PHASE_DECL;
+#endif
 
-    for (int w = tid; w < P.bm_words; w += nthr) s.bm[w] = 0u;
-    for (int w = tid; w < n_warps * K; w += nthr) s.cnt[w] = 0;
-    if (!P.time_windowed) for (int w = tid; w < 2 * K; w += nthr) s.rl[w] = 0u;
-    if (tid < 2) s.acc[tid] = 0ull;
-    __syncthreads();
+    if (!zeroed) {
+        gj_vrp_eval_zero(P, s);
+        __syncthreads();
+    GJ_PHASE_MARK(3);
+    }
 
     // pass 1: customer bitmap + per-warp-block vehicle histogram.  Warp w owns the
     // contiguous block of stops [w*blk, (w+1)*blk) so that block order == stop order.
@@ -265,10 +295,9 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         }
     }
     __syncthreads();
+    GJ_PHASE_MARK(4);
 
-    // exclusive scan over (vehicle major, warp minor): cnt[w][v] -> first slot of warp
-    // w's stops of vehicle v; start[v] = route start.  K is small: one thread per vehicle
-    // sums its column, then a single warp scans the K totals.
+#if !GJ_VRP_SCAN_WARP0
     for (int v = tid; v < K; v += nthr) {
         int tot = 0;
         for (int w = 0; w < n_warps; ++w) tot += s.cnt[w * K + v];
@@ -276,6 +305,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     }
     if (tid == 0) s.start[0] = 0;
     __syncthreads();
+    GJ_PHASE_MARK(5);
     if (warp == 0) {
         int carry = 0;
         for (int base = 0; base < K; base += 32) {
@@ -290,7 +320,14 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
             carry += __shfl_sync(GJ_FULL_MASK, x, 31);
         }
     }
+    if (warp == n_warps - 1) {
+        int uniq = 0;
+        for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(s.bm[w]);
+        uniq = gj_warp_sum(uniq);
+        if (lane == 0) s.acc[2] = (unsigned long long)uniq;
+    }
     __syncthreads();
+    GJ_PHASE_MARK(6);
     for (int v = tid; v < K; v += nthr) {
         int off = s.start[v];
         for (int w = 0; w < n_warps; ++w) {
@@ -300,7 +337,47 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         }
     }
     __syncthreads();
+    GJ_PHASE_MARK(7);
+#else
+    // exclusive scan over (vehicle major, warp minor): cnt[w][v] -> first slot of warp w's stops of
+    // vehicle v; start[v] = route start.  Warp 0 alone, 32 vehicles per round (column sums, warp scan,
+    // offsets written back) -- no CTA barrier inside; meanwhile the last warp counts the distinct
+    // customers, which nothing but the final score needs.
+    if (warp == 0) {
+        int carry = 0;
+        if (lane == 0) s.start[0] = 0;
+        for (int base = 0; base < K; base += 32) {
+            const int v = base + lane;
+            int tot = 0;
+            if (v < K) for (int w = 0; w < n_warps; ++w) tot += s.cnt[w * K + v];
+            int x = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(GJ_FULL_MASK, x, o);
+                if (lane >= o) x += y;
+            }
+            if (v < K) {
+                s.start[v + 1] = x + carry;
+                int off = x + carry - tot;
+                for (int w = 0; w < n_warps; ++w) {
+                    const int c = s.cnt[w * K + v];
+                    s.cnt[w * K + v] = off;
+                    off += c;
+                }
+            }
+            carry += __shfl_sync(GJ_FULL_MASK, x, 31);
+        }
+    }
+    if (warp == n_warps - 1) {
+        int uniq = 0;
+        for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(s.bm[w]);
+        uniq = gj_warp_sum(uniq);
+        if (lane == 0) s.acc[2] = (unsigned long long)uniq;
+    }
+    __syncthreads();
+    GJ_PHASE_MARK(8);
 
+#endif
     // pass 2: stable scatter.  Each warp walks its block in order, 32 stops at a time;
     // lanes with the same vehicle are ranked by lane id (= stop order).
     for (int base = lo; base < hi; base += 32) {
@@ -320,6 +397,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         __syncwarp();
     }
     __syncthreads();
+    GJ_PHASE_MARK(9);
 
     // route walks: one WARP per vehicle.  The 32 stops of a chunk gather their customer facts and leg
     // lengths in parallel (one L2 round trip per chunk instead of one per stop); demand and lateness are
@@ -337,6 +415,18 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         // (a route's first stop gets a leg nobody reads.)  leg[] lies over cust / veh, last read before the
         // barrier that closed pass 2.  Eight gathers per thread in flight before the first store.
         {
+            // the two depot legs of a route ride along with the first batch of leg gathers (threads < K):
+            // the fold below then reads shared memory only
+            double d_first = 0.0, d_last = 0.0;
+            const bool has_route = tid < K;
+            if (has_route) {
+                const int b = s.start[tid], e = s.start[tid + 1];
+                if (e != b) {
+                    const size_t depot = (size_t)P.veh_depot[tid];
+                    d_first = __ldg(&D[depot * L + (size_t)s.bucket[b]]);
+                    d_last = __ldg(&D[(size_t)s.bucket[e - 1] * L + depot]);
+                }
+            }
             constexpr int U = 8;
             for (int i0 = tid; i0 < n; i0 += U * nthr) {
                 double d[U];
@@ -352,16 +442,26 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
                     if (i < n) s.leg[i] = d[u];
                 }
             }
+            if (has_route) { s.dfl[tid] = d_first; s.dfl[K + tid] = d_last; }
+            for (int v = nthr + tid; v < K; v += nthr) {          // K > CTA width: the remaining routes
+                const int b = s.start[v], e = s.start[v + 1];
+                double f = 0.0, l = 0.0;
+                if (e != b) {
+                    const size_t depot = (size_t)P.veh_depot[v];
+                    f = __ldg(&D[depot * L + (size_t)s.bucket[b]]);
+                    l = __ldg(&D[(size_t)s.bucket[e - 1] * L + depot]);
+                }
+                s.dfl[v] = f; s.dfl[K + v] = l;
+            }
         }
         __syncthreads();
+        GJ_PHASE_MARK(10);
         for (int v = tid; v < K; v += nthr) {
             const int b = s.start[v], e = s.start[v + 1];
             double current_distance = 0.0;
             const unsigned long long route_load = (unsigned long long)s.rl[v] + ((unsigned long long)s.rl[K + v] << 16);
             if (e != b) {
-                const size_t depot = (size_t)P.veh_depot[v];
-                const double d_first = __ldg(&D[depot * L + (size_t)s.bucket[b]]);
-                const double d_last = __ldg(&D[(size_t)s.bucket[e - 1] * L + depot]);
+                const double d_first = s.dfl[v], d_last = s.dfl[K + v];
                 // the loads run ahead of the dependent DADD chain, four legs at a time
                 double fold = 0.0;
                 int i = b + 1;
@@ -464,26 +564,24 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     if (my_cap) atomicAdd(&s.acc[0], my_cap);
     if (my_late) atomicAdd(&s.acc[1], my_late);
     __syncthreads();
+    GJ_PHASE_MARK(11);
 
-    if (warp == 0) {
-        int uniq = 0;
-        for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(s.bm[w]);
-        uniq = gj_warp_sum(uniq);
-        if (lane == 0) {
-            // vehicle_distances.iter().sum(): sequential, vehicle order (ISC :132)
-            double sum_distance = 0.0;
-            int v = 0;
-            for (; v + 4 <= K; v += 4) {
-                const double x0 = s.vdist[v], x1 = s.vdist[v + 1], x2 = s.vdist[v + 2], x3 = s.vdist[v + 3];
-                sum_distance += x0; sum_distance += x1; sum_distance += x2; sum_distance += x3;
-            }
-            for (; v < K; ++v) sum_distance += s.vdist[v];
-            dist = sum_distance;
-            dup1000 = 1000.0 * (double)(n - uniq);
-            cap = (double)s.acc[0];
-            late = (double)s.acc[1];
+    if (tid == 0) {
+        const int uniq = (int)s.acc[2];
+        // vehicle_distances.iter().sum(): sequential, vehicle order (ISC :132)
+        double sum_distance = 0.0;
+        int v = 0;
+        for (; v + 4 <= K; v += 4) {
+            const double x0 = s.vdist[v], x1 = s.vdist[v + 1], x2 = s.vdist[v + 2], x3 = s.vdist[v + 3];
+            sum_distance += x0; sum_distance += x1; sum_distance += x2; sum_distance += x3;
         }
+        for (; v < K; ++v) sum_distance += s.vdist[v];
+        dist = sum_distance;
+        dup1000 = 1000.0 * (double)(n - uniq);
+        cap = (double)s.acc[0];
+        late = (double)s.acc[1];
     }
+    GJ_PHASE_MARK(12);
 }
 
 // ---- weighted combination -------------------------------------------------------------

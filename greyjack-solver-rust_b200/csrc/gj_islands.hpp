@@ -90,6 +90,7 @@ struct gj_islands {
     int32_t* cand_rows = nullptr;  // [I][n_cand][stride]
     int* order = nullptr;          // [I][pop] rank -> row index after the sort
     int* ga_src = nullptr;         // [I][pop] replacement source (trace)
+    int32_t* ga_pairs = nullptr;   // [I][n_cand][2 + 2 * GJ_MOVE_MAXPAIRS] planned small moves as (column, value) pairs
     int* ga_parent = nullptr;      // [I][n_cand] population slot every planned offspring descends from
     int* ga_rank = nullptr;        // [I][pop] rank scratch of the counting sort (kept zeroed)
     double* ga_trace_sel = nullptr;  // [I][half][8] trace of the parent draws (gj_islands_ga_trace_generation)

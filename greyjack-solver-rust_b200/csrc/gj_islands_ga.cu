@@ -109,6 +109,31 @@ __global__ void k_round_scores(GjProblemDev P, double* scores, int64_t n) {
     }
 }
 
+static constexpr int kGaPairInts = 2 + 2 * GJ_MOVE_MAXPAIRS;
+
+// Applies a planned move to a row copy: `pr` = the plan's pair list (shared memory), rd reads the parent.
+template <class Rd, class Wr>
+__device__ __forceinline__ void gj_ga_apply_planned(const GjProblemDev& P, const GjGroups& G, const GjMove& m,
+                                                    const int32_t* pr, bool noop, Rd rd, Wr wr) {
+    const int np = pr[0];
+    if (np >= 0) {
+        if (threadIdx.x == 0)
+            for (int i = 0; i < np; ++i) wr(pr[2 + 2 * i], pr[3 + 2 * i]);
+        return;
+    }
+    (void)noop;
+    if (m.kind == GJ_MOVE_NULL) return;
+    const int32_t* g = G.ids + G.offsets[m.group];          // the segment half of gj_apply_move
+    int lo, hi;
+    gj_segment_bounds(m, lo, hi);
+    const int len = hi - lo + 1;
+    for (int t = threadIdx.x; t < len; t += blockDim.x) {
+        const int sl = gj_segment_src_slot(m, false, t, len);
+        const int col = g[lo + t];
+        wr(col, gj_fix_column(P, col, rd(g[lo + sl])));
+    }
+}
+
 // ---- VRP models: offspring are never materialised -----------------------------------------------------
 // cross() hands integer genes over whole (rint(w) in {0, 1}), so an offspring is ONE parent
 // plus one plain-form move.  k_ga_plan draws parents and moves (one thread per offspring), the scorer
@@ -117,8 +142,9 @@ __global__ void k_round_scores(GjProblemDev P, double* scores, int64_t n) {
 // are ever written (k_ga_replace_planned).  A generation moves 2 x 131 MB less through HBM than
 // copy -> score -> copy.
 __global__ void __launch_bounds__(128)
-k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int* __restrict__ order,
-          int* __restrict__ parent_slot, GjMove* __restrict__ moves, const uint32_t* __restrict__ tabu_bits,
+k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int32_t* __restrict__ pop_rows,
+          const int* __restrict__ order, int* __restrict__ parent_slot, GjMove* __restrict__ moves,
+          int32_t* __restrict__ pairs, const uint32_t* __restrict__ tabu_bits,
           int tabu_words_per_island, const int32_t* __restrict__ tabu_word_off, double* __restrict__ trace_sel) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)A.I * A.n_cand) return;
@@ -139,27 +165,53 @@ k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int* __
         if (w == 0.0) { int tmp = r1; r1 = r2; r2 = tmp; }
     }
     if (tr) { tr[6] = u_cross; tr[7] = w_raw; }
-    parent_slot[t] = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
+    const int slot = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
+    parent_slot[t] = slot;
     const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
-    moves[t] = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, bits,
-                                tabu_word_off);
+    const GjMove m = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, bits,
+                                      tabu_word_off);
+    moves[t] = m;
+    // a small move as the final (column, value) pairs of Mover::do_move(plain) + fix_variables, in emission
+    // order: what the scorer and the replacement apply.  pairs[0] = count, -1 = segment move (applied from
+    // the descriptor), pairs from [2].
+    int32_t* pr = pairs + (size_t)t * kGaPairInts;
+    int np = 0;
+    if (m.kind == GJ_MOVE_NULL) np = 0;
+    else if (m.kind > 3) np = -1;
+    else {
+        const int32_t* parent = pop_rows + ((size_t)island * A.pop + slot) * A.stride;
+        int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
+        np = gj_small_move_pairs(m, G.ids + G.offsets[m.group], false, A.noop != 0,
+                                 [&](int id) { return __ldg(parent + id); }, cols, vals);
+        for (int i = 0; i < np; ++i) { pr[2 + 2 * i] = cols[i]; pr[3 + 2 * i] = gj_fix_column(P, cols[i], vals[i]); }
+    }
+    pr[0] = np;
 }
 
 // request_score_plain on an offspring = parent row + move, one CTA per offspring, PSC semantics,
 // rounded (agent_base.rs:284-287).  `cand_out` (trace only): the offspring row.
-__global__ void __launch_bounds__(kVrpWarps * 32)
+#ifndef GJ_GA_SCORE_MINBLOCKS
+#define GJ_GA_SCORE_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(kVrpWarps * 32, GJ_GA_SCORE_MINBLOCKS)
 k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
                        const int* __restrict__ parent_slot, const GjMove* __restrict__ moves,
-                       double* __restrict__ scores, int32_t* __restrict__ cand_out) {
+                       const int32_t* __restrict__ pairs, double* __restrict__ scores, int32_t* __restrict__ cand_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ GjMove sh_move;
+    __shared__ int32_t sh_pairs[kGaPairInts];
     const int n = P.n_entities;
     GjVrpSmem s = gj_vrp_carve(smem_raw, n, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int64_t j = blockIdx.x;
     const int island = (int)(j / A.n_cand);
+#ifdef GJ_VRP_PHASE_CLOCKS
+    GJ_PHASE_DECL;
+#endif
     const int32_t* parent = pop_rows + ((size_t)island * A.pop + parent_slot[j]) * A.stride;
     if (threadIdx.x < (int)(sizeof(GjMove) / 4))
         reinterpret_cast<int32_t*>(&sh_move)[threadIdx.x] = reinterpret_cast<const int32_t*>(moves + j)[threadIdx.x];
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + kGaPairInts)
+        sh_pairs[threadIdx.x - 32] = pairs[(size_t)j * kGaPairInts + threadIdx.x - 32];
     {
         constexpr int U = 8;
         for (int i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
@@ -177,26 +229,38 @@ k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __
             }
         }
     }
+    gj_vrp_eval_zero(P, s);
     __syncthreads();
-    // Mover::do_move(.., incremental = false) + fix_variables(changed columns), reads from the parent
-    gj_apply_move(P, sh_move, G, false, A.noop != 0, threadIdx.x, blockDim.x,
-                  [&](int id) { return __ldg(parent + id); },
-                  [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; });
+    GJ_PHASE_MARK(0);
+    // Mover::do_move(.., incremental = false) + fix_variables(changed columns): the planned pairs of a
+    // small move, or a segment move shifted along the parent's row
+    gj_ga_apply_planned(P, G, sh_move, sh_pairs, A.noop != 0, [&](int id) { return __ldg(parent + id); },
+                        [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; });
     __syncthreads();
+    GJ_PHASE_MARK(1);
     if (cand_out) {
         int32_t* out = cand_out + (size_t)j * A.stride;
         for (int i = threadIdx.x; i < n; i += blockDim.x) { out[2 * i] = s.veh[i]; out[2 * i + 1] = s.cust[i]; }
         __syncthreads();
     }
     double dup1000 = 0, cap = 0, dist = 0, late = 0;
-    gj_vrp_eval_cta(P, s, GJ_TW_PSC, dup1000, cap, dist, late);
+    gj_vrp_eval_cta(P, s, GJ_TW_PSC, dup1000, cap, dist, late, nullptr, true);
     if (threadIdx.x == 0) {
         GjScore sc = {};
         gj_combine_vrp(P, false, dup1000, cap, dist, late, sc.v);
         gj_score_round(sc, P);
         for (int l = 0; l < 3; ++l) scores[j * 3 + l] = sc.v[l];
     }
+    GJ_PHASE_MARK(13);
 }
+
+#ifdef GJ_VRP_PHASE_CLOCKS
+extern "C" __attribute__((visibility("default"))) int gj_debug_vrp_phases(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, gj_vrp_phase_cycles, sizeof(gj_vrp_phase_cycles));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(gj_vrp_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 // build_updated_population for planned offspring: slot i takes offspring i (= its parent's row with the
 // move applied) or a random p-worst native (:198-213).
@@ -204,11 +268,15 @@ __global__ void __launch_bounds__(128)
 k_ga_replace_planned(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
                      const double* __restrict__ pop_scores, const int* __restrict__ order,
                      const int* __restrict__ parent_slot, const GjMove* __restrict__ moves,
-                     const double* __restrict__ cand_scores, int32_t* __restrict__ pop_next,
+                     const int32_t* __restrict__ pairs, const double* __restrict__ cand_scores,
+                     int32_t* __restrict__ pop_next,
                      double* __restrict__ pop_scores_next, int* __restrict__ ga_src, double* __restrict__ trace_rep) {
     __shared__ int sh_from_cand, sh_src;
     __shared__ GjMove sh_move;
+    __shared__ int32_t sh_pairs[kGaPairInts];
     const int island = blockIdx.x / A.pop, i = blockIdx.x % A.pop;
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + kGaPairInts)
+        sh_pairs[threadIdx.x - 32] = pairs[((size_t)island * A.n_cand + i) * kGaPairInts + threadIdx.x - 32];
     if (threadIdx.x == 0) {
         GjPhilox rng;
         gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
@@ -237,8 +305,8 @@ k_ga_replace_planned(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __re
     for (int k = threadIdx.x; k < A.stride / 4; k += blockDim.x) d4[k] = s4[k];
     if (sh_from_cand) {
         __syncthreads();
-        gj_apply_move(P, sh_move, G, false, A.noop != 0, threadIdx.x, blockDim.x,
-                      [&](int id) { return __ldg(src + id); }, [&](int id, int v) { dst[id] = v; });
+        gj_ga_apply_planned(P, G, sh_move, sh_pairs, A.noop != 0, [&](int id) { return __ldg(src + id); },
+                            [&](int id, int v) { dst[id] = v; });
     }
 }
 
@@ -474,6 +542,7 @@ gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* 
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_rank))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_src))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->ga_parent))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand * kGaPairInts, &g->ga_pairs))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->best_score))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)stride, &g->gbest))) return rc;
@@ -541,8 +610,8 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         const int64_t S = (int64_t)g->I * g->n_cand;
         const bool trace = g->ga_trace_sel != nullptr;
         if (planned) {
-            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->order, g->ga_parent, g->moves,
-                                                                  g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
+            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->ga_parent, g->moves,
+                                                                  g->ga_pairs, g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
             GJ_LAUNCH_CHECK();
         } else {
             k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves,
@@ -560,8 +629,10 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
             const size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
             if (smem > 48 * 1024)
                 GJ_CUDA_TRY(cudaFuncSetAttribute(k_ga_score_planned_vrp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // (no shared-memory carve-out preference: the L1 the default leaves serves the customer-fact
+            // gathers; asking for the maximum carve-out cost 100 us per generation)
             k_ga_score_planned_vrp<<<(unsigned)S, kVrpWarps * 32, smem, st>>>(P, g->groups, A, g->pop_rows, g->ga_parent, g->moves,
-                                                                             g->cand_scores, trace ? g->cand_rows : nullptr);
+                                                                             g->ga_pairs, g->cand_scores, trace ? g->cand_rows : nullptr);
             GJ_LAUNCH_CHECK();
         } else {
             if ((rc = gj_launch_score_plain_i32(g->p, g->cand_rows, g->stride, S, g->cand_scores, false, st))) return rc;
@@ -569,7 +640,7 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         if ((rc = gj_prof_end(g, st))) return rc;
         if (planned) {
             k_ga_replace_planned<<<g->I * g->pop, 128, 0, st>>>(P, g->groups, A, g->pop_rows, g->pop_scores, g->order, g->ga_parent,
-                                                               g->moves, g->cand_scores, g->pop_next, g->pop_scores_next,
+                                                               g->moves, g->ga_pairs, g->cand_scores, g->pop_next, g->pop_scores_next,
                                                                g->ga_src, g->ga_trace_rep);
             GJ_LAUNCH_CHECK();
         } else {

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-LIB_PATH = os.path.join(_PKG_ROOT, "libgreyjack_b200.so")
+LIB_PATH = os.environ.get("GREYJACK_B200_LIB") or os.path.join(_PKG_ROOT, "libgreyjack_b200.so")
 
 GJ_OK = 0
 

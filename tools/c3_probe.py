@@ -25,3 +25,16 @@ torch.cuda.synchronize()
 t = time.perf_counter() - t0
 ms, n = isl.profile_read()
 print("C3 generation %.1f us, scorer kernel %.1f us, %.2f M candidates/s" % (1e6 * t / steps, 1e3 * ms / n, steps * 8192 / t / 1e6))
+
+import ctypes
+L = ctypes.CDLL(gj.LIB_PATH)
+if hasattr(L, "gj_debug_vrp_phases"):
+    buf = (ctypes.c_ulonglong * 16)()
+    L.gj_debug_vrp_phases(buf, 1)
+    isl.step(4)
+    torch.cuda.synchronize()
+    L.gj_debug_vrp_phases(buf, 0)
+    names = ["load", "apply", "-", "zero", "pass1", "o5", "o6", "o7", "scan", "scatter", "legs", "fold", "final", "store"]
+    tot = sum(buf)
+    print("phase cycles per CTA (thread 0):", ", ".join("%s %.0f" % (nm, buf[i] / (4 * 8192)) for i, nm in enumerate(names) if buf[i]),
+          "| total %.0f" % (tot / (4 * 8192)))
