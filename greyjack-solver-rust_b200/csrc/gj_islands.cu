@@ -655,6 +655,8 @@ gj_islands::~gj_islands() {
             fprintf(stderr, "[gj phase] P0 until the bulk copies landed: island0 %8lld cycles, mean %10.0f\n", h[6] - h[0], mean / I);
         }
     }
+    if (ga_side) { cudaStreamSynchronize(ga_side); cudaStreamDestroy(ga_side); }
+    for (auto& e : ga_ev) if (e) cudaEventDestroy(e);
     for (void* a : allocs) cudaFree(a);
     for (auto& e : prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
 }

@@ -10,6 +10,7 @@
 //   k_ga_migrate_*  send_updates / receive_updates for Population agents (:337-341, 405-412)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "gj_islands_dev.cuh"
@@ -142,9 +143,8 @@ __device__ __forceinline__ void gj_ga_apply_planned(const GjProblemDev& P, const
 // are ever written (k_ga_replace_planned).  A generation moves 2 x 131 MB less through HBM than
 // copy -> score -> copy.
 __global__ void __launch_bounds__(128)
-k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int32_t* __restrict__ pop_rows,
-          const int* __restrict__ order, int* __restrict__ parent_slot, GjMove* __restrict__ moves,
-          int32_t* __restrict__ pairs, const uint32_t* __restrict__ tabu_bits,
+k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int* __restrict__ order,
+          int* __restrict__ parent_slot, GjMove* __restrict__ moves, const uint32_t* __restrict__ tabu_bits,
           int tabu_words_per_island, const int32_t* __restrict__ tabu_word_off, double* __restrict__ trace_sel) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)A.I * A.n_cand) return;
@@ -168,24 +168,8 @@ k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int32_t
     const int slot = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
     parent_slot[t] = slot;
     const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
-    const GjMove m = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, bits,
-                                      tabu_word_off);
-    moves[t] = m;
-    // a small move as the final (column, value) pairs of Mover::do_move(plain) + fix_variables, in emission
-    // order: what the scorer and the replacement apply.  pairs[0] = count, -1 = segment move (applied from
-    // the descriptor), pairs from [2].
-    int32_t* pr = pairs + (size_t)t * kGaPairInts;
-    int np = 0;
-    if (m.kind == GJ_MOVE_NULL) np = 0;
-    else if (m.kind > 3) np = -1;
-    else {
-        const int32_t* parent = pop_rows + ((size_t)island * A.pop + slot) * A.stride;
-        int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
-        np = gj_small_move_pairs(m, G.ids + G.offsets[m.group], false, A.noop != 0,
-                                 [&](int id) { return __ldg(parent + id); }, cols, vals);
-        for (int i = 0; i < np; ++i) { pr[2 + 2 * i] = cols[i]; pr[3 + 2 * i] = gj_fix_column(P, cols[i], vals[i]); }
-    }
-    pr[0] = np;
+    moves[t] = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, bits,
+                                tabu_word_off);
 }
 
 // request_score_plain on an offspring = parent row + move, one CTA per offspring, PSC semantics,
@@ -196,7 +180,7 @@ k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int32_t
 __global__ void __launch_bounds__(kVrpWarps * 32, GJ_GA_SCORE_MINBLOCKS)
 k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
                        const int* __restrict__ parent_slot, const GjMove* __restrict__ moves,
-                       const int32_t* __restrict__ pairs, double* __restrict__ scores, int32_t* __restrict__ cand_out) {
+                       int32_t* __restrict__ pairs, double* __restrict__ scores, int32_t* __restrict__ cand_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ GjMove sh_move;
     __shared__ int32_t sh_pairs[kGaPairInts];
@@ -208,23 +192,42 @@ k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __
     GJ_PHASE_DECL;
 #endif
     const int32_t* parent = pop_rows + ((size_t)island * A.pop + parent_slot[j]) * A.stride;
-    if (threadIdx.x < (int)(sizeof(GjMove) / 4))
-        reinterpret_cast<int32_t*>(&sh_move)[threadIdx.x] = reinterpret_cast<const int32_t*>(moves + j)[threadIdx.x];
-    else if (threadIdx.x >= 32 && threadIdx.x < 32 + kGaPairInts)
-        sh_pairs[threadIdx.x - 32] = pairs[(size_t)j * kGaPairInts + threadIdx.x - 32];
-    {
+    if (threadIdx.x == 0) {
+        // Thread 0 expands a small move into the final (column, value) pairs of Mover::do_move(plain) +
+        // fix_variables, in emission order, reading the parent's values itself -- under the shadow of the
+        // row load the other 255 threads are waiting for.  pairs[0] = count, -1 = segment move (applied
+        // from the descriptor); the list also goes to HBM for k_ga_copy_planned.
+        const GjMove m = moves[j];
+        sh_move = m;
+        int np = 0;
+        if (m.kind != GJ_MOVE_NULL && m.kind > 3) np = -1;
+        else if (m.kind != GJ_MOVE_NULL) {
+            int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
+            np = gj_small_move_pairs(m, G.ids + G.offsets[m.group], false, A.noop != 0,
+                                     [&](int id) { return __ldg(parent + id); }, cols, vals);
+            int32_t* pg = pairs + (size_t)j * kGaPairInts;
+            for (int i = 0; i < np; ++i) {
+                const int v = gj_fix_column(P, cols[i], vals[i]);
+                sh_pairs[2 + 2 * i] = cols[i]; sh_pairs[3 + 2 * i] = v;
+                pg[2 + 2 * i] = cols[i]; pg[3 + 2 * i] = v;
+            }
+        }
+        sh_pairs[0] = np;
+        pairs[(size_t)j * kGaPairInts] = np;
+    } else {
         constexpr int U = 8;
-        for (int i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
+        const int lt = threadIdx.x - 1, ln = blockDim.x - 1;
+        for (int i0 = lt; i0 < n; i0 += U * ln) {
             int2 pr[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * blockDim.x;
+                const int i = i0 + u * ln;
                 pr[u] = make_int2(0, 0);
                 if (i < n) pr[u] = __ldg(reinterpret_cast<const int2*>(parent + 2 * i));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * blockDim.x;
+                const int i = i0 + u * ln;
                 if (i < n) { s.veh[i] = (uint16_t)pr[u].x; s.cust[i] = pr[u].y; }
             }
         }
@@ -262,48 +265,57 @@ extern "C" __attribute__((visibility("default"))) int gj_debug_vrp_phases(unsign
 }
 #endif
 
-// build_updated_population for planned offspring: slot i takes offspring i (= its parent's row with the
-// move applied) or a random p-worst native (:198-213).
+// build_updated_population for planned offspring (:198-213), in two launches so that the sort of the
+// new scores (k_ga_rank, side stream) runs while the rows are being copied:
+//   k_ga_decide   slot i takes offspring i or a random p-worst native -> scores of the new population, source
+//   k_ga_copy_planned   the rows: the native's, or the parent's with the planned move applied
+__global__ void __launch_bounds__(256)
+k_ga_decide(GjGaArgs A, const double* __restrict__ pop_scores, const int* __restrict__ order,
+            const int* __restrict__ parent_slot, const double* __restrict__ cand_scores,
+            double* __restrict__ pop_scores_next, int* __restrict__ take_src, int* __restrict__ ga_src,
+            double* __restrict__ trace_rep) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)A.I * A.pop) return;
+    const int island = (int)(t / A.pop), i = (int)(t % A.pop);
+    GjPhilox rng;
+    gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
+                (uint32_t)(A.step >> 32), 0x80000000u + (uint32_t)i);
+    const int rank = gj_ga_p_rank(rng, A.p_best_rate, A.pop, true, trace_rep ? trace_rep + (size_t)t * 3 : nullptr);
+    const int native = order[(size_t)island * A.pop + rank];
+    GjScore c, w;
+    for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+        c.v[l] = (l < A.levels) ? cand_scores[((size_t)island * A.n_cand + i) * A.levels + l] : 0.0;
+        w.v[l] = pop_scores[((size_t)island * A.pop + native) * GJ_MAX_LEVELS + l];
+    }
+    const bool take = gj_score_le(c, w, A.levels);      // :207
+    for (int l = 0; l < GJ_MAX_LEVELS; ++l) pop_scores_next[(size_t)t * GJ_MAX_LEVELS + l] = take ? c.v[l] : w.v[l];
+    take_src[t] = take ? (parent_slot[(size_t)island * A.n_cand + i] | (int)0x80000000) : native;
+    if (ga_src) ga_src[t] = take ? i : -(rank + 1);
+}
+
 __global__ void __launch_bounds__(128)
-k_ga_replace_planned(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
-                     const double* __restrict__ pop_scores, const int* __restrict__ order,
-                     const int* __restrict__ parent_slot, const GjMove* __restrict__ moves,
-                     const int32_t* __restrict__ pairs, const double* __restrict__ cand_scores,
-                     int32_t* __restrict__ pop_next,
-                     double* __restrict__ pop_scores_next, int* __restrict__ ga_src, double* __restrict__ trace_rep) {
-    __shared__ int sh_from_cand, sh_src;
+k_ga_copy_planned(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __restrict__ pop_rows,
+                  const int* __restrict__ take_src, const GjMove* __restrict__ moves,
+                  const int32_t* __restrict__ pairs, int32_t* __restrict__ pop_next) {
     __shared__ GjMove sh_move;
     __shared__ int32_t sh_pairs[kGaPairInts];
     const int island = blockIdx.x / A.pop, i = blockIdx.x % A.pop;
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + kGaPairInts)
-        sh_pairs[threadIdx.x - 32] = pairs[((size_t)island * A.n_cand + i) * kGaPairInts + threadIdx.x - 32];
-    if (threadIdx.x == 0) {
-        GjPhilox rng;
-        gj_rng_init(rng, A.seed, (uint32_t)(A.island_base + island), (uint32_t)A.step,
-                    (uint32_t)(A.step >> 32), 0x80000000u + (uint32_t)i);
-        const int rank = gj_ga_p_rank(rng, A.p_best_rate, A.pop, true,
-                                      trace_rep ? trace_rep + ((size_t)island * A.pop + i) * 3 : nullptr);
-        const int native = order[(size_t)island * A.pop + rank];
-        GjScore c, w;
-        for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
-            c.v[l] = (l < A.levels) ? cand_scores[((size_t)island * A.n_cand + i) * A.levels + l] : 0.0;
-            w.v[l] = pop_scores[((size_t)island * A.pop + native) * GJ_MAX_LEVELS + l];
-        }
-        const bool take = gj_score_le(c, w, A.levels);      // :207
-        sh_from_cand = take ? 1 : 0;
-        sh_src = take ? parent_slot[(size_t)island * A.n_cand + i] : native;
-        if (take) sh_move = moves[(size_t)island * A.n_cand + i];
-        for (int l = 0; l < GJ_MAX_LEVELS; ++l)
-            pop_scores_next[((size_t)island * A.pop + i) * GJ_MAX_LEVELS + l] = take ? c.v[l] : w.v[l];
-        if (ga_src) ga_src[(size_t)island * A.pop + i] = take ? i : -(rank + 1);
+    const int ts = take_src[blockIdx.x];
+    const bool from_cand = ts < 0;
+    const int src_slot = ts & 0x7fffffff;
+    if (from_cand) {
+        const size_t c = (size_t)island * A.n_cand + i;
+        if (threadIdx.x < (int)(sizeof(GjMove) / 4))
+            reinterpret_cast<int32_t*>(&sh_move)[threadIdx.x] = reinterpret_cast<const int32_t*>(moves + c)[threadIdx.x];
+        else if (threadIdx.x >= 32 && threadIdx.x < 32 + kGaPairInts)
+            sh_pairs[threadIdx.x - 32] = pairs[c * kGaPairInts + threadIdx.x - 32];
     }
-    __syncthreads();
-    const int32_t* src = pop_rows + ((size_t)island * A.pop + sh_src) * A.stride;
+    const int32_t* src = pop_rows + ((size_t)island * A.pop + src_slot) * A.stride;
     int32_t* dst = pop_next + ((size_t)island * A.pop + i) * A.stride;
     const int4* s4 = reinterpret_cast<const int4*>(src);
     int4* d4 = reinterpret_cast<int4*>(dst);
     for (int k = threadIdx.x; k < A.stride / 4; k += blockDim.x) d4[k] = s4[k];
-    if (sh_from_cand) {
+    if (from_cand) {
         __syncthreads();
         gj_ga_apply_planned(P, G, sh_move, sh_pairs, A.noop != 0, [&](int id) { return __ldg(src + id); },
                             [&](int id, int v) { dst[id] = v; });
@@ -430,6 +442,65 @@ __global__ void k_ga_top(int pop, int stride, int n_vars, int levels, int n_cand
     }
 }
 
+// population.sort() + update_top_individual (+ update_global_top's publish half when the group is one
+// island) in one launch: order[rank[t]] = t; the CTA that meets rank 0 of an island compares that
+// individual with the agent's top (agent_base.rs:220-224) and, if it wins, copies the row.
+__global__ void __launch_bounds__(256)
+k_ga_finish(int pop, int I, int stride, int n_vars, int levels, int n_cand, int* __restrict__ rank,
+            int* __restrict__ order, const int32_t* __restrict__ pop_rows, const double* __restrict__ pop_scores,
+            int32_t* best, double* best_score, int32_t* gbest, double* gbest_score, unsigned long long* counters) {
+    __shared__ int sh_first, sh_take, sh_gtake;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool mine = false;                                 // this thread holds an island's rank-0 individual
+    if (t < (int64_t)pop * I) {
+        const int r = rank[t];
+        order[(t / pop) * pop + r] = (int)(t % pop);
+        rank[t] = 0;                                   // ready for the next generation
+        mine = r == 0;
+    }
+    // a CTA meets one rank-0 individual per island it spans (usually none or one)
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh_first = -1;
+        __syncthreads();
+        if (mine) atomicMax(&sh_first, (int)t);
+        __syncthreads();
+        const int first = sh_first;
+        if (first < 0) break;
+        if ((int)t == first) mine = false;
+        const int island = first / pop, r0 = first % pop;
+        if (threadIdx.x == 0) {
+            GjScore c = {}, tp = {}, g = {};
+            for (int l = 0; l < GJ_MAX_LEVELS; ++l) {
+                c.v[l] = pop_scores[(size_t)first * GJ_MAX_LEVELS + l];
+                tp.v[l] = best_score[(size_t)island * GJ_MAX_LEVELS + l];
+                g.v[l] = gbest_score[l];
+            }
+            const bool take = gj_score_le(c, tp, levels);
+            if (take) for (int l = 0; l < GJ_MAX_LEVELS; ++l) best_score[(size_t)island * GJ_MAX_LEVELS + l] = c.v[l];
+            sh_take = take ? 1 : 0;
+            // a group of one island: its top is the only candidate for the group's global top
+            // (update_global_top's publish half, agent_base.rs:451-461)
+            const GjScore nt = take ? c : tp;
+            const bool gt = (I == 1) && !gj_score_le(g, nt, levels);
+            if (gt) for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = nt.v[l];
+            sh_gtake = gt ? 1 : 0;
+            if (counters) {
+                atomicAdd(&counters[0], (unsigned long long)n_cand);
+                if (island == 0) atomicAdd(&counters[1], 1ull);
+            }
+        }
+        __syncthreads();
+        const int32_t* src = pop_rows + ((size_t)island * pop + r0) * stride;
+        if (sh_take)
+            for (int i = threadIdx.x; i < n_vars; i += blockDim.x) best[(size_t)island * stride + i] = src[i];
+        if (sh_gtake) {
+            const int32_t* gsrc = sh_take ? src : best + (size_t)island * stride;
+            for (int i = threadIdx.x; i < n_vars; i += blockDim.x) gbest[i] = gsrc[i];
+        }
+    }
+}
+
 // migrants = the island's first ceil(migration_rate * pop) individuals by rank
 // mailbox slot s (s = 0..I): [migrants][stride int32 + 3 f64]
 __global__ void k_ga_migrate_pack(int pop, int stride, int migrants, const int32_t* __restrict__ pop_rows,
@@ -542,6 +613,7 @@ gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* 
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_rank))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_src))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->ga_parent))) return rc;
+    if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_take))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand * kGaPairInts, &g->ga_pairs))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * GJ_MAX_LEVELS, &g->best_score))) return rc;
@@ -599,6 +671,20 @@ static gj_status ga_migrate_recv(gj_islands* g, cudaStream_t st) {
     return ga_sort_and_top(g, st, false);
 }
 
+// side stream + events of the overlapped generation, created on first use (GJ_GA_OVERLAP=0 switches it off)
+static bool ga_side_ready(gj_islands* g) {
+    if (g->ga_side_state == 0) {
+        const char* e = getenv("GJ_GA_OVERLAP");
+        g->ga_side_state = -1;
+        if (!(e && e[0] == '0')) {
+            bool ok = cudaStreamCreateWithFlags(&g->ga_side, cudaStreamNonBlocking) == cudaSuccess;
+            for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&g->ga_ev[i], cudaEventDisableTiming) == cudaSuccess;
+            if (ok) g->ga_side_state = 1;
+        }
+    }
+    return g->ga_side_state == 1;
+}
+
 gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
     const GjProblemDev& P = g->p->dev;
     gj_status rc;
@@ -610,16 +696,25 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         const int64_t S = (int64_t)g->I * g->n_cand;
         const bool trace = g->ga_trace_sel != nullptr;
         if (planned) {
-            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->ga_parent, g->moves,
-                                                                  g->ga_pairs, g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
+            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->order, g->ga_parent, g->moves,
+                                                                  g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
             GJ_LAUNCH_CHECK();
         } else {
             k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves,
                                                              g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
             GJ_LAUNCH_CHECK();
         }
+        // the mover's tabu deque and, later, the sort of the new population run on a side stream next to
+        // the scorer and the row copies (both only have to be done before the next generation is planned)
+        const bool overlap = planned && ga_side_ready(g);
         if (g->tabu_bits) {
-            k_ga_tabu_update<<<g->I, 256, 0, st>>>(g->groups, g->n_cand, g->groups.n_groups, g->moves, g->tabu_bits, g->tabu_words,
+            cudaStream_t ts = st;
+            if (overlap) {
+                GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[0], st));
+                GJ_CUDA_TRY(cudaStreamWaitEvent(g->ga_side, g->ga_ev[0], 0));
+                ts = g->ga_side;
+            }
+            k_ga_tabu_update<<<g->I, 256, 0, ts>>>(g->groups, g->n_cand, g->groups.n_groups, g->moves, g->tabu_bits, g->tabu_words,
                                                    g->tabu_word_off, g->tabu_ring[g->step & 1], g->tabu_ring[(g->step + 1) & 1],
                                                    g->tabu_ring_len, g->tabu_ring_off, g->tabu_size, g->tabu_fill);
             GJ_LAUNCH_CHECK();
@@ -639,9 +734,29 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         }
         if ((rc = gj_prof_end(g, st))) return rc;
         if (planned) {
-            k_ga_replace_planned<<<g->I * g->pop, 128, 0, st>>>(P, g->groups, A, g->pop_rows, g->pop_scores, g->order, g->ga_parent,
-                                                               g->moves, g->ga_pairs, g->cand_scores, g->pop_next, g->pop_scores_next,
-                                                               g->ga_src, g->ga_trace_rep);
+            const int64_t NP = (int64_t)g->I * g->pop;
+            k_ga_decide<<<(unsigned)((NP + 255) / 256), 256, 0, st>>>(A, g->pop_scores, g->order, g->ga_parent, g->cand_scores,
+                                                                     g->pop_scores_next, g->ga_take, g->ga_src, g->ga_trace_rep);
+            GJ_LAUNCH_CHECK();
+            cudaStream_t rs = st;
+            if (overlap) {
+                GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[1], st));
+                GJ_CUDA_TRY(cudaStreamWaitEvent(g->ga_side, g->ga_ev[1], 0));
+                rs = g->ga_side;
+            }
+            const int i_tiles = (g->pop + kRankTile - 1) / kRankTile;
+            const int j_slices = std::max(1, std::min((g->pop + kRankTile - 1) / kRankTile, (148 * 8) / std::max(1, i_tiles * g->I)));
+            k_ga_rank<<<dim3(i_tiles, j_slices, g->I), kRankTile, 0, rs>>>(g->pop, g->levels, j_slices, g->pop_scores_next, g->ga_rank);
+            GJ_LAUNCH_CHECK();
+            if (overlap) GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[2], g->ga_side));
+            k_ga_copy_planned<<<g->I * g->pop, 128, 0, st>>>(P, g->groups, A, g->pop_rows, g->ga_take, g->moves, g->ga_pairs, g->pop_next);
+            GJ_LAUNCH_CHECK();
+            if (overlap) GJ_CUDA_TRY(cudaStreamWaitEvent(st, g->ga_ev[2], 0));
+            std::swap(g->pop_rows, g->pop_next);
+            std::swap(g->pop_scores, g->pop_scores_next);
+            k_ga_finish<<<(unsigned)((NP + 255) / 256), 256, 0, st>>>(g->pop, g->I, g->stride, g->n_vars, g->levels, g->n_cand, g->ga_rank,
+                                                                     g->order, g->pop_rows, g->pop_scores, g->best, g->best_score,
+                                                                     g->gbest, g->gbest_score, g->counters);
             GJ_LAUNCH_CHECK();
         } else {
             k_round_scores<<<(unsigned)std::min<int64_t>((S + 255) / 256, 1184), 256, 0, st>>>(P, g->cand_scores, S);   // agent_base.rs:284-287
@@ -649,10 +764,10 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
             k_ga_replace<<<g->I * g->pop, 128, 0, st>>>(A, g->pop_rows, g->pop_scores, g->order, g->cand_rows, g->cand_scores,
                                                        g->pop_next, g->pop_scores_next, g->ga_src, g->ga_trace_rep);
             GJ_LAUNCH_CHECK();
+            std::swap(g->pop_rows, g->pop_next);
+            std::swap(g->pop_scores, g->pop_scores_next);
+            if ((rc = ga_sort_and_top(g, st, true))) return rc;
         }
-        std::swap(g->pop_rows, g->pop_next);
-        std::swap(g->pop_scores, g->pop_scores_next);
-        if ((rc = ga_sort_and_top(g, st, true))) return rc;
         g->step += 1;
         g->steps_to_send -= 1;
         if (g->steps_to_send <= 0) {
@@ -665,7 +780,7 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
             }
             g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
         }
-        if ((rc = gj_ga_global_top(g, st))) return rc;
+        if (!(planned && g->I == 1) && (rc = gj_ga_global_top(g, st))) return rc;
     }
     return GJ_OK;
 }

@@ -1,5 +1,7 @@
 // gj_islands_vrp_chain.cu -- translation unit of the VRP LateAcceptance / SimulatedAnnealing chains
 // (kernels: gj_islands_vrp_chain.cuh).
+#include <algorithm>
+
 #include "gj_islands_dev.cuh"
 #include "gj_islands_vrp_chain.cuh"
 
@@ -18,8 +20,8 @@ gj_status gj_launch_vrp_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t
     // warps of a CTA -- which re-align every step -- are the ones that share its instruction cache
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->p->device);
-    int vw = 4;
-    while (vw < kVrpStepWarps && (int64_t)vw * sms < g->I) vw *= 2;
+    // (not a power of two: 4096 chains are 28 per SM on 147 SMs, where 32 per CTA left 20 SMs idle)
+    int vw = (int)std::min<int64_t>(kVrpStepWarps, std::max<int64_t>(4, (g->I + sms - 1) / sms));
     const unsigned vgrid = (unsigned)((g->I + vw - 1) / vw);
     const size_t vsmem = sizeof(GjVrpcScratch) * vw;
     if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE) {

@@ -27,6 +27,7 @@ static constexpr int kVrpStepWarps = GJ_VRPC_STEP_WARPS;   // step kernel: warps
 #define GJ_VRPC_Q 48             // 32 stops of the old route + <= 16 arrivals
 
 struct GjVrpcScratch {
+    alignas(16) double qd[32];   // a chunk of leg / route lengths on its way through the sequential fold
     int32_t qc[GJ_VRPC_Q];       // customers
     int32_t qs[GJ_VRPC_Q];       // stop indices
     // the move: changed stops (new / old labels), arrivals of the route being walked
@@ -41,6 +42,7 @@ struct GjVrpcScratch {
 
 // what a walk without a move needs (rebuilds): the merged-run buffers only
 struct GjVrpcScratchLite {
+    alignas(16) double qd[32];
     int32_t qc[GJ_VRPC_Q];
     int32_t qs[GJ_VRPC_Q];
     int cs_stop[1], cs_v[1], cs_c[1], arr_stop[1], arr_c[1];
@@ -130,8 +132,19 @@ __device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int t
                 lateness += lt;
                 arrival = __shfl_sync(GJ_FULL_MASK, after, 31);
             }
+            // the chunk's leg lengths are added strictly in stop order: through shared memory, two per
+            // broadcast LDS.128 and one DADD each (a shuffle per stop cost twice the instructions).  Lanes
+            // past the run's end hold 0.0, and x + 0.0 == x.
             const int cntk = min(32, m - b2);
-            for (int k = 0; k < cntk; ++k) fold = fold + __shfl_sync(GJ_FULL_MASK, d, k);
+            q.qd[lane] = d;
+            __syncwarp();
+            const double2* qd2 = reinterpret_cast<const double2*>(q.qd);
+            for (int k = 0; k < cntk; k += 2) {
+                const double2 x = qd2[k >> 1];
+                fold = fold + x.x;
+                fold = fold + x.y;
+            }
+            __syncwarp();
         }
         if (m > 0) {
             if (first < 0) first = q.qc[0];
@@ -155,14 +168,22 @@ __device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int t
 
 // sum over the K routes in the reference's order (vehicle_distances.iter().sum()), touched routes
 // substituted by their re-walked value
-__device__ __forceinline__ double gj_vrpc_sum_routes(const double* rdist, int K, const GjVrpcScratch& q, int nav, int lane) {
+__device__ __forceinline__ double gj_vrpc_sum_routes(const double* rdist, int K, GjVrpcScratch& q, int nav, int lane) {
     double sum = 0.0;
+    const double2* qd2 = reinterpret_cast<const double2*>(q.qd);
     for (int v0 = 0; v0 < K; v0 += 32) {
         const int v = v0 + lane;
         double x = v < K ? rdist[v] : 0.0;
         for (int a = 0; a < nav; ++a) if (q.av[a] == v) x = q.nd[a];
+        q.qd[lane] = x;                                   // 0.0 past the last route: x + 0.0 == x
+        __syncwarp();
         const int m = min(32, K - v0);
-        for (int i = 0; i < m; ++i) sum += __shfl_sync(GJ_FULL_MASK, x, i);
+        for (int i = 0; i < m; i += 2) {
+            const double2 y = qd2[i >> 1];
+            sum += y.x;
+            sum += y.y;
+        }
+        __syncwarp();
     }
     return sum;
 }
@@ -397,6 +418,14 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
 #ifndef GJ_VRPC_MINBLOCKS
 #define GJ_VRPC_MINBLOCKS 8
 #endif
+#ifndef GJ_VRPC_SYNC
+#define GJ_VRPC_SYNC 1          // development knob: 0 drops the per-step re-alignment barriers
+#endif
+#if GJ_VRPC_SYNC
+#define GJ_VRPC_REALIGN() __syncthreads()
+#else
+#define GJ_VRPC_REALIGN() do { } while (0)
+#endif
 template <int AGENT>            // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING: one rule per instantiation
 __global__ void __launch_bounds__(kVrpStepWarps * 32, 1)
 k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
@@ -462,7 +491,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     for (int it = 0; it < A.n_steps; ++it) {
         // the warps of a CTA run the same code on different chains; re-aligning them every step keeps
         // them in the same instruction-cache lines (instruction fetch was the top stall without it)
-        __syncthreads();
+        GJ_VRPC_REALIGN();
         const uint64_t step = A.step0 + (uint64_t)it;
         // ---- generate (every lane computes the same move) -----------------------------------------------
         GjMoverParams M = A.M;
@@ -550,7 +579,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             off += r.len;
             __syncwarp();
         }
-        __syncthreads();                                // re-align (see the top of the loop)
+        GJ_VRPC_REALIGN();                              // re-align (see the top of the loop)
         // ---- totals -----------------------------------------------------------------------------------
         unsigned long long cap_pen = tot[1], late_pen = tot[2];
         for (int a = 0; a < nav; ++a) {
