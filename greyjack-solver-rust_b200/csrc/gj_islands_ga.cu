@@ -112,6 +112,43 @@ __global__ void k_round_scores(GjProblemDev P, double* scores, int64_t n) {
 
 static constexpr int kGaPairInts = 2 + 2 * GJ_MOVE_MAXPAIRS;
 
+// Mover::do_move(plain) of a small move, literally: the reference's own sequence of assignments / swaps on
+// the candidate (mover.rs:145-317), executed by ONE thread on a row it can read and write (`rd` / `wr`,
+// e.g. the shared-memory copy).  `touch(col)` is called for every column the move may have changed, in
+// emission order (repeats possible).  Same result as gj_small_move_pairs(incremental = false) without its
+// scratch arrays -- that expansion kept one thread busy for ~10 000 cycles per offspring.
+template <class Ids, class Rd, class Wr, class Touch>
+__device__ __forceinline__ void gj_ga_small_move_inplace(const GjMove& m, Ids g, Rd rd, Wr wr, Touch touch) {
+    const int k = m.k;
+    auto swp = [&](int ca, int cb) { const int x = rd(ca), y = rd(cb); wr(ca, y); wr(cb, x); };
+    switch (m.kind) {
+        case 0:     // change_move
+            for (int i = 0; i < k; ++i) wr(g[m.a[i]], m.v[i]);
+            for (int i = 0; i < k; ++i) touch(g[m.a[i]]);
+            break;
+        case 1:     // swap_move: candidate.swap(c[i-1], c[i])
+            for (int i = 1; i < k; ++i) swp(g[m.a[i - 1]], g[m.a[i]]);
+            for (int i = 0; i < k; ++i) touch(g[m.a[i]]);
+            break;
+        case 2:     // swap_edges_move: edges.rotate_left(1), then swaps of the left ends and of the right ends
+            for (int i = 1; i < k; ++i) {
+                const int pa = m.a[i], pb = m.a[(i + 1 == k) ? 0 : i + 1];     // rotated edges i-1 and i
+                swp(g[pa], g[pb]);
+                swp(g[pa + 1], g[pb + 1]);
+            }
+            for (int i = 0; i < k; ++i) { touch(g[m.a[i]]); touch(g[m.a[i] + 1]); }
+            break;
+        case 3: {   // scramble_move: candidate.swap(native[i], scrambled[i])
+            const int start = m.a[0];
+            for (int i = 0; i < k; ++i) swp(g[start + i], g[start + m.v[i]]);
+            for (int i = 0; i < k; ++i) touch(g[start + i]);
+            break;
+        }
+        default: break;
+    }
+}
+
+
 // Applies a planned move to a row copy: `pr` = the plan's pair list (shared memory), rd reads the parent.
 template <class Rd, class Wr>
 __device__ __forceinline__ void gj_ga_apply_planned(const GjProblemDev& P, const GjGroups& G, const GjMove& m,
@@ -192,42 +229,21 @@ k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __
     GJ_PHASE_DECL;
 #endif
     const int32_t* parent = pop_rows + ((size_t)island * A.pop + parent_slot[j]) * A.stride;
-    if (threadIdx.x == 0) {
-        // Thread 0 expands a small move into the final (column, value) pairs of Mover::do_move(plain) +
-        // fix_variables, in emission order, reading the parent's values itself -- under the shadow of the
-        // row load the other 255 threads are waiting for.  pairs[0] = count, -1 = segment move (applied
-        // from the descriptor); the list also goes to HBM for k_ga_copy_planned.
-        const GjMove m = moves[j];
-        sh_move = m;
-        int np = 0;
-        if (m.kind != GJ_MOVE_NULL && m.kind > 3) np = -1;
-        else if (m.kind != GJ_MOVE_NULL) {
-            int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
-            np = gj_small_move_pairs(m, G.ids + G.offsets[m.group], false, A.noop != 0,
-                                     [&](int id) { return __ldg(parent + id); }, cols, vals);
-            int32_t* pg = pairs + (size_t)j * kGaPairInts;
-            for (int i = 0; i < np; ++i) {
-                const int v = gj_fix_column(P, cols[i], vals[i]);
-                sh_pairs[2 + 2 * i] = cols[i]; sh_pairs[3 + 2 * i] = v;
-                pg[2 + 2 * i] = cols[i]; pg[3 + 2 * i] = v;
-            }
-        }
-        sh_pairs[0] = np;
-        pairs[(size_t)j * kGaPairInts] = np;
-    } else {
+    if (threadIdx.x < (int)(sizeof(GjMove) / 4))
+        reinterpret_cast<int32_t*>(&sh_move)[threadIdx.x] = reinterpret_cast<const int32_t*>(moves + j)[threadIdx.x];
+    {
         constexpr int U = 8;
-        const int lt = threadIdx.x - 1, ln = blockDim.x - 1;
-        for (int i0 = lt; i0 < n; i0 += U * ln) {
+        for (int i0 = threadIdx.x; i0 < n; i0 += U * blockDim.x) {
             int2 pr[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * ln;
+                const int i = i0 + u * blockDim.x;
                 pr[u] = make_int2(0, 0);
                 if (i < n) pr[u] = __ldg(reinterpret_cast<const int2*>(parent + 2 * i));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * ln;
+                const int i = i0 + u * blockDim.x;
                 if (i < n) { s.veh[i] = (uint16_t)pr[u].x; s.cust[i] = pr[u].y; }
             }
         }
@@ -235,10 +251,38 @@ k_ga_score_planned_vrp(GjProblemDev P, GjGroups G, GjGaArgs A, const int32_t* __
     gj_vrp_eval_zero(P, s);
     __syncthreads();
     GJ_PHASE_MARK(0);
-    // Mover::do_move(.., incremental = false) + fix_variables(changed columns): the planned pairs of a
-    // small move, or a segment move shifted along the parent's row
-    gj_ga_apply_planned(P, G, sh_move, sh_pairs, A.noop != 0, [&](int id) { return __ldg(parent + id); },
-                        [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; });
+    // Mover::do_move(.., incremental = false) + fix_variables(changed columns).  A small move: thread 0 runs
+    // the reference's own assignments / swaps on the shared-memory copy and leaves the changed (column,
+    // value) pairs in HBM for k_ga_copy_planned (pairs[0] = count, -1 = segment move).  A segment move is
+    // shifted along the parent's row by all threads.
+    {
+        auto rd_s = [&](int id) { return (id & 1) ? s.cust[id >> 1] : (int)s.veh[id >> 1]; };
+        auto wr_s = [&](int id, int v) { if (id & 1) s.cust[id >> 1] = v; else s.veh[id >> 1] = (uint16_t)v; };
+        const int kind = sh_move.kind;
+        if (kind != GJ_MOVE_NULL && kind > 3) {
+            if (threadIdx.x == 0) pairs[(size_t)j * kGaPairInts] = -1;
+            sh_pairs[0] = -1;           // every thread writes the same value: no barrier needed before the call
+            gj_ga_apply_planned(P, G, sh_move, sh_pairs, A.noop != 0, [&](int id) { return __ldg(parent + id); }, wr_s);
+        } else if (threadIdx.x == 0) {
+            int32_t* pg = pairs + (size_t)j * kGaPairInts;
+            int np = 0;
+            if (kind != GJ_MOVE_NULL) {
+                const int4 info = G.info[sh_move.group];
+                // uniform group: every column has the same bounds, values moved inside it (and the change
+                // move's in-bounds draws) never clamp -- fix_variables is the identity
+                const bool fix = info.z == 0;
+                auto touch = [&](int col) {
+                    int v = rd_s(col);                          // all swaps are done when touch() runs
+                    if (fix) { v = gj_fix_column(P, col, v); wr_s(col, v); }
+                    pg[2 + 2 * np] = col; pg[3 + 2 * np] = v;
+                    ++np;
+                };
+                if (info.y != 0) gj_ga_small_move_inplace(sh_move, GjAffineIds{info.x, info.y}, rd_s, wr_s, touch);
+                else gj_ga_small_move_inplace(sh_move, G.ids + G.offsets[sh_move.group], rd_s, wr_s, touch);
+            }
+            pg[0] = np;
+        }
+    }
     __syncthreads();
     GJ_PHASE_MARK(1);
     if (cand_out) {

@@ -35,8 +35,15 @@ enum { GJ_MOVE_NULL = 255 };
 // `rd(var_id)` reads the base.  incremental = the ISC form (TS / LA); otherwise the result
 // of the plain form's sequential swaps, expressed as final (column, value) pairs.
 // Returns the number of pairs; later pairs win on repeated columns.
-template <class Rd>
-__device__ __forceinline__ int gj_small_move_pairs(const GjMove& m, const int32_t* __restrict__ g,
+// ids of an affine semantic group (GjGroups::info): position k is variable first + k * step
+struct GjAffineIds {
+    int first, step;
+    __device__ __forceinline__ int operator[](int k) const { return first + k * step; }
+};
+
+// `g[k]`: variable id of group position k (the group's id list, or GjAffineIds)
+template <class Ids, class Rd>
+__device__ __forceinline__ int gj_small_move_pairs(const GjMove& m, Ids g,
                                                    bool incremental, bool noop_quirk, Rd rd,
                                                    int* cols, int* vals) {
     const int k = m.k;
