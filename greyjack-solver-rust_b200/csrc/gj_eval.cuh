@@ -159,9 +159,7 @@ static __device__ unsigned long long gj_vrp_phase_cycles[16];
 #define GJ_PHASE_MARK(k) do { } while (0)
 #endif
 
-#ifndef GJ_VRP_SCAN_WARP0
-#define GJ_VRP_SCAN_WARP0 1
-#endif
+
 
 // Shared-memory plan of one VRP candidate (one CTA).  `legs` (models without time windows): the decoded
 // columns are dead once the stops are bucketed, so their space -- padded to 8 bytes per stop -- is
@@ -173,6 +171,7 @@ struct GjVrpSmem {
     double* vdist;           // [K] per-vehicle distance
     unsigned long long* acc; // [0] capacity penalty, [1] lateness penalty
     uint16_t* veh;           // [n_stops] decoded vehicle ids (relative to veh_lo)
+    uint16_t* pos;           // [n_stops] rank of the stop among its warp block's stops of the same vehicle
     int32_t* cust;           // [n_stops] decoded customer ids
     int32_t* bucket;         // [n_stops] customers grouped by vehicle, stop order kept
     double* wfold;           // [n_warps][32] leg lengths of the chunk a warp is folding
@@ -192,9 +191,9 @@ __host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_w
     b += (size_t)K * 8;
     b += 32;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)n_warps * 32 * 8;
+    if (!legs) b += (size_t)n_warps * 32 * 8;
     b += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
-    b += legs ? (size_t)n_stops * 8 : (size_t)n_stops * 4 + (((size_t)n_stops * 2 + 7) & ~(size_t)7);
+    b += legs ? (size_t)n_stops * 8 : (size_t)n_stops * 4 + 2 * (((size_t)n_stops * 2 + 7) & ~(size_t)7);
     return b;
 }
 
@@ -213,11 +212,13 @@ __device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_sto
     s.vdist = (double*)(smem + o); o += (size_t)K * 8;
     s.acc = (unsigned long long*)(smem + o); o += 32;      // capacity, lateness, distinct customers, -
     o = (o + 15) & ~(size_t)15;
-    s.wfold = (double*)(smem + o); o += (size_t)n_warps * 32 * 8;
+    s.wfold = (double*)(smem + o);
+    if (!legs) o += (size_t)n_warps * 32 * 8;
     s.bucket = (int32_t*)(smem + o); o += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
-    s.leg = (double*)(smem + o);                     // [n_stops] f64 over cust (4 B / stop) + veh (2 B) + pad
+    s.leg = (double*)(smem + o);                     // [n_stops] f64 over cust (4 B / stop) + veh (2 B) + pos (2 B)
     s.cust = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
     s.veh = (uint16_t*)(smem + o);
+    s.pos = legs ? s.veh + n_stops : (uint16_t*)(smem + o + (((size_t)n_stops * 2 + 7) & ~(size_t)7));
     return s;
 }
 
@@ -261,33 +262,55 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     GJ_PHASE_MARK(3);
     }
 
-    // pass 1: customer bitmap + per-warp-block vehicle histogram.  Warp w owns the
-    // contiguous block of stops [w*blk, (w+1)*blk) so that block order == stop order.
+    // pass 1: customer bitmap + per-warp-block vehicle histogram.  Warp w owns the contiguous block of
+    // stops [w*blk, (w+1)*blk) so that block order == stop order, and walks it 32 stops at a time: lanes
+    // with the same vehicle are ranked by lane id (= stop order), the first of them advances the block's
+    // counter of that vehicle, and every stop keeps its rank among the block's stops of its vehicle
+    // (pos) -- pass 2 then needs neither a match nor a serial chain.  Four chunks' loads (and, without time
+    // windows, their demand gathers) are issued before the first ranked chunk.
     const int blk = (n + n_warps - 1) / n_warps;
     const int lo = warp * blk;
     const int hi = min(n, lo + blk);
     int* mycnt = s.cnt + warp * K;
     const bool legs = !P.time_windowed;
-    for (int i0 = lo + lane; i0 < hi; i0 += 4 * 32) {
+    for (int i0 = lo + lane; i0 < hi + lane; i0 += 4 * 32) {
         int c[4], v[4];
         unsigned dem[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = i0 + u * 32;
-            c[u] = 0; v[u] = 0; dem[u] = 0u;
+            c[u] = 0; v[u] = 0x10000 + lane; dem[u] = 0u;
             if (i < hi) {
                 c[u] = s.cust[i]; v[u] = s.veh[i];
                 // the demand a route carries does not depend on the stop order: summed here
                 if (legs) dem[u] = P.cust[c[u]].x;
             }
         }
+        // the four matches are independent of each other: issued back to back, ahead of the counter chain
+        unsigned grp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) grp[u] = __match_any_sync(GJ_FULL_MASK, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 - lane + u * 32 >= hi) break;                          // uniform over the warp
+            const bool on = i0 + u * 32 < hi;
+            const int rank = __popc(grp[u] & ((1u << lane) - 1u));
+            int old = 0;
+            if (on && rank == 0) { old = mycnt[v[u]]; mycnt[v[u]] = old + __popc(grp[u]); }
+            __syncwarp();                                                 // the counters, before the next chunk reads them
+            old = __shfl_sync(GJ_FULL_MASK, old, __ffs(grp[u]) - 1);
+            if (on) s.pos[i0 + u * 32] = (uint16_t)(old + rank);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (i0 + u * 32 >= hi) continue;
             const unsigned b = (unsigned)(c[u] - P.val_lo);
             atomicOr(&s.bm[b >> 5], 1u << (b & 31));
-            atomicAdd(&mycnt[v[u]], 1);
-            if (legs) {
+        }
+        if (legs) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i0 + u * 32 >= hi) continue;
                 // 16-bit halves apart, so that 32-bit shared atomics cannot overflow
                 atomicAdd(&s.rl[v[u]], dem[u] & 0xffffu);
                 if (dem[u] >> 16) atomicAdd(&s.rl[K + v[u]], dem[u] >> 16);
@@ -297,48 +320,6 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     __syncthreads();
     GJ_PHASE_MARK(4);
 
-#if !GJ_VRP_SCAN_WARP0
-    for (int v = tid; v < K; v += nthr) {
-        int tot = 0;
-        for (int w = 0; w < n_warps; ++w) tot += s.cnt[w * K + v];
-        s.start[v + 1] = tot;
-    }
-    if (tid == 0) s.start[0] = 0;
-    __syncthreads();
-    GJ_PHASE_MARK(5);
-    if (warp == 0) {
-        int carry = 0;
-        for (int base = 0; base < K; base += 32) {
-            int v = base + lane;
-            int x = (v < K) ? s.start[v + 1] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int y = __shfl_up_sync(GJ_FULL_MASK, x, o);
-                if (lane >= o) x += y;
-            }
-            if (v < K) s.start[v + 1] = x + carry;
-            carry += __shfl_sync(GJ_FULL_MASK, x, 31);
-        }
-    }
-    if (warp == n_warps - 1) {
-        int uniq = 0;
-        for (int w = lane; w < P.bm_words; w += 32) uniq += __popc(s.bm[w]);
-        uniq = gj_warp_sum(uniq);
-        if (lane == 0) s.acc[2] = (unsigned long long)uniq;
-    }
-    __syncthreads();
-    GJ_PHASE_MARK(6);
-    for (int v = tid; v < K; v += nthr) {
-        int off = s.start[v];
-        for (int w = 0; w < n_warps; ++w) {
-            int c = s.cnt[w * K + v];
-            s.cnt[w * K + v] = off;
-            off += c;
-        }
-    }
-    __syncthreads();
-    GJ_PHASE_MARK(7);
-#else
     // exclusive scan over (vehicle major, warp minor): cnt[w][v] -> first slot of warp w's stops of
     // vehicle v; start[v] = route start.  Warp 0 alone, 32 vehicles per round (column sums, warp scan,
     // offsets written back) -- no CTA barrier inside; meanwhile the last warp counts the distinct
@@ -377,24 +358,11 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     __syncthreads();
     GJ_PHASE_MARK(8);
 
-#endif
-    // pass 2: stable scatter.  Each warp walks its block in order, 32 stops at a time;
-    // lanes with the same vehicle are ranked by lane id (= stop order).
-    for (int base = lo; base < hi; base += 32) {
-        const int i = base + lane;
-        const bool on = i < hi;
-        const int v = on ? (int)s.veh[i] : (0x10000 + lane);
-        const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
-        const int rank = __popc(grp & ((1u << lane) - 1u));
-        int slot = 0;
-        if (on) slot = mycnt[v];
-        __syncwarp();
-        if (on) {
-            s.bucket[slot + rank] = s.cust[i];
-            if (out) out->bstop[slot + rank] = i;
-            if (rank == 0) mycnt[v] = slot + __popc(grp);
-        }
-        __syncwarp();
+    // pass 2: stable scatter: slot = first slot of (warp block, vehicle) + rank inside the block
+    for (int i = lo + lane; i < hi; i += 32) {
+        const int slot = mycnt[s.veh[i]] + (int)s.pos[i];
+        s.bucket[slot] = s.cust[i];
+        if (out) out->bstop[slot] = i;
     }
     __syncthreads();
     GJ_PHASE_MARK(9);
