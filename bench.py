@@ -349,9 +349,10 @@ def other_configs(gj, inst, ring, torch, D, rank, world, local_rank, args):
         return {"value": n / s, "unit": UNIT, "cores": thr, "kind": "port",
                 "sample": f"2 generations x {thr} agents x 8192 offspring ({s:.1f} s); " + cpu_note("PSC")}
 
-    run("C3 cvrp-2000x50 GeneticAlgorithm pop 8192, one island per GPU", c3, 10, 3, 10, 1, "k_plain_vrp",
+    run("C3 cvrp-2000x50 GeneticAlgorithm pop 8192, one island per GPU", c3, 10, 3, 10, 1, "k_ga_score_planned_vrp",
         40424.0, "A_full: 4*4000 + 8*2050 + 4*2000 + 24 B", c3_cpu,
-        note="population 8192 x 4000 int32 = 131 MB per generation: larger than L2, no flush needed")
+        note="offspring are scored from their parent's row + move and written only when they survive; the population "
+             "(8192 x 4000 int32 = 131 MB, rewritten every generation) is larger than L2, no flush needed")
 
     # ---- C4: vrp_service VRPTW 5000 stops, LateAcceptance islands --------------------------------------------
     spec4 = inst.vrptw(5000, 125, n_depots=5, seed=3, service_variant=True, greedy=False)

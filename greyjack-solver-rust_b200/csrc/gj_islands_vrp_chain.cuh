@@ -376,7 +376,11 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
     if (!adopted && !stale && !dirty) return;
     GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
     if (adopted) {
-        for (int i = lane; i < A.n_vars; i += 32) row[i] = A.gbest[i];
+        {   // stride is a multiple of 4 ints, rows are 16-byte aligned
+            const int4* g4 = reinterpret_cast<const int4*>(A.gbest);
+            int4* r4 = reinterpret_cast<int4*>(row);
+            for (int i = lane; i < A.stride / 4; i += 32) r4[i] = g4[i];
+        }
         if (is_la && lane == 0) {   // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
             double* late_g = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
             const int head = (A.late_head[island] + A.late_size - 1) % A.late_size;
@@ -419,12 +423,17 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
 #define GJ_VRPC_MINBLOCKS 8
 #endif
 #ifndef GJ_VRPC_SYNC
-#define GJ_VRPC_SYNC 1          // development knob: 0 drops the per-step re-alignment barriers
+#define GJ_VRPC_SYNC 3          // development knob: bit 0 = barrier at the top of a step, bit 1 = before the totals
 #endif
-#if GJ_VRPC_SYNC
-#define GJ_VRPC_REALIGN() __syncthreads()
+#if GJ_VRPC_SYNC & 1
+#define GJ_VRPC_REALIGN_TOP() __syncthreads()
 #else
-#define GJ_VRPC_REALIGN() do { } while (0)
+#define GJ_VRPC_REALIGN_TOP() do { } while (0)
+#endif
+#if GJ_VRPC_SYNC & 2
+#define GJ_VRPC_REALIGN_MID() __syncthreads()
+#else
+#define GJ_VRPC_REALIGN_MID() do { } while (0)
 #endif
 template <int AGENT>            // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING: one rule per instantiation
 __global__ void __launch_bounds__(kVrpStepWarps * 32, 1)
@@ -491,8 +500,10 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     for (int it = 0; it < A.n_steps; ++it) {
         // the warps of a CTA run the same code on different chains; re-aligning them every step keeps
         // them in the same instruction-cache lines (instruction fetch was the top stall without it)
-        GJ_VRPC_REALIGN();
+        GJ_VRPC_REALIGN_TOP();
         const uint64_t step = A.step0 + (uint64_t)it;
+        // the chain's totals are needed after the route walks: requested now, the round trip hides under them
+        const unsigned long long tot0 = tot[0], tot1 = tot[1], tot2 = tot[2];
         // ---- generate (every lane computes the same move) -----------------------------------------------
         GjMoverParams M = A.M;
         const GjMove m = gj_generate_move<true>(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
@@ -579,9 +590,9 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             off += r.len;
             __syncwarp();
         }
-        GJ_VRPC_REALIGN();                              // re-align (see the top of the loop)
+        GJ_VRPC_REALIGN_MID();                          // re-align (see the top of the loop)
         // ---- totals -----------------------------------------------------------------------------------
-        unsigned long long cap_pen = tot[1], late_pen = tot[2];
+        unsigned long long cap_pen = tot1, late_pen = tot2;
         for (int a = 0; a < nav; ++a) {
             const int v = q.av[a];
             const unsigned long long capv = P.veh_capacity[v];
@@ -592,7 +603,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             late_pen += q.nt[a];
         }
         const double sum_distance = gj_vrpc_sum_routes(rdist, K, q, nav, lane);
-        const long long dups = (long long)tot[0] - (long long)q.d_uniq;
+        const long long dups = (long long)tot0 - (long long)q.d_uniq;
         GjScore sc;
         gj_combine_vrp(P, true, 1000.0 * (double)dups, (double)cap_pen, sum_distance, (double)late_pen, sc.v);
         gj_score_round(sc, P);                          // agent_base.rs:311-314
