@@ -481,243 +481,6 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     unsigned long long* rload = V.rload + (size_t)island * K;
     unsigned long long* rlate = V.rlate + (size_t)island * K;
     unsigned long long* tot = V.tot + (size_t)island * 4;
-        tot[0] = (unsigned long long)(n - distinct);
-        tot[1] = cap_pen;
-        tot[2] = late_pen;
-        V.stale[island] = 0;
-    }
-    __syncwarp();
-}
-
-// Route index of the published global top (slot I), once per published version.  One CTA: warp 0
-// buckets the stops, then the warps share the K route walks and the flattening of the stop lists.
-static constexpr int kGindexWarps = 32;
-__global__ void __launch_bounds__(kGindexWarps * 32)
-k_vrp_chain_gindex(GjProblemDev P, int I, const int32_t* gbest, const int* gver, GjVrpChainState V) {
-    __shared__ GjVrpcScratchLite sh_q[kGindexWarps];
-    __shared__ int sh_rlen[GJ_VRPC_KSM];
-    __shared__ unsigned long long sh_pen[2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ver = *gver;
-    if (ver == *V.gidx_ver) return;                   // uniform over the CTA
-    const int n = P.n_entities, K = P.n_vehicles;
-    const int tw_mode = gj_vrp_tw_mode(P);
-    const int32_t* rs = V.rs + (size_t)I * K * n;
-    int32_t* rlen = V.rlen + (size_t)I * K;
-    if (threadIdx.x < 2) sh_pen[threadIdx.x] = 0ull;
-    if (warp == 0) gj_vrpc_bucket(P, gbest, V, I, K <= GJ_VRPC_KSM ? sh_rlen : nullptr, lane);
-    __syncthreads();
-    unsigned long long cap_pen = 0ull, late_pen = 0ull;
-    for (int v = warp; v < K; v += kGindexWarps) {
-        const GjRouteStat r = gj_vrpc_walk(P, tw_mode, v, gbest, rs + (size_t)v * n, rlen[v], 0, 0, nullptr, sh_q[warp], lane);
-        if (lane == 0) {
-            V.rdist[(size_t)I * K + v] = r.dist;
-            V.rload[(size_t)I * K + v] = r.load;
-            V.rlate[(size_t)I * K + v] = r.late;
-        }
-        const unsigned long long capv = P.veh_capacity[v];
-        if (r.load > capv) cap_pen += r.load - capv;
-        late_pen += r.late;
-    }
-    if (lane == 0) { atomicAdd(&sh_pen[0], cap_pen); atomicAdd(&sh_pen[1], late_pen); }
-    // flattened stop lists: offsets = exclusive prefix of the route lengths (warp 0, into goff)
-    if (warp == 0) {
-        int run = 0;
-        for (int v0 = 0; v0 < K; v0 += 32) {
-            const int v = v0 + lane;
-            const int len = v < K ? rlen[v] : 0;
-            int inc = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(GJ_FULL_MASK, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (v < K) V.goff[v] = run + inc - len;
-            run += __shfl_sync(GJ_FULL_MASK, inc, 31);
-        }
-    }
-    __syncthreads();
-    for (int v = warp; v < K; v += kGindexWarps) {
-        const int len = rlen[v], p = V.goff[v];
-        for (int i = lane; i < len; i += 32) { V.gstop[p + i] = rs[(size_t)v * n + i]; V.gdst[p + i] = v * n + i; }
-    }
-    if (warp == 0) {
-        const int32_t* cnt = V.cnt + (size_t)I * V.cnt_stride;
-        int distinct = 0;
-        for (int i = lane; i < V.cnt_stride; i += 32) distinct += cnt[i] > 0 ? 1 : 0;
-        distinct = gj_warp_sum(distinct);
-        distinct = __shfl_sync(GJ_FULL_MASK, distinct, 0);
-        if (lane == 0) {
-            unsigned long long* tot = V.tot + (size_t)I * 4;
-            tot[0] = (unsigned long long)(n - distinct);
-            tot[1] = sh_pen[0];
-            tot[2] = sh_pen[1];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *V.gidx_ver = ver;
-}
-
-// Between launches (cold path): update_global_top adopt half (agent_base.rs:465-489), route index of
-// chains whose solution was replaced (adopted global top: copy of slot I; migrant / creation:
-// rebuild), update_top_individual for the replaced solution.  One warp per chain; chains with
-// nothing pending leave after three loads.
-__global__ void __launch_bounds__(kVrpChainWarps * 32)
-k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
-    __shared__ GjVrpcScratchLite sh_q[kVrpChainWarps];
-    __shared__ int sh_rlen[kVrpChainWarps][GJ_VRPC_KSM];
-    constexpr int LV = 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int island = blockIdx.x * kVrpChainWarps + warp;
-    if (island >= A.I) return;
-    GjVrpcScratchLite& q = sh_q[warp];
-    const int n = P.n_entities, K = P.n_vehicles;
-    int32_t* row = A.cur + (size_t)island * A.stride;
-    int32_t* best_row = A.best + (size_t)island * A.stride;
-    const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
-    // update_global_top, adopt half: the test the reference makes at the end of every iteration
-    // (agent_base.rs:465-489) -- here for the last iteration of the previous launch; the step kernel
-    // makes the later ones itself ("holding").  gseen[island] == version <=> the stored solution IS
-    // that version's gbest row; dirty == 1: a migrant replaced it since.
-    int adopted = 0;
-    const int stale = V.stale[island], dirty = A.dirty[island];
-    if (lane == 0 && A.gver) {
-        const int ver = *A.gver;
-        const bool cur_is_g = ver != 0 && A.gseen[island] == ver && dirty != 1;
-        if (ver != 0 && !cur_is_g) {
-            const GjScore g = gj_load_score(A.gbest_score, LV);
-            const GjScore mytop = gj_load_score(A.best_score + (size_t)island * GJ_MAX_LEVELS, LV);
-            adopted = gj_score_le(mytop, g, LV) ? 0 : 1;                 // global < agent_top
-            if (adopted && *V.gidx_ver == ver) adopted = 2;              // ... and its route index is ready
-            A.gseen[island] = adopted ? ver : 0;
-        }
-    }
-    adopted = __shfl_sync(GJ_FULL_MASK, adopted, 0);
-    if (!adopted && !stale && !dirty) return;
-    GjScore cur = gj_load_score(A.cur_score + (size_t)island * GJ_MAX_LEVELS, LV);
-    if (adopted) {
-        {   // stride is a multiple of 4 ints, rows are 16-byte aligned
-            const int4* g4 = reinterpret_cast<const int4*>(A.gbest);
-            int4* r4 = reinterpret_cast<int4*>(row);
-            for (int i0 = lane; i0 < A.stride / 4; i0 += 128) {
-                int4 x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; x[u] = i < A.stride / 4 ? g4[i] : make_int4(0, 0, 0, 0); }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; if (i < A.stride / 4) r4[i] = x[u]; }
-            }
-        }
-        if (is_la && lane == 0) {   // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
-            double* late_g = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
-            const int head = (A.late_head[island] + A.late_size - 1) % A.late_size;
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)head * GJ_MAX_LEVELS + l] = cur.v[l];
-            A.late_head[island] = head;
-            A.late_len[island] = min(A.late_len[island] + 1, A.late_size);
-        }
-        cur = gj_load_score(A.gbest_score, LV);
-        if (lane == 0)
-            for (int l = 0; l < GJ_MAX_LEVELS; ++l) A.cur_score[(size_t)island * GJ_MAX_LEVELS + l] = cur.v[l];
-        __syncwarp();
-    }
-    if (adopted == 2) {
-        // copy the global top's route index (slot I) instead of re-walking all K routes
-        const size_t gI = (size_t)A.I;
-        int32_t* rs = V.rs + (size_t)island * K * n;
-        // (four independent loads in flight per lane: the copy is latency-, not bandwidth-bound)
-        for (int p0 = lane; p0 < n; p0 += 128) {
-            int d[4], x[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int p = p0 + 32 * u;
-                d[u] = p < n ? V.gdst[p] : -1;
-                x[u] = p < n ? V.gstop[p] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (d[u] >= 0) rs[d[u]] = x[u];
-        }
-        for (int v = lane; v < K; v += 32) {
-            V.rlen[(size_t)island * K + v] = V.rlen[gI * K + v]; V.rdist[(size_t)island * K + v] = V.rdist[gI * K + v];
-            V.rload[(size_t)island * K + v] = V.rload[gI * K + v]; V.rlate[(size_t)island * K + v] = V.rlate[gI * K + v];
-        }
-        {
-            const int32_t* csrc = V.cnt + gI * V.cnt_stride;
-            int32_t* cdst = V.cnt + (size_t)island * V.cnt_stride;
-            for (int i0 = lane; i0 < V.cnt_stride; i0 += 128) {
-                int x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; x[u] = i < V.cnt_stride ? csrc[i] : 0; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; if (i < V.cnt_stride) cdst[i] = x[u]; }
-            }
-        }
-        if (lane < 3) V.tot[(size_t)island * 4 + lane] = V.tot[gI * 4 + lane];
-        if (lane == 0) V.stale[island] = 0;
-    } else if (stale || adopted) {
-        gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, sh_rlen[warp], lane);
-    }
-    // A solution that arrived between steps meets the agent's top only after the next step
-    // (update_top_individual runs once per iteration, agent_base.rs:149-152): the step kernel owes
-    // that comparison.  row and best_row are unrelated vectors from here on.
-    if ((adopted || dirty) && lane == 0) {
-        V.pend[island] = 1;
-        V.ndiff[island] = -1;
-        A.dirty[island] = 0;
-    }
-}
-
-#ifndef GJ_VRPC_MINBLOCKS
-#define GJ_VRPC_MINBLOCKS 8
-#endif
-#ifndef GJ_VRPC_SYNC
-#define GJ_VRPC_SYNC 3          // development knob: bit 0 = barrier at the top of a step, bit 1 = before the totals
-#endif
-#if GJ_VRPC_SYNC & 1
-#define GJ_VRPC_REALIGN_TOP() __syncthreads()
-#else
-#define GJ_VRPC_REALIGN_TOP() do { } while (0)
-#endif
-#if GJ_VRPC_SYNC & 2
-#define GJ_VRPC_REALIGN_MID() __syncthreads()
-#else
-#define GJ_VRPC_REALIGN_MID() do { } while (0)
-#endif
-template <int AGENT>            // GJ_AGENT_LATE_ACCEPTANCE / GJ_AGENT_SIMULATED_ANNEALING: one rule per instantiation
-__global__ void __launch_bounds__(kVrpStepWarps * 32, 1)
-k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
-    extern __shared__ __align__(16) unsigned char vrpc_smem[];
-    GjVrpcScratch* sh_q = reinterpret_cast<GjVrpcScratch*>(vrpc_smem);
-    constexpr int LV = 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int island = blockIdx.x * (blockDim.x >> 5) + warp;    // 4..kVrpStepWarps warps per CTA (host picks)
-    if (island >= A.I) return;                       // whole warps only: the barrier below counts live warps
-    GjVrpcScratch& q = sh_q[warp];
-    const int n = P.n_entities, K = P.n_vehicles;
-    const int tw_mode = gj_vrp_tw_mode(P);
-    int32_t* row = A.cur + (size_t)island * A.stride;
-    int32_t* best_row = A.best + (size_t)island * A.stride;
-    int32_t* rs = V.rs + (size_t)island * K * n;
-    int32_t* rlen = V.rlen + (size_t)island * K;
-    double* rdist = V.rdist + (size_t)island * K;
-    unsigned long long* rload = V.rload + (size_t)island * K;
-    unsigned long long* rlate = V.rlate + (size_t)island * K;
-    // The per-route statistics of the chain (28 B per route) are read every step -- the K-term distance sum
-    // alone walks all of rdist -- so they live in shared memory for the length of the launch when they fit
-    // (A.stats_in_smem, decided by the host): loaded here, written back after the last step.
-    int32_t* const rlen_g = rlen; double* const rdist_g = rdist;
-    unsigned long long* const rload_g = rload; unsigned long long* const rlate_g = rlate;
-    if (A.stats_in_smem) {
-        const size_t Kp = (size_t)((K + 1) & ~1);          // even: keeps every warp's slice 8-byte aligned
-        unsigned char* base = vrpc_smem + sizeof(GjVrpcScratch) * (blockDim.x >> 5) + (size_t)warp * Kp * 28;
-        rdist = reinterpret_cast<double*>(base);
-        rload = reinterpret_cast<unsigned long long*>(base + Kp * 8);
-        rlate = reinterpret_cast<unsigned long long*>(base + Kp * 16);
-        rlen = reinterpret_cast<int32_t*>(base + Kp * 24);
-        for (int v = lane; v < K; v += 32) {
-            rdist[v] = rdist_g[v]; rload[v] = rload_g[v]; rlate[v] = rlate_g[v]; rlen[v] = rlen_g[v];
-        }
-        __syncwarp();
-    }
-    unsigned long long* tot = V.tot + (size_t)island * 4;
     int32_t* cnt = V.cnt + (size_t)island * V.cnt_stride;
     int32_t* spare = V.spare + (size_t)island * n;
     int32_t* diff = V.diff + (size_t)island * GJ_VRPC_DIFF;
