@@ -498,7 +498,18 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     int ndiff = V.ndiff[island];
     auto materialize_top = [&]() {
         if (ndiff < 0) {
-            for (int i = lane; i < A.n_vars; i += 32) best_row[i] = row[i];
+            // whole-row copy (once per adopted / migrated solution): 16-byte vectors, four loads in flight --
+            // the other chains of the CTA wait for this one at the next step's barrier
+            const int4* r4 = reinterpret_cast<const int4*>(row);
+            int4* b4 = reinterpret_cast<int4*>(best_row);
+            const int n4 = A.stride / 4;
+            for (int i0 = lane; i0 < n4; i0 += 128) {
+                int4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; x[u] = i < n4 ? r4[i] : make_int4(0, 0, 0, 0); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; if (i < n4) b4[i] = x[u]; }
+            }
         } else {
             for (int i = lane; i < ndiff; i += 32) {
                 const int st = diff[i];
