@@ -6,6 +6,15 @@
 #include "gj_islands_vrp_chain.cuh"
 
 gj_status gj_launch_vrp_gindex(gj_islands* g, cudaStream_t st) {
+    const GjProblemDev& P = g->p->dev;
+    const size_t smem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
+    if (smem <= 200 * 1024) {
+        gj_status rc;
+        if ((rc = opt_in_smem(k_vrp_chain_gindex_cta, smem))) return rc;
+        k_vrp_chain_gindex_cta<<<1, kVrpWarps * 32, smem, st>>>(P, g->I, g->gbest, g->gver, g->vcs);
+        GJ_LAUNCH_CHECK();
+        return GJ_OK;
+    }
     k_vrp_chain_gindex<<<1, kGindexWarps * 32, 0, st>>>(g->p->dev, g->I, g->gbest, g->gver, g->vcs);
     GJ_LAUNCH_CHECK();
     return GJ_OK;

@@ -338,6 +338,52 @@ k_vrp_chain_gindex(GjProblemDev P, int I, const int32_t* gbest, const int* gver,
     if (threadIdx.x == 0) *V.gidx_ver = ver;
 }
 
+// The same route index by ONE full evaluation of the CTA evaluator (gj_vrp_eval_cta: all warps bucket the
+// stops, one warp per route) -- its by-products are exactly the index: the stop of every bucket slot is
+// the flattened stop list, start[] the offsets, vdist / rload / rlate the per-route statistics (the same
+// bits as the walk's: both fold in the reference's order).  Used whenever the evaluator's shared-memory
+// plan fits; k_vrp_chain_gindex above (one warp buckets 32 stops at a time) took 5x as long on C4.
+__global__ void __launch_bounds__(kVrpWarps * 32)
+k_vrp_chain_gindex_cta(GjProblemDev P, int I, const int32_t* __restrict__ gbest, const int* gver, GjVrpChainState V) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ver = *gver;
+    if (ver == *V.gidx_ver) return;                   // uniform over the CTA
+    const int n = P.n_entities, K = P.n_vehicles;
+    GjVrpSmem s = gj_vrp_carve(smem_raw, n, K, P.bm_words, kVrpWarps, !P.time_windowed);
+    int32_t* cnt = V.cnt + (size_t)I * V.cnt_stride;
+    for (int i = threadIdx.x; i < V.cnt_stride; i += blockDim.x) cnt[i] = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int2 pr = *reinterpret_cast<const int2*>(gbest + 2 * i);
+        s.veh[i] = (uint16_t)pr.x;
+        s.cust[i] = pr.y;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cnt[s.cust[i] - P.val_lo], 1);
+    GjVrpOut out{V.gstop, V.rload + (size_t)I * K, V.rlate + (size_t)I * K};
+    double dup1000 = 0, cap = 0, dist = 0, late = 0;
+    gj_vrp_eval_cta(P, s, gj_vrp_tw_mode(P), dup1000, cap, dist, late, &out);
+    __syncthreads();
+    int32_t* rs = V.rs + (size_t)I * K * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int v = warp; v < K; v += n_warps) {
+        const int b = s.start[v], len = s.start[v + 1] - b;
+        for (int i = lane; i < len; i += 32) { rs[(size_t)v * n + i] = V.gstop[b + i]; V.gdst[b + i] = v * n + i; }
+        if (lane == 0) {
+            V.rlen[(size_t)I * K + v] = len;
+            V.rdist[(size_t)I * K + v] = s.vdist[v];
+            V.goff[v] = b;
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long* tot = V.tot + (size_t)I * 4;
+        tot[0] = (unsigned long long)llrint(dup1000 / 1000.0);
+        tot[1] = s.acc[0];
+        tot[2] = s.acc[1];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *V.gidx_ver = ver;
+}
+
 // Between launches (cold path): update_global_top adopt half (agent_base.rs:465-489), route index of
 // chains whose solution was replaced (adopted global top: copy of slot I; migrant / creation:
 // rebuild), update_top_individual for the replaced solution.  One warp per chain; chains with
@@ -420,14 +466,16 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
             V.rload[(size_t)island * K + v] = V.rload[gI * K + v]; V.rlate[(size_t)island * K + v] = V.rlate[gI * K + v];
         }
         {
-            const int32_t* csrc = V.cnt + gI * V.cnt_stride;
-            int32_t* cdst = V.cnt + (size_t)island * V.cnt_stride;
-            for (int i0 = lane; i0 < V.cnt_stride; i0 += 128) {
-                int x[4];
+            // cnt_stride is a multiple of 32 ints: 16-byte vectors
+            const int4* csrc = reinterpret_cast<const int4*>(V.cnt + gI * V.cnt_stride);
+            int4* cdst = reinterpret_cast<int4*>(V.cnt + (size_t)island * V.cnt_stride);
+            const int c4 = V.cnt_stride / 4;
+            for (int i0 = lane; i0 < c4; i0 += 128) {
+                int4 x[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; x[u] = i < V.cnt_stride ? csrc[i] : 0; }
+                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; x[u] = i < c4 ? csrc[i] : make_int4(0, 0, 0, 0); }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; if (i < V.cnt_stride) cdst[i] = x[u]; }
+                for (int u = 0; u < 4; ++u) { const int i = i0 + 32 * u; if (i < c4) cdst[i] = x[u]; }
             }
         }
         if (lane < 3) V.tot[(size_t)island * 4 + lane] = V.tot[gI * 4 + lane];
