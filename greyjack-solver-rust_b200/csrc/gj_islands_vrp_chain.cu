@@ -23,8 +23,15 @@ gj_status gj_launch_vrp_gindex(gj_islands* g, cudaStream_t st) {
 gj_status gj_launch_vrp_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t st) {
     const GjProblemDev& P = g->p->dev;
     gj_status rc;
-    k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs);
+    const size_t esmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
+    const int cta_rebuild = esmem <= 200 * 1024 ? 1 : 0;
+    k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs, cta_rebuild);
     GJ_LAUNCH_CHECK();
+    if (cta_rebuild) {
+        if ((rc = opt_in_smem(k_vrp_chain_rebuild_cta, esmem))) return rc;
+        k_vrp_chain_rebuild_cta<<<(unsigned)g->I, kVrpWarps * 32, esmem, st>>>(P, g->stride, g->cur, g->vcs);
+        GJ_LAUNCH_CHECK();
+    }
     // warps (chains) per CTA: as many as share an SM anyway, so that every SM gets chains and the
     // warps of a CTA -- which re-align every step -- are the ones that share its instruction cache
     int sms = 148;

@@ -343,45 +343,66 @@ k_vrp_chain_gindex(GjProblemDev P, int I, const int32_t* gbest, const int* gver,
 // the flattened stop list, start[] the offsets, vdist / rload / rlate the per-route statistics (the same
 // bits as the walk's: both fold in the reference's order).  Used whenever the evaluator's shared-memory
 // plan fits; k_vrp_chain_gindex above (one warp buckets 32 stops at a time) took 5x as long on C4.
-__global__ void __launch_bounds__(kVrpWarps * 32)
-k_vrp_chain_gindex_cta(GjProblemDev P, int I, const int32_t* __restrict__ gbest, const int* gver, GjVrpChainState V) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ver = *gver;
-    if (ver == *V.gidx_ver) return;                   // uniform over the CTA
+// slot: the chain (or I = the global top) whose index is built from `row`; flat: also the flattened lists
+__device__ __forceinline__ void gj_vrpc_index_cta(const GjProblemDev& P, unsigned char* smem_raw, const int32_t* __restrict__ row,
+                                                  int slot, const GjVrpChainState& V, int32_t* bstop, bool flat) {
     const int n = P.n_entities, K = P.n_vehicles;
     GjVrpSmem s = gj_vrp_carve(smem_raw, n, K, P.bm_words, kVrpWarps, !P.time_windowed);
-    int32_t* cnt = V.cnt + (size_t)I * V.cnt_stride;
+    int32_t* cnt = V.cnt + (size_t)slot * V.cnt_stride;
     for (int i = threadIdx.x; i < V.cnt_stride; i += blockDim.x) cnt[i] = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int2 pr = *reinterpret_cast<const int2*>(gbest + 2 * i);
+        const int2 pr = *reinterpret_cast<const int2*>(row + 2 * i);
         s.veh[i] = (uint16_t)pr.x;
         s.cust[i] = pr.y;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&cnt[s.cust[i] - P.val_lo], 1);
-    GjVrpOut out{V.gstop, V.rload + (size_t)I * K, V.rlate + (size_t)I * K};
+    GjVrpOut out{bstop, V.rload + (size_t)slot * K, V.rlate + (size_t)slot * K};
     double dup1000 = 0, cap = 0, dist = 0, late = 0;
     gj_vrp_eval_cta(P, s, gj_vrp_tw_mode(P), dup1000, cap, dist, late, &out);
     __syncthreads();
-    int32_t* rs = V.rs + (size_t)I * K * n;
+    int32_t* rs = V.rs + (size_t)slot * K * n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int v = warp; v < K; v += n_warps) {
         const int b = s.start[v], len = s.start[v + 1] - b;
-        for (int i = lane; i < len; i += 32) { rs[(size_t)v * n + i] = V.gstop[b + i]; V.gdst[b + i] = v * n + i; }
+        for (int i = lane; i < len; i += 32) {
+            rs[(size_t)v * n + i] = bstop[b + i];
+            if (flat) V.gdst[b + i] = v * n + i;
+        }
         if (lane == 0) {
-            V.rlen[(size_t)I * K + v] = len;
-            V.rdist[(size_t)I * K + v] = s.vdist[v];
-            V.goff[v] = b;
+            V.rlen[(size_t)slot * K + v] = len;
+            V.rdist[(size_t)slot * K + v] = s.vdist[v];
+            if (flat) V.goff[v] = b;
         }
     }
     if (threadIdx.x == 0) {
-        unsigned long long* tot = V.tot + (size_t)I * 4;
+        unsigned long long* tot = V.tot + (size_t)slot * 4;
         tot[0] = (unsigned long long)llrint(dup1000 / 1000.0);
         tot[1] = s.acc[0];
         tot[2] = s.acc[1];
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(kVrpWarps * 32)
+k_vrp_chain_gindex_cta(GjProblemDev P, int I, const int32_t* __restrict__ gbest, const int* gver, GjVrpChainState V) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ver = *gver;
+    if (ver == *V.gidx_ver) return;                   // uniform over the CTA
+    gj_vrpc_index_cta(P, smem_raw, gbest, I, V, V.gstop, true);
     if (threadIdx.x == 0) *V.gidx_ver = ver;
+}
+
+// Route index of the chains k_vrp_chain_prepare flagged (creation, an accepted migrant, an adopted global
+// top whose index was not ready): one CTA per chain, the others leave at once.  The merged-route spare list
+// of the chain, idle between launches, takes the evaluator's stop-per-slot by-product.
+__global__ void __launch_bounds__(kVrpWarps * 32)
+k_vrp_chain_rebuild_cta(GjProblemDev P, int stride, const int32_t* __restrict__ cur, GjVrpChainState V) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int island = blockIdx.x;
+    if (!V.stale[island]) return;                     // uniform over the CTA
+    gj_vrpc_index_cta(P, smem_raw, cur + (size_t)island * stride, island, V, V.spare + (size_t)island * P.n_entities, false);
+    if (threadIdx.x == 0) V.stale[island] = 0;
 }
 
 // Between launches (cold path): update_global_top adopt half (agent_base.rs:465-489), route index of
@@ -389,7 +410,7 @@ k_vrp_chain_gindex_cta(GjProblemDev P, int I, const int32_t* __restrict__ gbest,
 // rebuild), update_top_individual for the replaced solution.  One warp per chain; chains with
 // nothing pending leave after three loads.
 __global__ void __launch_bounds__(kVrpChainWarps * 32)
-k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
+k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V, int cta_rebuild) {
     __shared__ GjVrpcScratchLite sh_q[kVrpChainWarps];
     __shared__ int sh_rlen[kVrpChainWarps][GJ_VRPC_KSM];
     constexpr int LV = 3;
@@ -481,7 +502,10 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V) {
         if (lane < 3) V.tot[(size_t)island * 4 + lane] = V.tot[gI * 4 + lane];
         if (lane == 0) V.stale[island] = 0;
     } else if (stale || adopted) {
-        gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, sh_rlen[warp], lane);
+        // (one warp re-walking 125 routes took as long as everything else in this kernel together: the
+        // flagged chains go to k_vrp_chain_rebuild_cta, one CTA each, when the evaluator's plan fits)
+        if (cta_rebuild) { if (lane == 0) V.stale[island] = 1; }
+        else gj_vrpc_rebuild(P, gj_vrp_tw_mode(P), row, V, island, q, sh_rlen[warp], lane);
     }
     // A solution that arrived between steps meets the agent's top only after the next step
     // (update_top_individual runs once per iteration, agent_base.rs:149-152): the step kernel owes
