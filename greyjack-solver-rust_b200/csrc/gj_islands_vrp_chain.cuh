@@ -520,8 +520,13 @@ k_vrp_chain_prepare(GjProblemDev P, GjChainArgs A, GjVrpChainState V, int cta_re
 #ifndef GJ_VRPC_MINBLOCKS
 #define GJ_VRPC_MINBLOCKS 8
 #endif
+#ifndef GJ_VRPC_SYNC_EVERY
+#define GJ_VRPC_SYNC_EVERY 1    // development knob: re-align only every n-th step
+#endif
 #ifndef GJ_VRPC_SYNC
-#define GJ_VRPC_SYNC 3          // development knob: bit 0 = barrier at the top of a step, bit 1 = before the totals
+#define GJ_VRPC_SYNC 1          // bit 0 = barrier at the top of a step, bit 1 = before the totals (measured on
+                                // C4: 1 -> 49.7 us per step, 3 -> 51.6, none -> 54; a barrier only every 2nd / 4th /
+                                // 8th step -> 55 / 61 / 63; one more before every route walk -> 53.3)
 #endif
 #if GJ_VRPC_SYNC & 1
 #define GJ_VRPC_REALIGN_TOP() __syncthreads()
@@ -609,7 +614,11 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
     for (int it = 0; it < A.n_steps; ++it) {
         // the warps of a CTA run the same code on different chains; re-aligning them every step keeps
         // them in the same instruction-cache lines (instruction fetch was the top stall without it)
+#if GJ_VRPC_SYNC_EVERY > 1
+        if ((it % GJ_VRPC_SYNC_EVERY) == 0) { GJ_VRPC_REALIGN_TOP(); }
+#else
         GJ_VRPC_REALIGN_TOP();
+#endif
         const uint64_t step = A.step0 + (uint64_t)it;
         // the chain's totals are needed after the route walks: requested now, the round trip hides under them
         const unsigned long long tot0 = tot[0], tot1 = tot[1], tot2 = tot[2];
