@@ -30,7 +30,7 @@ struct GjChainSmem {
     uint32_t* bm;       // [words] full-evaluator bitmap
     uint32_t* tabu;     // [ctabu_words] the chain's tabu state
     double* edge;       // [n + 1] TSP
-    double* late;       // [late_size][GJ_MAX_LEVELS]
+    double* late;       // [late_size][levels of the model]
 };
 
 
@@ -105,14 +105,17 @@ __device__ __forceinline__ void gj_chain_combine(const GjProblemDev& P, double r
 }
 
 
-template <int KIND>
-__global__ void __launch_bounds__(kChainWarps * 32)
+// MAXW = warps (chains) per CTA at most.  Two instantiations: 4 (several CTAs per SM, no register cap) and
+// kChainWarpsWide = 28 (ONE CTA per SM, <= 72 registers): 4096 chains are 27.7 per SM, and at 96 registers
+// only 20 fit -- the narrow variant then runs a second, 38 % full wave that takes as long as the first.
+template <int KIND, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, MAXW > 4 ? 1 : 5)
 k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ GjMove sh_mv[kChainWarps];
+    __shared__ GjMove sh_mv[MAXW];
     constexpr int LV = (KIND == GJ_NQUEENS) ? 1 : 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int island = blockIdx.x * kChainWarps + warp;
+    const int island = blockIdx.x * (blockDim.x >> 5) + warp;
     if (island >= A.I) return;                       // whole warps only; no CTA-wide barrier below
     const int n = A.n_vars;
     const int words = P.bm_words + P.desc_words + P.asc_words;
@@ -149,7 +152,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     uint32_t* tabu_g = A.ctabu ? A.ctabu + (size_t)island * A.ctabu_words_per_island : nullptr;
     if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) s.tabu[w] = tabu_g[w];
     double* late_g = A.late + (size_t)island * A.late_size * GJ_MAX_LEVELS;
-    if (A.late) for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) s.late[i] = late_g[i];
+    if (A.late) for (int i = lane; i < A.late_size * LV; i += 32) s.late[i] = late_g[(size_t)(i / LV) * GJ_MAX_LEVELS + (i % LV)];
     const bool is_la = A.agent == GJ_AGENT_LATE_ACCEPTANCE;
     int late_head = is_la ? A.late_head[island] : 0, late_len = is_la ? A.late_len[island] : 0;
     double temp[GJ_MAX_LEVELS] = {1.0, 1.0, 1.0};
@@ -169,7 +172,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         if (is_la) {          // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
             late_head = (late_head + A.late_size - 1) % A.late_size;
             if (lane == 0)
-                for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = cur.v[l];
+                for (int l = 0; l < LV; ++l) s.late[(size_t)late_head * LV + l] = cur.v[l];
             late_len = min(late_len + 1, A.late_size);
             __syncwarp();
         }
@@ -218,7 +221,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         bool accept;
         if (is_la) {
             GjScore late_native = cur;
-            if (late_len > 0) late_native = gj_load_score(s.late + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
+            if (late_len > 0) late_native = gj_load_score(s.late + (size_t)((late_head + late_len - 1) % A.late_size) * LV, LV);
             accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
         } else {
             // SimulatedAnnealing (simulated_annealing_base.rs:198-233); every lane evaluates the same rule
@@ -251,7 +254,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                 for (int rep = 0; rep < 2; ++rep) {
                     late_head = (late_head + A.late_size - 1) % A.late_size;
                     if (lane == 0)
-                        for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+                        for (int l = 0; l < LV; ++l) s.late[(size_t)late_head * LV + l] = sc.v[l];
                     late_len = min(late_len + 1, A.late_size);
                 }
             }
@@ -343,7 +346,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                 // push_front; pop_back when longer than late_acceptance_size
                 late_head = (late_head + A.late_size - 1) % A.late_size;
                 if (lane == 0)
-                    for (int l = 0; l < GJ_MAX_LEVELS; ++l) s.late[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
+                    for (int l = 0; l < LV; ++l) s.late[(size_t)late_head * LV + l] = sc.v[l];
                 late_len = min(late_len + 1, A.late_size);
             }
             __syncwarp();
@@ -393,7 +396,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     // ---- finish: write the chain back ---------------------------------------------------------------
     for (int i = lane; i < n; i += 32) cur_row[i] = s.t[i];
     if (tabu_g) for (int w = lane; w < A.ctabu_words_per_island; w += 32) tabu_g[w] = s.tabu[w];
-    if (A.late) for (int i = lane; i < A.late_size * GJ_MAX_LEVELS; i += 32) late_g[i] = s.late[i];
+    if (A.late) for (int i = lane; i < A.late_size * LV; i += 32) late_g[(size_t)(i / LV) * GJ_MAX_LEVELS + (i % LV)] = s.late[i];
     __syncwarp();
     // stored scores are FULL evaluations of the stored vectors (reference summation order): float
     // drift of the delta sums never outlives a launch

@@ -347,11 +347,12 @@ __host__ __device__ inline size_t gj_chain_smem_bytes(int n_vars, int words, int
     b += (((size_t)ctabu_words + 3) & ~(size_t)3) * 4;
     b = (b + 15) & ~(size_t)15;
     if (tsp) b += (((size_t)n_vars + 2) & ~(size_t)1) * 8;
-    b += (size_t)late_size * GJ_MAX_LEVELS * 8;
+    b += (size_t)late_size * (tsp ? 2 : 1) * 8;          // the late list, one entry per level of the model
     return (b + 15) & ~(size_t)15;
 }
 
-static constexpr int kChainWarps = 4;          // k_la_chains: chains (warps) per CTA
+static constexpr int kChainWarps = 4;          // k_la_chains: chains (warps) per CTA, narrow variant
+static constexpr int kChainWarpsWide = 28;     // ... wide variant: one CTA per SM holds every chain of the SM (<= 72 registers)
 #define GJ_VRPC_DIFF 512          // stops the agent's top may trail the chain by before a whole-row copy
 
 // static + dynamic shared memory beyond 48 KB needs the opt-in; kernels here carry up to ~19 KB of
