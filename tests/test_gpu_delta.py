@@ -269,6 +269,45 @@ def test_la_chain_many_steps_per_launch_equal_single_steps(mk, oracle):
     a.close(); b.close(); gp.close()
 
 
+@pytest.mark.parametrize("mk", [lambda: inst.tsp(60, seed=2, greedy=False), lambda: inst.nqueens(64)], ids=["tsp", "nqueens"])
+def test_la_chain_wide_and_narrow_launch_shapes_run_the_same_chains(mk, oracle):
+    """More than 20 chains per SM switch k_la_chains to its wide shape (one CTA per SM, <= 72 registers,
+    every chain of the SM resident -- the C1 bench shape).  Within one launch chains are independent, and a
+    chain's random stream is keyed by its island id: the first chains of a wide group must end exactly where
+    the same chains of a small (narrow-shape) group end."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    spec = mk()
+    op = oracle.OracleProblem(spec)
+    probas = [0.0, 1.0, 0.0, 0.0, 0.0, 0.0] if spec.kind == inst.NQUEENS else [0.1, 0.3, 0.1, 0.1, 0.2, 0.2]
+    gp = Problem(spec)
+    n_wide = 24 * sms + 5
+    mkb = lambda n: LateAcceptance(8, 0.2, None, probas, 1000, scoring="delta", chain_steps_per_launch=48).build_agent(
+        gp, n_islands=n, seed=5)
+    a, b = mkb(n_wide), mkb(4)
+    assert a.step_path == "chain" and b.step_path == "chain"
+    start = [b.best(i)[1].copy() for i in range(4)]
+    a.step(48); b.step(48)
+    # (the agent tops are compared: reading a current solution first lands the pending adoption of the
+    # group's global top, which the 3 500 other chains of the wide group have improved)
+    for i in range(4):
+        ba, bsa = a.best(i)
+        bb, bsb = b.best(i)
+        assert np.array_equal(ba, bb) and np.array_equal(bsa, bsb)
+    assert a.stats()["accepted"] >= b.stats()["accepted"] > 0
+    assert any(oracle.score_cmp(b.best(i)[1], start[i]) < 0 for i in range(4))      # the chains did move
+    for i in (n_wide // 2, n_wide - 1):
+        v, sc = a.current(i)
+        assert _same_score(sc, op.score_incremental(v, [[]])[0], spec, oracle)
+        v, sc = a.best(i)
+        assert _same_score(sc, op.score_incremental(v, [[]])[0], spec, oracle)
+    assert a.stats()["candidates"] == 48 * n_wide
+    a.step(96)                                            # adoption of the global top + migration on the wide shape
+    v, sc = a.best(-1)
+    assert _same_score(sc, op.score_incremental(v, [[]])[0], spec, oracle)
+    a.close(); b.close(); gp.close()
+
+
 # ---- SimulatedAnnealing (SURVEY.md section 8f row 1) on the same chain kernel ---------------------------
 @pytest.mark.parametrize("cooling", [0.98, None], ids=["cooling", "accomplish-rate"])
 @pytest.mark.parametrize("mk", [lambda: inst.tsp(90, seed=6), lambda: inst.nqueens(40)], ids=["tsp", "nqueens"])
