@@ -173,7 +173,8 @@ struct GjVrpSmem {
     uint16_t* veh;           // [n_stops] decoded vehicle ids (relative to veh_lo)
     uint16_t* pos;           // [n_stops] rank of the stop among its warp block's stops of the same vehicle
     int32_t* cust;           // [n_stops] decoded customer ids
-    int32_t* bucket;         // [n_stops] customers grouped by vehicle, stop order kept
+    uint16_t* bucket;        // [n_stops] customers grouped by vehicle, stop order kept (location ids < 65536:
+                             // checked by gj_problem_create)
     double* wfold;           // [n_warps][32] leg lengths of the chunk a warp is folding
     double* leg;             // legs: [n_stops] D[bucket[i-1]][bucket[i]], over cust / veh
     uint32_t* rl;            // legs: [2][K] per-route demand, low and high 16-bit halves summed apart
@@ -192,7 +193,7 @@ __host__ __device__ inline size_t gj_vrp_smem_bytes(int n_stops, int K, int bm_w
     b += 32;
     b = (b + 15) & ~(size_t)15;
     if (!legs) b += (size_t)n_warps * 32 * 8;
-    b += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
+    b += ((size_t)n_stops * 2 + 7) & ~(size_t)7;
     b += legs ? (size_t)n_stops * 8 : (size_t)n_stops * 4 + 2 * (((size_t)n_stops * 2 + 7) & ~(size_t)7);
     return b;
 }
@@ -214,7 +215,7 @@ __device__ __forceinline__ GjVrpSmem gj_vrp_carve(unsigned char* smem, int n_sto
     o = (o + 15) & ~(size_t)15;
     s.wfold = (double*)(smem + o);
     if (!legs) o += (size_t)n_warps * 32 * 8;
-    s.bucket = (int32_t*)(smem + o); o += ((size_t)n_stops * 4 + 7) & ~(size_t)7;
+    s.bucket = (uint16_t*)(smem + o); o += ((size_t)n_stops * 2 + 7) & ~(size_t)7;
     s.leg = (double*)(smem + o);                     // [n_stops] f64 over cust (4 B / stop) + veh (2 B) + pos (2 B)
     s.cust = (int32_t*)(smem + o); o += (size_t)n_stops * 4;
     s.veh = (uint16_t*)(smem + o);
@@ -361,7 +362,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
     // pass 2: stable scatter: slot = first slot of (warp block, vehicle) + rank inside the block
     for (int i = lo + lane; i < hi; i += 32) {
         const int slot = mycnt[s.veh[i]] + (int)s.pos[i];
-        s.bucket[slot] = s.cust[i];
+        s.bucket[slot] = (uint16_t)s.cust[i];
         if (out) out->bstop[slot] = i;
     }
     __syncthreads();
@@ -454,7 +455,7 @@ __device__ __forceinline__ void gj_vrp_eval_cta(const GjProblemDev& P, const GjV
         double current_distance = 0.0;
         unsigned long long route_load = 0ull, route_late = 0ull;
         if (len != 0) {
-            const int32_t* st = s.bucket + b;
+            const uint16_t* st = s.bucket + b;
             const size_t depot = (size_t)P.veh_depot[v];
             const int upto = (tw_mode == GJ_TW_PSC) ? len - 1 : len;      // the PSC walk skips the last stop (Q3)
             unsigned long long arrival = P.day_start[v];

@@ -333,6 +333,8 @@ extern "C" gj_status gj_problem_create(const gj_problem_desc* desc, int32_t devi
         size_t smem = gj_vrp_smem_bytes(P.n_entities, K, P.bm_words, kVrpWarps, !P.time_windowed);
         if (smem > 220 * 1024)
             return gj_fail(GJ_ERR_UNSUPPORTED, "VRP instance too large for the shared-memory route sort");
+        if (L > 65536)
+            return gj_fail(GJ_ERR_UNSUPPORTED, "VRP models are limited to 65536 locations (16-bit ids in the route sort)");
     }
     GJ_CUDA_TRY(cudaDeviceSynchronize());
     *out = p.release();
