@@ -21,7 +21,7 @@
 
 static constexpr int kVrpChainWarps = 4;        // prepare kernel
 #ifndef GJ_VRPC_STEP_WARPS
-#define GJ_VRPC_STEP_WARPS 32
+#define GJ_VRPC_STEP_WARPS 28     // 28 x 32 threads leave 72 registers per thread (32 warps: 64, 500 B more spills)
 #endif
 static constexpr int kVrpStepWarps = GJ_VRPC_STEP_WARPS;   // step kernel: warps of a CTA re-align every step
 #define GJ_VRPC_Q 48             // 32 stops of the old route + <= 16 arrivals
