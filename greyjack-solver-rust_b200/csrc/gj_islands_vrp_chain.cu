@@ -1,6 +1,7 @@
 // gj_islands_vrp_chain.cu -- translation unit of the VRP LateAcceptance / SimulatedAnnealing chains
 // (kernels: gj_islands_vrp_chain.cuh).
 #include <algorithm>
+#include <cstdlib>
 
 #include "gj_islands_dev.cuh"
 #include "gj_islands_vrp_chain.cuh"
@@ -38,6 +39,7 @@ gj_status gj_launch_vrp_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->p->device);
     // (not a power of two: 4096 chains are 28 per SM on 147 SMs, where 32 per CTA left 20 SMs idle)
     int vw = (int)std::min<int64_t>(kVrpStepWarps, std::max<int64_t>(4, (g->I + sms - 1) / sms));
+    if (const char* e = getenv("GJ_VRPC_CTA_WARPS")) vw = std::max(1, std::min(kVrpStepWarps, atoi(e)));   // development knob
     const unsigned vgrid = (unsigned)((g->I + vw - 1) / vw);
     const size_t vsmem = sizeof(GjVrpcScratch) * vw;
     if (g->prm.agent == GJ_AGENT_LATE_ACCEPTANCE) {
