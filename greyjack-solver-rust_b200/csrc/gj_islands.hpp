@@ -55,6 +55,9 @@ struct gj_islands {
     // fused single-kernel step (gj_islands_fused.cuh)
     bool fused = false;
     bool fused_lean = false;             // long solutions: only the solution is staged in shared memory
+    // lean layout: the edge lengths / unrounded terms of the published global top, for adopters to copy
+    int* top_is_cur = nullptr;           // [I] the agent's top row IS its current row (set at the end of a step)
+    double* gedge = nullptr; double* graw = nullptr; int* gedge_ver = nullptr;
     int fused_threads = 0, fused_clones = 0, fused_mb = 0;
     size_t fused_smem = 0;
     long long* phase_clocks = nullptr;   // GJ_PHASE_TIMING=1 development aid

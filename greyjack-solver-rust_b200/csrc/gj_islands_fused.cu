@@ -16,6 +16,7 @@ gj_status gj_launch_fused_step(gj_islands* g, cudaStream_t st, bool trace) {
     F.moves_out = trace ? g->moves : nullptr;
     F.worklist = g->worklist;
     F.phase_clocks = g->phase_clocks;
+    F.top_is_cur = g->top_is_cur; F.gedge = g->gedge; F.graw = g->graw; F.gedge_ver = g->gedge_ver;
     gj_status rc;
     // registers per thread are capped by the CTA size (64 K registers per SM): 1024 threads -> 64,
     // 512 -> 128.  The kernel keeps a neighbour's move, its score keys and the RNG in registers.

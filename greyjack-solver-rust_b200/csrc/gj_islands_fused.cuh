@@ -30,6 +30,9 @@ struct GjFusedArgs {
     GjMove* moves_out;          // trace only
     int* worklist;              // [I][K]
     long long* phase_clocks;    // development aid (GJ_PHASE_TIMING=1): [I][8] clock64 at phase ends
+    // lean layout: edge lengths / unrounded terms published with the global top (k_global_top), valid for
+    // version *gedge_ver; top_is_cur[island]: the agent's top row is its current row
+    int* top_is_cur; const double* gedge; const double* graw; const int* gedge_ver;
 };
 
 struct GjFusedSmem {
@@ -336,6 +339,15 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
     __syncthreads();
     if (adopted)
         for (int i = tid; i < n; i += blockDim.x) cur_row[i] = s.t[i];
+    if constexpr (KIND == GJ_TSP) {
+        // lean layout: the adopted row came with its edge lengths and score terms (see k_global_top) --
+        // a sequential copy instead of n + 1 gathers from a matrix that does not fit in L2
+        if (adopted && F.lean && F.gedge && *F.gedge_ver == *A.gver) {
+            for (int i = tid; i <= n; i += blockDim.x) s.edge[i] = F.gedge[i];
+            if (tid == 0) { raw_g[0] = F.graw[0]; raw_g[1] = F.graw[1]; F.S.stale[island] = 0; }
+            __syncthreads();
+        }
+    }
     gj_fused_counts<KIND>(P, s, cnt_stride);
     const int state_stale = F.S.stale[island];
     // edge lengths: shared memory does not outlive the launch, so they are re-gathered every step;
@@ -524,6 +536,13 @@ k_ls_step_fused(GjProblemDev P, GjGroups G, GjFusedArgs F) {
         __syncthreads();
     }
     gj_update_top(island, levels, A.stride, n, A.cur, A.cur_score, A.best, A.best_score, A.dirty);
+    if (F.top_is_cur && tid == 0) {
+        // update_top_individual copies on `<=`: after it, equal scores <=> the top row is the current row
+        bool same = true;
+        for (int l = 0; l < levels; ++l)
+            same = same && A.best_score[(size_t)island * GJ_MAX_LEVELS + l] == A.cur_score[(size_t)island * GJ_MAX_LEVELS + l];
+        F.top_is_cur[island] = same ? 1 : 0;
+    }
 
     stamp(4);
     // ---- P4: tabu deque update (see k_select) --------------------------------------------------------------
