@@ -1610,6 +1610,7 @@ extern "C" gj_status gj_islands_set_external_ring(gj_islands* g, int32_t on, int
     if (!g) return gj_fail(GJ_ERR_INVALID, "null handle");
     g->external_ring = on != 0;
     g->island_base = island_base;
+    g->ga_moves_step = -1;          // moves generated ahead were keyed by the old island ids
     return GJ_OK;
 }
 

@@ -95,7 +95,8 @@ struct gj_islands {
     int* ga_src = nullptr;         // [I][pop] replacement source (trace)
     int32_t* ga_pairs = nullptr;   // [I][n_cand][2 + 2 * GJ_MOVE_MAXPAIRS] planned small moves as (column, value) pairs
     int* ga_take = nullptr;        // [I][pop] source slot of every new individual, bit 31 = offspring of that slot
-    cudaStream_t ga_side = nullptr; cudaEvent_t ga_ev[3] = {nullptr, nullptr, nullptr}; int ga_side_state = 0;
+    cudaStream_t ga_side = nullptr; cudaEvent_t ga_ev[4] = {nullptr, nullptr, nullptr, nullptr}; int ga_side_state = 0;
+    GjMove* ga_moves_next = nullptr; int64_t ga_moves_step = -1;   // moves of generation ga_moves_step, generated ahead
     int* ga_parent = nullptr;      // [I][n_cand] population slot every planned offspring descends from
     int* ga_rank = nullptr;        // [I][pop] rank scratch of the counting sort (kept zeroed)
     double* ga_trace_sel = nullptr;  // [I][half][8] trace of the parent draws (gj_islands_ga_trace_generation)

@@ -204,9 +204,25 @@ k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int* __
     if (tr) { tr[6] = u_cross; tr[7] = w_raw; }
     const int slot = order[(size_t)island * A.pop + (child == 0 ? r1 : r2)];
     parent_slot[t] = slot;
+    if (!moves) return;                                // generated ahead of time (k_ga_gen_moves)
     const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
     moves[t] = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), A.step, (uint32_t)c, bits,
                                 tabu_word_off);
+}
+
+// The moves of generation `step` depend on the RNG counters and on the mover's tabu deque only -- not on
+// the population -- so they are generated on the side stream as soon as the deque of the generation
+// before has advanced, off the critical path plan -> score -> replace -> sort.
+__global__ void __launch_bounds__(128)
+k_ga_gen_moves(GjProblemDev P, GjGroups G, GjMoverParams M, uint64_t seed, uint64_t step, int island_base, int I,
+               int n_cand, GjMove* __restrict__ moves, const uint32_t* __restrict__ tabu_bits,
+               int tabu_words_per_island, const int32_t* __restrict__ tabu_word_off) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)I * n_cand) return;
+    const int island = (int)(t / n_cand);
+    const int c = (int)(t % n_cand);
+    const uint32_t* bits = tabu_bits ? tabu_bits + (size_t)island * tabu_words_per_island : nullptr;
+    moves[t] = gj_generate_move(P, G, M, seed, (uint32_t)(island_base + island), step, (uint32_t)c, bits, tabu_word_off);
 }
 
 // request_score_plain on an offspring = parent row + move, one CTA per offspring, PSC semantics,
@@ -657,6 +673,7 @@ gj_status gj_ga_create(gj_problem* p, const gj_agent_params* prm, const double* 
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_rank))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_src))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->ga_parent))) return rc;
+    if (p->dev.kind >= GJ_VRP && (rc = ga_alloc(g.get(), (size_t)I * g->n_cand, &g->ga_moves_next))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * pop, &g->ga_take))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * g->n_cand * kGaPairInts, &g->ga_pairs))) return rc;
     if ((rc = ga_alloc(g.get(), (size_t)I * stride, &g->best))) return rc;
@@ -722,7 +739,7 @@ static bool ga_side_ready(gj_islands* g) {
         g->ga_side_state = -1;
         if (!(e && e[0] == '0')) {
             bool ok = cudaStreamCreateWithFlags(&g->ga_side, cudaStreamNonBlocking) == cudaSuccess;
-            for (int i = 0; ok && i < 3; ++i) ok = cudaEventCreateWithFlags(&g->ga_ev[i], cudaEventDisableTiming) == cudaSuccess;
+            for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&g->ga_ev[i], cudaEventDisableTiming) == cudaSuccess;
             if (ok) g->ga_side_state = 1;
         }
     }
@@ -740,8 +757,15 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         const int64_t S = (int64_t)g->I * g->n_cand;
         const bool trace = g->ga_trace_sel != nullptr;
         if (planned) {
-            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->order, g->ga_parent, g->moves,
-                                                                  g->tabu_bits, g->tabu_words, g->tabu_word_off, g->ga_trace_sel);
+            // moves generated ahead on the side stream (see k_ga_gen_moves)?
+            const bool ahead = g->ga_moves_next && g->ga_moves_step == (int64_t)g->step && g->ga_side_state == 1;
+            if (ahead) {
+                std::swap(g->moves, g->ga_moves_next);
+                GJ_CUDA_TRY(cudaStreamWaitEvent(st, g->ga_ev[3], 0));
+            }
+            k_ga_plan<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(P, g->groups, g->mover, A, g->order, g->ga_parent,
+                                                                  ahead ? nullptr : g->moves, g->tabu_bits, g->tabu_words,
+                                                                  g->tabu_word_off, g->ga_trace_sel);
             GJ_LAUNCH_CHECK();
         } else {
             k_ga_offspring<<<g->I * g->n_cand, 128, 0, st>>>(P, g->groups, g->mover, A, g->pop_rows, g->order, g->cand_rows, g->moves,
@@ -751,17 +775,25 @@ gj_status gj_ga_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
         // the mover's tabu deque and, later, the sort of the new population run on a side stream next to
         // the scorer and the row copies (both only have to be done before the next generation is planned)
         const bool overlap = planned && ga_side_ready(g);
+        if (overlap) {
+            GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[0], st));
+            GJ_CUDA_TRY(cudaStreamWaitEvent(g->ga_side, g->ga_ev[0], 0));
+        }
         if (g->tabu_bits) {
-            cudaStream_t ts = st;
-            if (overlap) {
-                GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[0], st));
-                GJ_CUDA_TRY(cudaStreamWaitEvent(g->ga_side, g->ga_ev[0], 0));
-                ts = g->ga_side;
-            }
-            k_ga_tabu_update<<<g->I, 256, 0, ts>>>(g->groups, g->n_cand, g->groups.n_groups, g->moves, g->tabu_bits, g->tabu_words,
-                                                   g->tabu_word_off, g->tabu_ring[g->step & 1], g->tabu_ring[(g->step + 1) & 1],
-                                                   g->tabu_ring_len, g->tabu_ring_off, g->tabu_size, g->tabu_fill);
+            k_ga_tabu_update<<<g->I, 256, 0, overlap ? g->ga_side : st>>>(
+                g->groups, g->n_cand, g->groups.n_groups, g->moves, g->tabu_bits, g->tabu_words, g->tabu_word_off,
+                g->tabu_ring[g->step & 1], g->tabu_ring[(g->step + 1) & 1], g->tabu_ring_len, g->tabu_ring_off, g->tabu_size,
+                g->tabu_fill);
             GJ_LAUNCH_CHECK();
+        }
+        if (overlap && g->ga_moves_next) {
+            // the next generation's moves, behind this generation's deque update on the side stream
+            k_ga_gen_moves<<<(unsigned)((S + 127) / 128), 128, 0, g->ga_side>>>(
+                P, g->groups, g->mover, g->prm.seed, g->step + 1, g->island_base, g->I, g->n_cand, g->ga_moves_next, g->tabu_bits,
+                g->tabu_words, g->tabu_word_off);
+            GJ_LAUNCH_CHECK();
+            GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[3], g->ga_side));
+            g->ga_moves_step = (int64_t)g->step + 1;
         }
         if ((rc = gj_prof_begin(g, st))) return rc;
         if (planned) {
