@@ -1464,6 +1464,21 @@ static gj_status launch_chain_steps(gj_islands* g, int n, cudaStream_t st, bool 
     return GJ_OK;
 }
 
+// side stream + events (shared with the GeneticAlgorithm generation, gj_islands_ga.cu), created on first use;
+// GJ_LS_OVERLAP=0 switches the overlap off
+static bool ls_side_ready(gj_islands* g) {
+    if (g->ga_side_state == 0) {
+        const char* e = getenv("GJ_LS_OVERLAP");
+        g->ga_side_state = -1;
+        if (!(e && e[0] == '0')) {
+            bool ok = cudaStreamCreateWithFlags(&g->ga_side, cudaStreamNonBlocking) == cudaSuccess;
+            for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreateWithFlags(&g->ga_ev[i], cudaEventDisableTiming) == cudaSuccess;
+            if (ok) g->ga_side_state = 1;
+        }
+    }
+    return g->ga_side_state == 1;
+}
+
 static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
     gj_status rc;
     if (g->chain) {
@@ -1478,6 +1493,17 @@ static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
             if ((rc = gj_prof_end(g, st))) return rc;
             left -= n;
             g->steps_to_send -= n;
+            // update_global_top reads and writes the agent tops / the global top only, the ring migration the
+            // current solutions only: on VRP chains, where publishing includes one CTA re-indexing the new
+            // global top (80 us), the two run side by side on two streams
+            const bool migrate_now = g->steps_to_send <= 0 && !g->external_ring;
+            const bool side = migrate_now && g->vrp_chain && ls_side_ready(g);
+            if (side) {
+                GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[0], st));
+                GJ_CUDA_TRY(cudaStreamWaitEvent(g->ga_side, g->ga_ev[0], 0));
+                if ((rc = gj_ls_global_top(g, g->ga_side))) return rc;
+                GJ_CUDA_TRY(cudaEventRecord(g->ga_ev[1], g->ga_side));
+            }
             if (g->steps_to_send <= 0) {
                 if (!g->external_ring) {
                     if ((rc = gj_ls_migrate_pack(g, st))) return rc;
@@ -1487,7 +1513,8 @@ static gj_status ls_step(gj_islands* g, int64_t n_steps, cudaStream_t st) {
                 }
                 g->steps_to_send = std::max<int64_t>(1, g->prm.migration_frequency);
             }
-            if ((rc = gj_ls_global_top(g, st))) return rc;
+            if (side) GJ_CUDA_TRY(cudaStreamWaitEvent(st, g->ga_ev[1], 0));
+            else if ((rc = gj_ls_global_top(g, st))) return rc;
         }
         return GJ_OK;
     }
