@@ -5,8 +5,10 @@
 // evaluation per step (late_acceptance_base.rs:116-141 -> vrp_service ISC :32-143).  A change / swap
 // move re-labels a handful of stops, i.e. touches 2-4 of the 125 routes.  Every chain therefore keeps
 // a ROUTE INDEX of its current solution in HBM (L2-resident between the steps of a launch):
-//     rs   [K][n]     the stop indices of every route, ascending (= the reference's visiting order:
-//                     stops are bucketed by vehicle in stop order, ISC :87-98)
+//     rs   [K][n]     the stops of every route, ascending (= the reference's visiting order: stops are
+//                     bucketed by vehicle in stop order, ISC :87-98), each entry (stop << 16) | customer --
+//                     both below 65536 (gj_problem_create) -- so that a walk needs no second, dependent
+//                     read of the solution row per stop
 //     rlen / rdist / rload / rlate [K]   length, distance, demand, lateness of every route
 //     cnt  [locations]                   customer occurrence counts;  tot: duplicates, capacity, lateness
 // and a step re-walks only the touched routes: the warp loads 32 stops of the old route at a time,
@@ -66,8 +68,9 @@ __device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int t
     for (int ch = 0; ch < nchunks; ++ch) {
         const int idx = (ch << 5) + lane;
         bool keep = idx < len;
-        const int s = keep ? rs_v[idx] : 0x7fffffff;
-        int c = keep ? row[2 * s + 1] : 0;
+        const int e = keep ? rs_v[idx] : 0;
+        const int s = keep ? (int)((unsigned)e >> 16) : 0x7fffffff;
+        int c = e & 0xffff;
         for (int j = 0; j < ncs; ++j)
             if (q.cs_stop[j] == s) {
                 if (q.cs_v[j] != v) keep = false; else c = q.cs_c[j];
@@ -105,7 +108,7 @@ __device__ __forceinline__ GjRouteStat gj_vrpc_walk(const GjProblemDev& P, int t
             if (on) {
                 f = P.cust[ci];
                 if (prev >= 0) d = __ldg(&D[(size_t)prev * L + (size_t)ci]);
-                if (out) out[outn + i] = q.qs[i];
+                if (out) out[outn + i] = (q.qs[i] << 16) | ci;
             }
             load += (unsigned long long)__reduce_add_sync(GJ_FULL_MASK, f.x & 0xffffu) +
                     ((unsigned long long)__reduce_add_sync(GJ_FULL_MASK, f.x >> 16) << 16);
@@ -222,7 +225,7 @@ __device__ __forceinline__ void gj_vrpc_bucket(const GjProblemDev& P, const int3
             const unsigned grp = __match_any_sync(GJ_FULL_MASK, v);
             if (on) {
                 const int rank = __popc(grp & ((1u << lane) - 1u));
-                rs[(size_t)v * n + rlen[v] + rank] = s;
+                rs[(size_t)v * n + rlen[v] + rank] = (s << 16) | vc.y;
                 atomicAdd(&cnt[vc.y - P.val_lo], 1);
             }
             __syncwarp();
@@ -366,8 +369,9 @@ __device__ __forceinline__ void gj_vrpc_index_cta(const GjProblemDev& P, unsigne
     for (int v = warp; v < K; v += n_warps) {
         const int b = s.start[v], len = s.start[v + 1] - b;
         for (int i = lane; i < len; i += 32) {
-            rs[(size_t)v * n + i] = bstop[b + i];
-            if (flat) V.gdst[b + i] = v * n + i;
+            const int e = (bstop[b + i] << 16) | (int)s.bucket[b + i];
+            rs[(size_t)v * n + i] = e;
+            if (flat) { bstop[b + i] = e; V.gdst[b + i] = v * n + i; }     // bstop == V.gstop: the flattened lists
         }
         if (lane == 0) {
             V.rlen[(size_t)slot * K + v] = len;
