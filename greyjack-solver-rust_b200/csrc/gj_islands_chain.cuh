@@ -170,7 +170,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
     if (have_g) gsc = gj_load_score(A.gbest_score, LV);
     if (adopted) {
         if (is_la) {          // LateAcceptance remembers the score it leaves behind (agent_base.rs:467-471)
-            late_head = (late_head + A.late_size - 1) % A.late_size;
+            late_head = (late_head == 0 ? A.late_size : late_head) - 1;
             if (lane == 0)
                 for (int l = 0; l < LV; ++l) s.late[(size_t)late_head * LV + l] = cur.v[l];
             late_len = min(late_len + 1, A.late_size);
@@ -221,7 +221,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         bool accept;
         if (is_la) {
             GjScore late_native = cur;
-            if (late_len > 0) late_native = gj_load_score(s.late + (size_t)((late_head + late_len - 1) % A.late_size) * LV, LV);
+            if (late_len > 0) late_native = gj_load_score(s.late + (size_t)gj_wrap_once(late_head + late_len - 1, A.late_size) * LV, LV);
             accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
         } else {
             // SimulatedAnnealing (simulated_annealing_base.rs:198-233); every lane evaluates the same rule
@@ -252,7 +252,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
             accepted_total += 1;
             if (is_la) {
                 for (int rep = 0; rep < 2; ++rep) {
-                    late_head = (late_head + A.late_size - 1) % A.late_size;
+                    late_head = (late_head == 0 ? A.late_size : late_head) - 1;
                     if (lane == 0)
                         for (int l = 0; l < LV; ++l) s.late[(size_t)late_head * LV + l] = sc.v[l];
                     late_len = min(late_len + 1, A.late_size);
@@ -344,7 +344,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
             accepted_total += 1;
             if (is_la) {
                 // push_front; pop_back when longer than late_acceptance_size
-                late_head = (late_head + A.late_size - 1) % A.late_size;
+                late_head = (late_head == 0 ? A.late_size : late_head) - 1;
                 if (lane == 0)
                     for (int l = 0; l < LV; ++l) s.late[(size_t)late_head * LV + l] = sc.v[l];
                 late_len = min(late_len + 1, A.late_size);
@@ -383,7 +383,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                             fill += 1;
                         }
                         ring[head] = pos;
-                        head = (head + 1) % T;
+                        head = (head + 1 == T) ? 0 : head + 1;
                         bits[pos >> 5] |= 1u << (pos & 31);
                     }
                 }

@@ -7,6 +7,9 @@
 #include "gj_eval.cuh"
 #include "gj_islands.hpp"
 
+// x mod m for 0 <= x < 2m (ring indices), without the integer division
+__device__ __forceinline__ int gj_wrap_once(int x, int m) { return x >= m ? x - m : x; }
+
 __device__ __forceinline__ int gj_vrp_tw_mode(const GjProblemDev& P) {
     return P.kind == GJ_VRP_SERVICE ? GJ_TW_ISC_SERVICE : GJ_TW_ISC_FILE;      // islands score with the ISC
 }

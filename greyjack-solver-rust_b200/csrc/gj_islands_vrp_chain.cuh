@@ -733,7 +733,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
         bool accept;
         if constexpr (is_la) {
             GjScore late_native = cur;                  // late_acceptance_base.rs:196-213
-            if (late_len > 0) late_native = gj_load_score(late_g + (size_t)((late_head + late_len - 1) % A.late_size) * GJ_MAX_LEVELS, LV);
+            if (late_len > 0) late_native = gj_load_score(late_g + (size_t)gj_wrap_once(late_head + late_len - 1, A.late_size) * GJ_MAX_LEVELS, LV);
             accept = gj_score_le(sc, late_native, LV) || gj_score_le(sc, cur, LV);
         } else {
             const double u = gj_accept_uniform(A.seed, (uint32_t)(A.island_base + island), step);
@@ -757,7 +757,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             accepted_total += 1;
             if (is_la) {
                 for (int rep = 0; rep < 2; ++rep) {
-                    late_head = (late_head + A.late_size - 1) % A.late_size;
+                    late_head = (late_head == 0 ? A.late_size : late_head) - 1;
                     if (lane == 0)
                         for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
                     late_len = min(late_len + 1, A.late_size);
@@ -814,7 +814,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
             cur = sc;
             accepted_total += 1;
             if (is_la) {
-                late_head = (late_head + A.late_size - 1) % A.late_size;
+                late_head = (late_head == 0 ? A.late_size : late_head) - 1;
                 if (lane == 0)
                     for (int l = 0; l < GJ_MAX_LEVELS; ++l) late_g[(size_t)late_head * GJ_MAX_LEVELS + l] = sc.v[l];
                 late_len = min(late_len + 1, A.late_size);
@@ -850,7 +850,7 @@ k_vrp_chains(GjProblemDev P, GjGroups G, GjChainArgs A, GjVrpChainState V) {
                             fill += 1;
                         }
                         ring[head] = pos;
-                        head = (head + 1) % T;
+                        head = (head + 1 == T) ? 0 : head + 1;
                         bits[pos >> 5] |= 1u << (pos & 31);
                     }
                 }
