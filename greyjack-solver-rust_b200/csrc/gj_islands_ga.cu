@@ -8,6 +8,16 @@
 //   k_ga_rank       population.sort() (agent_base.rs:149-151) by counting -> rank table
 //   k_ga_top        update_top_individual (agent_base.rs:220-224)
 //   k_ga_migrate_*  send_updates / receive_updates for Population agents (:337-341, 405-412)
+//
+// VRP models (one CTA scores one candidate) run the same generation without ever materialising the
+// offspring -- an offspring is one parent plus one plain-form move (see k_ga_plan):
+//
+//   k_ga_gen_moves           the moves of the NEXT generation, on the side stream (RNG + tabu deque only)
+//   k_ga_plan                select_p_best x2 + cross -> parent slot of every offspring
+//   k_ga_score_planned_vrp   parent row -> shared memory, move applied in place, PSC score, round
+//   k_ga_decide              build_updated_population: scores / sources of the new population
+//   k_ga_copy_planned || k_ga_rank (side stream)   rows of the survivors  ||  population.sort()
+//   k_ga_finish              order from rank, update_top_individual, one-island global top
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -177,7 +187,7 @@ __device__ __forceinline__ void gj_ga_apply_planned(const GjProblemDev& P, const
 // plus one plain-form move.  k_ga_plan draws parents and moves (one thread per offspring), the scorer
 // below rebuilds the offspring in shared memory straight from the parent's row -- parents are the p-best
 // slice of the population, i.e. L2-resident -- and only the offspring that survive build_updated_population
-// are ever written (k_ga_replace_planned).  A generation moves 2 x 131 MB less through HBM than
+// are ever written (k_ga_decide + k_ga_copy_planned).  A generation moves 2 x 131 MB less through HBM than
 // copy -> score -> copy.
 __global__ void __launch_bounds__(128)
 k_ga_plan(GjProblemDev P, GjGroups G, GjMoverParams M, GjGaArgs A, const int* __restrict__ order,
