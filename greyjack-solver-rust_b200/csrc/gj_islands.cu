@@ -1426,7 +1426,11 @@ gj_status gj_ls_global_top(gj_islands* g, cudaStream_t st) {
         k_apply_adoption<<<g->I, 128, 0, st>>>(gj_make_select_args(g, false, false));
         GJ_LAUNCH_CHECK();
     }
-    if (g->vrp_chain) {
+    // VRP chains: the route index of the global top is built lazily, by the first launch that follows
+    // (gj_launch_vrp_chains; the kernel returns at once when the index is current) -- a publication here
+    // and a better top merged from another GPU right after cost one re-index, not two.  On the side stream
+    // (next to the in-GPU ring migration) it is built right away: that is what the overlap is for.
+    if (g->vrp_chain && g->ga_side && st == g->ga_side) {
         gj_status rc = gj_launch_vrp_gindex(g, st);
         if (rc) return rc;
     }

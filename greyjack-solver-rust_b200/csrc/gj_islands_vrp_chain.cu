@@ -24,6 +24,8 @@ gj_status gj_launch_vrp_gindex(gj_islands* g, cudaStream_t st) {
 gj_status gj_launch_vrp_chains(gj_islands* g, const GjChainArgs& A, cudaStream_t st) {
     const GjProblemDev& P = g->p->dev;
     gj_status rc;
+    // the global top's route index, if a newer top was published since it was built (else: one CTA, two loads)
+    if (g->gver && (rc = gj_launch_vrp_gindex(g, st))) return rc;
     const size_t esmem = gj_vrp_smem_bytes(P.n_entities, P.n_vehicles, P.bm_words, kVrpWarps, !P.time_windowed);
     const int cta_rebuild = esmem <= 200 * 1024 ? 1 : 0;
     k_vrp_chain_prepare<<<(unsigned)((g->I + kVrpChainWarps - 1) / kVrpChainWarps), kVrpChainWarps * 32, 0, st>>>(P, A, g->vcs, cta_rebuild);

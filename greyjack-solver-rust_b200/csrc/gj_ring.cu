@@ -247,7 +247,7 @@ extern "C" gj_status gj_ring_exchange(gj_ring* r, void* stream) {
                                              g->stride, g->n_vars, g->levels, g->gbest, g->gbest_score, g->gver,
                                              g->ts_fast ? g->ts_pub : nullptr, g->step, r->missed);
         GJ_LAUNCH_CHECK();
-        if (g->vrp_chain && (rc = gj_launch_vrp_gindex(g, st))) return rc;
+        // (VRP chains re-index the global top lazily, at the start of their next launch: gj_launch_vrp_chains)
     }
     r->seq += 1;
     return GJ_OK;
@@ -320,6 +320,6 @@ extern "C" gj_status gj_islands_import_global_top(gj_islands* g, const void* d_r
                                      g->n_vars, g->levels, g->gbest, g->gbest_score, g->gver,
                                      g->ts_fast ? g->ts_pub : nullptr, g->step);
     GJ_LAUNCH_CHECK();
-    if (g->vrp_chain) return gj_launch_vrp_gindex(g, st);
+    // (VRP chains re-index the global top lazily, at the start of their next launch: gj_launch_vrp_chains)
     return GJ_OK;
 }
