@@ -1146,6 +1146,8 @@ static gj_status ls_create(gj_problem* p, const gj_agent_params* prm_in, const d
                 if ((rc = dev_alloc(g.get(), (size_t)I * g->ts_edge_stride, &g->ts_edge))) return rc;
                 if ((rc = dev_alloc(g.get(), 1, &g->done_counter))) return rc;
                 if ((rc = dev_alloc(g.get(), 4, &g->ts_pub, false))) return rc;
+                if ((rc = dev_alloc(g.get(), (size_t)g->ts_edge_stride, &g->gedge))) return rc;
+                if ((rc = dev_alloc(g.get(), (size_t)1, &g->gedge_ver))) return rc;
                 {
                     const unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
                     GJ_CUDA_TRY(cudaMemcpy(g->ts_pub, init, sizeof(init), cudaMemcpyHostToDevice));

@@ -35,6 +35,7 @@ gj_status gj_launch_tsfast_step(gj_islands* g, cudaStream_t st, bool trace) {
     F.phase_clocks = g->phase_clocks;
     F.done_counter = trace ? nullptr : g->done_counter;   // a trace bypasses the global-top bookkeeping
     F.pub = (trace || g->I > 4096) ? nullptr : g->ts_pub;
+    F.gedge = g->gedge; F.gedge_ver = g->gedge_ver;
     gj_status rc;
 #define GJ_LAUNCH_TSFAST(NT, MB, TR)                                                         \
     do {                                                                                     \
@@ -53,7 +54,8 @@ gj_status gj_launch_tsfast_step(gj_islands* g, cudaStream_t st, bool trace) {
 #undef GJ_LAUNCH_TSFAST
     if (F.pub) {
         GJ_LAUNCH_CHECK();
-        k_ts_publish<<<1, 256, 0, st>>>(g->ts_pub, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score, g->gver);
+        k_ts_publish<<<1, 256, 0, st>>>(g->ts_pub, g->stride, g->n_vars, g->best, g->best_score, g->gbest, g->gbest_score, g->gver,
+                                        g->cur_score, g->ds.stale, g->dirty, g->ts_edge, g->ts_edge_stride, g->gedge, g->gedge_ver);
     }
     GJ_LAUNCH_CHECK();
     return GJ_OK;

@@ -44,6 +44,9 @@ struct GjTsFastArgs {
     // not null: update_global_top's publish half by key tournament (see the end of the kernel):
     // pub[0] = best key offered so far, pub[1] = key of the published global top
     unsigned long long* pub;
+    // edge lengths of the published global top (k_ts_publish), valid for version *gedge_ver: an adopting
+    // island copies them with the row instead of re-gathering n + 1 matrix entries
+    const double* gedge; const int* gedge_ver;
 };
 
 __host__ __device__ inline size_t gj_tsfast_smem_bytes(int n_vars, int tabu_words, int cnt_stride) {
@@ -92,14 +95,25 @@ __device__ __forceinline__ unsigned long long gj_tsf_top_key(double hard, double
 // published one (strictly better score only, agent_base.rs:451) -> row, score, version.  One CTA.
 __global__ void __launch_bounds__(256)
 k_ts_publish(unsigned long long* pub, int stride, int n_vars, const int32_t* __restrict__ best,
-             const double* __restrict__ best_score, int32_t* gbest, double* gbest_score, int* gver) {
+             const double* __restrict__ best_score, int32_t* gbest, double* gbest_score, int* gver,
+             const double* __restrict__ cur_score, const int* __restrict__ stale, const int* __restrict__ dirty,
+             const double* __restrict__ edge, int edge_stride, double* gedge, int* gedge_ver) {
     const unsigned long long k = pub[0], pk = pub[1];
     if ((k >> 12) >= (pk >> 12)) return;                       // uniform over the CTA
     const int owner = (int)(k & 0xfffull);
     for (int i = threadIdx.x; i < n_vars; i += blockDim.x) gbest[i] = best[(size_t)owner * stride + i];
+    // update_top_individual copies on `<=`, so after a step equal scores <=> the owner's top row IS its
+    // current row -- whose edge lengths the step keeps in HBM: published with the row
+    bool with_edges = gedge != nullptr && stale[owner] == 0 && dirty[owner] == 0;
+    for (int l = 0; l < 2; ++l)
+        with_edges = with_edges && best_score[(size_t)owner * GJ_MAX_LEVELS + l] == cur_score[(size_t)owner * GJ_MAX_LEVELS + l];
+    if (with_edges)
+        for (int i = threadIdx.x; i < edge_stride; i += blockDim.x) gedge[i] = edge[(size_t)owner * edge_stride + i];
+    __syncthreads();
     if (threadIdx.x == 0) {
         for (int l = 0; l < GJ_MAX_LEVELS; ++l) gbest_score[l] = best_score[(size_t)owner * GJ_MAX_LEVELS + l];
         *gver += 1;
+        if (gedge_ver) *gedge_ver = with_edges ? *gver : 0;
         pub[1] = k;
     }
 }
@@ -160,7 +174,7 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     __shared__ __align__(8) uint64_t sh_mbar;
     __shared__ long long sh_curkey;
     __shared__ long long sh_bestkey;
-    __shared__ int sh_accept, sh_best, sh_nwork, sh_adopt;
+    __shared__ int sh_accept, sh_best, sh_nwork, sh_adopt, sh_gedge;
     __shared__ GjMove sh_mv;
     __shared__ GjScore sh_gs[32];
     __shared__ int sh_gi[32];
@@ -244,9 +258,14 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
         // the issuing thread polls the mbarrier (a spinning try_wait burns issue slots: with all eight
         // warps on it the poll loop was ~45 % of the kernel's executed instructions); the rest sleep
         gj_mbar_wait(&sh_mbar, 0);
+        sh_gedge = 0;
         if (adopt) {
-            gj_mbar_expect_tx(&sh_mbar, row_bytes);
+            // the adopted row comes with its edge lengths when the publisher could provide them
+            const bool ge = F.gedge != nullptr && *F.gedge_ver == *A.gver;
+            sh_gedge = ge ? 1 : 0;
+            gj_mbar_expect_tx(&sh_mbar, row_bytes + (ge ? edge_bytes : 0u));
             gj_tma_load_1d(t, A.gbest, row_bytes, &sh_mbar);
+            if (ge) gj_tma_load_1d(e64, F.gedge, edge_bytes, &sh_mbar);
             gj_mbar_wait(&sh_mbar, 1);
         }
     }
@@ -258,7 +277,12 @@ k_ts_step_fast(const __grid_constant__ GjProblemDev P, const __grid_constant__ G
     if (adopted)
         for (int i = tid; i < n; i += NT) cur_row[i] = t[i];
     __syncthreads();
-    if (state_stale) {
+    if (state_stale && adopted && sh_gedge) {
+        // the tour was replaced by the global top, whose edge lengths arrived with it
+        for (int i = tid; i <= n; i += NT) edge_g[i] = e64[i];
+        if (tid == 0) F.stale[island] = 0;
+        __syncthreads();
+    } else if (state_stale) {
         // the tour was replaced since the last step: all n + 1 edge lengths from the matrix
         for (int i = tid; i <= n; i += NT) {
             const double d = __ldg(&P.D[(size_t)t[i - 1] * L + (size_t)t[i]]);
