@@ -291,12 +291,10 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                     // small move: <= 16 (column, value) pairs, later pairs win
                     if (lane == 0) {
                         const int32_t* g = G.ids + G.offsets[ms.group];
-                        int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
-                        const int np = gj_small_move_pairs(ms, g, true, A.noop != 0,
-                                                           [&](int id) { return s.t[id]; }, cols, vals);
-                        s.scratch[0] = np;
-                        for (int i = 0; i < np; ++i) {
-                            const int c = cols[i], v = gj_fix_column(P, c, vals[i]), o = s.t[c];
+                        // one (column, value) pair: counts, then the value; the column is remembered for the
+                        // edge refresh below
+                        auto put = [&](int i, int c, int vraw) {
+                            const int v = gj_fix_column(P, c, vraw), o = s.t[c];
                             if (v != o) {
                                 s.cnt[o - P.val_lo] -= 1; s.cnt[v - P.val_lo] += 1;
                                 if constexpr (KIND == GJ_NQUEENS) {
@@ -308,6 +306,22 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                                 s.t[c] = v;
                             }
                             s.scratch[1 + i] = c;
+                        };
+                        if (ms.kind == 1 && ms.k == 2) {
+                            // a swap of two stops (the common move): both values are read before the first
+                            // write, as the generic expansion does -- without its scratch arrays, which live
+                            // in local memory (L2, with this kernel's shared-memory carve-out)
+                            const int c0 = g[sh_mv[warp].a[0]], c1 = g[sh_mv[warp].a[1]];
+                            const int v0 = s.t[c1], v1 = s.t[c0];
+                            s.scratch[0] = 2;
+                            put(0, c0, v0);
+                            put(1, c1, v1);
+                        } else {
+                            int cols[GJ_MOVE_MAXPAIRS], vals[GJ_MOVE_MAXPAIRS];
+                            const int np = gj_small_move_pairs(ms, g, true, A.noop != 0,
+                                                               [&](int id) { return s.t[id]; }, cols, vals);
+                            s.scratch[0] = np;
+                            for (int i = 0; i < np; ++i) put(i, cols[i], vals[i]);
                         }
                     }
                     __syncwarp();
