@@ -190,8 +190,15 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         const uint64_t step = A.step0 + (uint64_t)it;
         // ---- generate (every lane computes the same move: no divergence, no broadcast) ----------
         GjMoverParams M = A.M;
-        const GjMove m = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
-                                          tabu_g ? s.tabu : nullptr, A.ctabu_off);
+        {
+            // the move is parked in shared memory: 18 registers the rest of the step does not have (72-register
+            // cap of the wide shape) would otherwise sit in local memory, which is L2 under its carve-out
+            const GjMove gen = gj_generate_move(P, G, M, A.seed, (uint32_t)(A.island_base + island), step, 0u,
+                                                tabu_g ? s.tabu : nullptr, A.ctabu_off);
+            if (lane == 0) sh_mv[warp] = gen;
+            __syncwarp();
+        }
+        const GjMove& m = sh_mv[warp];
         // ---- score -----------------------------------------------------------------------------
         int d_uniq = 0; double d_dist = 0.0;
         bool ok;
@@ -204,7 +211,6 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
         double n0 = raw0 - (double)d_uniq, n1 = raw1 + d_dist;
         if (!ok) {
             // scratch clone + full evaluator (a move the delta evaluator does not cover)
-            if (lane == 0) sh_mv[warp] = m;
             for (int i = lane; i < n; i += 32) s.scratch[i] = s.t[i];
             __syncwarp();
             const GjMove ms = sh_mv[warp];
@@ -266,8 +272,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                 } else {
                     for (int i = lane; i < n; i += 32) best_row[i] = s.t[i];
                     __syncwarp();
-                    if (lane == 0) sh_mv[warp] = m;
-                    __syncwarp();
+                            __syncwarp();
                     const GjMove ms = sh_mv[warp];
                     gj_apply_move(P, ms, G, true, A.noop != 0, lane, 32,
                                   [&](int id) { return s.t[id]; }, [&](int id, int v) { best_row[id] = v; });
@@ -284,8 +289,7 @@ k_la_chains(GjProblemDev P, GjGroups G, GjChainArgs A, size_t per_chain_bytes) {
                 gj_chain_counts<KIND>(P, s, lane);
                 if constexpr (KIND == GJ_TSP) gj_chain_edges(P, s, 0, n, lane);
             } else if (m.kind != GJ_MOVE_NULL) {
-                if (lane == 0) sh_mv[warp] = m;
-                __syncwarp();
+                    __syncwarp();
                 const GjMove ms = sh_mv[warp];
                 if (ms.kind <= 3) {
                     // small move: <= 16 (column, value) pairs, later pairs win
